@@ -1,0 +1,379 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[g] (+)= alpha * opA(A[g]) * opB(B[g])     g in [0, G)   (G > 1 == grouped / batched GEMM)
+//
+// * operands are staged global -> shared by TMA (128B swizzle), multiplied by tcgen05.mma with the
+//   fp32 accumulator in TMEM (double buffered: the epilogue of tile i overlaps the main loop of tile i+1)
+// * A and B can each be K-major or MN-major, which covers the three training layouts without any
+//   transposition pass:   fwd  "TN":  Y[M,N]  = X[M,K]  * W[N,K]^T      (A K-major, B K-major)
+//                         dgrad "NN": dX[M,K] = dY[M,N] * W[N,K]        (A K-major, B MN-major)
+//                         wgrad "NT": dW[N,K] += dY[M,N]^T * X[M,K]     (A MN-major, B MN-major, fp32 accumulate)
+// * bf16 (kind::f16) and fp8 e4m3 (kind::f8f6f4, per-tensor scale folded into alpha) inputs
+// * output bf16 or fp32; `accumulate` adds into the existing fp32/bf16 C (Megatron main_grad semantics)
+//
+// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> global), one TMEM lane quarter each.
+//
+// Replaces the reference's TE general_gemm / general_grouped_gemm (cuBLASLt) measurement back-end
+// (/root/reference/simu_tools/efficency_test/test_gemm_efficiency.py:78-152,
+//  test_grouped_gemm_efficiency.py:52-68).
+#include "sm100_common.cuh"
+
+namespace smx {
+
+constexpr int kBlockM = 128;
+constexpr int kRowBytes = 128;  // one swizzle-128B row
+constexpr int kNumThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kABytes = kBlockM * kRowBytes;
+  static constexpr int kBBytes = BLOCK_N * kRowBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  int G, M, N, K;            // per-group problem
+  int m_tiles, n_tiles;      // tiles per group
+  long long ldc;             // elements
+  long long c_batch_stride;  // elements
+  float alpha;
+  int accumulate;
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN, bool OUT_F32, int ELEM_BYTES>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    void* __restrict__ c_ptr, const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int BLOCK_K = kRowBytes / ELEM_BYTES;  // 64 bf16 / 128 fp8
+  constexpr int UMMA_K = 32 / ELEM_BYTES;          // 16 bf16 / 32 fp8
+  constexpr int kKSteps = BLOCK_K / UMMA_K;        // 4
+  static_assert(!(ELEM_BYTES == 1 && (A_MN || B_MN)), "fp8 path is K-major only");
+  // bytes between consecutive 64-element MN chunks of an MN-major operand tile
+  constexpr uint32_t kMnChunkBytes = BLOCK_K * kRowBytes;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) tmem_alloc<1>(tmem_base_ptr, Cfg::kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  const int tiles_per_group = p.m_tiles * p.n_tiles;
+  const int num_tiles = tiles_per_group * p.G;
+  const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  // grouped rasterisation: walk 8 M-tiles down before moving to the next N-tile (L2 reuse of B)
+  auto tile_coords = [&](int t, int& g, int& m_blk, int& n_blk) {
+    g = t / tiles_per_group;
+    int r = t - g * tiles_per_group;
+    constexpr int kGroupM = 8;
+    int width = kGroupM * p.n_tiles;
+    int group_id = r / width;
+    int first_m = group_id * kGroupM;
+    int gsz = min(p.m_tiles - first_m, kGroupM);
+    int in_group = r - group_id * width;
+    m_blk = first_m + in_group % gsz;
+    n_blk = in_group / gsz;
+  };
+
+  if (warp_idx == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int g, m_blk, n_blk;
+        tile_coords(t, g, m_blk, n_blk);
+        const int m0 = m_blk * kBlockM, n0 = n_blk * BLOCK_N;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          const int k0 = kb * BLOCK_K;
+          if constexpr (!A_MN) {
+            tma_load_3d(&tmap_a, &full_bar[stage], sa, k0, m0, g);
+          } else {
+#pragma unroll
+            for (int c = 0; c < kBlockM / 64; ++c)
+              tma_load_3d(&tmap_a, &full_bar[stage], sa + c * kMnChunkBytes, m0 + c * 64, k0, g);
+          }
+          if constexpr (!B_MN) {
+            tma_load_3d(&tmap_b, &full_bar[stage], sb, k0, n0, g);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 64; ++c)
+              tma_load_3d(&tmap_b, &full_bar[stage], sb + c * kMnChunkBytes, n0 + c * 64, k0, g);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ============================ MMA issuer ============================
+    constexpr uint32_t kFmt = (ELEM_BYTES == 2) ? 1u /*bf16*/ : 0u /*e4m3*/;
+    constexpr uint32_t idesc = make_idesc(kFmt, kFmt, A_MN ? 1u : 0u, B_MN ? 1u : 0u, kBlockM, BLOCK_N);
+    // descriptor start-address advance (in 16 B units) per UMMA_K step
+    constexpr uint32_t a_kstep = A_MN ? (UMMA_K * kRowBytes) >> 4 : (UMMA_K * ELEM_BYTES) >> 4;
+    constexpr uint32_t b_kstep = B_MN ? (UMMA_K * kRowBytes) >> 4 : (UMMA_K * ELEM_BYTES) >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(sa), A_MN ? kMnChunkBytes : 16, 1024);
+          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(sb), B_MN ? kMnChunkBytes : 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kKSteps; ++k) {
+            umma_f16_or_f8<ELEM_BYTES>(tmem_d, a_desc + k * a_kstep, b_desc + k * b_kstep, idesc,
+                                       (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit<1>(&empty_bar[stage]);
+          if (kb == num_k_blocks - 1) umma_commit<1>(&tmem_full_bar[as]);
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  } else {
+    // ============================ epilogue ============================
+    const int q = warp_idx % 4;  // TMEM lane quarter this warp may access
+    using OutT = typename std::conditional<OUT_F32, float, __nv_bfloat16>::type;
+    OutT* c_base = reinterpret_cast<OutT*>(c_ptr);
+    const bool vec_ok = OUT_F32 ? (p.ldc % 4 == 0) : (p.ldc % 8 == 0);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int g, m_blk, n_blk;
+      tile_coords(t, g, m_blk, n_blk);
+      const int row = m_blk * kBlockM + q * 32 + lane;
+      const int n0 = n_blk * BLOCK_N;
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tcgen05_fence_after();
+      OutT* c_row = c_base + (long long)g * p.c_batch_stride + (long long)row * p.ldc;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N + c * 32;
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row < p.M && col0 < p.N) {
+          if (vec_ok && col0 + 32 <= p.N) {
+            if constexpr (OUT_F32) {
+              float4* dst = reinterpret_cast<float4*>(c_row + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 v = make_float4(__uint_as_float(r[4 * j]) * p.alpha, __uint_as_float(r[4 * j + 1]) * p.alpha,
+                                       __uint_as_float(r[4 * j + 2]) * p.alpha, __uint_as_float(r[4 * j + 3]) * p.alpha);
+                if (p.accumulate) {
+                  float4 o = dst[j];
+                  v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                }
+                dst[j] = v;
+              }
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(c_row + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[8 * j + e]) * p.alpha;
+                if (p.accumulate) {
+                  uint4 o = dst[j];
+                  const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&o);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    float2 of = __bfloat1622float2(ob[e]);
+                    f[2 * e] += of.x;
+                    f[2 * e + 1] += of.y;
+                  }
+                }
+                uint4 v;
+                v.x = pack_bf16x2(f[0], f[1]);
+                v.y = pack_bf16x2(f[2], f[3]);
+                v.z = pack_bf16x2(f[4], f[5]);
+                v.w = pack_bf16x2(f[6], f[7]);
+                dst[j] = v;
+              }
+            }
+          } else {
+            for (int j = 0; j < 32; ++j) {
+              if (col0 + j < p.N) {
+                float v = __uint_as_float(r[j]) * p.alpha;
+                if constexpr (OUT_F32) {
+                  if (p.accumulate) v += c_row[col0 + j];
+                  c_row[col0 + j] = v;
+                } else {
+                  if (p.accumulate) v += __bfloat162float(c_row[col0 + j]);
+                  c_row[col0 + j] = __float2bfloat16(v);
+                }
+              }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<1>(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace smx
+
+// ----------------------------------------------------------------------------------------------
+// host launcher (C ABI, called through ctypes)
+// ----------------------------------------------------------------------------------------------
+namespace {
+
+template <int BLOCK_N, bool A_MN, bool B_MN, bool OUT_F32, int EB>
+int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const smx::GemmParams& p, int num_sms,
+               cudaStream_t stream) {
+  using Cfg = smx::GemmCfg<BLOCK_N>;
+  auto kern = smx::gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, OUT_F32, EB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  int tiles = p.G * p.m_tiles * p.n_tiles;
+  int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, smx::kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, C, p);
+  return (int)cudaGetLastError();
+}
+
+template <bool A_MN, bool B_MN, bool OUT_F32, int EB>
+int launch_bn(int block_n, const CUtensorMap& ta, const CUtensorMap& tb, void* C, const smx::GemmParams& p,
+              int num_sms, cudaStream_t stream) {
+  switch (block_n) {
+    case 256: return launch_cfg<256, A_MN, B_MN, OUT_F32, EB>(ta, tb, C, p, num_sms, stream);
+    case 128: return launch_cfg<128, A_MN, B_MN, OUT_F32, EB>(ta, tb, C, p, num_sms, stream);
+    case 64: return launch_cfg<64, A_MN, B_MN, OUT_F32, EB>(ta, tb, C, p, num_sms, stream);
+    default: return -10;
+  }
+}
+
+int pick_block_n(int G, int M, int N, int num_sms) {
+  const int cands[3] = {256, 128, 64};
+  long long best_cost = -1;
+  int best = 256;
+  long long m_tiles = (M + smx::kBlockM - 1) / smx::kBlockM;
+  for (int i = 0; i < 3; ++i) {
+    int bn = cands[i];
+    long long tiles = (long long)G * m_tiles * ((N + bn - 1) / bn);
+    long long waves = (tiles + num_sms - 1) / num_sms;
+    // per-tile cost ~ bn columns of MMA + a fixed prologue/epilogue-exposure term
+    long long cost = waves * (bn + 24);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+}  // namespace
+
+extern "C" {
+
+// dtype: 0 = bf16 inputs, 1 = fp8 e4m3 inputs.  a_mn / b_mn: operand stored MN-major ([K, MN] row-major).
+// lda / ldb / ldc and batch strides are in elements.  Returns 0 on success (cudaError / negative on failure).
+int smx_gemm(const void* A, const void* B, void* C, int G, int M, int N, int K, int a_mn, int b_mn, int dtype,
+             int out_f32, int accumulate, float alpha, long long lda, long long ldb, long long ldc,
+             long long a_bs, long long b_bs, long long c_bs, int block_n, int num_sms, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (G <= 0 || M <= 0 || N <= 0 || K <= 0) return 0;
+  const int eb = dtype == 0 ? 2 : 1;
+  const int block_k = 128 / eb;
+  if (block_n <= 0) block_n = pick_block_n(G, M, N, num_sms);
+  if (dtype == 1 && (a_mn || b_mn)) return -11;
+  CUtensorMapDataType dt = dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn) rc = smx::make_tmap_3d(&ta, dt, A, K, M, G, lda * eb, a_bs * eb, block_k, smx::kBlockM);
+  else       rc = smx::make_tmap_3d(&ta, dt, A, M, K, G, lda * eb, a_bs * eb, 64, block_k);
+  if (rc) return rc;
+  if (!b_mn) rc = smx::make_tmap_3d(&tb, dt, B, K, N, G, ldb * eb, b_bs * eb, block_k, block_n);
+  else       rc = smx::make_tmap_3d(&tb, dt, B, N, K, G, ldb * eb, b_bs * eb, 64, block_k);
+  if (rc) return rc;
+  smx::GemmParams p;
+  p.G = G; p.M = M; p.N = N; p.K = K;
+  p.m_tiles = (M + smx::kBlockM - 1) / smx::kBlockM;
+  p.n_tiles = (N + block_n - 1) / block_n;
+  p.ldc = ldc; p.c_batch_stride = c_bs; p.alpha = alpha; p.accumulate = accumulate;
+  if (dtype == 0) {
+    if (!a_mn && !b_mn) return out_f32 ? launch_bn<false, false, true, 2>(block_n, ta, tb, C, p, num_sms, stream)
+                                       : launch_bn<false, false, false, 2>(block_n, ta, tb, C, p, num_sms, stream);
+    if (!a_mn && b_mn)  return out_f32 ? launch_bn<false, true, true, 2>(block_n, ta, tb, C, p, num_sms, stream)
+                                       : launch_bn<false, true, false, 2>(block_n, ta, tb, C, p, num_sms, stream);
+    if (a_mn && b_mn)   return out_f32 ? launch_bn<true, true, true, 2>(block_n, ta, tb, C, p, num_sms, stream)
+                                       : launch_bn<true, true, false, 2>(block_n, ta, tb, C, p, num_sms, stream);
+    return out_f32 ? launch_bn<true, false, true, 2>(block_n, ta, tb, C, p, num_sms, stream)
+                   : launch_bn<true, false, false, 2>(block_n, ta, tb, C, p, num_sms, stream);
+  }
+  return out_f32 ? launch_bn<false, false, true, 1>(block_n, ta, tb, C, p, num_sms, stream)
+                 : launch_bn<false, false, false, 1>(block_n, ta, tb, C, p, num_sms, stream);
+}
+
+int smx_gemm_pick_block_n(int G, int M, int N, int num_sms) { return pick_block_n(G, M, N, num_sms); }
+
+}  // extern "C"

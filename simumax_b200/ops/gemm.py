@@ -1,0 +1,121 @@
+"""tcgen05 GEMM front-end (bf16 / fp8-e4m3, plain and grouped).
+
+Layout names follow the reference's calibration keys (``layout=TN|NN|NT``,
+/root/reference/simu_tools/efficency_test/test_gemm_efficiency.py:90-101):
+
+* ``TN``  fwd  :  out[M,N]  = a[M,K]  @ b[N,K]^T
+* ``NN``  dgrad:  out[M,N]  = a[M,K]  @ b[K,N]          (b is the [out,in] weight read "untransposed")
+* ``NT``  wgrad:  out[M,N] (+)= a[K,M]^T @ b[K,N]       (reduction over tokens; fp32 accumulate target)
+
+All three run on the same kernel by telling tcgen05 whether each shared-memory operand tile is
+K-major or MN-major; no transposed copy is ever materialised.
+"""
+from __future__ import annotations
+
+import ctypes
+from functools import lru_cache
+
+import torch
+
+from . import _lib
+
+_LAYOUTS = {"TN": (0, 0), "NN": (0, 1), "NT": (1, 1), "TT": (1, 0)}
+
+
+@lru_cache(maxsize=None)
+def _num_sms(device_index: int) -> int:
+    return torch.cuda.get_device_properties(device_index).multi_processor_count
+
+
+def _fn():
+    f = _lib.lib().smx_gemm
+    if not getattr(f, "_configured", False):
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 9 + [ctypes.c_float] + \
+            [ctypes.c_longlong] * 6 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        f._configured = True
+    return f
+
+
+def _as3d(t: torch.Tensor) -> torch.Tensor:
+    return t if t.dim() == 3 else t.unsqueeze(0)
+
+
+def _tma_ready(t3: torch.Tensor) -> torch.Tensor:
+    """TMA needs a contiguous inner dim, 16-byte aligned base and 16-byte-multiple outer strides.
+
+    Tensors that already satisfy this (every shape in the model zoo) pass through untouched; odd ones
+    are copied once into a row-padded buffer and viewed back to their logical width.
+    """
+    es = t3.element_size()
+    ok = (t3.stride(-1) == 1 and t3.data_ptr() % 16 == 0 and (t3.stride(1) * es) % 16 == 0
+          and (t3.shape[0] == 1 or (t3.stride(0) * es) % 16 == 0))
+    if ok:
+        return t3
+    per16 = 16 // es
+    cols = t3.shape[-1]
+    padded = (cols + per16 - 1) // per16 * per16
+    buf = torch.zeros(t3.shape[0], t3.shape[1], padded, device=t3.device, dtype=t3.dtype)
+    buf[:, :, :cols].copy_(t3)
+    return buf[:, :, :cols]
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, layout: str = "TN", out: torch.Tensor | None = None,
+         out_dtype: torch.dtype | None = None, accumulate: bool = False, alpha: float = 1.0,
+         block_n: int = 0, sm_limit: int = 0) -> torch.Tensor:
+    """out (+)= alpha * op(a) @ op(b).  2-D inputs = one GEMM, 3-D inputs = grouped GEMM over dim 0.
+
+    The innermost dimension of every operand must be contiguous; row strides only need 16-byte
+    alignment (so column-sliced views work without a copy).
+    """
+    a_mn, b_mn = _LAYOUTS[layout]
+    if a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16:
+        dtype = 0
+    elif a.dtype == torch.float8_e4m3fn and b.dtype == torch.float8_e4m3fn:
+        dtype = 1
+    else:
+        raise TypeError(f"unsupported operand dtypes {a.dtype} x {b.dtype}")
+    squeeze = a.dim() == 2
+    a3, b3 = _as3d(a), _as3d(b)
+    a3, b3 = _tma_ready(a3), _tma_ready(b3)
+    G = a3.shape[0]
+    if a_mn:
+        K, M = a3.shape[1], a3.shape[2]
+    else:
+        M, K = a3.shape[1], a3.shape[2]
+    if b_mn:
+        Kb, N = b3.shape[1], b3.shape[2]
+    else:
+        N, Kb = b3.shape[1], b3.shape[2]
+    if Kb != K or b3.shape[0] != G:
+        raise ValueError(f"shape mismatch: a{tuple(a.shape)} b{tuple(b.shape)} layout {layout}")
+    if out is None:
+        if accumulate:
+            raise ValueError("accumulate=True needs an `out` tensor")
+        od = out_dtype or torch.bfloat16
+        out = torch.empty((G, M, N), device=a.device, dtype=od)
+        out3 = out
+    else:
+        out3 = _as3d(out)
+        if out3.shape != (G, M, N) or out3.stride(-1) != 1:
+            raise ValueError(f"bad out shape/stride {tuple(out.shape)} for G,M,N={G},{M},{N}")
+    if out3.dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError("out must be bf16 or fp32")
+    stream = torch.cuda.current_stream(a.device).cuda_stream
+    nsm = _num_sms(a.device.index if a.device.index is not None else torch.cuda.current_device())
+    if sm_limit:
+        nsm = min(nsm, sm_limit)
+    rc = _fn()(a3.data_ptr(), b3.data_ptr(), out3.data_ptr(), G, M, N, K, a_mn, b_mn, dtype,
+               1 if out3.dtype == torch.float32 else 0, 1 if accumulate else 0, float(alpha),
+               a3.stride(1), b3.stride(1), out3.stride(1),
+               a3.stride(0) if G > 1 else 0, b3.stride(0) if G > 1 else 0, out3.stride(0) if G > 1 else 0,
+               block_n, nsm, stream)
+    _lib.check(rc, f"gemm[{layout}] G{G} M{M} N{N} K{K}")
+    _lib.count_launch()
+    if out.dim() == 3 and squeeze and out is out3:
+        return out3[0]
+    return out
+
+
+def gemm_flops(M: int, N: int, K: int, G: int = 1) -> float:
+    return 2.0 * G * M * N * K
