@@ -1,0 +1,314 @@
+"""Model assembly: transformer block / full stage chunk as a flat, evaluated op list.
+
+Structure being modelled (reference transformer/language_model.py:98-353, dense_module.py:2454-2976):
+
+    chunk  = [Embedding] + N x block + [final RMSNorm + vocab LinearCol + ParallelCE]
+    block  = RMSNorm -> attention -> RMSNorm -> mlp            (residual adds are not modelled)
+    attn   = LinearCol(qkv) -> CoreAttention -> LinearRow      (MLA: see models/mla.py)
+    mlp    = LinearCol(fc1) -> SwiGLU|GeLU -> LinearRow(fc2)   (MoE: see models/moe.py)
+
+Op names reproduce the reference's dotted attribute paths (``self.layer_3.mlp.linear_fc1``) because they show
+up in result files (peak_path) and in trace scopes.
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+from typing import Dict, List, Optional
+
+from ..core.config import AttentionRecomputeConfig, MLPRecomputeConfig, ModelConfig, StrategyConfig, SystemConfig
+from ..core.ir import PHASES, OpNode, evaluate, ishape
+from ..core.memory import assign_recompute_status, walk_activations
+from ..core.records import ComputeInfo, CostInfo, MemoryInfo, PeakPoint
+from . import dense as D
+
+
+class Emitter:
+    """Collects ops in execution order while tracking the scope (composite-module) stack."""
+
+    def __init__(self, model: ModelConfig, strategy: StrategyConfig, system: SystemConfig):
+        self.model, self.st, self.system = model, strategy, system
+        self.nodes: List[OpNode] = []
+        self._names: List[str] = ["self"]
+        self._scopes: List[str] = []
+        self.scope_tree: List[tuple] = []      # (depth, scope display name, first op index, last op index)
+
+    # naming -------------------------------------------------------------------------------------
+    def name(self, leaf: str) -> str:
+        return ".".join(self._names + [leaf])
+
+    class _Scope:
+        def __init__(self, em, attr, display):
+            self.em, self.attr, self.display = em, attr, display
+
+        def __enter__(self):
+            self.em._names.append(self.attr)
+            self.em._scopes.append(self.display)
+            self.start = len(self.em.nodes)
+            self.depth = len(self.em._scopes)
+            return self
+
+        def __exit__(self, *exc):
+            self.em.scope_tree.append((self.depth, self.display, self.start, len(self.em.nodes), tuple(self.em._scopes)))
+            self.em._names.pop()
+            self.em._scopes.pop()
+
+    def scope(self, attr: str, display: str):
+        return Emitter._Scope(self, attr, display)
+
+    def add(self, node: OpNode) -> OpNode:
+        node.scope = tuple(self._scopes)
+        self.nodes.append(node)
+        return node
+
+
+# ------------------------------------------------------------------------------------------------
+# composites
+# ------------------------------------------------------------------------------------------------
+def _maybe_quantize(em: Emitter, attr: str, shape, enable_recompute: bool):
+    """fp8: every linear is preceded by a cast op (QuantizedCol/RowLinear, dense_module.py:2397-2452)."""
+    if not em.st.fp8:
+        return None
+    node, _ = D.fp8_quantizer(em.st, shape, em.name("quntizer"), enable_recompute=enable_recompute)
+    return em.add(node)
+
+
+def _linear(em: Emitter, attr: str, kind: str, in_f, out_f, shape, display, **kw):
+    """Emit a (possibly fp8-wrapped) linear under attribute ``attr``; returns (linear node, out shape)."""
+    ctor = D.linear_col if kind == "col" else D.linear_row
+    if em.st.fp8 and kw.pop("wrap_fp8", True):
+        with em.scope(attr, "QuantizedColLinear"):
+            _maybe_quantize(em, attr, shape, kw.get("enable_recompute", False))
+            node, out = ctor(em.st, in_f, out_f, shape, em.name("linear"), display=display, **kw)
+            em.add(node)
+        return node, out
+    kw.pop("wrap_fp8", None)
+    node, out = ctor(em.st, in_f, out_f, shape, em.name(attr), display=display, **kw)
+    em.add(node)
+    return node, out
+
+
+def emit_attention(em: Emitter, layer_idx: int, shape, rc: AttentionRecomputeConfig):
+    cfg, st = em.model, em.st
+    qkv_out = cfg.head_num * cfg.head_size + 2 * cfg.kv_head_num * cfg.head_size
+    tail = rc.megatron_layernorm
+    with em.scope("attention", "SelfAttention"):
+        _, shape = _linear(em, "linear_qkv", "col", cfg.hidden_size, qkv_out, shape, "ColumnParallelLinear",
+                           layer_idx=layer_idx, has_cached_inputs=tail,
+                           enable_recompute=rc.q_up_recompute or tail, is_last_recompute=tail,
+                           use_variance_tail_model=tail)
+        node, shape = D.core_attention(st, em.system, cfg.head_size, cfg.head_num, cfg.kv_head_num, shape,
+                                       em.name("attention"), enable_recompute=rc.core_attn_recompute,
+                                       is_last_recompute=True, cache_outputs=bool(st.use_flash_sdp and st.fp8))
+        em.add(node)
+        _, shape = _linear(em, "linear_out", "row", cfg.head_num * cfg.head_size, cfg.hidden_size, shape,
+                           "RowParallelLinear", layer_idx=layer_idx, enable_recompute=rc.out_recompute)
+    return shape
+
+
+def emit_mlp(em: Emitter, layer_idx, shape, rc: MLPRecomputeConfig, *, attr="mlp", display="MLP",
+             intermediate_size=None):
+    cfg, st = em.model, em.st
+    is_shared = isinstance(layer_idx, str) and "shareExpert" in layer_idx
+    dense_ckpt = rc.linear_recompute or (rc.megatron_mlp and not is_shared)
+    shared_ckpt = rc.shared_linear_recompute or (rc.megatron_moe and is_shared)
+    local_inter = cfg.intermediate_size if intermediate_size is None else intermediate_size
+    fc1_out = 2 * local_inter if cfg.use_swiglu else local_inter
+    enable = shared_ckpt if is_shared else dense_ckpt
+    tail = rc.megatron_layernorm and not is_shared
+    with em.scope(attr, display):
+        fc1, shape = _linear(em, "linear_fc1", "col", cfg.hidden_size, fc1_out, shape, "ColumnParallelLinear",
+                             layer_idx=layer_idx, has_cached_inputs=tail, enable_recompute=enable or tail,
+                             is_last_recompute=tail, use_variance_tail_model=tail)
+        if st.recompute_granularity == "selective_recompute" and rc.megatron_layernorm and enable:
+            fc1.is_breakpoint = True
+        if cfg.use_swiglu:
+            node, shape = D.swiglu(st, shape, em.name("activation_layer"), enable_recompute=enable)
+        else:
+            node, shape = D.gelu(st, shape, em.name("activation_layer"), enable_recompute=enable)
+        em.add(node)
+        _, shape = _linear(em, "linear_fc2", "row", local_inter, cfg.hidden_size, shape, "RowParallelLinear",
+                           layer_idx=layer_idx, enable_recompute=enable, is_last_recompute=True)
+    return shape
+
+
+def emit_block(em: Emitter, layer_idx: int, shape, use_dense: bool):
+    cfg, st = em.model, em.st
+    arc = st.parse_attention_recompute(layer_idx)
+    mrc = st.parse_mlp_recompute(layer_idx)
+    with em.scope(f"layer_{layer_idx}", f"TransformerLayer{layer_idx}"):
+        first_index = len(em.nodes)
+        node, shape = D.layernorm(st, cfg.hidden_size, shape, em.name("layernorm_input"),
+                                  enable_recompute=arc.input_layernorm_recompute)
+        em.add(node)
+        if getattr(cfg, "attention_type", None) == "mla":
+            from .mla import emit_mla_attention
+            shape = emit_mla_attention(em, layer_idx, shape, arc)
+        else:
+            shape = emit_attention(em, layer_idx, shape, arc)
+        node, shape = D.layernorm(st, cfg.hidden_size, shape, em.name("pre_mlp_layernorm"),
+                                  enable_recompute=mrc.pre_mlp_norm_recompute)
+        em.add(node)
+        if cfg.expert_num == 1 or use_dense:
+            shape = emit_mlp(em, layer_idx, shape, mrc)
+        else:
+            from .moe import emit_expert_mlp
+            shape = emit_expert_mlp(em, layer_idx, shape, mrc)
+    return shape, first_index
+
+
+# ------------------------------------------------------------------------------------------------
+# stage chunk
+# ------------------------------------------------------------------------------------------------
+class StageChunk:
+    """All ops a pipeline stage executes for one micro-batch, evaluated against a system config.
+
+    API-compatible stand-in for the reference ``LLMModel`` instance stored in ``PerfLLM.model_chunk_dict``.
+    """
+
+    def __init__(self, layer_num: int, dense_layers: int = 0, preprocess: bool = True, postprocess: bool = True,
+                 model_config: ModelConfig = None, strategy: StrategyConfig = None, system: SystemConfig = None,
+                 specific_name: str = "GPTModel_0"):
+        self.layer_num = layer_num
+        self.dense_layers = dense_layers
+        self.preprocess, self.postprocess = preprocess, postprocess
+        self.model_config = deepcopy(model_config)
+        self.strategy, self.system = strategy, system
+        self.specific_name = specific_name
+        self.nodes: List[OpNode] = []
+        self.layer_first_nodes: List[OpNode] = []
+        self.scope_tree: List[tuple] = []
+        self.input_shape = None
+        self._model_info = MemoryInfo()
+        self._compute_info = ComputeInfo()
+        self._cost_info = CostInfo()
+        self._info_ready = False
+
+    # -- build + evaluate ---------------------------------------------------------------------------
+    def __call__(self, input_shape, _ctx=None):
+        cfg, st = self.model_config, self.strategy
+        em = Emitter(cfg, st, self.system)
+        shape = ishape(getattr(input_shape, "shape", input_shape))
+        self.input_shape = shape
+        if self.preprocess:
+            node, shape = D.embedding(st, cfg.hidden_size, cfg.vocab_size, shape, em.name("embedding"))
+            em.add(node)
+        firsts = []
+        for i in range(self.layer_num):
+            shape, first_idx = emit_block(em, i, shape, use_dense=(i < self.dense_layers))
+            firsts.append(first_idx)
+        if self.postprocess:
+            node, shape = D.layernorm(st, cfg.hidden_size, shape, em.name("layernorm"))
+            em.add(node)
+            node, shape = D.linear_col(st, cfg.hidden_size, cfg.vocab_size, shape, em.name("linear_out"),
+                                       layer_idx=-1, enable_fp8=False, display="ColumnParallelLinear")
+            em.add(node)
+            node, shape = D.parallel_ce(st, shape, em.name("parallel_ce"))
+            em.add(node)
+        self.nodes = em.nodes
+        self.scope_tree = em.scope_tree
+        self.layer_first_nodes = [self.nodes[i] for i in firsts if i < len(self.nodes)]
+        assign_recompute_status(self.nodes)
+        mem, comp, cost = MemoryInfo(), ComputeInfo(), CostInfo()
+        for n in self.nodes:
+            evaluate(n, self.system)
+            mem = mem + n.mem
+            comp = comp + n.compute
+            cost = cost + n.cost
+        self._model_info, self._compute_info, self._cost_info = mem, comp, cost
+        self._info_ready = True
+        return shape
+
+    def compute_activations(self) -> PeakPoint:
+        return walk_activations(self.nodes, self.layer_first_nodes, self.strategy.enable_recompute)
+
+    # -- reference-compatible accessors ---------------------------------------------------------------
+    @property
+    def main_grad_element_size(self) -> int:
+        from ..core.ir import main_grad_bytes
+        return main_grad_bytes(self.strategy)
+
+    def get_model_info(self) -> MemoryInfo:
+        assert self._info_ready, "model info not ready, please call the module to compute info"
+        return self._model_info
+
+    def get_compute_info(self) -> ComputeInfo:
+        assert self._info_ready
+        return self._compute_info
+
+    def get_cost_info(self) -> CostInfo:
+        assert self._info_ready
+        return self._cost_info
+
+    def get_all_leaf_modules(self) -> List[OpNode]:
+        return self.nodes
+
+    def get_all_gemm_cost_info(self) -> Dict[str, list]:
+        """Per-GEMM table (fwd / dgrad / wgrad rows) -- also the shape enumeration the calibration sweeps."""
+        cols = ["Module", "type", "B", "M", "K", "N", "layout", "accumulate", "out_dtype", "compute_cost",
+                "memory_cost", "cost", "bound"]
+        out = {c: [] for c in cols}
+        for n in self.nodes:
+            if n.gemm is None or n.kind not in ("LinearCol", "LinearRow", "GroupLinearCol", "GroupLinearRow", "Router"):
+                continue
+            if n.kind == "Router":
+                continue
+            for key in ("B", "M", "K", "N", "layout", "accumulate", "out_dtype"):
+                out[key].extend(n.gemm[key])
+            cc = [n.details[p]["compute_details"]["compute_only_time"] for p in PHASES]
+            mc = [n.details[p]["io_details"]["io_time"] for p in PHASES]
+            out["compute_cost"].extend(cc)
+            out["memory_cost"].extend(mc)
+            out["bound"].extend(["IO bound" if m > c else "compute bound" for m, c in zip(mc, cc)])
+            out["cost"].extend(n.cost.get_all_costs())
+            out["Module"].extend([n.name + ".fwd", n.name + ".bwd_act", n.name + ".bwd_w"])
+            out["type"].extend([n.kind] * 3)
+        return out
+
+    def analysis_op_info(self, return_details: bool = False) -> Dict[str, list]:
+        """Per-op table: shapes, flops, IO bytes, time, roofline side (language_model.py:514-595)."""
+        cols = ["op", "input_shapes", "output_shapes", "flops", "IO", "cost", "compute_only_time", "IO_time", "bound"]
+        out = {c: [] for c in cols}
+        if return_details:
+            out["compute_only_details"], out["IO_details"] = [], []
+
+        def push(label, ins, outs, flops, io, cost, det):
+            out["op"].append(label)
+            out["input_shapes"].append(ins)
+            out["output_shapes"].append(outs)
+            out["flops"].append(flops)
+            out["IO"].append(io)
+            out["cost"].append(cost)
+            ct, it = det["compute_details"]["compute_only_time"], det["io_details"]["io_time"]
+            out["compute_only_time"].append(ct)
+            out["IO_time"].append(it)
+            out["bound"].append("IO bound" if it > ct else "Compute bound")
+            if return_details:
+                out["compute_only_details"].append(det["compute_details"])
+                out["IO_details"].append(det["io_details"])
+
+        for n in self.nodes:
+            w = [n.weight_shape] if n.weight_shape is not None else []
+            is_linear = n.gemm is not None
+            push(n.kind, n.in_shapes + (w if not is_linear else []), n.out_shapes, n.compute.fwd_flops,
+                 n.compute.fwd_accessed_mem, n.cost.fwd_compute_time, n.details["fwd"])
+            wt = [list(reversed(n.weight_shape))] if (is_linear and n.weight_shape) else w
+            push(n.kind + "_bwd_act", n.out_shapes + wt, n.in_shapes, n.compute.bwd_grad_act_flops,
+                 n.compute.bwd_grad_act_accessed_mem, n.cost.bwd_grad_act_time, n.details["bwd_grad_act"])
+            if is_linear and n.weight_shape:
+                lhs = [list(n.in_shapes[0][:-2]) + [n.in_shapes[0][-1], n.in_shapes[0][-2]]] if len(n.in_shapes[0]) >= 2 else n.in_shapes
+                push(n.kind + "_bwd_w", lhs + n.out_shapes, [n.weight_shape], n.compute.bwd_grad_w_flops,
+                     n.compute.bwd_grad_w_accessed_mem, n.cost.bwd_grad_w_time, n.details["bwd_grad_w"])
+        return out
+
+    def __repr__(self) -> str:
+        lines = [f"{self.specific_name}(layers={self.layer_num}, pre={self.preprocess}, post={self.postprocess})"]
+        for n in self.nodes:
+            c = n.cost
+            lines.append(f"  {n.name:<60s} {n.kind:<18s} fwd={c.fwd_compute_time * 1e3:9.2f}us net={c.fwd_net_time * 1e3:8.2f}us "
+                         f"bwd={c.bwd_compute_time * 1e3:9.2f}us net={c.bwd_net_time * 1e3:8.2f}us "
+                         f"cache={n.act.activation_mem_cache / 2 ** 20:9.2f}MB rc={n.recompute_status}")
+        return "\n".join(lines)
+
+
+# reference class name, so `from ... import LLMModel` style code keeps working
+LLMModel = StageChunk
