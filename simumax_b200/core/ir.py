@@ -155,6 +155,9 @@ def evaluate(node: OpNode, system: SystemConfig) -> OpNode:
     if node.enable_recompute and node.is_variance_node:
         cost.recompute_compute_time = 0
     node.cost = cost
+    hook = getattr(node, "post_evaluate", None)
+    if hook is not None:
+        hook(node)
     return node
 
 
@@ -166,7 +169,7 @@ def default_sim_steps(node: OpNode) -> List[SimStep]:
 # ------------------------------------------------------------------------------------------------
 # helpers shared by the leaf constructors
 # ------------------------------------------------------------------------------------------------
-DT = {"fp32": 4, "fp16": 2, "bf16": 2, "fp8": 1}
+DT = {"fp32": 4, "fp16": 2, "bf16": 2, "fp8": 1, "int32": 4, "int64": 8}
 
 
 def numel(shape) -> float:

@@ -93,9 +93,8 @@ def convert_final_result_to_human_format(result: dict) -> None:
         if isinstance(v, dict):
             convert_final_result_to_human_format(v)
             continue
-        if isinstance(v, bool) or not isinstance(v, (int, float)):
-            if not isinstance(v, (int, float)):
-                continue
+        if not isinstance(v, (int, float)):
+            continue
         if "time" in k:
             result[k] = human_readable_times(v)
         elif "mem" in k or "bytes" in k:
