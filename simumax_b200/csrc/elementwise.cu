@@ -1,0 +1,538 @@
+// Memory-bound kernels for sm_100a: RMSNorm fwd/bwd, SwiGLU fwd/bwd, RoPE (in place, fwd/bwd), fused
+// cross-entropy fwd+bwd (online softmax, one pass over the logits, gradient written in place),
+// fused Adam (fp32 master + bf16 model copy), squared-L2 norm, MoE token permute / unpermute.
+//
+// Design rules (B200: 148 SMs, ~6.6 TB/s measured HBM): 16-byte vector accesses, one row per CTA (or warp)
+// with the row kept in registers between the reduction and the normalisation so every tensor is read once,
+// grid sized to the row count (>> 148 x resident CTAs), fp32 math, bf16 I/O.
+//
+// These replace the reference's library calls in the calibration suite (TE fused CE, TE permute:
+// /root/reference/simu_tools/efficency_test/test_ce_permute_efficiency.py:216-293) and are the building
+// blocks of the measured training step.
+#include "sm100_common.cuh"
+
+namespace smx {
+
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+SMX_DEVICE void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  bf16x8 r = *reinterpret_cast<const bf16x8*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(r.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+SMX_DEVICE void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  bf16x8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<bf16x8*>(p) = r;
+}
+
+template <int THREADS>
+SMX_DEVICE float block_sum(float v, float* smem) {
+  v = warp_sum(v);
+  const int w = threadIdx.x / 32, l = threadIdx.x % 32;
+  if (l == 0) smem[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < THREADS / 32) ? smem[threadIdx.x] : 0.f;
+  if (w == 0) {
+    t = warp_sum(t);
+    if (l == 0) smem[0] = t;
+  }
+  __syncthreads();
+  t = smem[0];
+  __syncthreads();
+  return t;
+}
+template <int THREADS>
+SMX_DEVICE float block_max(float v, float* smem) {
+  v = warp_max(v);
+  const int w = threadIdx.x / 32, l = threadIdx.x % 32;
+  if (l == 0) smem[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < THREADS / 32) ? smem[threadIdx.x] : -INFINITY;
+  if (w == 0) {
+    t = warp_max(t);
+    if (l == 0) smem[0] = t;
+  }
+  __syncthreads();
+  t = smem[0];
+  __syncthreads();
+  return t;
+}
+
+// ----------------------------------------------------------------------------------------------
+// RMSNorm.  One CTA per row, H <= THREADS * 8 * VPT elements kept in registers.
+// ----------------------------------------------------------------------------------------------
+template <int THREADS, int VPT>
+__global__ void __launch_bounds__(THREADS) rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                             const __nv_bfloat16* __restrict__ gamma,
+                                                             __nv_bfloat16* __restrict__ y, float* __restrict__ rstd,
+                                                             int H, float eps) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  const __nv_bfloat16* xr = x + row * H;
+  float v[VPT][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * THREADS + threadIdx.x) * 8;
+    if (c < H) {
+      load8(xr + c, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
+    }
+  }
+  ss = block_sum<THREADS>(ss, red);
+  const float r = rsqrtf(ss / H + eps);
+  if (threadIdx.x == 0 && rstd) rstd[row] = r;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * THREADS + threadIdx.x) * 8;
+    if (c < H) {
+      float g[8], o[8];
+      load8(gamma + c, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = v[i][j] * r * g[j];
+      store8(y + row * H + c, o);
+    }
+  }
+}
+
+// dx = rstd * (g*dy - xhat * mean(g*dy*xhat)); dgamma partials accumulated per CTA-stripe with atomics on fp32.
+template <int THREADS, int VPT>
+__global__ void __launch_bounds__(THREADS) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                             const __nv_bfloat16* __restrict__ gamma,
+                                                             const __nv_bfloat16* __restrict__ dy,
+                                                             const float* __restrict__ rstd,
+                                                             __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+                                                             int rows, int H, int add_to_dx) {
+  __shared__ float red[32];
+  float dg[VPT][8];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dg[i][j] = 0.f;
+  float g[VPT][8];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * THREADS + threadIdx.x) * 8;
+    if (c < H) load8(gamma + c, g[i]);
+  }
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float r = rstd[row];
+    float xv[VPT][8], gy[VPT][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = (i * THREADS + threadIdx.x) * 8;
+      if (c < H) {
+        float d[8];
+        load8(x + row * H + c, xv[i]);
+        load8(dy + row * H + c, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = xv[i][j] * r;
+          dg[i][j] += d[j] * xh;
+          gy[i][j] = d[j] * g[i][j];
+          dot += gy[i][j] * xh;
+          xv[i][j] = xh;
+        }
+      }
+    }
+    dot = block_sum<THREADS>(dot, red) / H;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = (i * THREADS + threadIdx.x) * 8;
+      if (c < H) {
+        float o[8];
+        if (add_to_dx) load8(dx + row * H + c, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = r * (gy[i][j] - xv[i][j] * dot);
+          o[j] = add_to_dx ? o[j] + t : t;
+        }
+        store8(dx + row * H + c, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * THREADS + threadIdx.x) * 8;
+    if (c < H) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(dgamma + c + j, dg[i][j]);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// SwiGLU: y = silu(a) * b with [a | b] = x[:, :F], x[:, F:]
+// ----------------------------------------------------------------------------------------------
+__global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long rows,
+                                  int F) {
+  const long long vec_per_row = F / 8;
+  const long long total = rows * vec_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const int c = (int)(i - r * vec_per_row) * 8;
+    float a[8], b[8], o[8];
+    load8(x + r * 2 * F + c, a);
+    load8(x + r * 2 * F + F + c, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = a[j] / (1.f + __expf(-a[j])) * b[j];
+    store8(y + r * F + c, o);
+  }
+}
+__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                  __nv_bfloat16* __restrict__ dx, long long rows, int F) {
+  const long long vec_per_row = F / 8;
+  const long long total = rows * vec_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const int c = (int)(i - r * vec_per_row) * 8;
+    float a[8], b[8], d[8], da[8], db[8];
+    load8(x + r * 2 * F + c, a);
+    load8(x + r * 2 * F + F + c, b);
+    load8(dy + r * F + c, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = 1.f / (1.f + __expf(-a[j]));
+      const float silu = a[j] * s;
+      db[j] = d[j] * silu;
+      da[j] = d[j] * b[j] * (s + silu * (1.f - s));
+    }
+    store8(dx + r * 2 * F + c, da);
+    store8(dx + r * 2 * F + F + c, db);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// RoPE (rotate-half, Llama convention) applied in place to the q and k heads of a packed qkv row.
+// qkv row layout: [q heads (nq*d) | k heads (nk*d) | v heads].  One thread handles 8 (i, i+d/2) pairs.
+// ----------------------------------------------------------------------------------------------
+__global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cos_t,
+                            const float* __restrict__ sin_t, long long tokens, int seq_len, int row_stride,
+                            int n_rot_heads, int d, float sign) {
+  const int half = d / 2;
+  const int vec_per_head = half / 8;
+  const long long total = tokens * n_rot_heads * vec_per_head;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vec_per_head);
+    const long long th = i / vec_per_head;
+    const int h = (int)(th % n_rot_heads);
+    const long long t = th / n_rot_heads;
+    const int pos = (int)(t % seq_len);
+    __nv_bfloat16* p = qkv + t * row_stride + h * d + v * 8;
+    float x1[8], x2[8], o1[8], o2[8];
+    load8(p, x1);
+    load8(p + half, x2);
+    const float* c = cos_t + (long long)pos * half + v * 8;
+    const float* s = sin_t + (long long)pos * half + v * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float cs = c[j], sn = s[j] * sign;
+      o1[j] = x1[j] * cs - x2[j] * sn;
+      o2[j] = x2[j] * cs + x1[j] * sn;
+    }
+    store8(p, o1);
+    store8(p + half, o2);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Fused cross entropy: per row loss = logsumexp(z) - z[target]; writes dlogits = (softmax - onehot) * scale
+// in place over the logits (bf16).  One CTA per row; two passes over the row (max+sum online, then grad),
+// the second pass usually hits L2 (row = V * 2 B <= 256 KB).
+// ----------------------------------------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) cross_entropy_fwd_bwd_kernel(__nv_bfloat16* __restrict__ logits,
+                                                                       const long long* __restrict__ targets,
+                                                                       float* __restrict__ loss, int V, long long ld,
+                                                                       float grad_scale, int write_grad) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  __nv_bfloat16* z = logits + row * ld;
+  const int nvec = V / 8;
+  float m = -INFINITY, s = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += THREADS) {
+    float f[8];
+    load8(z + i * 8, f);
+    float lm = f[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) lm = fmaxf(lm, f[j]);
+    const float nm = fmaxf(m, lm);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += __expf(f[j] - nm);
+    s = s * __expf(m - nm) + acc;
+    m = nm;
+  }
+  for (int i = nvec * 8 + threadIdx.x; i < V; i += THREADS) {
+    const float f = __bfloat162float(z[i]);
+    const float nm = fmaxf(m, f);
+    s = s * __expf(m - nm) + __expf(f - nm);
+    m = nm;
+  }
+  const float gm = block_max<THREADS>(m, red);
+  s = (m == -INFINITY) ? 0.f : s * __expf(m - gm);
+  const float gs = block_sum<THREADS>(s, red);
+  const long long tgt = targets[row];
+  const float lse = gm + __logf(gs);
+  if (threadIdx.x == 0) loss[row] = (tgt >= 0 && tgt < V) ? lse - __bfloat162float(z[tgt]) : 0.f;
+  if (!write_grad) return;
+  __syncthreads();  // z[tgt] must be read before any thread overwrites the row with the gradient
+  const float inv = 1.f / gs;
+  const float sc = (tgt >= 0 && tgt < V) ? grad_scale : 0.f;
+  for (int i = threadIdx.x; i < nvec; i += THREADS) {
+    float f[8];
+    load8(z + i * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float p = __expf(f[j] - gm) * inv;
+      if (i * 8 + j == tgt) p -= 1.f;
+      f[j] = p * sc;
+    }
+    store8(z + i * 8, f);
+  }
+  for (int i = nvec * 8 + threadIdx.x; i < V; i += THREADS) {
+    float p = __expf(__bfloat162float(z[i]) - gm) * inv;
+    if (i == tgt) p -= 1.f;
+    z[i] = __float2bfloat16(p * sc);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Optimizer: squared L2 norm of fp32 grads (per-CTA partials + one atomic), fused AdamW step on
+// flat fp32 master / m / v with bf16 model-param write-back and grad clipping scale.
+// ----------------------------------------------------------------------------------------------
+__global__ void sqnorm_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  const long long nv = n / 4;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = g4[i];
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (long long i = nv * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    acc += g[i] * g[i];
+  acc = block_sum<256>(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+__global__ void adamw_kernel(float* __restrict__ master, float* __restrict__ m, float* __restrict__ v,
+                             float* __restrict__ grad, __nv_bfloat16* __restrict__ param, long long n, float lr,
+                             float beta1, float beta2, float eps, float wd, float bc1, float bc2,
+                             const float* __restrict__ sqnorm, float max_norm, float grad_prescale, int zero_grad) {
+  float clip = 1.f;
+  if (sqnorm) {
+    const float nrm = sqrtf(*sqnorm) * grad_prescale;
+    if (max_norm > 0.f && nrm > max_norm) clip = max_norm / (nrm + 1e-6f);
+  }
+  const float gscale = grad_prescale * clip;
+  const long long nv = n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    float4 g4 = reinterpret_cast<float4*>(grad)[i];
+    float4 m4 = reinterpret_cast<float4*>(m)[i];
+    float4 v4 = reinterpret_cast<float4*>(v)[i];
+    float4 w4 = reinterpret_cast<float4*>(master)[i];
+    float gg[4] = {g4.x, g4.y, g4.z, g4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w},
+          ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float g = gg[j] * gscale;
+      mm[j] = beta1 * mm[j] + (1.f - beta1) * g;
+      vv[j] = beta2 * vv[j] + (1.f - beta2) * g * g;
+      const float upd = (mm[j] / bc1) / (sqrtf(vv[j] / bc2) + eps);
+      ww[j] = ww[j] * (1.f - lr * wd) - lr * upd;
+    }
+    reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    reinterpret_cast<float4*>(master)[i] = make_float4(ww[0], ww[1], ww[2], ww[3]);
+    if (param) {
+      uint2 pk;
+      pk.x = pack_bf16x2(ww[0], ww[1]);
+      pk.y = pack_bf16x2(ww[2], ww[3]);
+      reinterpret_cast<uint2*>(param)[i] = pk;
+    }
+    if (zero_grad) reinterpret_cast<float4*>(grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// MoE permute / unpermute.  `row_map[i]` = source token of permuted row i (permute: gather) ;
+// unpermute = weighted scatter-add back: out[token] += prob[i] * x[i] (topk rows per token, done as a gather
+// over the inverse map so no atomics are needed).
+// ----------------------------------------------------------------------------------------------
+__global__ void permute_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                    const int* __restrict__ row_map, long long n_rows, int H) {
+  const int vec_per_row = H / 8;
+  const long long total = n_rows * vec_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const int c = (int)(i - r * vec_per_row) * 8;
+    const int s = row_map[r];
+    bf16x8 v;
+    if (s >= 0) v = *reinterpret_cast<const bf16x8*>(src + (long long)s * H + c);
+    else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v.v[j] = __floats2bfloat162_rn(0.f, 0.f);
+    }
+    *reinterpret_cast<bf16x8*>(dst + r * H + c) = v;
+  }
+}
+// out[t] = sum_k prob[t,k] * x[inv_map[t,k]]
+__global__ void unpermute_combine_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                         const int* __restrict__ inv_map, const float* __restrict__ probs,
+                                         long long tokens, int topk, int H) {
+  const int vec_per_row = H / 8;
+  const long long total = tokens * vec_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / vec_per_row;
+    const int c = (int)(i - t * vec_per_row) * 8;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < topk; ++k) {
+      const int r = inv_map[t * topk + k];
+      if (r < 0) continue;
+      const float p = probs ? probs[t * topk + k] : 1.f;
+      float f[8];
+      load8(x + (long long)r * H + c, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += p * f[j];
+    }
+    store8(out + t * H + c, acc);
+  }
+}
+
+// residual add: y = a + b (bf16) -- used by the training harness between sub-layers
+__global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                           __nv_bfloat16* __restrict__ y, long long n) {
+  const long long nv = n / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    float x[8], z[8];
+    load8(a + i * 8, x);
+    load8(b + i * 8, z);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += z[j];
+    store8(y + i * 8, x);
+  }
+}
+
+// streaming copy (the "default" memory-bandwidth calibration op)
+__global__ void copy_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n16) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+}  // namespace smx
+
+// ----------------------------------------------------------------------------------------------
+// C ABI
+// ----------------------------------------------------------------------------------------------
+using bf16 = __nv_bfloat16;
+static inline int grid_for(long long work_items, int threads, int cap = 148 * 16) {
+  long long g = (work_items + threads - 1) / threads;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+#define SMX_STREAM reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+int smx_rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, long long rows, int H, float eps,
+                    void* stream) {
+  if (H % 8) return -20;
+  if (H <= 2048) smx::rmsnorm_fwd_kernel<256, 1><<<(unsigned)rows, 256, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (bf16*)y, rstd, H, eps);
+  else if (H <= 4096) smx::rmsnorm_fwd_kernel<256, 2><<<(unsigned)rows, 256, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (bf16*)y, rstd, H, eps);
+  else if (H <= 8192) smx::rmsnorm_fwd_kernel<512, 2><<<(unsigned)rows, 512, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (bf16*)y, rstd, H, eps);
+  else if (H <= 16384) smx::rmsnorm_fwd_kernel<512, 4><<<(unsigned)rows, 512, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (bf16*)y, rstd, H, eps);
+  else return -21;
+  return (int)cudaGetLastError();
+}
+
+int smx_rmsnorm_bwd(const void* x, const void* gamma, const void* dy, const float* rstd, void* dx, float* dgamma,
+                    long long rows, int H, int add_to_dx, void* stream) {
+  if (H % 8) return -20;
+  int grid = rows < 148 * 4 ? (int)rows : 148 * 4;
+  if (H <= 2048) smx::rmsnorm_bwd_kernel<256, 1><<<grid, 256, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)dy, rstd, (bf16*)dx, dgamma, (int)rows, H, add_to_dx);
+  else if (H <= 4096) smx::rmsnorm_bwd_kernel<256, 2><<<grid, 256, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)dy, rstd, (bf16*)dx, dgamma, (int)rows, H, add_to_dx);
+  else if (H <= 8192) smx::rmsnorm_bwd_kernel<512, 2><<<grid, 512, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)dy, rstd, (bf16*)dx, dgamma, (int)rows, H, add_to_dx);
+  else if (H <= 16384) smx::rmsnorm_bwd_kernel<512, 4><<<grid, 512, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)dy, rstd, (bf16*)dx, dgamma, (int)rows, H, add_to_dx);
+  else return -21;
+  return (int)cudaGetLastError();
+}
+
+int smx_swiglu_fwd(const void* x, void* y, long long rows, int F, void* stream) {
+  if (F % 8) return -20;
+  smx::swiglu_fwd_kernel<<<grid_for(rows * (F / 8), 256), 256, 0, SMX_STREAM>>>((const bf16*)x, (bf16*)y, rows, F);
+  return (int)cudaGetLastError();
+}
+int smx_swiglu_bwd(const void* x, const void* dy, void* dx, long long rows, int F, void* stream) {
+  if (F % 8) return -20;
+  smx::swiglu_bwd_kernel<<<grid_for(rows * (F / 8), 256), 256, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, rows, F);
+  return (int)cudaGetLastError();
+}
+
+// sign = +1 forward rotation, -1 inverse rotation (= backward of RoPE)
+int smx_rope(void* qkv, const float* cos_t, const float* sin_t, long long tokens, int seq_len, int row_stride,
+             int n_rot_heads, int d, float sign, void* stream) {
+  if ((d / 2) % 8) return -20;
+  smx::rope_kernel<<<grid_for(tokens * n_rot_heads * (d / 16), 256), 256, 0, SMX_STREAM>>>((bf16*)qkv, cos_t, sin_t, tokens, seq_len, row_stride, n_rot_heads, d, sign);
+  return (int)cudaGetLastError();
+}
+
+int smx_cross_entropy(void* logits, const long long* targets, float* loss, long long rows, int V, long long ld,
+                      float grad_scale, int write_grad, void* stream) {
+  if (ld % 8) return -20;
+  smx::cross_entropy_fwd_bwd_kernel<1024><<<(unsigned)rows, 1024, 0, SMX_STREAM>>>((bf16*)logits, targets, loss, V, ld, grad_scale, write_grad);
+  return (int)cudaGetLastError();
+}
+
+int smx_sqnorm(const float* g, long long n, float* out, void* stream) {
+  smx::sqnorm_kernel<<<grid_for(n / 4, 256, 148 * 8), 256, 0, SMX_STREAM>>>(g, n, out);
+  return (int)cudaGetLastError();
+}
+int smx_adamw(float* master, float* m, float* v, float* grad, void* param, long long n, float lr, float beta1,
+              float beta2, float eps, float wd, float bc1, float bc2, const float* sqnorm, float max_norm,
+              float grad_prescale, int zero_grad, void* stream) {
+  if (n % 4) return -20;
+  smx::adamw_kernel<<<grid_for(n / 4, 256, 148 * 8), 256, 0, SMX_STREAM>>>(master, m, v, grad, (bf16*)param, n, lr, beta1, beta2, eps, wd, bc1, bc2, sqnorm, max_norm, grad_prescale, zero_grad);
+  return (int)cudaGetLastError();
+}
+
+int smx_permute_rows(const void* src, void* dst, const int* row_map, long long n_rows, int H, void* stream) {
+  if (H % 8) return -20;
+  smx::permute_rows_kernel<<<grid_for(n_rows * (H / 8), 256), 256, 0, SMX_STREAM>>>((const bf16*)src, (bf16*)dst, row_map, n_rows, H);
+  return (int)cudaGetLastError();
+}
+int smx_unpermute_combine(const void* x, void* out, const int* inv_map, const float* probs, long long tokens, int topk,
+                          int H, void* stream) {
+  if (H % 8) return -20;
+  smx::unpermute_combine_kernel<<<grid_for(tokens * (H / 8), 256), 256, 0, SMX_STREAM>>>((const bf16*)x, (bf16*)out, inv_map, probs, tokens, topk, H);
+  return (int)cudaGetLastError();
+}
+int smx_add(const void* a, const void* b, void* y, long long n, void* stream) {
+  if (n % 8) return -20;
+  smx::add_kernel<<<grid_for(n / 8, 256), 256, 0, SMX_STREAM>>>((const bf16*)a, (const bf16*)b, (bf16*)y, n);
+  return (int)cudaGetLastError();
+}
+int smx_copy(const void* src, void* dst, long long nbytes, void* stream) {
+  if (nbytes % 16) return -20;
+  smx::copy_kernel<<<grid_for(nbytes / 16, 256, 148 * 8), 256, 0, SMX_STREAM>>>((const uint4*)src, (uint4*)dst, nbytes / 16);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -552,8 +552,7 @@ def parallel_ce(st: StrategyConfig, in_shape, name, display="_VocabParallelCross
 # ------------------------------------------------------------------------------------------------
 def fp8_quantizer(st: StrategyConfig, in_shape, name, *, enable_recompute=False, display="Float8Quantizer") -> Tuple[OpNode, list]:
     x = numel(in_shape) * DT["bf16"]
-    # the reference's Float8Tensor keeps the default (bf16) element size, so "output" bytes equal input bytes
-    y = numel(in_shape) * DT["bf16"]
+    y = numel(in_shape) * DT["fp8"]
     node = OpNode(name=name, kind="Float8Quantizer", display=display, in_shapes=[ishape(in_shape)],
                   out_shapes=[ishape(in_shape)], in_bytes=x, enable_recompute=enable_recompute)
     node.act.fwd_peak_mem_no_cache = x + y

@@ -1,0 +1,189 @@
+"""Python front-ends of the memory-bound sm_100a kernels (csrc/elementwise.cu).
+
+Every wrapper validates shapes/dtypes, launches on the current CUDA stream and counts the launch
+(``_lib.launches()`` feeds bench.py's ``gpu_launches``).  There is no PyTorch fallback: on a GPU box a
+missing kernel library is an error.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_c = ctypes
+_SIGS = {
+    "smx_rmsnorm_fwd": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_float, _c.c_void_p],
+    "smx_rmsnorm_bwd": [_c.c_void_p] * 6 + [_c.c_longlong, _c.c_int, _c.c_int, _c.c_void_p],
+    "smx_swiglu_fwd": [_c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_void_p],
+    "smx_swiglu_bwd": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_void_p],
+    "smx_rope": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_void_p],
+    "smx_cross_entropy": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_longlong, _c.c_float, _c.c_int, _c.c_void_p],
+    "smx_sqnorm": [_c.c_void_p, _c.c_longlong, _c.c_void_p, _c.c_void_p],
+    "smx_adamw": [_c.c_void_p] * 5 + [_c.c_longlong] + [_c.c_float] * 7 + [_c.c_void_p, _c.c_float, _c.c_float, _c.c_int, _c.c_void_p],
+    "smx_permute_rows": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_void_p],
+    "smx_unpermute_combine": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_void_p],
+    "smx_add": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_void_p],
+    "smx_copy": [_c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_void_p],
+}
+_fns = {}
+
+
+def _fn(name):
+    f = _fns.get(name)
+    if f is None:
+        f = getattr(_lib.lib(), name)
+        f.restype = _c.c_int
+        f.argtypes = _SIGS[name]
+        _fns[name] = f
+    return f
+
+
+def _stream(t: torch.Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _call(name, *args):
+    rc = _fn(name)(*args)
+    _lib.check(rc, name)
+    _lib.count_launch()
+
+
+def _bf16c(t: torch.Tensor, what: str):
+    if t.dtype != torch.bfloat16 or not t.is_contiguous():
+        raise TypeError(f"{what} must be a contiguous bf16 tensor, got {t.dtype} contiguous={t.is_contiguous()}")
+
+
+# ------------------------------------------------------------------------------------------------
+def rmsnorm_fwd(x: torch.Tensor, gamma: torch.Tensor, eps: float = 1e-5, out: Optional[torch.Tensor] = None
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """y = x * rsqrt(mean(x^2) + eps) * gamma over the last dim; returns (y, rstd[rows] fp32)."""
+    _bf16c(x, "x"); _bf16c(gamma, "gamma")
+    H = x.shape[-1]
+    rows = x.numel() // H
+    y = torch.empty_like(x) if out is None else out
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    _call("smx_rmsnorm_fwd", x.data_ptr(), gamma.data_ptr(), y.data_ptr(), rstd.data_ptr(), rows, H, eps, _stream(x))
+    return y, rstd
+
+
+def rmsnorm_bwd(x, gamma, dy, rstd, dgamma_fp32: torch.Tensor, dx: Optional[torch.Tensor] = None,
+                accumulate_dx: bool = False) -> torch.Tensor:
+    """dx (optionally += into an existing residual gradient) and dgamma += (fp32 main-grad accumulate)."""
+    _bf16c(x, "x"); _bf16c(dy, "dy")
+    H = x.shape[-1]
+    rows = x.numel() // H
+    if dx is None:
+        assert not accumulate_dx
+        dx = torch.empty_like(x)
+    assert dgamma_fp32.dtype == torch.float32 and dgamma_fp32.numel() == H
+    _call("smx_rmsnorm_bwd", x.data_ptr(), gamma.data_ptr(), dy.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
+          dgamma_fp32.data_ptr(), rows, H, 1 if accumulate_dx else 0, _stream(x))
+    return dx
+
+
+def swiglu_fwd(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x = [gate | up] along the last dim -> silu(gate) * up."""
+    _bf16c(x, "x")
+    F = x.shape[-1] // 2
+    rows = x.numel() // (2 * F)
+    y = torch.empty(*x.shape[:-1], F, device=x.device, dtype=x.dtype) if out is None else out
+    _call("smx_swiglu_fwd", x.data_ptr(), y.data_ptr(), rows, F, _stream(x))
+    return y
+
+
+def swiglu_bwd(x: torch.Tensor, dy: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _bf16c(x, "x"); _bf16c(dy, "dy")
+    F = x.shape[-1] // 2
+    rows = x.numel() // (2 * F)
+    dx = torch.empty_like(x) if out is None else out
+    _call("smx_swiglu_bwd", x.data_ptr(), dy.data_ptr(), dx.data_ptr(), rows, F, _stream(x))
+    return dx
+
+
+def rope_tables(seq_len: int, head_dim: int, theta: float = 500000.0, device="cuda"):
+    half = head_dim // 2
+    inv = 1.0 / (theta ** (torch.arange(0, half, device=device, dtype=torch.float32) / half))
+    ang = torch.arange(seq_len, device=device, dtype=torch.float32)[:, None] * inv[None, :]
+    return ang.cos().contiguous(), ang.sin().contiguous()
+
+
+def rope_inplace(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, seq_len: int, n_rot_heads: int,
+                 head_dim: int, inverse: bool = False) -> torch.Tensor:
+    """Rotate the first ``n_rot_heads`` heads (q then k) of each packed [tokens, (nq+2nk)*d] row in place."""
+    _bf16c(qkv, "qkv")
+    row = qkv.shape[-1]
+    tokens = qkv.numel() // row
+    _call("smx_rope", qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), tokens, seq_len, row, n_rot_heads, head_dim,
+          -1.0 if inverse else 1.0, _stream(qkv))
+    return qkv
+
+
+def cross_entropy_(logits: torch.Tensor, targets: torch.Tensor, grad_scale: float = 1.0, write_grad: bool = True
+                   ) -> torch.Tensor:
+    """Fused CE: returns per-row loss (fp32) and overwrites ``logits`` with d loss / d logits * grad_scale."""
+    assert logits.dtype == torch.bfloat16 and logits.stride(-1) == 1 and logits.dim() == 2
+    assert targets.dtype == torch.int64 and targets.is_contiguous()
+    rows, V = logits.shape
+    loss = torch.empty(rows, device=logits.device, dtype=torch.float32)
+    _call("smx_cross_entropy", logits.data_ptr(), targets.data_ptr(), loss.data_ptr(), rows, V, logits.stride(0),
+          float(grad_scale), 1 if write_grad else 0, _stream(logits))
+    return loss
+
+
+def sqnorm(g: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out += sum(g^2) (fp32, device scalar)."""
+    assert g.dtype == torch.float32 and g.is_contiguous()
+    if out is None:
+        out = torch.zeros(1, device=g.device, dtype=torch.float32)
+    _call("smx_sqnorm", g.data_ptr(), g.numel(), out.data_ptr(), _stream(g))
+    return out
+
+
+def adamw_(master, m, v, grad, param_bf16, lr, beta1, beta2, eps, weight_decay, step, sqnorm_t=None,
+           max_norm: float = 0.0, grad_prescale: float = 1.0, zero_grad: bool = True) -> None:
+    """One fused AdamW step on flat fp32 buffers; writes the bf16 model copy and (optionally) zeroes the grads."""
+    n = master.numel()
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    _call("smx_adamw", master.data_ptr(), m.data_ptr(), v.data_ptr(), grad.data_ptr(),
+          param_bf16.data_ptr() if param_bf16 is not None else None, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2,
+          sqnorm_t.data_ptr() if sqnorm_t is not None else None, float(max_norm), float(grad_prescale),
+          1 if zero_grad else 0, _stream(master))
+
+
+def permute_rows(src: torch.Tensor, row_map: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dst[i] = src[row_map[i]] (row_map int32, -1 = zero row): MoE dispatch permutation."""
+    _bf16c(src, "src")
+    assert row_map.dtype == torch.int32
+    H = src.shape[-1]
+    n = row_map.numel()
+    dst = torch.empty(n, H, device=src.device, dtype=src.dtype) if out is None else out
+    _call("smx_permute_rows", src.data_ptr(), dst.data_ptr(), row_map.data_ptr(), n, H, _stream(src))
+    return dst
+
+
+def unpermute_combine(x: torch.Tensor, inv_map: torch.Tensor, probs: Optional[torch.Tensor], tokens: int, topk: int,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[t] = sum_k probs[t,k] * x[inv_map[t,k]]: MoE combine."""
+    _bf16c(x, "x")
+    H = x.shape[-1]
+    y = torch.empty(tokens, H, device=x.device, dtype=x.dtype) if out is None else out
+    _call("smx_unpermute_combine", x.data_ptr(), y.data_ptr(), inv_map.data_ptr(),
+          probs.data_ptr() if probs is not None else None, tokens, topk, H, _stream(x))
+    return y
+
+
+def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _bf16c(a, "a"); _bf16c(b, "b")
+    y = torch.empty_like(a) if out is None else out
+    _call("smx_add", a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), _stream(a))
+    return y
+
+
+def copy_(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    nbytes = src.numel() * src.element_size()
+    _call("smx_copy", src.data_ptr(), dst.data_ptr(), nbytes, _stream(src))
+    return dst
