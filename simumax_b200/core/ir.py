@@ -161,6 +161,15 @@ def evaluate(node: OpNode, system: SystemConfig) -> OpNode:
     return node
 
 
+def comm_step(system: SystemConfig, op: str, size, comm_num: int, net: str, label: str, *, fwd: bool = True,
+              bwd: bool = True, group: str = "tp", stage: str = "unkonw") -> SimStep:
+    """Simulator collective with its own cost lookup (the replay uses slightly different collectives than the
+    analytic model in a few places, e.g. reduce-scatter for the SP embedding; reference prefill() methods)."""
+    cost = system.compute_net_op_time(op, size, comm_num=comm_num, net=net, comm_stage=stage)
+    return SimStep(kind="comm", name=label, fwd_cost=cost if fwd else 0.0, bwd_cost=cost if bwd else 0.0,
+                   comm_op=op, group=group, comm_num=comm_num, stage=stage)
+
+
 def default_sim_steps(node: OpNode) -> List[SimStep]:
     return [SimStep(kind="atom", name="", fwd_cost=node.cost.fwd_compute_time,
                     bwd_cost=node.cost.bwd_grad_act_time + node.cost.bwd_grad_w_time)]

@@ -10,7 +10,7 @@ from __future__ import annotations
 from typing import List, Optional, Tuple
 
 from ..core.config import ModelConfig, StrategyConfig, SystemConfig
-from ..core.ir import (DT, CollectiveSpec, OpNode, SimStep, dense_param_memory, ishape, linear_gemm_table,
+from ..core.ir import (DT, CollectiveSpec, OpNode, SimStep, comm_step, dense_param_memory, ishape, linear_gemm_table,
                        linear_shape_key, numel, record_te_dummy_wgrad)
 
 
@@ -51,19 +51,18 @@ def embedding(st: StrategyConfig, hidden, vocab, in_shape, name, display="Langua
         if st.enable_sequence_parallel:
             node.comms.append(_tp_comm(st, "all_gather", out_numel * e, "Embedding", "bwd_grad_w"))
 
-    def sim(n: OpNode) -> List[SimStep]:
+    def sim(n: OpNode, system) -> List[SimStep]:
         steps = [_atom(n)]
         if st.tp_size > 1:
             size = out_numel * e
             if st.enable_sequence_parallel:
-                steps.append(SimStep("comm", comm_op="reduce_scatter", group="tp", comm_num=st.tp_size, stage="Embedding",
-                                     name=f"{size}"))
+                steps.append(comm_step(system, "reduce_scatter", size, st.tp_size, st.tp_net, "reduce_scatter",
+                                       stage="Embedding"))
             else:
-                steps.append(SimStep("comm", comm_op="all_reduce", group="tp", comm_num=st.tp_size, stage="Embedding",
-                                     name=f"{size}"))
+                steps.append(comm_step(system, "all_reduce", size, st.tp_size, st.tp_net, "all_reduce", bwd=False,
+                                       stage="Embedding"))
         return steps
     node.sim_steps = sim
-    node.sim_payload = out_numel * e
     return node, out_shape
 
 
@@ -126,17 +125,16 @@ def linear_col(st: StrategyConfig, in_features, out_features, in_shape, name, *,
             node.comms.append(_tp_comm(st, "all_gather", size, "LinearCol_BWD_W_SP", "bwd_grad_w"))
         else:
             node.comms.append(_tp_comm(st, "all_reduce", size, "LinearCol_BWD_ACT_TP", "bwd_grad_act"))
-    node.sim_payload = size
 
-    def sim(n: OpNode) -> List[SimStep]:
+    def sim(n: OpNode, system) -> List[SimStep]:
         steps = []
         if st.tp_size > 1 and st.enable_sequence_parallel:
-            steps.append(SimStep("comm", comm_op="all_gather", group="tp", comm_num=st.tp_size, name="sp_gather"))
+            steps.append(comm_step(system, "all_gather", size, st.tp_size, st.tp_net, "all_gather"))
         elif st.tp_size > 1:
-            steps.append(SimStep("comm", comm_op="all_reduce_bwd", group="tp", comm_num=st.tp_size, name="tp_dgrad"))
+            steps.append(comm_step(system, "all_reduce", size, st.tp_size, st.tp_net, "all_reduce", fwd=False))
         steps.append(_atom(n, "Linear"))
         if st.tp_size > 1 and st.enable_sequence_parallel:
-            steps.append(SimStep("comm", comm_op="all_gather_bwd", group="tp", comm_num=st.tp_size, name="sp_regather"))
+            steps.append(comm_step(system, "all_gather", size, st.tp_size, st.tp_net, "all_gather", fwd=False))
         return steps
     node.sim_steps = sim
     return node, out_shape
@@ -189,14 +187,13 @@ def linear_row(st: StrategyConfig, in_features, out_features, in_shape, name, *,
             node.comms.append(_tp_comm(st, "all_gather", size, "LinearROW_BWD_SP", "bwd_grad_act"))
         else:
             node.comms.append(_tp_comm(st, "all_reduce", size, "LinearROW_FWD_TP", "fwd"))
-    node.sim_payload = size
 
-    def sim(n: OpNode) -> List[SimStep]:
+    def sim(n: OpNode, system) -> List[SimStep]:
         steps = [_atom(n, "Linear")]
         if st.tp_size > 1 and st.enable_sequence_parallel:
-            steps.append(SimStep("comm", comm_op="reduce_scatter", group="tp", comm_num=st.tp_size, name="sp_scatter"))
+            steps.append(comm_step(system, "reduce_scatter", size, st.tp_size, st.tp_net, "reduce_scatter"))
         elif st.tp_size > 1:
-            steps.append(SimStep("comm", comm_op="all_reduce", group="tp", comm_num=st.tp_size, name="tp_fwd"))
+            steps.append(comm_step(system, "all_reduce", size, st.tp_size, st.tp_net, "all_reduce", bwd=False))
         return steps
     node.sim_steps = sim
     return node, out_shape
@@ -235,7 +232,7 @@ def layernorm(st: StrategyConfig, norm_size, in_shape, name, *, has_cached_input
         node.compute.bwd_grad_w_accessed_mem = 2 * y_bytes + g_bytes
         node.compute.bwd_grad_act_accessed_mem = (y_bytes + x32) + (x_bytes + x32) + (11 * x32 + 5 * rstd + x_bytes + g_bytes)
     node.mem = dense_param_memory(st, norm_size, e, norm_size)
-    node.sim_steps = lambda nd: [_atom(nd)]
+    node.sim_steps = lambda nd, system=None: [_atom(nd)]
     return node, out_shape
 
 
@@ -411,17 +408,16 @@ def core_attention(st: StrategyConfig, system: SystemConfig, head_size, head_num
             raise NotImplementedError(f"cp_comm_type {st.cp_comm_type} not implemented yet.")
     node.cp_specs = specs
 
-    def sim(n: OpNode) -> List[SimStep]:
+    def sim(n: OpNode, system) -> List[SimStep]:
         steps = []
         if specs is not None:
-            for stage_name, size in specs["fwd_pre"]:
-                steps.append(SimStep("comm", comm_op="all2all_fwd", group="cp", comm_num=st.cp_size, stage=stage_name, name=f"{size}"))
-            for stage_name, size in reversed(specs["bwd_post"]):
-                steps.append(SimStep("comm", comm_op="all2all_bwd", group="cp", comm_num=st.cp_size, stage=stage_name, name=f"{size}"))
-            for stage_name, size in specs["fwd_post"]:
-                steps.append(SimStep("comm", comm_op="all2all_fwd", group="cp", comm_num=st.cp_size, stage=stage_name, name=f"{size}"))
-            for stage_name, size in reversed(specs["bwd_pre"]):
-                steps.append(SimStep("comm", comm_op="all2all_bwd", group="cp", comm_num=st.cp_size, stage=stage_name, name=f"{size}"))
+            def a2a(stage_name, size, fwd):
+                return comm_step(system, "all2all", size, st.cp_size, st.cp_net, "all2all", fwd=fwd, bwd=not fwd,
+                                 group="cp", stage=stage_name)
+            steps += [a2a(nm, sz, True) for nm, sz in specs["fwd_pre"]]
+            steps += [a2a(nm, sz, False) for nm, sz in reversed(specs["bwd_post"])]
+            steps += [a2a(nm, sz, True) for nm, sz in specs["fwd_post"]]
+            steps += [a2a(nm, sz, False) for nm, sz in reversed(specs["bwd_pre"])]
         steps.append(_atom(n, "AttentionScore"))
         return steps
     node.sim_steps = sim
@@ -435,7 +431,7 @@ def passthrough(kind, in_shapes, out_shapes, name, *, enable_recompute=False, di
     node = OpNode(name=name, kind=kind, display=display or kind, in_shapes=[ishape(s) for s in in_shapes],
                   out_shapes=[ishape(s) for s in out_shapes],
                   in_bytes=sum(numel(s) for s in in_shapes) * DT["bf16"], enable_recompute=enable_recompute)
-    node.sim_steps = lambda nd: [SimStep("atom", fwd_cost=0, bwd_cost=0)]
+    node.sim_steps = lambda nd, system=None: []
     return node
 
 
@@ -471,7 +467,7 @@ def swiglu(st: StrategyConfig, in_shape, name, *, is_fused=None, has_cached_inpu
         node.act.bwd_peak_mem_no_cache += probs_numel * 8
         node.compute.fwd_accessed_mem += probs_numel * e
         node.compute.bwd_grad_act_accessed_mem += probs_numel * e
-    node.sim_steps = lambda nd: [_atom(nd)]
+    node.sim_steps = lambda nd, system=None: [_atom(nd)]
     return node, out_shape
 
 
@@ -487,7 +483,7 @@ def gelu(st: StrategyConfig, in_shape, name, *, has_cached_inputs=False, enable_
     node.act.bwd_peak_mem_no_cache = 2 * x
     node.compute.fwd_accessed_mem = 2 * x
     node.compute.bwd_grad_act_accessed_mem = 2 * x
-    node.sim_steps = lambda nd: [_atom(nd)]
+    node.sim_steps = lambda nd, system=None: [_atom(nd)]
     return node, out_shape
 
 
@@ -534,14 +530,14 @@ def parallel_ce(st: StrategyConfig, in_shape, name, display="_VocabParallelCross
             node.comms.append(_tp_comm(st, "all_reduce", scalar, "ParallelCE_FWD_TP", "fwd"))
     node.ce_scalar = scalar
 
-    def sim(nd: OpNode) -> List[SimStep]:
-        steps = [_atom(nd)]
-        steps.append(SimStep("comm", comm_op="all_reduce", group="tp", comm_num=st.tp_size, name=f"{scalar}"))
+    def sim(nd: OpNode, system) -> List[SimStep]:
+        def ar(size):
+            return comm_step(system, "all_reduce", size, st.tp_size, st.tp_net, "all_reduce", bwd=False)
+        steps = [_atom(nd), ar(scalar)]
         if st.cross_entropy_loss_fusion:
-            steps.append(SimStep("comm", comm_op="all_reduce", group="tp", comm_num=st.tp_size, name=f"{2 * scalar}"))
+            steps.append(ar(2 * scalar))
         else:
-            steps.append(SimStep("comm", comm_op="all_reduce", group="tp", comm_num=st.tp_size, name=f"{scalar}"))
-            steps.append(SimStep("comm", comm_op="all_reduce", group="tp", comm_num=st.tp_size, name=f"{scalar}"))
+            steps += [ar(scalar), ar(scalar)]
         return steps
     node.sim_steps = sim
     return node, [1]
@@ -557,5 +553,5 @@ def fp8_quantizer(st: StrategyConfig, in_shape, name, *, enable_recompute=False,
                   out_shapes=[ishape(in_shape)], in_bytes=x, enable_recompute=enable_recompute)
     node.act.fwd_peak_mem_no_cache = x + y
     node.compute.fwd_accessed_mem = x + y
-    node.sim_steps = lambda nd: [_atom(nd)]
+    node.sim_steps = lambda nd, system=None: []      # the cast is not replayed as a separate op
     return node, ishape(in_shape)

@@ -13,7 +13,7 @@ from copy import deepcopy
 from typing import List, Tuple
 
 from ..core.config import MLPRecomputeConfig, StrategyConfig, SystemConfig
-from ..core.ir import (DT, PHASES, CollectiveSpec, OpNode, SimStep, dense_param_memory, ishape, linear_gemm_table,
+from ..core.ir import (DT, PHASES, CollectiveSpec, OpNode, SimStep, comm_step, dense_param_memory, ishape, linear_gemm_table,
                        linear_shape_key, moe_param_memory, numel, record_te_dummy_wgrad)
 from ..core.records import CostInfo
 from . import dense as D
@@ -52,7 +52,7 @@ def router(st: StrategyConfig, hidden, expert_num, in_shape, name, *, layer_idx=
     s_full = S * st.tp_size if st.enable_sequence_parallel else S
     node.gemm = linear_gemm_table(st, B, s_full, hidden, expert_num)
     node.shape_key = linear_shape_key(node.gemm)
-    node.sim_steps = lambda nd: [D._atom(nd)]
+    node.sim_steps = lambda nd, system=None: [D._atom(nd)]
     return node, out_shape
 
 
@@ -117,16 +117,16 @@ def permutation(st: StrategyConfig, system: SystemConfig, expert_num, topk, pad_
     node.recompute_net_follows_fwd = True
     node.post_evaluate = _layout_cost(node, system, [k1, k2])
 
-    def sim(nd: OpNode) -> List[SimStep]:
+    def sim(nd: OpNode, system_=None) -> List[SimStep]:
         def atom(nm, nbytes):
             f = system.compute_end2end_time(0, system.compute_mem_access_time("permute_fwd", nbytes))
             b = system.compute_end2end_time(0, system.compute_mem_access_time("permute_bwd", nbytes))
             return SimStep("atom", name=nm, fwd_cost=f, bwd_cost=b)
         steps = [atom("permute1", k1)]
         if st.ep_size > 1:
-            steps.append(SimStep("comm", comm_op="all2all", group="ep", comm_num=st.ep_size, name=f"{permuted * e}"))
-        if st.etp_size > 1:
-            steps.append(SimStep("comm", comm_op="all_gather", group="tp", comm_num=st.tp_size, name=f"{permuted * e * st.etp_size}"))
+            steps.append(comm_step(system, "all2all", permuted * e, st.ep_size, st.ep_net, "all2all", group="ep"))
+        if st.etp_size > 1:   # the replay uses the tp group / net here (reference moe_module.py:294-309)
+            steps.append(comm_step(system, "all_gather", permuted * e * st.etp_size, st.tp_size, st.tp_net, "all_gather"))
         steps.append(atom("permute2", k2))
         return steps
     node.sim_steps = sim
@@ -169,16 +169,16 @@ def unpermutation(st: StrategyConfig, system: SystemConfig, in_shape, ori_shape,
     node.recompute_net_follows_fwd = True
     node.post_evaluate = _layout_cost(node, system, [k1, k2])
 
-    def sim(nd: OpNode) -> List[SimStep]:
+    def sim(nd: OpNode, system_=None) -> List[SimStep]:
         def atom(nm, nbytes):
             f = system.compute_end2end_time(0, system.compute_mem_access_time("permute_fwd", nbytes))
             b = system.compute_end2end_time(0, system.compute_mem_access_time("permute_bwd", nbytes))
             return SimStep("atom", name=nm, fwd_cost=f, bwd_cost=b)
         steps = [atom("unpermute1", k1)]
         if st.etp_size > 1:
-            steps.append(SimStep("comm", comm_op="reduce_scatter", group="tp", comm_num=st.tp_size, name=f"{before * e * st.etp_size}"))
+            steps.append(comm_step(system, "reduce_scatter", before * e * st.etp_size, st.tp_size, st.tp_net, "reduce_scatter"))
         if st.ep_size > 1:
-            steps.append(SimStep("comm", comm_op="all2all", group="ep", comm_num=st.ep_size, name=f"{before * e}"))
+            steps.append(comm_step(system, "all2all", before * e, st.ep_size, st.ep_net, "all2all", group="ep"))
         steps.append(atom("unpermutate2_and_combine", k2))
         return steps
     node.sim_steps = sim
@@ -249,7 +249,7 @@ def group_linear(st: StrategyConfig, kind: str, in_features, out_features, local
     node.gemm = dict(B=[local_experts] * 3, M=[m, m, int(out_f)], K=[int(in_f), int(out_f), m],
                      N=[int(out_f), int(in_f), int(in_f)], layout=["TN", "NN", "NT"],
                      accumulate=[False, False, True], out_dtype=["bf16", "bf16", wdt])
-    node.sim_steps = lambda nd: [D._atom(nd, "Linear")]
+    node.sim_steps = lambda nd, system=None: [D._atom(nd, "Linear")]
     return node, out_shape
 
 

@@ -1,0 +1,53 @@
+"""tcgen05 flash-attention forward vs an fp32 PyTorch reference."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(q, k, v, causal, scale):
+    B, Sq, H, D = q.shape
+    Hk = k.shape[2]
+    qf = q.float().permute(0, 2, 1, 3)
+    kf = k.float().permute(0, 2, 1, 3).repeat_interleave(H // Hk, dim=1)
+    vf = v.float().permute(0, 2, 1, 3).repeat_interleave(H // Hk, dim=1)
+    s = qf @ kf.transpose(-1, -2) * scale
+    if causal:
+        Skv = k.shape[1]
+        mask = torch.ones(Sq, Skv, device=q.device, dtype=torch.bool).tril(Skv - Sq)
+        s = s.masked_fill(~mask, float("-inf"))
+    lse = torch.logsumexp(s, -1)
+    o = torch.softmax(s, -1) @ vf
+    return o.permute(0, 2, 1, 3), lse
+
+
+@pytest.mark.parametrize("causal", [True, False])
+@pytest.mark.parametrize("cfg", [(1, 256, 4, 4, 128, 128), (2, 512, 8, 2, 128, 128), (1, 384, 4, 1, 64, 64),
+                                 (1, 1024, 4, 4, 192, 128), (1, 200, 2, 2, 128, 128)])
+def test_fmha_fwd(cfg, causal):
+    from simumax_b200.ops.attention import fmha_fwd
+    torch.manual_seed(0)
+    B, S, H, Hk, D, Dv = cfg
+    q = torch.randn(B, S, H, D, device="cuda").bfloat16()
+    k = torch.randn(B, S, Hk, D, device="cuda").bfloat16()
+    v = torch.randn(B, S, Hk, Dv, device="cuda").bfloat16()
+    scale = 1.0 / math.sqrt(D)
+    o, lse = fmha_fwd(q, k, v, causal=causal, scale=scale)
+    ro, rlse = _ref(q, k, v, causal, scale)
+    torch.testing.assert_close(o.float(), ro, atol=2e-2, rtol=2e-2)
+    torch.testing.assert_close(lse, rlse, atol=2e-2, rtol=1e-3)
+
+
+def test_fmha_packed_qkv_view():
+    from simumax_b200.ops.attention import fmha_fwd
+    torch.manual_seed(1)
+    B, S, H, Hk, D = 1, 512, 8, 2, 128
+    qkv = torch.randn(B, S, (H + 2 * Hk) * D, device="cuda").bfloat16()
+    q = qkv[..., : H * D].view(B, S, H, D)
+    k = qkv[..., H * D: (H + Hk) * D].view(B, S, Hk, D)
+    v = qkv[..., (H + Hk) * D:].view(B, S, Hk, D)
+    o, _ = fmha_fwd(q, k, v, causal=True)
+    ro, _ = _ref(q, k, v, True, 1.0 / math.sqrt(D))
+    torch.testing.assert_close(o.float(), ro, atol=2e-2, rtol=2e-2)
