@@ -195,6 +195,89 @@ class InterleavedPlan:
         return recv
 
 
+def interleaved_sync_ops(plan: "InterleavedPlan") -> list:
+    """Abstract op order of one rank for *blocking* interleaved 1F1B.
+
+    Items: ("F", chunk, mb) | ("B", chunk, mb) | ("comm", [(role, tag), ...], batched) where role is one of
+    send_prev / recv_prev / send_next / recv_next in Megatron's batch_isend_irecv submission order and ``tag``
+    identifies the tensor (direction, destination virtual stage, micro-batch) so both peers derive the same key.
+    Shared by the simulator program builder and the analytic sync-VPP evaluator.
+    """
+    pp, rank, total, last_stage = plan.pp, plan.rank, plan.total, plan.total_stages - 1
+    ftag = lambda v, mb: f"forward-v{v}-mb{mb}"
+    btag = lambda v, mb: f"backward-v{v}-mb{mb}"
+    ops: list = []
+
+    def batch(send_prev=None, recv_prev=None, send_next=None, recv_next=None):
+        sub = [x for x in (send_prev, recv_prev, send_next, recv_next) if x is not None]
+        if sub:
+            ops.append(("comm", sub, True))
+
+    if rank != 0:
+        mb0, _, v0, _ = plan.fwd_ref(0)
+        if v0 > 0:
+            ops.append(("comm", [("recv_prev", ftag(v0, mb0))], False))
+    for k in range(plan.warmup):
+        mb, chunk, v, _ = plan.fwd_ref(k)
+        ops.append(("F", chunk, mb))
+        need_next = plan.need_recv(k, True) and k != total - 1
+        sn = ("send_next", ftag(v + 1, mb)) if v < last_stage else None
+        rp = rn = None
+        if k + 1 < total and need_next:
+            nmb, _, nv, _ = plan.fwd_ref(k + 1)
+            if nv > 0:
+                rp = ("recv_prev", ftag(nv, nmb))
+        elif plan.remaining == 0 and rank == 0 and k + 1 < total:
+            nmb, _, nv, _ = plan.fwd_ref(k + 1)
+            if nv > 0:
+                rp = ("recv_prev", ftag(nv, nmb))
+        if k == plan.warmup - 1 and plan.remaining > 0 and rank != pp - 1:
+            bmb, _, bv, _ = plan.bwd_ref(0)
+            if bv < last_stage:
+                rn = ("recv_next", btag(bv, bmb))
+        batch(recv_prev=rp, send_next=sn, recv_next=rn)
+    if plan.remaining == 0 and rank != pp - 1:
+        bmb, _, bv, _ = plan.bwd_ref(0)
+        if bv < last_stage:
+            ops.append(("comm", [("recv_next", btag(bv, bmb))], False))
+    for k in range(plan.remaining):
+        fk, bk = k + plan.warmup, k
+        fmb, fchunk, fv, _ = plan.fwd_ref(fk)
+        ops.append(("F", fchunk, fmb))
+        bmb, bchunk, bv, _ = plan.bwd_ref(bk)
+        ops.append(("B", bchunk, bmb))
+        need_f = plan.need_recv(fk, True) and k != plan.remaining - 1
+        need_b = plan.need_recv(bk, False)
+        sn = ("send_next", ftag(fv + 1, fmb)) if fv < last_stage else None
+        sp = ("send_prev", btag(bv - 1, bmb)) if bv > 0 else None
+        rp = rn = None
+        if fk + 1 < total and need_f:
+            nmb, _, nv, _ = plan.fwd_ref(fk + 1)
+            if nv > 0:
+                rp = ("recv_prev", ftag(nv, nmb))
+        if bk + 1 < total and need_b:
+            nmb, _, nv, _ = plan.bwd_ref(bk + 1)
+            if nv < last_stage:
+                rn = ("recv_next", btag(nv, nmb))
+        batch(send_prev=sp, recv_prev=rp, send_next=sn, recv_next=rn)
+    for k in range(plan.remaining, total):
+        bmb, bchunk, bv, _ = plan.bwd_ref(k)
+        ops.append(("B", bchunk, bmb))
+        need_b = plan.need_recv(k, False) and k != total - 1
+        sp = ("send_prev", btag(bv - 1, bmb)) if bv > 0 else None
+        rn = None
+        if k + 1 < total and need_b:
+            nmb, _, nv, _ = plan.bwd_ref(k + 1)
+            if nv < last_stage:
+                rn = ("recv_next", btag(nv, nmb))
+        elif plan.remaining == 0 and rank == pp - 1 and k + 1 < total:
+            nmb, _, nv, _ = plan.bwd_ref(k + 1)
+            if nv < last_stage:
+                rn = ("recv_next", btag(nv, nmb))
+        batch(send_prev=sp, recv_next=rn)
+    return ops
+
+
 def build_interleaved_program(perf, stage_chunks: list, args: RankArgs, with_memory: bool) -> list:
     """Megatron interleaved schedule (sync: batched blocking p2p groups; async: isend/irecv bundles + waits)."""
     st, system = perf.strategy, perf.system
@@ -230,70 +313,17 @@ def build_interleaved_program(perf, stage_chunks: list, args: RankArgs, with_mem
             jobs.append(item)
 
     if not use_async:
-        def batch(send_prev=None, recv_prev=None, send_next=None, recv_next=None):
-            add(_wrap([send_prev, recv_prev, send_next, recv_next], name=f"rank{args.rank}-batch_pp_comm", batch=True))
-        if rank != 0:
-            mb0, _, v0, _ = plan.fwd_ref(0)
-            if v0 > 0:
-                add(_wrap([p2p.recv_prev(ftag(v0, mb0))]))
-        for k in range(plan.warmup):
-            mb, chunk, v, _ = plan.fwd_ref(k)
-            model(chunk, mb, "fwd")
-            need_next = plan.need_recv(k, True) and k != total - 1
-            sn = p2p.send_next(ftag(v + 1, mb)) if v < last_stage else None
-            rp = rn = None
-            if k + 1 < total and need_next:
-                nmb, _, nv, _ = plan.fwd_ref(k + 1)
-                if nv > 0:
-                    rp = p2p.recv_prev(ftag(nv, nmb))
-            elif plan.remaining == 0 and rank == 0 and k + 1 < total:
-                nmb, _, nv, _ = plan.fwd_ref(k + 1)
-                if nv > 0:
-                    rp = p2p.recv_prev(ftag(nv, nmb))
-            if k == plan.warmup - 1 and plan.remaining > 0 and rank != pp - 1:
-                bmb, _, bv, _ = plan.bwd_ref(0)
-                if bv < last_stage:
-                    rn = p2p.recv_next(btag(bv, bmb))
-            batch(recv_prev=rp, send_next=sn, recv_next=rn)
-        if plan.remaining == 0 and rank != pp - 1:
-            bmb, _, bv, _ = plan.bwd_ref(0)
-            if bv < last_stage:
-                add(_wrap([p2p.recv_next(btag(bv, bmb))]))
-        for k in range(plan.remaining):
-            fk, bk = k + plan.warmup, k
-            fmb, fchunk, fv, _ = plan.fwd_ref(fk)
-            model(fchunk, fmb, "fwd")
-            bmb, bchunk, bv, _ = plan.bwd_ref(bk)
-            model(bchunk, bmb, "bwd")
-            need_f = plan.need_recv(fk, True) and k != plan.remaining - 1
-            need_b = plan.need_recv(bk, False)
-            sn = p2p.send_next(ftag(fv + 1, fmb)) if fv < last_stage else None
-            sp = p2p.send_prev(btag(bv - 1, bmb)) if bv > 0 else None
-            rp = rn = None
-            if fk + 1 < total and need_f:
-                nmb, _, nv, _ = plan.fwd_ref(fk + 1)
-                if nv > 0:
-                    rp = p2p.recv_prev(ftag(nv, nmb))
-            if bk + 1 < total and need_b:
-                nmb, _, nv, _ = plan.bwd_ref(bk + 1)
-                if nv < last_stage:
-                    rn = p2p.recv_next(btag(nv, nmb))
-            batch(send_prev=sp, recv_prev=rp, send_next=sn, recv_next=rn)
-        for k in range(plan.remaining, total):
-            bmb, bchunk, bv, _ = plan.bwd_ref(k)
-            model(bchunk, bmb, "bwd")
-            need_b = plan.need_recv(k, False) and k != total - 1
-            sp = p2p.send_prev(btag(bv - 1, bmb)) if bv > 0 else None
-            rn = None
-            if k + 1 < total and need_b:
-                nmb, _, nv, _ = plan.bwd_ref(k + 1)
-                if nv < last_stage:
-                    rn = p2p.recv_next(btag(nv, nmb))
-            elif plan.remaining == 0 and rank == pp - 1 and k + 1 < total:
-                nmb, _, nv, _ = plan.bwd_ref(k + 1)
-                if nv < last_stage:
-                    rn = p2p.recv_next(btag(nv, nmb))
-            batch(send_prev=sp, recv_next=rn)
+        mk = {"send_next": p2p.send_next, "recv_prev": p2p.recv_prev, "send_prev": p2p.send_prev,
+              "recv_next": p2p.recv_next}
+        for op in interleaved_sync_ops(plan):
+            if op[0] == "F":
+                model(op[1], op[2], "fwd")
+            elif op[0] == "B":
+                model(op[1], op[2], "bwd")
+            else:
+                _, subops, batched = op
+                built = [mk[role](tag) for role, tag in subops]
+                add(_wrap(built, name=f"rank{args.rank}-batch_pp_comm" if batched else "", batch=batched))
         return jobs
 
     # ---- async: bundles of isend/irecv posts, waits right before the consuming compute
