@@ -116,7 +116,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_kv_tiles; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_wait(&kv_empty[stage], phase ^ 1, 1);
         uint8_t* sK = sKV + stage * Cfg::kStageBytes;
         uint8_t* sV = sK + Cfg::kKBytes;
         mbar_arrive_expect_tx(&kv_full[stage], Cfg::kStageBytes);
@@ -132,12 +132,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // ============================ MMA issuer ============================
     constexpr uint32_t idesc_s = make_idesc(1, 1, 0, 0, BQ, BKV);   // Q (K-major) x K (K-major) -> S[128, 64]
     constexpr uint32_t idesc_o = make_idesc(1, 1, 0, 1, BQ, D_V);   // P (K-major) x V (MN-major) -> O[128, D_V]
-    mbar_wait(q_full, 0);
+    mbar_wait(q_full, 0, 2);
     int stage = 0;
     uint32_t phase = 0;
     auto issue_qk = [&](int j, int st) {
       // S_j = Q K_j^T  (needs: K_j landed, softmax has drained S_{j-1})
-      if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
+      if (j > 0) mbar_wait(s_empty, (j - 1) & 1, 3);
       tcgen05_fence_after();
       if (elect_one()) {
         uint8_t* sK = sKV + st * Cfg::kStageBytes;
@@ -152,7 +152,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       __syncwarp();
     };
     if (n_kv_tiles > 0) {
-      mbar_wait(&kv_full[0], 0);
+      mbar_wait(&kv_full[0], 0, 4);
       issue_qk(0, 0);
     }
     for (int j = 0; j < n_kv_tiles; ++j) {
@@ -161,11 +161,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       uint32_t nphase = phase;
       if (nstage == kFmhaStages) { nstage = 0; nphase ^= 1; }
       if (j + 1 < n_kv_tiles) {
-        mbar_wait(&kv_full[nstage], nphase);
+        mbar_wait(&kv_full[nstage], nphase, 5);
         issue_qk(j + 1, nstage);
       }
       // O += P_j V_j
-      mbar_wait(p_full, j & 1);
+      mbar_wait(p_full, j & 1, 6);
       tcgen05_fence_after();
       if (elect_one()) {
         uint8_t* sV = sKV + stage * Cfg::kStageBytes + Cfg::kKBytes;
@@ -192,7 +192,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     float l = 0.f;
     const int causal_shift = p.S_kv - p.S_q;
     for (int j = 0; j < n_kv_tiles; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(s_full, j & 1, 7);
       tcgen05_fence_after();
       uint32_t r[64];
       {
@@ -228,7 +228,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const bool any_grow = __any_sync(0xffffffffu, grow);
       // P smem and the O accumulator are only safe to touch once PV_{j-1} has retired
       if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);
+        mbar_wait(pv_done, (j - 1) & 1, 8);
         tcgen05_fence_after();
       }
       if (any_grow && j > 0) {
@@ -273,7 +273,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     // ---- epilogue
     if (n_kv_tiles > 0) {
-      mbar_wait(pv_done, (n_kv_tiles - 1) & 1);
+      mbar_wait(pv_done, (n_kv_tiles - 1) & 1, 9);
       tcgen05_fence_after();
     }
     const float inv_l = (l > 0.f) ? 1.f / l : 0.f;

@@ -10,6 +10,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <type_traits>
 
 #ifndef SMX_DEVICE
@@ -86,8 +87,18 @@ SMX_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-SMX_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded spin: a protocol bug becomes a trap with a diagnostic instead of a hung GPU.
+#ifndef SMX_MBAR_SPIN_LIMIT
+#define SMX_MBAR_SPIN_LIMIT (1u << 26)
+#endif
+SMX_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++spins > SMX_MBAR_SPIN_LIMIT) {
+      printf("simumax_b200: mbarrier wait timeout tag=%d parity=%u block=(%d,%d,%d) thread=%d\n", tag, parity,
+             (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x);
+      __trap();
+    }
   }
 }
 
