@@ -1,0 +1,69 @@
+import math
+
+import pytest
+
+from simumax_b200.core.config import SystemConfig
+from simumax_b200.core.schedule import one_f_one_b, one_f_one_b_simple, straggler_increase_ratio
+
+from helpers import reference_system
+from simumax_b200.configs import get_simu_system_config
+
+
+def nominal():
+    return SystemConfig.init_from_config_file(get_simu_system_config("b200_nominal"))
+
+
+def test_net_time_formula_matches_closed_form():
+    s = nominal()
+    size, n = 160e6, 4
+    t = s.compute_net_op_time("reduce_scatter", size, n, "high_intra_node", comm_stage="dp_cp")
+    op = s.networks["high_intra_node"].op["reduce_scatter"]
+    wire = size * 1 + (size / n) * (-1)
+    lat = op.latency_us * (n - 1) * 1 + op.fixed_latency_us
+    assert t == pytest.approx(wire / (900 * 1024 ** 3 * op.efficient_factor) * 1e3 + lat / 1e3, rel=1e-12)
+    assert s.compute_net_op_time("all_reduce", size, 1, "high_intra_node") == 0
+    rec = s.real_comm_bw["reduce_scatter"]["dp_cp"]
+    assert rec["comm_num"] == 4 and rec["real_bw"] == pytest.approx(900 * op.efficient_factor)
+
+
+def test_reference_b200_collective_record():
+    s = SystemConfig.init_from_config_file(reference_system())
+    s.compute_net_op_time("reduce_scatter", 160e6, 4, "high_intra_node", comm_stage="dp_cp")
+    rec = s.real_comm_bw["reduce_scatter"]["dp_cp"]
+    assert rec["latency"] == pytest.approx(24.0975, abs=1e-4)
+    assert rec["real_bw"] == pytest.approx(605.79, abs=1e-2)
+
+
+def test_roofline_and_shape_table():
+    s = nominal()
+    s.accelerator.op["matmul"].accurate_efficient_factor = {"k1": 0.5}
+    t_hit = s.compute_op_accuracy_time("matmul", 2.25e15, "k1")
+    t_miss = s.compute_op_accuracy_time("matmul", 2.25e15, "other")
+    assert t_hit == pytest.approx(2000.0) and t_miss == pytest.approx(1000.0 / 0.55)
+    assert "matmul" in s.hit_efficiency and "shape=other" in s.miss_efficiency["matmul"]
+    assert s.compute_end2end_time(3.0, 5.0) == 5.0
+    s.accelerator.mode = "only_compute"
+    assert s.compute_end2end_time(3.0, 5.0) == 3.0 and s.compute_end2end_time(0, 5.0) == 5.0
+
+
+def test_1f1b_properties():
+    ph = lambda f, b, p: {"fwd_recv": p, "fwd_compute": f, "fwd_send": p, "bwd_recv": p, "bwd_compute": b, "bwd_send": p}
+    # single stage: pure sum
+    one = {"fwd_recv": 0, "fwd_compute": 2.0, "fwd_send": 0, "bwd_recv": 0, "bwd_compute": 3.0, "bwd_send": 0}
+    assert one_f_one_b(1, 5, [one]) == pytest.approx(25.0)
+    # uniform stages without comm: classic bubble (pp - 1) * (f + b)
+    for pp, mbc in ((2, 4), (4, 8), (4, 3)):
+        # (a p2p time of exactly 0 removes the rendezvous ops altogether, so use a vanishing one)
+        stages = [ph(1.0, 2.0, 1e-9) for _ in range(pp)]
+        assert one_f_one_b(pp, mbc, stages) == pytest.approx((mbc + pp - 1) * 3.0, rel=1e-6)
+        assert one_f_one_b_simple(pp, mbc, [1.0] * pp, [2.0] * pp) == pytest.approx((mbc + pp - 1) * 3.0)
+    # p2p only adds time and total is monotone in micro-batch count
+    stages = [ph(1.0, 2.0, 0.1) for _ in range(4)]
+    t8, t9 = one_f_one_b(4, 8, stages), one_f_one_b(4, 9, stages)
+    assert t9 > t8 > (8 + 3) * 3.0
+
+
+def test_straggler_ratio():
+    assert straggler_increase_ratio(1) == 1.0
+    L = math.log2(8)
+    assert straggler_increase_ratio(8) == pytest.approx(1 + L / (L + 1) * 0.09 * math.sqrt(L))

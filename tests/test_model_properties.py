@@ -1,0 +1,65 @@
+"""Structural invariants of the op IR that must hold for any config (no reference data needed)."""
+import pytest
+
+from helpers import MOE, build
+
+CASES = [("tp2_pp1_dp4_mbs1", "llama3-8b", 4, {}, {}),
+         ("tp2_pp1_dp4_mbs1_selective_recompute", "llama3-70b", 3, {}, {"recompute_layer_num": 3}),
+         ("tp2_pp1_dp4_mbs1_full_recompute", "llama3-70b", 3, {}, {"recompute_layer_num": 2}),
+         ("ep8_pp1_dp8_mbs1", "deepseekv2", 3, MOE, {}),
+         ("ep8_pp1_dp8_mbs1", "deepseekv3", 3, MOE, {"dispatch_probs": True}),
+         ("tp2_pp1_dp4_mbs1", "llama3-70b", 2, {}, {"cp_size": 2, "seq_len": 8192}),
+         ("tp1_pp2_dp4_mbs1", "mixtral-8x7b", 4, {}, {"ep_size": 4, "fp8": True})]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[1]}-{i}" for i, c in enumerate(CASES)])
+def test_chunk_invariants(case):
+    strategy, model, layers, mover, sover = case
+    p = build(strategy, model, "b200_nominal", layers, mover, **sover)
+    for name, chunk in p.model_chunk_dict.items():
+        pk = p.pp_state_peak_point[name]
+        assert pk.peak_mem >= pk.activation_mem_cache >= 0
+        total = sum(n.cost.fwd_compute_time for n in chunk.nodes)
+        assert chunk.get_cost_info().fwd_compute_time == pytest.approx(total)
+        assert all(n.cost.fwd_compute_time >= 0 and n.cost.bwd_compute_time >= 0 for n in chunk.nodes)
+        # recompute never reduces time, and cached bytes with recompute never exceed the no-recompute cache
+        gemm = chunk.get_all_gemm_cost_info()
+        assert len(gemm["Module"]) == 3 * sum(1 for n in chunk.nodes if n.gemm is not None and n.kind != "Router")
+        info = chunk.analysis_op_info()
+        assert len(info["op"]) >= 2 * len(chunk.nodes)
+    mem = p.analysis_mem().data
+    cost = p.analysis_cost().data
+    assert cost["raw"]["duration_time_per_iter_ms"] > 0 and 0 < cost["mfu"] < 1
+
+
+def test_recompute_trades_memory_for_time():
+    base = build("tp2_pp1_dp4_mbs1", "llama3-70b", "b200_nominal", 4)
+    full = build("tp2_pp1_dp4_mbs1_full_recompute", "llama3-70b", "b200_nominal", 4, recompute_layer_num=4)
+    t0 = base.analysis_cost().data["raw"]["duration_time_per_iter_ms"]
+    t1 = full.analysis_cost().data["raw"]["duration_time_per_iter_ms"]
+    m0 = base.analysis_mem().data["raw"]["peak_mem"]
+    m1 = full.analysis_mem().data["raw"]["peak_mem"]
+    assert t1 > t0 and m1 < m0
+
+
+def test_tp_shards_weights():
+    a = build("tp2_pp1_dp4_mbs1", "llama3-8b", "b200_nominal", 2)
+    b = build("tp4_pp1_dp2_mbs1", "llama3-8b", "b200_nominal", 2)
+    wa = a.model_chunk_dict["first_stage_chunk"].get_model_info().dense_weight_bytes
+    wb = b.model_chunk_dict["first_stage_chunk"].get_model_info().dense_weight_bytes
+    assert wa > wb > wa / 2.2
+
+
+def test_result_files(tmp_path):
+    import json
+    p = build("tp1_pp2_dp4_mbs1", "llama3-8b", "b200_nominal", 4)
+    p.analysis(str(tmp_path), console_log=False)
+    for f in ("compute_result.json", "mem_result.json", "net_info.json", "base_info.json", "strategy_config.json",
+              "system_config.json", "model_config.json", "model_arch"):
+        assert (tmp_path / f).exists(), f
+    assert "duration_time_per_iter" in json.load(open(tmp_path / "compute_result.json"))
+    p.export_pp_schedule_trace(str(tmp_path / "pp.json"))
+    tr = json.load(open(tmp_path / "pp.json"))
+    assert tr["displayTimeUnit"] == "ms" and any(e.get("ph") == "X" for e in tr["traceEvents"])
+    g = p.capture(str(tmp_path))
+    assert len(g.nodes) > 10 and (tmp_path / "model_graph.json").exists()

@@ -1,0 +1,77 @@
+import json
+import pickle
+
+import pytest
+
+from helpers import MOE, build, reference_system
+
+
+def test_tiny_llama_trace_golden(tmp_path):
+    """llama2-tiny, 2 layers, tp2 on the reference A100 config: end 687.734 ms, 152 cache tokens, known peaks."""
+    p = build("tp2_pp1_dp4_mbs1", "llama2-tiny", reference_system("a100_pcie"), 2)
+    p.model_config.padded_vocab_size = True
+    r = p.simulate(str(tmp_path), merge_lanes=True)
+    assert r["end_time_ms"] == pytest.approx(687.734, abs=1e-3)
+    assert r["num_events"] == 981
+    assert r["memory"]["static_allocated_bytes_by_rank"]["rank0"] == 3001208832
+    assert r["memory"]["peak_allocated_bytes_by_rank"]["rank0"] == 3967209472
+    assert r["memory"]["peak_op_by_rank"]["rank0"] == {"op_name": "self.parallel_ce", "phase": "fwd"}
+    assert r["cache_tokens"] == 152
+    trace = json.load(open(tmp_path / "tracing_logs.json"))
+    assert any(e.get("ph") == "C" for e in trace) and any(e.get("tid") == "comm" for e in trace)
+    snap = json.load(open(tmp_path / "simu_memory_snapshot.json"))
+    assert snap["schema"] == "simumax_memory_snapshot_v1"
+    allocs = [e for e in snap["cache_tokens"] if e["action"] == "alloc"]
+    frees = [e for e in snap["cache_tokens"] if e["action"] == "free"]
+    assert len(allocs) == len(frees) == 152
+    viz = pickle.load(open(tmp_path / "simu_memory_viz_snapshot.pickle", "rb"))
+    assert "device_traces" in viz and "segments" in viz and viz["segments"][0]["total_size"] >= 3967209472
+
+
+CASES = [("tp1_pp2_dp4_mbs1", "llama3-8b", 4, {}, {}),
+         ("tp1_pp2_dp4_mbs1", "llama3-8b", 4, {}, {"pp_comm_async": False}),
+         ("tp1_pp2_dp4_mbs1", "llama3-8b", 8, {}, {"pp_size": 4, "micro_batch_num": 6}),
+         ("tp1_pp4_vp2_sync_mbs1_mbc8_no_ckpt", "llama3-70b", 8, {}, {}),
+         ("tp1_pp4_vp2_sync_mbs1_mbc8_no_ckpt", "llama3-70b", 8, {}, {"pp_comm_async": True}),
+         ("ep4_pp2_dp4_mbs1_full_recompute", "deepseekv2", 4, MOE, {"pp_comm_async": False}),
+         ("tp2_pp1_dp4_mbs1_selective_recompute", "llama3-70b", 2, {}, {"recompute_layer_num": 2})]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[1]}-{i}" for i, c in enumerate(CASES)])
+def test_simulation_consistent_with_analytic_model(case, tmp_path):
+    strategy, model, layers, mover, sover = case
+    p = build(strategy, model, "b200_nominal", layers, mover, enable_straggler_model=False, **sover)
+    r = p.simulate(str(tmp_path), merge_lanes=True)
+    assert r["ranks"] == [i * (p.strategy.world_size // p.strategy.pp_size) for i in range(p.strategy.pp_size)]
+    if not (p._vp_size() > 1 and p.strategy.pp_comm_async):
+        analytic = p.analysis_cost().data["raw"]["duration_time_per_iter_ms"]
+        # the replay adds 2 us per module scope and a 1 ms world barrier; otherwise both models must agree
+        assert r["end_time_ms"] == pytest.approx(analytic + 1.0, rel=0.03)
+    if "memory" in r:
+        mem = p.analysis_mem().data
+        stages = [mem] if "raw" in mem else list(mem.values())
+        for rank, stage in zip(sorted(r["memory"]["peak_allocated_bytes_by_rank"]), stages):
+            sim_peak = r["memory"]["peak_allocated_bytes_by_rank"][rank]
+            assert sim_peak == pytest.approx(stage["raw"]["peak_mem"], rel=0.02)
+        snap = json.load(open(tmp_path / "simu_memory_snapshot.json"))
+        last = {}
+        for e in snap["events"]:
+            last[e["rank"]] = e
+        assert all(e["cached_bytes"] == 0 for e in last.values())     # every cached activation was released
+
+
+def test_world_mode_rendezvous(tmp_path):
+    p = build("tp2_pp1_dp4_mbs1", "llama2-tiny", "b200_nominal", 2, micro_batch_num=2)
+    merged = p.simulate(str(tmp_path / "m"), merge_lanes=True)["end_time_ms"]
+    world = p.simulate(str(tmp_path / "w"), merge_lanes=False)
+    assert len(world["ranks"]) == 8
+    assert world["end_time_ms"] == pytest.approx(merged, rel=1e-6)
+
+
+def test_deadlock_is_detected():
+    from simumax_b200.sim.engine import BlockingP2P, Deadlock, Engine, Scope
+    eng = Engine()
+    eng.add_rank(0, [("fwd", Scope("a", [BlockingP2P("send", "x", 1.0)]))])
+    eng.add_rank(1, [("fwd", Scope("b", [BlockingP2P("recv", "y", 1.0)]))])
+    with pytest.raises(Deadlock):
+        eng.run()
