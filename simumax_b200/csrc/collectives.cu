@@ -1,0 +1,297 @@
+// In-kernel collectives over NVLink 5 / NVSwitch for sm_100a: every transfer is issued by SM threads on
+// symmetric (peer-mapped) memory -- plain ld/st.global on peer pointers, or multimem.* on the NVLS multicast
+// address when one exists -- so a collective can live inside (or right behind) a compute kernel instead of being
+// a separate NCCL launch.
+//
+//   all_gather      push: each rank stores its shard into every peer's output (multimem.st when NVLS: one store,
+//                   the switch replicates)
+//   reduce_scatter  pull: each rank reads slice[rank] of every peer and sums (multimem.ld_reduce when NVLS: the
+//                   switch performs the reduction)
+//   all_reduce      NVLS one-shot: ld_reduce own slice, multimem.st the result to everybody;  P2P: pull-reduce
+//                   own slice then push it (two-shot inside one kernel)
+//   all_to_all      push chunk[dst] of every rank into slot[src] of peer dst (EP dispatch/combine, Ulysses CP)
+//
+// Synchronisation: a per-(CTA, source-rank) flag word in a symmetric signal buffer, written with
+// st.release.sys and polled with ld.acquire.sys; flags carry a monotonically increasing epoch so they never
+// need resetting.  Every kernel does  barrier(epoch) -> data movement -> barrier(epoch+1): the first makes sure
+// all peers have entered the collective (their inputs are final and their outputs may be overwritten), the
+// second that all remote stores have landed before anybody returns.
+//
+// Replaces the reference's NCCL call sites (simu_tools/efficency_test/measure_comm_burst_window_worker.py:112-135).
+#include "sm100_common.cuh"
+
+namespace smx {
+
+constexpr int kMaxRanks = 8;
+
+struct PeerPtrs {
+  void* data[kMaxRanks];       // symmetric data buffer of every rank (as mapped in this process)
+  uint32_t* flags[kMaxRanks];  // symmetric signal buffer of every rank
+  void* mc_data;               // NVLS multicast address of the data buffer (nullptr if unsupported)
+  int rank, world;
+};
+
+SMX_DEVICE void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+SMX_DEVICE uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// All CTAs with the same blockIdx.x on all ranks meet.  Slot layout: flags[cta * kMaxRanks + src_rank].
+SMX_DEVICE void cta_barrier_all_ranks(const PeerPtrs& pp, uint32_t epoch) {
+  __syncthreads();
+  if (threadIdx.x < (unsigned)pp.world) {
+    const int peer = threadIdx.x;
+    __threadfence_system();
+    st_release_sys(pp.flags[peer] + blockIdx.x * kMaxRanks + pp.rank, epoch);
+    const uint32_t* mine = pp.flags[pp.rank] + blockIdx.x * kMaxRanks + peer;
+    const uint64_t t0 = global_timer_ns();
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+      if (global_timer_ns() - t0 > 20000000000ull) {  // 20 s: peers may still be launching
+        printf("simumax_b200: collective barrier timeout rank=%d peer=%d cta=%d epoch=%u\n", pp.rank, peer,
+               (int)blockIdx.x, epoch);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
+
+SMX_DEVICE uint4 ld_nc_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+SMX_DEVICE uint4 ld_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+SMX_DEVICE void st_v4(void* p, uint4 v) {
+  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+SMX_DEVICE uint4 multimem_ld_reduce_bf16x8(const void* mc) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+SMX_DEVICE void multimem_st_v4(void* mc, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+SMX_DEVICE uint4 add_bf16x8(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 fa = __bfloat1622float2(pa[i]), fb = __bfloat1622float2(pb[i]);
+    pr[i] = __floats2bfloat162_rn(fa.x + fb.x, fa.y + fb.y);
+  }
+  return r;
+}
+SMX_DEVICE void acc_bf16x8(float (&acc)[8], uint4 a) {
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(pa[i]);
+    acc[2 * i] += f.x;
+    acc[2 * i + 1] += f.y;
+  }
+}
+SMX_DEVICE uint4 pack_bf16x8(const float (&acc)[8]) {
+  uint4 r;
+  r.x = pack_bf16x2(acc[0], acc[1]);
+  r.y = pack_bf16x2(acc[2], acc[3]);
+  r.z = pack_bf16x2(acc[4], acc[5]);
+  r.w = pack_bf16x2(acc[6], acc[7]);
+  return r;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Symmetric buffer layout (bytes): [ region A : in ][ region B : out ] -- offsets passed by the host.
+// All sizes are multiples of 16 bytes.
+// ----------------------------------------------------------------------------------------------
+
+// all_gather: out[r * shard .. (r+1) * shard) on every rank <- in of rank r
+__global__ void __launch_bounds__(512) all_gather_kernel(PeerPtrs pp, long long in_off, long long out_off,
+                                                        long long shard_bytes, uint32_t epoch, int use_nvls) {
+  cta_barrier_all_ranks(pp, epoch);
+  const long long n16 = shard_bytes / 16;
+  const char* src = reinterpret_cast<const char*>(pp.data[pp.rank]) + in_off;
+  const long long dst_off = out_off + (long long)pp.rank * shard_bytes;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (use_nvls && pp.mc_data) {
+    char* mc = reinterpret_cast<char*>(pp.mc_data) + dst_off;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += stride)
+      multimem_st_v4(mc + i * 16, ld_nc_v4(src + i * 16));
+  } else {
+    // peers are visited in a rank-rotated order so that at any instant the 8 senders target 8 different receivers
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += stride) {
+      const uint4 v = ld_nc_v4(src + i * 16);
+#pragma unroll 1
+      for (int s = 0; s < pp.world; ++s) {
+        const int peer = (pp.rank + s) % pp.world;
+        st_v4(reinterpret_cast<char*>(pp.data[peer]) + dst_off + i * 16, v);
+      }
+    }
+  }
+  cta_barrier_all_ranks(pp, epoch + 1);
+}
+
+// reduce_scatter (bf16 sum): out <- sum_r in_r[rank * shard .. (rank+1) * shard)
+__global__ void __launch_bounds__(512) reduce_scatter_kernel(PeerPtrs pp, long long in_off, long long out_off,
+                                                            long long shard_bytes, uint32_t epoch, int use_nvls) {
+  cta_barrier_all_ranks(pp, epoch);
+  const long long n16 = shard_bytes / 16;
+  const long long src_off = in_off + (long long)pp.rank * shard_bytes;
+  char* dst = reinterpret_cast<char*>(pp.data[pp.rank]) + out_off;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (use_nvls && pp.mc_data) {
+    const char* mc = reinterpret_cast<const char*>(pp.mc_data) + src_off;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += stride)
+      st_v4(dst + i * 16, multimem_ld_reduce_bf16x8(mc + i * 16));
+  } else {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += stride) {
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      uint4 v[kMaxRanks];
+#pragma unroll
+      for (int s = 0; s < kMaxRanks; ++s)
+        if (s < pp.world) v[s] = ld_v4(reinterpret_cast<const char*>(pp.data[(pp.rank + s) % pp.world]) + src_off + i * 16);
+#pragma unroll
+      for (int s = 0; s < kMaxRanks; ++s)
+        if (s < pp.world) acc_bf16x8(acc, v[s]);
+      st_v4(dst + i * 16, pack_bf16x8(acc));
+    }
+  }
+  cta_barrier_all_ranks(pp, epoch + 1);
+}
+
+// all_reduce (bf16 sum), result written to out on every rank
+__global__ void __launch_bounds__(512) all_reduce_kernel(PeerPtrs pp, long long in_off, long long out_off,
+                                                        long long total_bytes, uint32_t epoch, int use_nvls) {
+  cta_barrier_all_ranks(pp, epoch);
+  const long long n16_total = total_bytes / 16;
+  // slice owned by this rank (16-byte granules, last rank takes the remainder)
+  const long long per = (n16_total + pp.world - 1) / pp.world;
+  const long long lo = per * pp.rank;
+  const long long hi = min(n16_total, lo + per);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (use_nvls && pp.mc_data) {
+    const char* mc_in = reinterpret_cast<const char*>(pp.mc_data) + in_off;
+    char* mc_out = reinterpret_cast<char*>(pp.mc_data) + out_off;
+    for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi; i += stride)
+      multimem_st_v4(mc_out + i * 16, multimem_ld_reduce_bf16x8(mc_in + i * 16));
+  } else {
+    for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi; i += stride) {
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      uint4 v[kMaxRanks];
+#pragma unroll
+      for (int s = 0; s < kMaxRanks; ++s)
+        if (s < pp.world) v[s] = ld_v4(reinterpret_cast<const char*>(pp.data[(pp.rank + s) % pp.world]) + in_off + i * 16);
+#pragma unroll
+      for (int s = 0; s < kMaxRanks; ++s)
+        if (s < pp.world) acc_bf16x8(acc, v[s]);
+      const uint4 r = pack_bf16x8(acc);
+#pragma unroll 1
+      for (int s = 0; s < pp.world; ++s)
+        st_v4(reinterpret_cast<char*>(pp.data[(pp.rank + s) % pp.world]) + out_off + i * 16, r);
+    }
+  }
+  cta_barrier_all_ranks(pp, epoch + 1);
+}
+
+// all_to_all: out_dst[src * chunk ..] <- in_src[dst * chunk ..]
+__global__ void __launch_bounds__(512) all_to_all_kernel(PeerPtrs pp, long long in_off, long long out_off,
+                                                        long long chunk_bytes, uint32_t epoch) {
+  cta_barrier_all_ranks(pp, epoch);
+  const long long n16 = chunk_bytes / 16;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const char* src_base = reinterpret_cast<const char*>(pp.data[pp.rank]) + in_off;
+  for (int s = 0; s < pp.world; ++s) {
+    const int peer = (pp.rank + s) % pp.world;
+    const char* src = src_base + (long long)peer * chunk_bytes;
+    char* dst = reinterpret_cast<char*>(pp.data[peer]) + out_off + (long long)pp.rank * chunk_bytes;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += stride)
+      st_v4(dst + i * 16, ld_nc_v4(src + i * 16));
+  }
+  cta_barrier_all_ranks(pp, epoch + 1);
+}
+
+// point-to-point put (pipeline send): dst rank's buffer <- local buffer; flag protocol as above restricted to a pair
+__global__ void __launch_bounds__(512) p2p_put_kernel(PeerPtrs pp, int dst_rank, long long in_off, long long out_off,
+                                                     long long nbytes) {
+  const long long n16 = nbytes / 16;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const char* src = reinterpret_cast<const char*>(pp.data[pp.rank]) + in_off;
+  char* dst = reinterpret_cast<char*>(pp.data[dst_rank]) + out_off;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += stride)
+    st_v4(dst + i * 16, ld_nc_v4(src + i * 16));
+}
+
+}  // namespace smx
+
+extern "C" {
+
+// ptrs: world data pointers then world flag pointers.  Returns cudaError.
+static smx::PeerPtrs make_pp(void* const* data_ptrs, void* const* flag_ptrs, void* mc, int rank, int world) {
+  smx::PeerPtrs pp;
+  for (int i = 0; i < smx::kMaxRanks; ++i) {
+    pp.data[i] = i < world ? data_ptrs[i] : nullptr;
+    pp.flags[i] = i < world ? reinterpret_cast<uint32_t*>(flag_ptrs[i]) : nullptr;
+  }
+  pp.mc_data = mc;
+  pp.rank = rank;
+  pp.world = world;
+  return pp;
+}
+
+int smx_coll_max_ctas() { return 64; }
+
+int smx_all_gather(void* const* data_ptrs, void* const* flag_ptrs, void* mc, int rank, int world, long long in_off,
+                   long long out_off, long long shard_bytes, unsigned epoch, int use_nvls, int ctas, void* stream) {
+  if (world > smx::kMaxRanks || shard_bytes % 16) return -40;
+  smx::all_gather_kernel<<<ctas, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      make_pp(data_ptrs, flag_ptrs, mc, rank, world), in_off, out_off, shard_bytes, epoch, use_nvls);
+  return (int)cudaGetLastError();
+}
+int smx_reduce_scatter(void* const* data_ptrs, void* const* flag_ptrs, void* mc, int rank, int world, long long in_off,
+                       long long out_off, long long shard_bytes, unsigned epoch, int use_nvls, int ctas, void* stream) {
+  if (world > smx::kMaxRanks || shard_bytes % 16) return -40;
+  smx::reduce_scatter_kernel<<<ctas, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      make_pp(data_ptrs, flag_ptrs, mc, rank, world), in_off, out_off, shard_bytes, epoch, use_nvls);
+  return (int)cudaGetLastError();
+}
+int smx_all_reduce(void* const* data_ptrs, void* const* flag_ptrs, void* mc, int rank, int world, long long in_off,
+                   long long out_off, long long total_bytes, unsigned epoch, int use_nvls, int ctas, void* stream) {
+  if (world > smx::kMaxRanks || total_bytes % 16) return -40;
+  smx::all_reduce_kernel<<<ctas, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      make_pp(data_ptrs, flag_ptrs, mc, rank, world), in_off, out_off, total_bytes, epoch, use_nvls);
+  return (int)cudaGetLastError();
+}
+int smx_all_to_all(void* const* data_ptrs, void* const* flag_ptrs, int rank, int world, long long in_off,
+                   long long out_off, long long chunk_bytes, unsigned epoch, int ctas, void* stream) {
+  if (world > smx::kMaxRanks || chunk_bytes % 16) return -40;
+  smx::all_to_all_kernel<<<ctas, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      make_pp(data_ptrs, flag_ptrs, nullptr, rank, world), in_off, out_off, chunk_bytes, epoch);
+  return (int)cudaGetLastError();
+}
+int smx_p2p_put(void* const* data_ptrs, void* const* flag_ptrs, int rank, int world, int dst_rank, long long in_off,
+                long long out_off, long long nbytes, int ctas, void* stream) {
+  if (world > smx::kMaxRanks || nbytes % 16) return -40;
+  smx::p2p_put_kernel<<<ctas, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      make_pp(data_ptrs, flag_ptrs, nullptr, rank, world), dst_rank, in_off, out_off, nbytes);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,585 @@
+// Flash-attention backward for sm_100a (head dim 128): five tcgen05 GEMMs per (128-key tile, 64-query tile) with every
+// accumulator in TMEM, dK/dV resident in TMEM for the whole CTA (summed over the GQA group's query heads, so no atomics
+// for dK/dV) and dQ pushed to an fp32 accumulator with TMA reduce-add.
+//
+//   per CTA: one (batch, kv head, 128-key tile);  loop over (query head in group) x (64-query tiles at/after the diagonal)
+//     S^T  = K Q^T                 M=128(kv) N=64(q)  K=128(d)    A=K  (K-major)   B=Q  (K-major)
+//     dP^T = V dO^T                M=128     N=64     K=128       A=V  (K-major)   B=dO (K-major)
+//     P^T  = exp2(S^T*c - lse)     softmax warps, one key row per thread -> bf16 -> swizzled smem
+//     dS^T = P^T o (dP^T - D) * scale                            -> bf16 -> swizzled smem
+//     dV  += P^T dO                M=128(kv) N=128(d) K=64(q)     A=P^T (K-major)  B=dO (MN-major, same smem tile)
+//     dK  += dS^T Q                M=128     N=128    K=64        A=dS^T(K-major)  B=Q  (MN-major, same smem tile)
+//     dQ^T = K^T dS^T              M=128(d)  N=64(q)  K=128(kv)   A=K  (MN-major, same smem tile)  B=dS^T (MN-major)
+//   dQ^T leaves through TMEM -> registers -> smem [64 q][128 d] fp32 -> cp.reduce.async.bulk.tensor (add) into dq_accum.
+//
+// TMEM columns: S^T [0,64)  dP^T [64,128)  dQ^T [128,192)  dV [192,320)  dK [320,448).
+// Warp roles (320 threads): warp0 TMA producer, warp1 MMA issuer (+TMEM alloc), warps 2..5 softmax / dK epilogue,
+// warps 6..9 dQ drain / dV epilogue.
+//
+// Pre-pass: D[b,h,s] = rowsum(dO o O); post-pass: dq = bf16(dq_accum).
+// Replaces the fused-attention backward the reference times through TE / cuDNN
+// (/root/reference/simu_tools/efficency_test/test_fa_efficiency.py:250-497).
+#include "sm100_common.cuh"
+
+namespace smx {
+
+SMX_DEVICE void bwd_tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* smem_dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+SMX_DEVICE void bwd_tma_reduce_add_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+SMX_DEVICE void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+constexpr int kBwdBKV = 128;
+constexpr int kBwdBQ = 64;
+constexpr int kBwdD = 128;
+constexpr int kBwdThreads = 320;
+constexpr int kBwdKVBytes = kBwdBKV * kBwdD * 2;      // 32 KB each for K and V
+constexpr int kBwdQBytes = kBwdBQ * kBwdD * 2;        // 16 KB each for Q_i and dO_i
+constexpr int kBwdStageBytes = 2 * kBwdQBytes;
+constexpr int kBwdPBytes = kBwdBKV * kBwdBQ * 2;      // 16 KB each for P^T and dS^T
+constexpr int kBwdDqBytes = kBwdBQ * kBwdD * 4;       // 32 KB fp32 staging for the dQ reduce
+constexpr int kBwdSmemBytes = 2 * kBwdKVBytes + 2 * kBwdStageBytes + 2 * kBwdPBytes + kBwdDqBytes + 2 * 2 * 64 * 4 + 256 + 1024;
+
+struct FmhaBwdParams {
+  int B, S_q, S_kv, H, H_kv;
+  float scale;
+  int causal;
+  const float* lse;   // [B, H, S_q]
+  const float* dsum;  // [B, H, S_q]  rowsum(dO o O)
+  __nv_bfloat16* dk;  // strides in elements
+  __nv_bfloat16* dv;
+  long long dk_sb, dk_ss, dk_sh, dv_sb, dv_ss, dv_sh;
+};
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                const __grid_constant__ CUtensorMap tmap_dq, const FmhaBwdParams p) {
+  constexpr int BKV = kBwdBKV, BQ = kBwdBQ, D = kBwdD;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + kBwdKVBytes;
+  uint8_t* sQdO = sV + kBwdKVBytes;                    // [2 stages][Q 16 KB | dO 16 KB]
+  uint8_t* sP = sQdO + 2 * kBwdStageBytes;
+  uint8_t* sdS = sP + kBwdPBytes;
+  float* sDq = reinterpret_cast<float*>(sdS + kBwdPBytes);
+  float* sLse = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sDq) + kBwdDqBytes);   // [2][64]
+  float* sDsum = sLse + 2 * 64;                                                            // [2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDsum + 2 * 64);
+  uint64_t* kv_full = bars;            // 1
+  uint64_t* qdo_full = bars + 1;       // [2]
+  uint64_t* qdo_empty = bars + 3;      // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_empty = bars + 6;
+  uint64_t* dp_full = bars + 7;
+  uint64_t* dp_empty = bars + 8;
+  uint64_t* p_full = bars + 9;
+  uint64_t* pv_done = bars + 10;
+  uint64_t* ds_full = bars + 11;
+  uint64_t* dkq_done = bars + 12;
+  uint64_t* dq_full = bars + 13;
+  uint64_t* dq_empty = bars + 14;
+  uint64_t* all_done = bars + 15;
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp_idx = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  const int kv_tile = blockIdx.x;
+  const int kv_head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int group = p.H / p.H_kv;
+  const int k0 = kv_tile * BKV;
+  const int shift = p.S_kv - p.S_q;
+  const int n_q_tiles = (p.S_q + BQ - 1) / BQ;
+  int i_begin = 0;
+  if (p.causal) i_begin = max(0, k0 - shift) / BQ;
+  const int nq_local = max(0, n_q_tiles - i_begin);
+  const int n_iter = nq_local * group;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_dq);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(dp_full, 1);
+    mbar_init(dp_empty, 4);
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    mbar_init(ds_full, 4);
+    mbar_init(dkq_done, 1);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 4);
+    mbar_init(all_done, 1);
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) tmem_alloc<1>(tmem_base_ptr, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_ptr;
+  const uint32_t tmem_s = tmem_base;
+  const uint32_t tmem_dp = tmem_base + 64;
+  const uint32_t tmem_dq = tmem_base + 128;
+  const uint32_t tmem_dv = tmem_base + 192;
+  const uint32_t tmem_dk = tmem_base + 320;
+
+  auto iter_head = [&](int it) { return kv_head * group + it / nq_local; };
+  auto iter_q0 = [&](int it) { return (i_begin + it % nq_local) * BQ; };
+
+  if (warp_idx == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0 && n_iter > 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * kBwdKVBytes);
+#pragma unroll
+      for (int c = 0; c < D / 64; ++c) {
+        bwd_tma_load_4d(&tmap_k, kv_full, sK + c * (BKV * 128), c * 64, k0, kv_head, batch);
+        bwd_tma_load_4d(&tmap_v, kv_full, sV + c * (BKV * 128), c * 64, k0, kv_head, batch);
+      }
+      for (int it = 0; it < n_iter; ++it) {
+        const int st = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&qdo_empty[st], ph ^ 1, 21);
+        uint8_t* sQ = sQdO + st * kBwdStageBytes;
+        uint8_t* sdO = sQ + kBwdQBytes;
+        mbar_arrive_expect_tx(&qdo_full[st], kBwdStageBytes);
+        const int head = iter_head(it), q0 = iter_q0(it);
+#pragma unroll
+        for (int c = 0; c < D / 64; ++c) {
+          bwd_tma_load_4d(&tmap_q, &qdo_full[st], sQ + c * (BQ * 128), c * 64, q0, head, batch);
+          bwd_tma_load_4d(&tmap_do, &qdo_full[st], sdO + c * (BQ * 128), c * 64, q0, head, batch);
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ============================ MMA issuer ============================
+    constexpr uint32_t idesc_s = make_idesc(1, 1, 0, 0, BKV, BQ);    // K (K-major) x Q (K-major)      -> S^T[128, 64]
+    constexpr uint32_t idesc_dv = make_idesc(1, 1, 0, 1, BKV, D);    // P^T (K-major) x dO (MN-major)  -> dV[128, 128]
+    constexpr uint32_t idesc_dq = make_idesc(1, 1, 1, 1, D, BQ);     // K (MN-major) x dS^T (MN-major) -> dQ^T[128, 64]
+    auto issue_s = [&](int it) {       // S^T(it) = K Q^T
+      const int st = it & 1;
+      mbar_wait(&qdo_full[st], (it >> 1) & 1, 22);
+      if (it > 0) mbar_wait(s_empty, (it - 1) & 1, 23);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        uint8_t* sQ = sQdO + st * kBwdStageBytes;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint64_t a = make_smem_desc_sw128(smem_u32(sK + (k / 4) * (BKV * 128)), 16, 1024) + (k % 4) * 2;
+          const uint64_t b = make_smem_desc_sw128(smem_u32(sQ + (k / 4) * (BQ * 128)), 16, 1024) + (k % 4) * 2;
+          umma_f16<1>(tmem_s, a, b, idesc_s, k > 0 ? 1u : 0u);
+        }
+        umma_commit<1>(s_full);
+      }
+      __syncwarp();
+    };
+    auto issue_dp = [&](int it) {      // dP^T(it) = V dO^T
+      const int st = it & 1;
+      if (it > 0) mbar_wait(dp_empty, (it - 1) & 1, 24);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        uint8_t* sdO = sQdO + st * kBwdStageBytes + kBwdQBytes;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint64_t a = make_smem_desc_sw128(smem_u32(sV + (k / 4) * (BKV * 128)), 16, 1024) + (k % 4) * 2;
+          const uint64_t b = make_smem_desc_sw128(smem_u32(sdO + (k / 4) * (BQ * 128)), 16, 1024) + (k % 4) * 2;
+          umma_f16<1>(tmem_dp, a, b, idesc_s, k > 0 ? 1u : 0u);
+        }
+        umma_commit<1>(dp_full);
+      }
+      __syncwarp();
+    };
+    if (n_iter > 0) {
+      mbar_wait(kv_full, 0, 25);
+      issue_s(0);
+      issue_dp(0);
+    }
+    for (int it = 0; it < n_iter; ++it) {
+      const int st = it & 1;
+      uint8_t* sQ = sQdO + st * kBwdStageBytes;
+      uint8_t* sdO = sQ + kBwdQBytes;
+      if (it + 1 < n_iter) issue_s(it + 1);
+      // dV += P^T dO
+      mbar_wait(p_full, it & 1, 26);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint64_t a0 = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
+        const uint64_t b0 = make_smem_desc_sw128(smem_u32(sdO), BQ * 128, 1024);
+#pragma unroll
+        for (int k = 0; k < BQ / 16; ++k)
+          umma_f16<1>(tmem_dv, a0 + k * 2, b0 + k * ((16 * 128) >> 4), idesc_dv, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit<1>(pv_done);
+      }
+      __syncwarp();
+      if (it + 1 < n_iter) issue_dp(it + 1);
+      // dK += dS^T Q ;  dQ^T = K^T dS^T
+      mbar_wait(ds_full, it & 1, 27);
+      if (it > 0) mbar_wait(dq_empty, (it - 1) & 1, 28);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint64_t a0 = make_smem_desc_sw128(smem_u32(sdS), 16, 1024);
+        const uint64_t b0 = make_smem_desc_sw128(smem_u32(sQ), BQ * 128, 1024);
+#pragma unroll
+        for (int k = 0; k < BQ / 16; ++k)
+          umma_f16<1>(tmem_dk, a0 + k * 2, b0 + k * ((16 * 128) >> 4), idesc_dv, (it > 0 || k > 0) ? 1u : 0u);
+        const uint64_t ak = make_smem_desc_sw128(smem_u32(sK), BKV * 128, 1024);
+        const uint64_t bs = make_smem_desc_sw128(smem_u32(sdS), BKV * 128, 1024);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)
+          umma_f16<1>(tmem_dq, ak + k * ((16 * 128) >> 4), bs + k * ((16 * 128) >> 4), idesc_dq, k > 0 ? 1u : 0u);
+        umma_commit<1>(dq_full);
+        umma_commit<1>(dkq_done);
+        umma_commit<1>(&qdo_empty[st]);
+        if (it + 1 == n_iter) umma_commit<1>(all_done);
+      }
+      __syncwarp();
+    }
+  } else if (warp_idx < 6) {
+    // ============================ softmax / dS (one key row per thread) ============================
+    const int quad = warp_idx % 4;
+    const int row_in_tile = quad * 32 + lane;
+    const int kv_row = k0 + row_in_tile;
+    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    const int tid = threadIdx.x - 64;     // 0..127
+    const float c_log2 = p.scale * 1.4426950408889634f;
+    for (int it = 0; it < n_iter; ++it) {
+      const int head = iter_head(it), q0 = iter_q0(it);
+      {
+        // stage lse (log2 units) and D for the 64 query columns of this tile
+        const int qi = q0 + (tid & 63);
+        const long long off = ((long long)batch * p.H + head) * p.S_q + qi;
+        float* dst = (tid < 64 ? sLse : sDsum) + (it & 1) * 64 + (tid & 63);
+        float v;
+        if (tid < 64) {
+          v = (qi < p.S_q) ? p.lse[off] * 1.4426950408889634f : INFINITY;
+          if (!(v > -INFINITY)) v = INFINITY;
+        } else {
+          v = (qi < p.S_q) ? p.dsum[off] : 0.f;
+        }
+        *dst = v;
+      }
+      named_bar_sync(1, 128);
+      const float* lse2 = sLse + (it & 1) * 64;
+      const float* dsum = sDsum + (it & 1) * 64;
+      mbar_wait(s_full, it & 1, 29);
+      tcgen05_fence_after();
+      uint32_t r[64];
+      {
+        uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+        uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+        tmem_ld_32x32b_x32(tmem_s + lane_addr, r0);
+        tmem_ld_32x32b_x32(tmem_s + lane_addr + 32, r1);
+        tmem_ld_wait();
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);
+      const bool need_mask = (p.causal && (k0 + BKV - 1 > q0 + shift)) || (k0 + BKV > p.S_kv);
+      float pr[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        float e = exp2f(__uint_as_float(r[i]) * c_log2 - lse2[i]);
+        if (need_mask) {
+          const bool ok = (kv_row < p.S_kv) && (!p.causal || kv_row <= q0 + i + shift);
+          e = ok ? e : 0.f;
+        }
+        pr[i] = e;
+      }
+      if (it > 0) mbar_wait(pv_done, (it - 1) & 1, 30);     // dV(it-1) has finished reading the P^T tile
+      {
+        uint8_t* prow = sP + row_in_tile * 128;
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16) {
+          uint4 pk;
+          pk.x = pack_bf16x2(pr[c16 * 8 + 0], pr[c16 * 8 + 1]);
+          pk.y = pack_bf16x2(pr[c16 * 8 + 2], pr[c16 * 8 + 3]);
+          pk.z = pack_bf16x2(pr[c16 * 8 + 4], pr[c16 * 8 + 5]);
+          pk.w = pack_bf16x2(pr[c16 * 8 + 6], pr[c16 * 8 + 7]);
+          *reinterpret_cast<uint4*>(prow + ((c16 ^ (row_in_tile & 7)) << 4)) = pk;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // dS^T = P^T o (dP^T - D) * scale
+      mbar_wait(dp_full, it & 1, 31);
+      tcgen05_fence_after();
+      {
+        uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+        uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+        tmem_ld_32x32b_x32(tmem_dp + lane_addr, r0);
+        tmem_ld_32x32b_x32(tmem_dp + lane_addr + 32, r1);
+        tmem_ld_wait();
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dp_empty);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) pr[i] = pr[i] * (__uint_as_float(r[i]) - dsum[i]) * p.scale;
+      if (it > 0) mbar_wait(dkq_done, (it - 1) & 1, 32);    // dK/dQ(it-1) have finished reading the dS^T tile
+      {
+        uint8_t* drow = sdS + row_in_tile * 128;
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16) {
+          uint4 pk;
+          pk.x = pack_bf16x2(pr[c16 * 8 + 0], pr[c16 * 8 + 1]);
+          pk.y = pack_bf16x2(pr[c16 * 8 + 2], pr[c16 * 8 + 3]);
+          pk.z = pack_bf16x2(pr[c16 * 8 + 4], pr[c16 * 8 + 5]);
+          pk.w = pack_bf16x2(pr[c16 * 8 + 6], pr[c16 * 8 + 7]);
+          *reinterpret_cast<uint4*>(drow + ((c16 ^ (row_in_tile & 7)) << 4)) = pk;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+    }
+    // ---- dK epilogue (rows = keys)
+    if (n_iter > 0) {
+      mbar_wait(all_done, 0, 33);
+      tcgen05_fence_after();
+    }
+    const bool row_ok = kv_row < p.S_kv;
+    __nv_bfloat16* out = p.dk + batch * p.dk_sb + (long long)(row_ok ? kv_row : 0) * p.dk_ss + kv_head * p.dk_sh;
+#pragma unroll 1
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t o[32];
+      if (n_iter > 0) {
+        tmem_ld_32x32b_x32(tmem_dk + lane_addr + c * 32, o);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0u;
+      }
+      if (row_ok) {
+        uint4* dst = reinterpret_cast<uint4*>(out + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[8 * i]), __uint_as_float(o[8 * i + 1]));
+          v.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]), __uint_as_float(o[8 * i + 3]));
+          v.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]), __uint_as_float(o[8 * i + 5]));
+          v.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]), __uint_as_float(o[8 * i + 7]));
+          dst[i] = v;
+        }
+      }
+    }
+  } else {
+    // ============================ dQ drain (one head-dim row of dQ^T per thread) ============================
+    const int quad = warp_idx % 4;
+    const int d_idx = quad * 32 + lane;
+    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    const int tid = threadIdx.x - 192;    // 0..127
+    for (int it = 0; it < n_iter; ++it) {
+      const int head = iter_head(it), q0 = iter_q0(it);
+      mbar_wait(dq_full, it & 1, 34);
+      tcgen05_fence_after();
+      uint32_t r[64];
+      {
+        uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+        uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+        tmem_ld_32x32b_x32(tmem_dq + lane_addr, r0);
+        tmem_ld_32x32b_x32(tmem_dq + lane_addr + 32, r1);
+        tmem_ld_wait();
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_empty);
+      // the previous tile's bulk reduce must have finished reading the staging buffer
+      if (tid == 0) tma_store_wait_read<0>();
+      named_bar_sync(2, 128);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) sDq[i * D + d_idx] = __uint_as_float(r[i]);
+      fence_proxy_async_smem();
+      named_bar_sync(3, 128);
+      if (tid == 0) {
+        bwd_tma_reduce_add_4d(&tmap_dq, sDq, 0, q0, head, batch);
+        tma_store_commit();
+      }
+    }
+    if (tid == 0) tma_store_wait_all<0>();
+    // ---- dV epilogue (rows = keys)
+    if (n_iter > 0) {
+      mbar_wait(all_done, 0, 35);
+      tcgen05_fence_after();
+    }
+    const int kv_row = k0 + d_idx;
+    const bool row_ok = kv_row < p.S_kv;
+    __nv_bfloat16* out = p.dv + batch * p.dv_sb + (long long)(row_ok ? kv_row : 0) * p.dv_ss + kv_head * p.dv_sh;
+#pragma unroll 1
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t o[32];
+      if (n_iter > 0) {
+        tmem_ld_32x32b_x32(tmem_dv + lane_addr + c * 32, o);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0u;
+      }
+      if (row_ok) {
+        uint4* dst = reinterpret_cast<uint4*>(out + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[8 * i]), __uint_as_float(o[8 * i + 1]));
+          v.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]), __uint_as_float(o[8 * i + 3]));
+          v.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]), __uint_as_float(o[8 * i + 5]));
+          v.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]), __uint_as_float(o[8 * i + 7]));
+          dst[i] = v;
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+// D[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]   (one warp per (b,s,h) row of 128)
+__global__ void fmha_bwd_dsum_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                                     float* __restrict__ dsum, int B, int S, int H, int D, long long o_sb, long long o_ss,
+                                     long long o_sh, long long do_sb, long long do_ss, long long do_sh) {
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x % 32;
+  const long long total = (long long)B * S * H;
+  if (warp >= total) return;
+  const int h = warp % H;
+  const int s = (warp / H) % S;
+  const int b = warp / ((long long)H * S);
+  const __nv_bfloat16* po = o + b * o_sb + s * o_ss + h * o_sh;
+  const __nv_bfloat16* pd = d_o + b * do_sb + s * do_ss + h * do_sh;
+  float acc = 0.f;
+  for (int i = lane * 4; i < D; i += 128) {
+    const uint2 a = *reinterpret_cast<const uint2*>(po + i);
+    const uint2 c = *reinterpret_cast<const uint2*>(pd + i);
+    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* c2 = reinterpret_cast<const __nv_bfloat162*>(&c);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float2 x = __bfloat1622float2(a2[j]), y = __bfloat1622float2(c2[j]);
+      acc += x.x * y.x + x.y * y.y;
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) dsum[((long long)b * H + h) * S + s] = acc;
+}
+
+// dq[b,s,h,:] = bf16(dq_accum[b,s,h,:])   (dq strided, accum contiguous [B,S,H,D])
+__global__ void fmha_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, long long rows,
+                                           int S, int H, int D, long long sb, long long ss, long long sh) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;     // one thread per 8 elements
+  const int per_row = D / 8;
+  if (idx >= rows * per_row) return;
+  const long long row = idx / per_row;
+  const int c = (idx % per_row) * 8;
+  const int h = row % H;
+  const int s = (row / H) % S;
+  const long long b = row / ((long long)H * S);
+  const float4 x = *reinterpret_cast<const float4*>(acc + row * D + c);
+  const float4 y = *reinterpret_cast<const float4*>(acc + row * D + c + 4);
+  uint4 v;
+  v.x = pack_bf16x2(x.x, x.y); v.y = pack_bf16x2(x.z, x.w); v.z = pack_bf16x2(y.x, y.y); v.w = pack_bf16x2(y.z, y.w);
+  *reinterpret_cast<uint4*>(dq + b * sb + s * ss + h * sh + c) = v;
+}
+
+inline int bwd_make_tmap_4d(CUtensorMap* out, CUtensorMapDataType dt, CUtensorMapSwizzle sw, const void* ptr, uint64_t d0,
+                            uint64_t d1, uint64_t d2, uint64_t d3, uint64_t s1_bytes, uint64_t s2_bytes,
+                            uint64_t s3_bytes, uint32_t box0, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[4] = {d0, d1, d2, d3};
+  cuuint64_t strides[3] = {s1_bytes, s2_bytes, s3_bytes};
+  cuuint32_t box[4] = {box0, box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, dt, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "simumax_b200: fmha_bwd cuTensorMapEncodeTiled failed (%d)\n", (int)r);
+    return -2;
+  }
+  return 0;
+}
+
+}  // namespace smx
+
+extern "C" {
+
+// Workspace: dsum [B,H,S_q] fp32 and dq_accum [B,S_q,H,128] fp32 (both provided by the caller; dq_accum is zeroed here).
+// All of q,k,v,o,do,dq,dk,dv are "bshd" views with element strides (last dim contiguous, 16B aligned).
+int smx_fmha_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse, void* dq,
+                 void* dk, void* dv, float* dsum, float* dq_accum, int B, int S_q, int S_kv, int H, int H_kv, int d,
+                 const long long* strides /* 8 x (sb, ss, sh): q k v o do dq dk dv */, float scale, int causal,
+                 cudaStream_t stream) {
+  using namespace smx;
+  if (d != kBwdD) return -31;
+  if (H % H_kv) return -30;
+  const long long* sq = strides; const long long* sk = strides + 3; const long long* sv = strides + 6;
+  const long long* so = strides + 9; const long long* sdo = strides + 12; const long long* sdq = strides + 15;
+  const long long* sdk = strides + 18; const long long* sdv = strides + 21;
+  CUtensorMap tq, tk, tv, tdo, tdq;
+  const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const auto SW = CU_TENSOR_MAP_SWIZZLE_128B;
+  int rc = bwd_make_tmap_4d(&tq, BF, SW, q, d, S_q, H, B, sq[1] * 2, sq[2] * 2, sq[0] * 2, 64, kBwdBQ);
+  if (rc) return rc;
+  rc = bwd_make_tmap_4d(&tk, BF, SW, k, d, S_kv, H_kv, B, sk[1] * 2, sk[2] * 2, sk[0] * 2, 64, kBwdBKV);
+  if (rc) return rc;
+  rc = bwd_make_tmap_4d(&tv, BF, SW, v, d, S_kv, H_kv, B, sv[1] * 2, sv[2] * 2, sv[0] * 2, 64, kBwdBKV);
+  if (rc) return rc;
+  rc = bwd_make_tmap_4d(&tdo, BF, SW, d_o, d, S_q, H, B, sdo[1] * 2, sdo[2] * 2, sdo[0] * 2, 64, kBwdBQ);
+  if (rc) return rc;
+  rc = bwd_make_tmap_4d(&tdq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE, dq_accum, d, S_q, H, B,
+                        (uint64_t)H * d * 4, (uint64_t)d * 4, (uint64_t)S_q * H * d * 4, kBwdD, kBwdBQ);
+  if (rc) return rc;
+  cudaError_t e = cudaMemsetAsync(dq_accum, 0, (size_t)B * S_q * H * d * sizeof(float), stream);
+  if (e != cudaSuccess) return (int)e;
+  {
+    const long long rows = (long long)B * S_q * H;
+    const int threads = 256;
+    const long long blocks = (rows * 32 + threads - 1) / threads;
+    fmha_bwd_dsum_kernel<<<(unsigned)blocks, threads, 0, stream>>>(
+        (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, dsum, B, S_q, H, d, so[0], so[1], so[2], sdo[0], sdo[1], sdo[2]);
+  }
+  FmhaBwdParams p;
+  p.B = B; p.S_q = S_q; p.S_kv = S_kv; p.H = H; p.H_kv = H_kv; p.scale = scale; p.causal = causal;
+  p.lse = lse; p.dsum = dsum; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
+  p.dk_sb = sdk[0]; p.dk_ss = sdk[1]; p.dk_sh = sdk[2]; p.dv_sb = sdv[0]; p.dv_ss = sdv[1]; p.dv_sh = sdv[2];
+  static bool attr_set = false;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(fmha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid((S_kv + kBwdBKV - 1) / kBwdBKV, H_kv, B);
+  fmha_bwd_kernel<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(tq, tk, tv, tdo, tdq, p);
+  {
+    const long long rows = (long long)B * S_q * H;
+    const long long n = rows * (d / 8);
+    fmha_bwd_dq_convert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dq_accum, (__nv_bfloat16*)dq, rows, S_q, H, d,
+                                                                                  sdq[0], sdq[1], sdq[2]);
+  }
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // extern "C"

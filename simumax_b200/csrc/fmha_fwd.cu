@@ -277,13 +277,16 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tcgen05_fence_after();
     }
     const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
-    if (row < p.S_q) {
-      __nv_bfloat16* orow = o_ptr + batch * p.o_stride_b + (long long)row * p.o_stride_s + head * p.o_stride_h;
+    // tcgen05.ld is warp-collective (.sync.aligned): every lane issues the loads, only the stores are predicated
+    // (a partially valid q tile has valid and invalid rows inside one warp).
+    const bool row_ok = row < p.S_q;
+    __nv_bfloat16* orow = o_ptr + batch * p.o_stride_b + (long long)(row_ok ? row : 0) * p.o_stride_s + head * p.o_stride_h;
 #pragma unroll 1
-      for (int c = 0; c < D_V / 32; ++c) {
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(tmem_o + lane_addr + c * 32, o);
-        tmem_ld_wait();
+    for (int c = 0; c < D_V / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tmem_o + lane_addr + c * 32, o);
+      tmem_ld_wait();
+      if (row_ok) {
         uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -295,18 +298,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           dst[i] = v;
         }
       }
-      if (lse_ptr)
-        lse_ptr[batch * p.lse_stride_b + head * p.lse_stride_h + row] =
-            (l > 0.f) ? m_used * p.scale + __logf(l) : -INFINITY;
-    } else {
-      // keep the warp-collective TMEM loads converged for partially valid tiles
-#pragma unroll 1
-      for (int c = 0; c < D_V / 32; ++c) {
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(tmem_o + lane_addr + c * 32, o);
-        tmem_ld_wait();
-      }
     }
+    if (row_ok && lse_ptr)
+      lse_ptr[batch * p.lse_stride_b + head * p.lse_stride_h + row] =
+          (l > 0.f) ? m_used * p.scale + __logf(l) : -INFINITY;
   }
 
   tcgen05_fence_before();

@@ -87,14 +87,21 @@ SMX_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug becomes a trap with a diagnostic instead of a hung GPU.
-#ifndef SMX_MBAR_SPIN_LIMIT
-#define SMX_MBAR_SPIN_LIMIT (1u << 26)
+// Bounded wait: a protocol bug becomes a trap with a diagnostic instead of a hung GPU.  try_wait suspends the
+// thread in hardware for an implementation-defined time, so the bound is wall-clock based (%globaltimer, ns).
+#ifndef SMX_MBAR_TIMEOUT_NS
+#define SMX_MBAR_TIMEOUT_NS 4000000000ull
 #endif
+SMX_DEVICE uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 SMX_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > SMX_MBAR_SPIN_LIMIT) {
+    if (global_timer_ns() - t0 > SMX_MBAR_TIMEOUT_NS) {
       printf("simumax_b200: mbarrier wait timeout tag=%d parity=%u block=(%d,%d,%d) thread=%d\n", tag, parity,
              (int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x);
       __trap();

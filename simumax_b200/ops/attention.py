@@ -35,7 +35,7 @@ def _check(t: torch.Tensor, name: str):
 
 
 def fmha_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = True, scale: Optional[float] = None,
-             out: Optional[torch.Tensor] = None, return_lse: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+             out: Optional[torch.Tensor] = None, return_lse: bool = True, lse: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _check(t, n)
     B, S_q, H, D = q.shape
@@ -45,7 +45,10 @@ def fmha_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = T
     if scale is None:
         scale = 1.0 / math.sqrt(D)
     o = torch.empty(B, S_q, H, Dv, device=q.device, dtype=q.dtype) if out is None else out
-    lse = torch.empty(B, H, S_q, device=q.device, dtype=torch.float32) if return_lse else None
+    if lse is None:
+        lse = torch.empty(B, H, S_q, device=q.device, dtype=torch.float32) if return_lse else None
+    else:
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * H * S_q
     rc = _fwd_fn()(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr() if lse is not None else None,
                    B, S_q, S_kv, H, H_kv, D, Dv,
                    q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
@@ -62,3 +65,60 @@ def attention_flops(B, S_q, S_kv, H, d_qk, d_v, causal: bool, backward: bool = F
     if causal:
         f *= 0.5
     return f * (2.5 if backward else 1.0)
+
+
+_bwd = None
+
+
+def _bwd_fn():
+    global _bwd
+    if _bwd is None:
+        f = _lib.lib().smx_fmha_bwd
+        f.restype = _c.c_int
+        f.argtypes = [_c.c_void_p] * 11 + [_c.c_int] * 6 + [_c.c_void_p, _c.c_float, _c.c_int, _c.c_void_p]
+        _bwd = f
+    return _bwd
+
+
+_bwd_ws = {}
+
+
+def _bwd_workspace(device, B, S_q, H, D):
+    """fp32 scratch (row sums of dO*O and the dQ accumulator), cached per shape so a training loop never reallocates."""
+    key = (device, B, S_q, H, D)
+    ws = _bwd_ws.get(key)
+    if ws is None:
+        ws = (torch.empty(B, H, S_q, device=device, dtype=torch.float32),
+              torch.empty(B, S_q, H, D, device=device, dtype=torch.float32))
+        _bwd_ws.clear()
+        _bwd_ws[key] = ws
+    return ws
+
+
+def fmha_bwd(d_o: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, lse: torch.Tensor,
+             dq: Optional[torch.Tensor] = None, dk: Optional[torch.Tensor] = None, dv: Optional[torch.Tensor] = None,
+             causal: bool = True, scale: Optional[float] = None):
+    """Backward of :func:`fmha_fwd` (csrc/fmha_bwd.cu; head dim 128). All tensors are bshd views; dq/dk/dv may be
+    slices of a packed d_qkv buffer. Returns (dq, dk, dv)."""
+    B, S_q, H, D = q.shape
+    _, S_kv, H_kv, _ = k.shape
+    if D != 128 or v.shape[-1] != 128:
+        raise NotImplementedError("fmha_bwd: head dim 128 only")
+    if scale is None:
+        scale = 1.0 / math.sqrt(D)
+    dq = torch.empty_like(q) if dq is None else dq
+    dk = torch.empty_like(k) if dk is None else dk
+    dv = torch.empty_like(v) if dv is None else dv
+    ts = (q, k, v, o, d_o, dq, dk, dv)
+    for t, n in zip(ts, ("q", "k", "v", "o", "do", "dq", "dk", "dv")):
+        _check(t, n)
+    assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * H * S_q
+    dsum, acc = _bwd_workspace(q.device, B, S_q, H, D)
+    strides = (_c.c_longlong * 24)(*[s for t in ts for s in (t.stride(0), t.stride(1), t.stride(2))])
+    rc = _bwd_fn()(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(), dq.data_ptr(),
+                   dk.data_ptr(), dv.data_ptr(), dsum.data_ptr(), acc.data_ptr(), B, S_q, S_kv, H, H_kv, D,
+                   _c.cast(strides, _c.c_void_p), float(scale), 1 if causal else 0,
+                   torch.cuda.current_stream(q.device).cuda_stream)
+    _lib.check(rc, f"fmha_bwd B{B} S{S_q}x{S_kv} H{H}/{H_kv} d{D}")
+    _lib.count_launch(3)
+    return dq, dk, dv

@@ -57,14 +57,15 @@ def _bf16c(t: torch.Tensor, what: str):
 
 
 # ------------------------------------------------------------------------------------------------
-def rmsnorm_fwd(x: torch.Tensor, gamma: torch.Tensor, eps: float = 1e-5, out: Optional[torch.Tensor] = None
-                ) -> Tuple[torch.Tensor, torch.Tensor]:
+def rmsnorm_fwd(x: torch.Tensor, gamma: torch.Tensor, eps: float = 1e-5, out: Optional[torch.Tensor] = None,
+                rstd: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """y = x * rsqrt(mean(x^2) + eps) * gamma over the last dim; returns (y, rstd[rows] fp32)."""
     _bf16c(x, "x"); _bf16c(gamma, "gamma")
     H = x.shape[-1]
     rows = x.numel() // H
     y = torch.empty_like(x) if out is None else out
-    rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    if rstd is None:
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
     _call("smx_rmsnorm_fwd", x.data_ptr(), gamma.data_ptr(), y.data_ptr(), rstd.data_ptr(), rows, H, eps, _stream(x))
     return y, rstd
 

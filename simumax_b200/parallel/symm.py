@@ -1,0 +1,124 @@
+"""Symmetric (peer-mapped) workspace + in-kernel collectives (csrc/collectives.cu).
+
+``SymmetricWorkspace`` allocates one data buffer and one flag buffer per rank through
+``torch.distributed._symmetric_memory`` (CUDA VMM + fabric/posix handle exchange under the hood), which gives every
+rank the peer pointers of all ranks and -- on NVSwitch systems -- an NVLS multicast address.  The collectives are
+our own kernels operating on those pointers; NCCL is only used for bootstrap (rendezvous) and as the baseline curve.
+
+Layout of the data buffer: ``[ in region : in_bytes ][ out region : out_bytes ]``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from ..ops import _lib
+
+_c = ctypes
+MAX_CTAS = 64
+MAX_RANKS = 8
+
+
+def _fn(name, argtypes):
+    f = getattr(_lib.lib(), name)
+    if not getattr(f, "_configured", False):
+        f.restype = _c.c_int
+        f.argtypes = argtypes
+        f._configured = True
+    return f
+
+
+_PTRS = _c.POINTER(_c.c_void_p)
+_SIG_COLL = [_PTRS, _PTRS, _c.c_void_p, _c.c_int, _c.c_int, _c.c_longlong, _c.c_longlong, _c.c_longlong, _c.c_uint,
+             _c.c_int, _c.c_int, _c.c_void_p]
+_SIG_A2A = [_PTRS, _PTRS, _c.c_int, _c.c_int, _c.c_longlong, _c.c_longlong, _c.c_longlong, _c.c_uint, _c.c_int, _c.c_void_p]
+_SIG_PUT = [_PTRS, _PTRS, _c.c_int, _c.c_int, _c.c_int, _c.c_longlong, _c.c_longlong, _c.c_longlong, _c.c_int, _c.c_void_p]
+
+
+class SymmetricWorkspace:
+    def __init__(self, in_bytes: int, out_bytes: int, group: Optional[dist.ProcessGroup] = None, device=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group or dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        assert self.world <= MAX_RANKS
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        align = lambda n: (n + 255) // 256 * 256
+        self.in_bytes, self.out_bytes = align(in_bytes), align(out_bytes)
+        try:
+            symm_mem.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:
+            pass
+        self.data = symm_mem.empty(self.in_bytes + self.out_bytes, dtype=torch.uint8, device=self.device)
+        self.flags = symm_mem.empty(MAX_CTAS * MAX_RANKS, dtype=torch.int32, device=self.device)
+        self.flags.zero_()
+        self._hd = symm_mem.rendezvous(self.data, self.group.group_name)
+        self._hf = symm_mem.rendezvous(self.flags, self.group.group_name)
+        self.data_ptrs = (_c.c_void_p * MAX_RANKS)(*[int(p) for p in self._hd.buffer_ptrs])
+        self.flag_ptrs = (_c.c_void_p * MAX_RANKS)(*[int(p) for p in self._hf.buffer_ptrs])
+        mc = getattr(self._hd, "multicast_ptr", 0) or 0
+        self.multicast_ptr = int(mc)
+        self.has_nvls = self.multicast_ptr != 0
+        self.epoch = 1
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+
+    # ---- typed views
+    def input(self, dtype, numel) -> torch.Tensor:
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        assert nbytes <= self.in_bytes
+        return self.data[:nbytes].view(dtype)
+
+    def output(self, dtype, numel) -> torch.Tensor:
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        assert nbytes <= self.out_bytes
+        return self.data[self.in_bytes:self.in_bytes + nbytes].view(dtype)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _next_epoch(self) -> int:
+        e = self.epoch
+        self.epoch = (self.epoch + 2) & 0x7FFFFFFF or 1
+        return e
+
+    def _coll(self, name, nbytes, use_nvls, ctas):
+        rc = _fn(name, _SIG_COLL)(self.data_ptrs, self.flag_ptrs, self.multicast_ptr if self.has_nvls else None,
+                                  self.rank, self.world, 0, self.in_bytes, nbytes, self._next_epoch(),
+                                  1 if (use_nvls and self.has_nvls) else 0, min(ctas, MAX_CTAS), self._stream())
+        _lib.check(rc, name)
+        _lib.count_launch()
+
+    # ---- collectives (operate in place on the workspace regions)
+    def all_gather(self, shard_bytes: int, use_nvls: bool = True, ctas: int = 32):
+        """out[r*shard:(r+1)*shard] on every rank <- in[:shard] of rank r."""
+        assert shard_bytes <= self.in_bytes and shard_bytes * self.world <= self.out_bytes
+        self._coll("smx_all_gather", shard_bytes, use_nvls, ctas)
+
+    def reduce_scatter(self, shard_bytes: int, use_nvls: bool = True, ctas: int = 32):
+        """out[:shard] <- sum over ranks of in[rank*shard:(rank+1)*shard]   (bf16)."""
+        assert shard_bytes * self.world <= self.in_bytes and shard_bytes <= self.out_bytes
+        self._coll("smx_reduce_scatter", shard_bytes, use_nvls, ctas)
+
+    def all_reduce(self, total_bytes: int, use_nvls: bool = True, ctas: int = 32):
+        """out[:total] <- sum over ranks of in[:total]   (bf16)."""
+        assert total_bytes <= self.in_bytes and total_bytes <= self.out_bytes
+        self._coll("smx_all_reduce", total_bytes, use_nvls, ctas)
+
+    def all_to_all(self, chunk_bytes: int, ctas: int = 32):
+        """out[src*chunk:(src+1)*chunk] of rank dst <- in[dst*chunk:(dst+1)*chunk] of rank src."""
+        assert chunk_bytes * self.world <= min(self.in_bytes, self.out_bytes)
+        rc = _fn("smx_all_to_all", _SIG_A2A)(self.data_ptrs, self.flag_ptrs, self.rank, self.world, 0, self.in_bytes,
+                                             chunk_bytes, self._next_epoch(), min(ctas, MAX_CTAS), self._stream())
+        _lib.check(rc, "smx_all_to_all")
+        _lib.count_launch()
+
+    def put(self, dst_rank: int, nbytes: int, ctas: int = 16):
+        """One-sided copy in[:nbytes] -> out[:nbytes] of ``dst_rank`` (pipeline send); caller orders with events."""
+        rc = _fn("smx_p2p_put", _SIG_PUT)(self.data_ptrs, self.flag_ptrs, self.rank, self.world, dst_rank, 0,
+                                          self.in_bytes, nbytes, min(ctas, MAX_CTAS), self._stream())
+        _lib.check(rc, "smx_p2p_put")
+        _lib.count_launch()

@@ -1,0 +1,297 @@
+"""Measured side of "predicted vs measured": a Megatron-style Llama training step built from this repo's sm_100a
+kernels (tcgen05 GEMMs for every linear incl. the fp32-accumulating wgrad, tcgen05 flash attention, fused
+RMSNorm / SwiGLU / RoPE / cross-entropy / AdamW kernels) with explicit forward/backward (no autograd), static
+activation storage and a ZeRO-1 distributed optimizer over data-parallel ranks.
+
+Semantics mirror what the analytical model assumes (reference docs/b200/b200_real_repro_guide.md:263-278):
+bf16 params + fp32 main-grad accumulation fused into the wgrad GEMM, fp32 master/m/v, no activation recompute,
+sequence-first flattened tokens ``[B*S, H]``, untied LM head, fused CE writing dlogits in place.
+
+Public API:  ``trainer = LlamaTrainer(model_cfg, micro_batch, seq_len, dp_group=None)``
+             ``loss = trainer.train_step(list_of_host_batches)``   (tokens/targets int64 on pinned host memory)
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ..ops import _lib
+from ..ops import elementwise as E
+from ..ops.attention import fmha_fwd
+from ..ops.gemm import gemm
+
+
+@dataclass
+class LlamaDims:
+    hidden: int
+    heads: int
+    kv_heads: int
+    head_dim: int
+    ffn: int
+    layers: int
+    vocab: int
+    rope_theta: float = 500000.0
+    eps: float = 1e-5
+
+    @classmethod
+    def from_model_config(cls, m, vocab_multiple: int = 128):
+        vocab = int(math.ceil(m.vocab_size / vocab_multiple) * vocab_multiple)
+        return cls(m.hidden_size, m.head_num, m.kv_head_num, m.head_size, m.intermediate_size, m.layer_num, vocab)
+
+    @property
+    def qkv_out(self):
+        return (self.heads + 2 * self.kv_heads) * self.head_dim
+
+    def layer_numel(self):
+        H, F = self.hidden, self.ffn
+        return H + self.qkv_out * H + H * self.heads * self.head_dim + H + 2 * F * H + H * F
+
+    def total_numel(self):
+        return self.vocab * self.hidden + self.layers * self.layer_numel() + self.hidden + self.vocab * self.hidden
+
+
+class _Flat:
+    """Carves named views out of one flat buffer (Megatron-style contiguous param / grad buffers)."""
+
+    def __init__(self, numel, dtype, device):
+        self.buf = torch.empty(numel, dtype=dtype, device=device)
+        self.off = 0
+
+    def take(self, *shape):
+        n = 1
+        for s in shape:
+            n *= s
+        v = self.buf[self.off:self.off + n].view(*shape)
+        self.off += n
+        return v
+
+
+class LlamaTrainer:
+    def __init__(self, dims: LlamaDims, micro_batch: int, seq_len: int, dp_group: Optional[dist.ProcessGroup] = None,
+                 lr: float = 1e-4, weight_decay: float = 0.1, betas=(0.9, 0.95), max_grad_norm: float = 1.0,
+                 attention_bwd: str = "auto", seed: int = 1234, device=None):
+        self.d = dims
+        self.B, self.S = micro_batch, seq_len
+        self.T = micro_batch * seq_len
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.group = dp_group
+        self.world = dist.get_world_size(dp_group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(dp_group) if dist.is_initialized() else 0
+        self.lr, self.wd, self.betas, self.max_norm = lr, weight_decay, betas, max_grad_norm
+        self.step_count = 0
+        d, dev = dims, self.device
+        P = d.total_numel()
+        pad = (-P) % (self.world * 1024)
+        self.P, self.Ppad = P, P + pad
+        # ---- parameters (bf16) and fp32 main grads, identical layouts
+        self.params = _Flat(self.Ppad, torch.bfloat16, dev)
+        self.grads = _Flat(self.Ppad, torch.float32, dev)
+        self.w, self.g = self._carve(self.params), self._carve(self.grads)
+        gen = torch.Generator(device=dev).manual_seed(seed)
+        self.params.buf.normal_(0.0, 0.02, generator=gen)
+        for name in ("ln1", "ln2"):
+            for t in self.w[name]:
+                t.fill_(1.0)
+        self.w["final_norm"].fill_(1.0)
+        self.grads.buf.zero_()
+        # ---- ZeRO-1 optimizer shard
+        self.shard = self.Ppad // self.world
+        lo = self.rank * self.shard
+        self.master = self.params.buf[lo:lo + self.shard].float()
+        self.m = torch.zeros(self.shard, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(self.shard, dtype=torch.float32, device=dev)
+        self.grad_shard = torch.empty(self.shard, dtype=torch.float32, device=dev) if self.world > 1 else None
+        self.sqnorm = torch.zeros(1, dtype=torch.float32, device=dev)
+        # ---- static activation storage
+        T, H, F, L = self.T, d.hidden, d.ffn, d.layers
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        self.act = {
+            "x": torch.empty(L + 1, T, H, **bf), "h1": torch.empty(L, T, H, **bf), "qkv": torch.empty(L, T, d.qkv_out, **bf),
+            "o": torch.empty(L, T, d.heads * d.head_dim, **bf), "x2": torch.empty(L, T, H, **bf),
+            "h2": torch.empty(L, T, H, **bf), "u": torch.empty(L, T, 2 * F, **bf), "g": torch.empty(L, T, F, **bf),
+            "rstd1": torch.empty(L, T, dtype=torch.float32, device=dev), "rstd2": torch.empty(L, T, dtype=torch.float32, device=dev),
+            "lse": torch.empty(L, self.B, d.heads, self.S, dtype=torch.float32, device=dev),
+            "xf": torch.empty(T, H, **bf), "rstdf": torch.empty(T, dtype=torch.float32, device=dev),
+        }
+        self.logits = torch.empty(T, d.vocab, **bf)
+        # backward scratch (reused by every layer)
+        self.dx = torch.empty(T, H, **bf)
+        self.dx_b = torch.empty(T, H, **bf)
+        self.d_big = torch.empty(T, 2 * F, **bf)
+        self.d_f = torch.empty(T, F, **bf)
+        self.d_qkv = torch.empty(T, d.qkv_out, **bf)
+        self.d_o = torch.empty(T, d.heads * d.head_dim, **bf)
+        self.tmp_h = torch.empty(T, H, **bf)
+        self.cos, self.sin = E.rope_tables(self.S, d.head_dim, d.rope_theta, device=dev)
+        self.tok_dev = torch.empty(T, dtype=torch.int64, device=dev)
+        self.tgt_dev = torch.empty(T, dtype=torch.int64, device=dev)
+        self.loss_rows = None
+        self.loss_acc = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.attention_bwd = self._pick_attention_bwd(attention_bwd)
+
+    # ------------------------------------------------------------------------------------------
+    def _carve(self, flat: _Flat):
+        d = self.d
+        H, F = d.hidden, d.ffn
+        out = {"embed": flat.take(d.vocab, H), "ln1": [], "wqkv": [], "wo": [], "ln2": [], "wfc1": [], "wfc2": []}
+        for _ in range(d.layers):
+            out["ln1"].append(flat.take(H))
+            out["wqkv"].append(flat.take(d.qkv_out, H))
+            out["wo"].append(flat.take(H, d.heads * d.head_dim))
+            out["ln2"].append(flat.take(H))
+            out["wfc1"].append(flat.take(2 * F, H))
+            out["wfc2"].append(flat.take(H, F))
+        out["final_norm"] = flat.take(H)
+        out["lm_head"] = flat.take(d.vocab, H)
+        return out
+
+    def _pick_attention_bwd(self, choice: str) -> str:
+        if choice != "auto":
+            return choice
+        try:
+            from ..ops.attention import fmha_bwd  # noqa: F401
+            return "smx"
+        except Exception:
+            pass
+        try:
+            import flash_attn  # noqa: F401
+            return "flash_attn"
+        except Exception:
+            return "sdpa_recompute"
+
+    def memory_bytes(self) -> dict:
+        act = sum(t.numel() * t.element_size() for t in self.act.values())
+        return {"params_bf16": self.params.buf.numel() * 2, "main_grads_fp32": self.grads.buf.numel() * 4,
+                "optimizer_fp32": self.shard * 12, "activations": act, "logits": self.logits.numel() * 2,
+                "torch_max_allocated": torch.cuda.max_memory_allocated(self.device)}
+
+    # ------------------------------------------------------------------------------------------
+    def _attention_views(self, qkv):
+        d = self.d
+        B, S = self.B, self.S
+        nq, nk, hd = d.heads, d.kv_heads, d.head_dim
+        t = qkv.view(B, S, d.qkv_out)
+        q = t[..., : nq * hd].view(B, S, nq, hd)
+        k = t[..., nq * hd: (nq + nk) * hd].view(B, S, nk, hd)
+        v = t[..., (nq + nk) * hd:].view(B, S, nk, hd)
+        return q, k, v
+
+    def forward(self, tokens: torch.Tensor, targets: torch.Tensor, loss_scale: float) -> torch.Tensor:
+        d, a, w = self.d, self.act, self.w
+        L = d.layers
+        torch.index_select(w["embed"], 0, tokens, out=a["x"][0])
+        for i in range(L):
+            x = a["x"][i]
+            E.rmsnorm_fwd(x, w["ln1"][i], d.eps, out=a["h1"][i], rstd=a["rstd1"][i])
+            gemm(a["h1"][i], w["wqkv"][i], "TN", out=a["qkv"][i])
+            E.rope_inplace(a["qkv"][i], self.cos, self.sin, self.S, d.heads + d.kv_heads, d.head_dim)
+            q, k, v = self._attention_views(a["qkv"][i])
+            o4 = a["o"][i].view(self.B, self.S, d.heads, d.head_dim)
+            fmha_fwd(q, k, v, causal=True, out=o4, lse=a["lse"][i])
+            gemm(a["o"][i], w["wo"][i], "TN", out=self.tmp_h)
+            E.add(x, self.tmp_h, out=a["x2"][i])
+            E.rmsnorm_fwd(a["x2"][i], w["ln2"][i], d.eps, out=a["h2"][i], rstd=a["rstd2"][i])
+            gemm(a["h2"][i], w["wfc1"][i], "TN", out=a["u"][i])
+            E.swiglu_fwd(a["u"][i], out=a["g"][i])
+            gemm(a["g"][i], w["wfc2"][i], "TN", out=self.tmp_h)
+            E.add(a["x2"][i], self.tmp_h, out=a["x"][i + 1])
+        E.rmsnorm_fwd(a["x"][L], w["final_norm"], d.eps, out=a["xf"], rstd=a["rstdf"])
+        gemm(a["xf"], w["lm_head"], "TN", out=self.logits)
+        loss_rows = E.cross_entropy_(self.logits, targets, grad_scale=loss_scale)      # logits now hold dlogits
+        return loss_rows
+
+    def backward(self, tokens: torch.Tensor) -> None:
+        d, a, w, g = self.d, self.act, self.w, self.g
+        L = d.layers
+        dl = self.logits
+        gemm(dl, a["xf"], "NT", out=g["lm_head"], accumulate=True)
+        gemm(dl, w["lm_head"], "NN", out=self.tmp_h)
+        E.rmsnorm_bwd(a["x"][L], w["final_norm"], self.tmp_h, a["rstdf"], g["final_norm"], dx=self.dx)
+        for i in reversed(range(L)):
+            dx3 = self.dx
+            # MLP
+            gemm(dx3, a["g"][i], "NT", out=g["wfc2"][i], accumulate=True)
+            gemm(dx3, w["wfc2"][i], "NN", out=self.d_f)
+            E.swiglu_bwd(a["u"][i], self.d_f, out=self.d_big)
+            gemm(self.d_big, a["h2"][i], "NT", out=g["wfc1"][i], accumulate=True)
+            gemm(self.d_big, w["wfc1"][i], "NN", out=self.tmp_h)
+            E.rmsnorm_bwd(a["x2"][i], w["ln2"][i], self.tmp_h, a["rstd2"][i], g["ln2"][i], dx=dx3, accumulate_dx=True)
+            # attention
+            gemm(dx3, a["o"][i], "NT", out=g["wo"][i], accumulate=True)
+            gemm(dx3, w["wo"][i], "NN", out=self.d_o)
+            self._attention_backward(i)
+            E.rope_inplace(self.d_qkv, self.cos, self.sin, self.S, d.heads + d.kv_heads, d.head_dim, inverse=True)
+            gemm(self.d_qkv, a["h1"][i], "NT", out=g["wqkv"][i], accumulate=True)
+            gemm(self.d_qkv, w["wqkv"][i], "NN", out=self.tmp_h)
+            E.rmsnorm_bwd(a["x"][i], w["ln1"][i], self.tmp_h, a["rstd1"][i], g["ln1"][i], dx=dx3, accumulate_dx=True)
+        g["embed"].index_add_(0, tokens, self.dx.float())
+
+    def _attention_backward(self, i: int) -> None:
+        d, a = self.d, self.act
+        q, k, v = self._attention_views(a["qkv"][i])
+        dq, dk, dv = self._attention_views(self.d_qkv)
+        o4 = a["o"][i].view(self.B, self.S, d.heads, d.head_dim)
+        do4 = self.d_o.view(self.B, self.S, d.heads, d.head_dim)
+        scale = 1.0 / math.sqrt(d.head_dim)
+        if self.attention_bwd == "smx":
+            from ..ops.attention import fmha_bwd
+            fmha_bwd(do4, q, k, v, o4, a["lse"][i], dq, dk, dv, causal=True, scale=scale)
+        elif self.attention_bwd == "flash_attn":
+            from flash_attn.flash_attn_interface import _flash_attn_backward
+            _flash_attn_backward(do4, q, k, v, o4, a["lse"][i], dq, dk, dv, 0.0, scale, True, -1, -1, 0.0, None, False)
+        else:
+            qa, ka, va = (t.detach().permute(0, 2, 1, 3).requires_grad_(True) for t in (q, k, v))
+            out = torch.nn.functional.scaled_dot_product_attention(qa, ka, va, is_causal=True, enable_gqa=True)
+            out.backward(do4.permute(0, 2, 1, 3))
+            dq.copy_(qa.grad.permute(0, 2, 1, 3)); dk.copy_(ka.grad.permute(0, 2, 1, 3)); dv.copy_(va.grad.permute(0, 2, 1, 3))
+
+    # ------------------------------------------------------------------------------------------
+    def optimizer_step(self) -> None:
+        """ZeRO-1: reduce-scatter fp32 main grads, clip by global norm, fused AdamW on the local shard, all-gather
+        the updated bf16 params."""
+        self.step_count += 1
+        b1, b2 = self.betas
+        if self.world > 1:
+            dist.reduce_scatter_tensor(self.grad_shard, self.grads.buf, op=dist.ReduceOp.AVG, group=self.group)
+            gsh = self.grad_shard
+        else:
+            gsh = self.grads.buf
+        self.sqnorm.zero_()
+        E.sqnorm(gsh, out=self.sqnorm)
+        if self.world > 1:
+            dist.all_reduce(self.sqnorm, group=self.group)
+        lo = self.rank * self.shard
+        E.adamw_(self.master, self.m, self.v, gsh, self.params.buf[lo:lo + self.shard], self.lr, b1, b2, 1e-8, self.wd,
+                 self.step_count, sqnorm_t=self.sqnorm, max_norm=self.max_norm, zero_grad=(self.world == 1))
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.params.buf, self.params.buf[lo:lo + self.shard], group=self.group)
+            self.grads.buf.zero_()
+
+    def run_microbatches(self, device_batches: List[Tuple[torch.Tensor, torch.Tensor]]) -> torch.Tensor:
+        n = len(device_batches)
+        self.loss_acc.zero_()
+        scale = 1.0 / (n * self.T)
+        for tok, tgt in device_batches:
+            rows = self.forward(tok, tgt, loss_scale=scale)
+            self.loss_acc += rows.sum() * scale
+            self.backward(tok)
+        self.optimizer_step()
+        return self.loss_acc
+
+    def train_step(self, host_batches: List[Tuple[torch.Tensor, torch.Tensor]]) -> float:
+        """Public end-to-end step: pinned-host token/target tensors in, python float loss out (H2D + D2H included)."""
+        n = len(host_batches)
+        self.loss_acc.zero_()
+        scale = 1.0 / (n * self.T)
+        for tok_h, tgt_h in host_batches:
+            self.tok_dev.copy_(tok_h.view(-1), non_blocking=True)
+            self.tgt_dev.copy_(tgt_h.view(-1), non_blocking=True)
+            rows = self.forward(self.tok_dev, self.tgt_dev, loss_scale=scale)
+            self.loss_acc += rows.sum() * scale
+            self.backward(self.tok_dev)
+        self.optimizer_step()
+        return float(self.loss_acc.item())

@@ -1,0 +1,79 @@
+"""Whole training step built from the sm_100a kernels vs a plain PyTorch fp32 autograd model of the same network."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch_reference(tr, tokens, targets):
+    d = tr.d
+    W = {k: ([t.detach().float().requires_grad_(True) for t in v] if isinstance(v, list) else v.detach().float().requires_grad_(True))
+         for k, v in tr.w.items()}
+    B, S = tr.B, tr.S
+    cos, sin = tr.cos, tr.sin
+
+    def rms(x, g):
+        return x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + d.eps) * g
+
+    def rope(t):  # t [B,S,h,hd], rotate-half convention
+        h = d.head_dim // 2
+        a, b = t[..., :h], t[..., h:]
+        c, s = cos[None, :, None, :], sin[None, :, None, :]
+        return torch.cat([a * c - b * s, b * c + a * s], -1)
+
+    x = W["embed"][tokens]
+    for i in range(d.layers):
+        h1 = rms(x, W["ln1"][i])
+        qkv = (h1 @ W["wqkv"][i].t()).view(B, S, -1)
+        nq, nk, hd = d.heads, d.kv_heads, d.head_dim
+        q = rope(qkv[..., : nq * hd].reshape(B, S, nq, hd))
+        k = rope(qkv[..., nq * hd:(nq + nk) * hd].reshape(B, S, nk, hd))
+        v = qkv[..., (nq + nk) * hd:].reshape(B, S, nk, hd)
+        o = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                                             is_causal=True, enable_gqa=True)
+        o = o.transpose(1, 2).reshape(B * S, nq * hd)
+        x = x + o @ W["wo"][i].t()
+        h2 = rms(x, W["ln2"][i])
+        u = h2 @ W["wfc1"][i].t()
+        F = d.ffn
+        x = x + (torch.nn.functional.silu(u[:, :F]) * u[:, F:]) @ W["wfc2"][i].t()
+    logits = rms(x, W["final_norm"]) @ W["lm_head"].t()
+    loss = torch.nn.functional.cross_entropy(logits, targets)
+    loss.backward()
+    return loss.item(), W
+
+
+@pytest.mark.parametrize("attn_bwd", ["auto"])
+def test_train_step_matches_pytorch(attn_bwd):
+    from simumax_b200.runtime.trainer import LlamaDims, LlamaTrainer
+    dims = LlamaDims(hidden=256, heads=2, kv_heads=1, head_dim=128, ffn=512, layers=2, vocab=512)
+    tr = LlamaTrainer(dims, micro_batch=2, seq_len=128, attention_bwd=attn_bwd, max_grad_norm=0.0)
+    tr.params.buf.mul_(4.0)      # larger weights -> non-trivial attention / loss
+    tr.master.copy_(tr.params.buf[: tr.shard].float())
+    g = torch.Generator(device="cuda").manual_seed(7)
+    tokens = torch.randint(0, dims.vocab, (tr.T,), device="cuda", generator=g)
+    targets = torch.randint(0, dims.vocab, (tr.T,), device="cuda", generator=g)
+    ref_loss, W = _torch_reference(tr, tokens, targets)
+    rows = tr.forward(tokens, targets, loss_scale=1.0 / tr.T)
+    loss = rows.mean().item()
+    tr.backward(tokens)
+    assert loss == pytest.approx(ref_loss, rel=2e-2)
+    for name in ("lm_head", "final_norm", "embed"):
+        ref, got = W[name].grad, tr.g[name]
+        err = (got - ref).norm() / ref.norm()
+        assert err < 5e-2, (name, err.item())
+    for name in ("wfc2", "wfc1", "wo", "wqkv", "ln1", "ln2"):
+        for i in range(dims.layers):
+            ref, got = W[name][i].grad, tr.g[name][i]
+            err = (got - ref).norm() / ref.norm()
+            assert err < 6e-2, (name, i, err.item())
+    # optimizer: loss must go down over a few steps on a fixed batch
+    before = tr.params.buf.clone()
+    tr.grads.buf.zero_()
+    l0 = tr.run_microbatches([(tokens, targets)]).item()
+    for _ in range(5):
+        l1 = tr.run_microbatches([(tokens, targets)]).item()
+    assert l1 < l0 and not torch.equal(before, tr.params.buf)
+    assert float(tr.grads.buf.abs().max()) == 0.0
