@@ -1,0 +1,133 @@
+"""One-click calibration: measure -> fit -> write ``<name>.json`` that ``PerfLLM`` loads as its system config.
+
+    # single GPU part (operator efficiencies + memory-bound kernels)
+    python -m simumax_b200.calib.calibrate ops --out gpurun_out/calib_ops.json
+    # multi GPU part, once per group size (collective curves, in-kernel + NCCL baseline)
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 -m simumax_b200.calib.collectives
+    # merge everything into a system config (CPU only)
+    python -m simumax_b200.calib.calibrate merge --ops gpurun_out/calib_ops.json \
+        --coll gpurun_out/coll_sweep_2.json gpurun_out/coll_sweep_4.json gpurun_out/coll_sweep_8.json \
+        --out simumax_b200/configs/system/b200_sm100a_calibrated.json
+
+Supplement mode: ``ops --supplement <existing system json>`` measures only the keys that file does not have yet
+(the reference's efficiency-cache behaviour, simu_tools/efficency_test/combine_efficiency.py:37-336 and
+run_one_click_benchmark.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+from typing import Dict, List, Optional
+
+from .collectives import apply_to_system, fit_all
+from .shapes import DEFAULT_WORKLOADS, collect_requests
+from .system_template import b200_template
+
+
+def _nominal_tflops(template: dict) -> Dict[str, float]:
+    return {op: v["tflops"] for op, v in template["accelerator"]["op"].items()}
+
+
+def run_ops(out_path: str, supplement: Optional[str] = None, limit_per_op: Optional[int] = None,
+            workloads=None, log=print) -> dict:
+    """GPU part: returns {"ops": {op: {key: {...}}}, "bandwidth": {...}, "meta": {...}}."""
+    import torch
+    from . import measure
+    template = b200_template()
+    requests = collect_requests(workloads or DEFAULT_WORKLOADS)
+    have = {}
+    if supplement and os.path.exists(supplement):
+        prev = json.load(open(supplement))
+        have = {op: set(v.get("accurate_efficient_factor", {}) or {}) for op, v in prev["accelerator"]["op"].items()}
+        for op in list(requests):
+            requests[op] = {k: r for k, r in requests[op].items() if k not in have.get(op, set())}
+        log(f"[calib] supplement mode: {sum(len(v) for v in requests.values())} keys missing from {supplement}")
+    t0 = time.time()
+    ops = measure.sweep(requests, _nominal_tflops(template), log=log, limit_per_op=limit_per_op)
+    bw = measure.measure_bandwidth_ops()
+    for name, rec in bw.items():
+        log(f"[calib] bandwidth {name:12s} {rec['gbs']:8.1f} GB/s")
+    res = {"ops": ops, "bandwidth": bw,
+           "meta": {"device": torch.cuda.get_device_name(0), "seconds": time.time() - t0,
+                    "requested": {op: len(v) for op, v in requests.items()}}}
+    os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
+    json.dump(res, open(out_path, "w"), indent=1)
+    return res
+
+
+def merge(ops_path: Optional[str], coll_paths: List[str], out_path: str, base: Optional[str] = None,
+          sys_name: str = "b200_sm100a_calibrated", coll_impl: str = "smx", measured_peaks: Optional[str] = None) -> dict:
+    """CPU part: fold measurements into a system JSON (schema = reference docs/system.md:77-148)."""
+    system = json.load(open(base)) if base else b200_template(sys_name)
+    system["sys_name"] = sys_name
+    acc = system["accelerator"]
+    notes = {"source": "simumax_b200.calib", "collectives": coll_impl}
+    if ops_path:
+        res = json.load(open(ops_path))
+        for op, table in res["ops"].items():
+            cfg = acc["op"][op]
+            tab = cfg.setdefault("accurate_efficient_factor", {}) or {}
+            for key, m in table.items():
+                tab[key] = m["efficiency"]
+            cfg["accurate_efficient_factor"] = tab
+            effs = [m["efficiency"] for m in table.values()]
+            if effs:          # default for unseen shapes: flop-weighted mean of what was measured
+                wts = [m["flops"] for m in table.values()]
+                cfg["efficient_factor"] = sum(e * w for e, w in zip(effs, wts)) / sum(wts)
+        gbps = acc["bandwidth"]["default"]["gbps"]
+        for name, rec in res["bandwidth"].items():
+            entry = acc["bandwidth"].setdefault(name, {"gbps": gbps, "latency_us": 30})
+            entry["efficient_factor"] = rec["gbs"] * 1e9 / (entry["gbps"] * 1024 ** 3)
+            entry["latency_us"] = 3.0          # kernel launch + tail; elementwise kernels here are single-launch
+        means = [acc["op"][o]["efficient_factor"] for o in ("matmul", "sdp_fwd", "sdp_bwd") if o in res["ops"]]
+        if means:
+            acc["op"]["default"]["efficient_factor"] = sum(means) / len(means)
+        notes["device"] = res["meta"].get("device")
+    fits = {}
+    for p in coll_paths:
+        sw = json.load(open(p))
+        fits[int(sw["world"])] = fit_all(sw, nominal_gbps=system["networks"]["high_intra_node"]["bandwidth"]["gbps"], which=coll_impl)
+    apply_to_system(system, fits)
+    if measured_peaks and os.path.exists(measured_peaks):
+        notes["measured_peaks"] = json.load(open(measured_peaks))
+    system["calibration_notes"] = notes
+    os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
+    json.dump(system, open(out_path, "w"), indent=1)
+    return system
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(prog="simumax_b200.calib.calibrate")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    o = sub.add_parser("ops", help="single-GPU operator sweeps")
+    o.add_argument("--out", default="gpurun_out/calib_ops.json")
+    o.add_argument("--supplement", default=None)
+    o.add_argument("--limit-per-op", type=int, default=None)
+    m = sub.add_parser("merge", help="write the system config (no GPU needed)")
+    m.add_argument("--ops", default=None)
+    m.add_argument("--coll", nargs="*", default=[])
+    m.add_argument("--base", default=None)
+    m.add_argument("--out", required=True)
+    m.add_argument("--name", default="b200_sm100a_calibrated")
+    m.add_argument("--coll-impl", default="smx", choices=["smx", "nccl"])
+    m.add_argument("--measured-peaks", default="MEASURED_PEAKS.json")
+    s = sub.add_parser("shapes", help="list the shapes the default workloads need (CPU)")
+    a = ap.parse_args(argv)
+    if a.cmd == "ops":
+        run_ops(a.out, a.supplement, a.limit_per_op)
+    elif a.cmd == "merge":
+        sysj = merge(a.ops, a.coll, a.out, a.base, a.name, a.coll_impl, a.measured_peaks)
+        print(f"wrote {a.out}: " + ", ".join(f"{op}:{len(v.get('accurate_efficient_factor') or {})}" for op, v in sysj["accelerator"]["op"].items()))
+    else:
+        for op, t in collect_requests().items():
+            print(op, len(t))
+            for k in t:
+                print("   ", k)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,79 @@
+"""Shape enumeration for calibration: run the analytical model with an empty efficiency table and harvest every
+(op, shape-key, flops) it had to guess (``system.miss_efficiency``).  These are exactly the strings the model will look
+up later, so whatever the sweeps write back is guaranteed to hit.
+
+(reference flow: simu_tools/efficency_test/test_*_efficiency.py enumerate shapes out of ``analysis_op_info`` dumps;
+here the cost function itself reports what it needs.)
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import warnings
+from dataclasses import dataclass, field
+from typing import Dict, Iterable, List, Optional, Tuple
+
+# (model, strategy preset, model overrides, strategy overrides) -- the reference's own example workloads on 8 GPUs
+DEFAULT_WORKLOADS: List[Tuple[str, str, dict, dict]] = [
+    ("llama3-8b", "tp1_pp1_dp8_mbs1", {}, {}),
+    ("llama3-8b", "tp1_pp2_dp4_mbs1", {}, {}),
+    ("llama3-8b", "tp2_pp1_dp4_mbs1", {}, {}),
+    ("llama3-8b", "tp8_pp1_dp1_mbs1", {}, {}),
+    ("llama3-70b", "tp2_pp1_dp4_mbs1", {"layer_num": 12}, {}),
+    ("llama3-70b", "tp4_pp1_dp2_mbs1", {"layer_num": 12}, {}),
+    ("deepseekv2", "ep8_pp1_dp8_mbs1", {"layer_num": 4}, {}),
+    ("deepseekv2", "ep4_pp2_dp4_mbs1", {"layer_num": 4}, {}),
+]
+
+
+@dataclass
+class ShapeRequest:
+    op: str                 # matmul | fp8_matmul | group_matmul | fp8_group_matmul | sdp_fwd | sdp_bwd
+    key: str                # exact table key (without the "shape=" prefix)
+    flops: float            # what the model divides by tflops*eff for this key
+    fields: Dict[str, str] = field(default_factory=dict)
+
+    def geti(self, name: str) -> int:
+        return int(self.fields[name])
+
+    def getb(self, name: str) -> bool:
+        return self.fields.get(name, "False") == "True"
+
+
+def parse_key(key: str) -> Dict[str, str]:
+    out = {}
+    for part in key.split(", "):
+        if "=" in part:
+            k, v = part.split("=", 1)
+            out[k.strip()] = v.strip()
+    return out
+
+
+def collect_requests(workloads: Optional[Iterable[Tuple[str, str, dict, dict]]] = None, system: str = "b200_nominal",
+                     extra_ops: bool = True) -> Dict[str, Dict[str, ShapeRequest]]:
+    """op -> key -> ShapeRequest for every shape the workloads touch."""
+    from ..configs import get_simu_model_config, get_simu_strategy_config, get_simu_system_config
+    from ..core.config import ModelConfig, StrategyConfig, SystemConfig
+    from ..core.perf_llm import PerfLLM
+    out: Dict[str, Dict[str, ShapeRequest]] = {}
+    for model, strategy, m_over, s_over in (workloads or DEFAULT_WORKLOADS):
+        st = StrategyConfig.init_from_config_file(get_simu_strategy_config(strategy))
+        for k, v in s_over.items():
+            setattr(st, k, v)
+        sysc = SystemConfig.init_from_config_file(get_simu_system_config(system))
+        for op in sysc.accelerator.op.values():      # force every lookup to miss
+            op.accurate_efficient_factor = {}
+        mc = ModelConfig.init_from_config_file(get_simu_model_config(model))
+        for k, v in m_over.items():
+            setattr(mc, k, v)
+        p = PerfLLM()
+        with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            p.configure(strategy_config=st, model_config=mc, system_config=sysc)
+            p.model_config.padded_vocab_size, p.model_config.make_vocab_size_divisible_by = True, 128
+            p.run_estimate()
+        for op, table in p.system.miss_efficiency.items():
+            for k, rec in table.items():
+                key = k[len("shape="):] if k.startswith("shape=") else k
+                out.setdefault(op, {})[key] = ShapeRequest(op, key, float(rec["flops"]), parse_key(key))
+    return out

@@ -551,6 +551,9 @@ class NetOpConfig:
     fixed_latency_us: Optional[float] = None
     fixed_latency_us_by_comm_num: Optional[Dict[str, float]] = None
     dp_fixed_bw: Optional[dict] = None
+    # extension over the reference schema: per-group-size fits written by simumax_b200.calib (absent -> scalar values)
+    efficient_factor_by_comm_num: Optional[Dict[str, float]] = None
+    latency_us_by_comm_num: Optional[Dict[str, float]] = None
 
 
 @dataclass
@@ -694,6 +697,7 @@ class SystemConfig(Config):
         assert op is not None, f"{op_name} not exist on {net_data}"
         scale, offset = op.scale, op.offset
         eff = op.efficient_factor if op.efficient_factor is not None else net_data.bandwidth.efficient_factor
+        eff = _by_comm_num(op.efficient_factor_by_comm_num, comm_num, eff)
 
         wire_bytes = size * scale
         wire_bytes += (wire_bytes / comm_num) * offset
@@ -725,6 +729,7 @@ class SystemConfig(Config):
                     bw /= min(self.num_per_node, strategy.ep_size * strategy.etp_size)
 
         base_latency = op.latency_us if op.latency_us is not None else net_data.bandwidth.latency_us
+        base_latency = _by_comm_num(op.latency_us_by_comm_num, comm_num, base_latency)
         fixed_latency = _by_comm_num(op.fixed_latency_us_by_comm_num, comm_num, op.fixed_latency_us)
         if fixed_latency is None:
             fixed_latency = _by_comm_num(net_data.bandwidth.fixed_latency_us_by_comm_num, comm_num,

@@ -132,6 +132,7 @@ class LlamaTrainer:
         self.loss_rows = None
         self.loss_acc = torch.zeros(1, dtype=torch.float32, device=dev)
         self.attention_bwd = self._pick_attention_bwd(attention_bwd)
+        self.debug_hook = None       # callable(layer_index, trainer) invoked after each layer's backward
 
     # ------------------------------------------------------------------------------------------
     def _carve(self, flat: _Flat):
@@ -228,6 +229,8 @@ class LlamaTrainer:
             gemm(self.d_qkv, a["h1"][i], "NT", out=g["wqkv"][i], accumulate=True)
             gemm(self.d_qkv, w["wqkv"][i], "NN", out=self.tmp_h)
             E.rmsnorm_bwd(a["x"][i], w["ln1"][i], self.tmp_h, a["rstd1"][i], g["ln1"][i], dx=dx3, accumulate_dx=True)
+            if self.debug_hook is not None:
+                self.debug_hook(i, self)
         g["embed"].index_add_(0, tokens, self.dx.float())
 
     def _attention_backward(self, i: int) -> None:

@@ -51,3 +51,31 @@ def test_fmha_packed_qkv_view():
     o, _ = fmha_fwd(q, k, v, causal=True)
     ro, _ = _ref(q, k, v, True, 1.0 / math.sqrt(D))
     torch.testing.assert_close(o.float(), ro, atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("causal", [True, False])
+@pytest.mark.parametrize("cfg", [(1, 256, 2, 2, 128), (2, 512, 8, 2, 128), (1, 200, 4, 1, 128), (1, 1024, 4, 4, 128)])
+def test_fmha_bwd(cfg, causal):
+    from simumax_b200.ops.attention import fmha_bwd, fmha_fwd
+    torch.manual_seed(3)
+    B, S, H, Hk, D = cfg
+    qkv = torch.randn(B, S, (H + 2 * Hk) * D, device="cuda").bfloat16()
+    q = qkv[..., : H * D].view(B, S, H, D)
+    k = qkv[..., H * D: (H + Hk) * D].view(B, S, Hk, D)
+    v = qkv[..., (H + Hk) * D:].view(B, S, Hk, D)
+    d_o = torch.randn(B, S, H, D, device="cuda").bfloat16()
+    scale = 1.0 / math.sqrt(D)
+    o, lse = fmha_fwd(q, k, v, causal=causal, scale=scale)
+    d_qkv = torch.full_like(qkv, float("nan"))
+    dq = d_qkv[..., : H * D].view(B, S, H, D)
+    dk = d_qkv[..., H * D: (H + Hk) * D].view(B, S, Hk, D)
+    dv = d_qkv[..., (H + Hk) * D:].view(B, S, Hk, D)
+    fmha_bwd(d_o, q, k, v, o, lse, dq, dk, dv, causal=causal, scale=scale)
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    ro, _ = _ref(qf, kf, vf, causal, scale)
+    ro.backward(d_o.float())
+    for name, got, ref in (("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
+        err = (got.float() - ref).norm() / ref.norm()
+        assert torch.isfinite(got.float()).all(), name
+        assert err < 2e-2, (name, err.item())
+        torch.testing.assert_close(got.float(), ref, atol=5e-2 * ref.abs().max().item(), rtol=0)
