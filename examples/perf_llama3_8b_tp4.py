@@ -1,0 +1,5 @@
+"""perf() of the llama3_8b_tp4 case (see _cases.py for the model / strategy / system triple)."""
+from _cases import run
+
+if __name__ == "__main__":
+    run("llama3_8b_tp4")
