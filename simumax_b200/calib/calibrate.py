@@ -22,7 +22,7 @@ import sys
 import time
 from typing import Dict, List, Optional
 
-from .collectives import apply_to_system, fit_all
+from .collectives import apply_to_system, fit_all, fixed_latency_from_burst
 from .shapes import DEFAULT_WORKLOADS, collect_requests
 from .system_template import b200_template
 
@@ -86,11 +86,14 @@ def merge(ops_path: Optional[str], coll_paths: List[str], out_path: str, base: O
         if means:
             acc["op"]["default"]["efficient_factor"] = sum(means) / len(means)
         notes["device"] = res["meta"].get("device")
-    fits = {}
+    fits, bursts = {}, {}
     for p in coll_paths:
         sw = json.load(open(p))
         fits[int(sw["world"])] = fit_all(sw, nominal_gbps=system["networks"]["high_intra_node"]["bandwidth"]["gbps"], which=coll_impl)
-    apply_to_system(system, fits)
+        if sw.get("burst"):
+            bursts[int(sw["world"])] = sw["burst"]
+    fixed = fixed_latency_from_burst(bursts, fits, which=coll_impl) if bursts else None
+    apply_to_system(system, fits, fixed=fixed)
     if measured_peaks and os.path.exists(measured_peaks):
         notes["measured_peaks"] = json.load(open(measured_peaks))
     system["calibration_notes"] = notes

@@ -54,7 +54,8 @@ def fit_bw_latency(op: str, n: int, sizes: Sequence[float], times_us: Sequence[f
 
 
 def apply_to_system(system: dict, fits_by_world: Dict[int, Dict[str, Dict[str, float]]],
-                    nets: Sequence[str] = ("high_intra_node", "low_intra_node")) -> dict:
+                    nets: Sequence[str] = ("high_intra_node", "low_intra_node"),
+                    fixed: Optional[Dict[str, dict]] = None) -> dict:
     """Write fitted collective parameters (largest world size = default, others in the ``*_by_comm_num`` tables)."""
     if not fits_by_world:
         return system
@@ -72,7 +73,10 @@ def apply_to_system(system: dict, fits_by_world: Dict[int, Dict[str, Dict[str, f
                                                    for ws in sorted(fits_by_world) if op in fits_by_world[ws]}
             cfg["latency_us_by_comm_num"] = {str(ws): round(fits_by_world[ws][op]["latency_us"], 4)
                                              for ws in sorted(fits_by_world) if op in fits_by_world[ws]}
-            cfg["fixed_latency_us_by_comm_num"] = {str(ws): 0.0 for ws in sorted(fits_by_world) if op in fits_by_world[ws]}
+            cfg["fixed_latency_us_by_comm_num"] = {}
+            if fixed and op in fixed:
+                cfg["fixed_latency_us"] = round(fixed[op]["fixed_latency_us"], 4)
+                cfg["fixed_latency_us_by_comm_num"] = {k: round(v, 4) for k, v in fixed[op]["fixed_latency_us_by_comm_num"].items()}
     return system
 
 
@@ -157,6 +161,84 @@ def sweep(sizes: Optional[List[int]] = None, max_bytes: int = 256 << 20, ctas_op
     return out
 
 
+def measure_burst(total_bytes: int = 32 << 20, ops_per_window: int = 20, keep: int = 10, ctas: int = 32) -> dict:
+    """Fixed-latency probe: collectives interleaved with a 6144^3 GEMM (this repo's tcgen05 kernel) the way a training
+    step interleaves them; each collective is bracketed by its own CUDA events so launch gaps and the wake-up after a
+    compute kernel are included.  Returns per-op mean microseconds over the middle ``keep`` of ``ops_per_window`` ops, max
+    over ranks.  (reference: measure_comm_burst_window_worker.py:64-71,112-135,201-218 does this with torch.mm + NCCL.)"""
+    import torch
+    import torch.distributed as dist
+    from ..ops.gemm import gemm
+    from ..parallel.symm import SymmetricWorkspace
+    world, rank = dist.get_world_size(), dist.get_rank()
+    ws = SymmetricWorkspace(total_bytes, total_bytes)
+    a = torch.randn(6144, 6144, device="cuda").bfloat16()
+    b = torch.randn(6144, 6144, device="cuda").bfloat16()
+    c = torch.empty(6144, 6144, device="cuda", dtype=torch.bfloat16)
+    src = torch.empty(total_bytes // 2, device="cuda", dtype=torch.bfloat16).normal_()
+    dst = torch.empty(total_bytes // 2, device="cuda", dtype=torch.bfloat16)
+    shard = total_bytes // world // 16 * 16
+    sh_el = shard // 2
+    nv = bool(ws.has_nvls)
+    runs = {
+        "smx": {"all_reduce": lambda: ws.all_reduce(total_bytes, use_nvls=nv, ctas=ctas),
+                "all_gather": lambda: ws.all_gather(shard, use_nvls=nv, ctas=ctas),
+                "reduce_scatter": lambda: ws.reduce_scatter(shard, use_nvls=nv, ctas=ctas),
+                "all2all": lambda: ws.all_to_all(shard, ctas=ctas)},
+        "nccl": {"all_reduce": lambda: dist.all_reduce(src),
+                 "all_gather": lambda: dist.all_gather_into_tensor(dst[:sh_el * world], src[:sh_el]),
+                 "reduce_scatter": lambda: dist.reduce_scatter_tensor(dst[:sh_el], src[:sh_el * world]),
+                 "all2all": lambda: dist.all_to_all_single(dst[:sh_el * world], src[:sh_el * world])},
+    }
+    sizes = {"all_reduce": total_bytes, "all_gather": shard * world, "reduce_scatter": shard * world, "all2all": shard * world}
+    out = {"world": world, "bytes": sizes, "smx": {}, "nccl": {}}
+    for impl, table in runs.items():
+        for op, run in table.items():
+            for _ in range(3):
+                gemm(a, b, "TN", out=c); run()
+            torch.cuda.synchronize(); dist.barrier()
+            evs = []
+            for _ in range(ops_per_window):
+                gemm(a, b, "TN", out=c)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); run(); e1.record()
+                evs.append((e0, e1))
+            torch.cuda.synchronize()
+            lo = (ops_per_window - keep) // 2
+            us = sum(e0.elapsed_time(e1) for e0, e1 in evs[lo:lo + keep]) / keep * 1e3
+            t = torch.tensor([us], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out[impl][op] = float(t)
+            src.normal_()
+    return out
+
+
+def fixed_latency_from_burst(burst_by_world: Dict[int, dict], fits_by_world: Dict[int, Dict[str, Dict[str, float]]],
+                             which: str = "smx", spread_us: float = 25.0) -> Dict[str, dict]:
+    """fixed_us = burst-measured time - what the fitted line predicts; one scalar per op when the group sizes agree
+    within ``spread_us``, otherwise a per-comm-num table (reference run_one_click_benchmark.py:371-414)."""
+    out: Dict[str, dict] = {}
+    ops = set()
+    for b in burst_by_world.values():
+        ops |= set(b[which])
+    for op in ops:
+        per = {}
+        for n, b in burst_by_world.items():
+            f = fits_by_world.get(n, {}).get(op)
+            if f is None or op not in b[which]:
+                continue
+            x = wire_bytes(op, b["bytes"][op], n)
+            model = x / (f["fit_bw_gibs"] * GIB) * 1e6 + f["fit_intercept_us"]
+            per[str(n)] = max(0.0, b[which][op] - model)
+        if not per:
+            continue
+        vals = list(per.values())
+        if max(vals) - min(vals) <= spread_us:
+            out[op] = {"fixed_latency_us": sum(vals) / len(vals), "fixed_latency_us_by_comm_num": {}}
+        else:
+            out[op] = {"fixed_latency_us": 0.0, "fixed_latency_us_by_comm_num": per}
+    return out
+
+
 def fit_all(sweep_result: dict, nominal_gbps: float = 900.0, which: str = "smx") -> Dict[str, Dict[str, float]]:
     n = sweep_result["world"]
     return {op: fit_bw_latency(op, n, d["sizes"], d["times_us"], nominal_gbps)
@@ -174,6 +256,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     res = sweep(max_bytes=a.max_bytes)
+    res["burst"] = measure_burst()
     if dist.get_rank() == 0:
         res["fit_smx"] = fit_all(res, which="smx")
         res["fit_nccl"] = fit_all(res, which="nccl")
