@@ -1,0 +1,137 @@
+#!/usr/bin/env python
+"""Predicted-vs-measured table: run real training steps with this repo's runtime (LlamaTrainer) and compare iteration
+time and peak memory with what ``PerfLLM`` predicts for the same (system, strategy, model) triple.
+
+    python tools/b200/perf_vs_real.py --system b200_sm100a_calibrated --out profiles/perf_vs_real.json        # 1 GPU
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/b200/perf_vs_real.py ...  # DP=8
+
+Cases are data-parallel only (the measured runtime implements DP + ZeRO-1); every row is device-timed (CUDA events,
+max over ranks) after warm-up, and memory is the CUDA high-water mark of the process.
+(reference: tools/b200/run_megatron_perf_real_pipeline.py / _batch.py drive Megatron-LM and regex its logs; here the
+"real" side is in-repo.)
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import gc
+import io
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+#        name                      model         layers  seq    mbs  mbc
+CASES = [
+    ("llama3_8b_full_s4096",       "llama3-8b",  None,   4096,  1,   4),
+    ("llama3_8b_l16_s4096_mbs2",   "llama3-8b",  16,     4096,  2,   2),
+    ("llama3_8b_l16_s8192",        "llama3-8b",  16,     8192,  1,   2),
+    ("llama3_70b_l4_s4096",        "llama3-70b", 4,      4096,  1,   4),
+    ("llama3_70b_l8_s4096",        "llama3-70b", 8,      4096,  1,   2),
+]
+
+
+def predict(model, layers, seq, mbs, mbc, world, system):
+    from simumax_b200 import PerfLLM
+    from simumax_b200.configs import get_simu_model_config, get_simu_strategy_config, get_simu_system_config
+    from simumax_b200.core.config import StrategyConfig
+    from simumax_b200.core.utils import parse_bytes
+    st = StrategyConfig.init_from_config_file(get_simu_strategy_config("tp1_pp1_dp8_mbs1"))
+    st.world_size, st.tp_size, st.pp_size = world, 1, 1
+    st.seq_len, st.micro_batch_size, st.micro_batch_num = seq, mbs, mbc
+    p = PerfLLM()
+    with contextlib.redirect_stdout(io.StringIO()):
+        p.configure(strategy_config=st, model_config=get_simu_model_config(model), system_config=get_simu_system_config(system))
+        if layers:
+            p.model_config.layer_num = layers
+        p.model_config.padded_vocab_size, p.model_config.make_vocab_size_divisible_by = True, 128
+        p.run_estimate()
+        cost, mem = p.analysis_cost().data, p.analysis_mem().data
+    tok_s = cost["throughput_per_accelerator"] * world
+    return {"iter_ms": mbs * mbc * world * seq / tok_s * 1e3, "tokens_per_s": tok_s, "mfu": cost["mfu"],
+            "peak_gib": parse_bytes(mem["peak_mem"]) / 2 ** 30 if isinstance(mem.get("peak_mem"), str) else None,
+            "miss": {k: len(v) for k, v in p.system.miss_efficiency.items()}}
+
+
+def measure(model, layers, seq, mbs, mbc, steps, warmup):
+    import torch
+    import torch.distributed as dist
+    from simumax_b200.configs import get_simu_model_config
+    from simumax_b200.core.config import ModelConfig
+    from simumax_b200.runtime.trainer import LlamaDims, LlamaTrainer
+    mc = ModelConfig.init_from_config_file(get_simu_model_config(model))
+    dims = LlamaDims.from_model_config(mc)
+    if layers:
+        dims.layers = layers
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    torch.cuda.reset_peak_memory_stats()
+    tr = LlamaTrainer(dims, mbs, seq, dp_group=dist.group.WORLD if world > 1 else None)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    batches = [(torch.randint(0, mc.vocab_size, (mbs * seq,), device="cuda", generator=g),
+                torch.randint(0, mc.vocab_size, (mbs * seq,), device="cuda", generator=g)) for _ in range(mbc)]
+    for _ in range(warmup):
+        tr.run_microbatches(batches)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        tr.run_microbatches(batches)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda")
+    peak = torch.tensor([float(torch.cuda.max_memory_allocated())], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(peak, op=dist.ReduceOp.MAX)
+    out = {"iter_ms": float(ms), "tokens_per_s": mbs * mbc * world * seq / float(ms) * 1e3, "peak_gib": float(peak) / 2 ** 30}
+    del tr, batches
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--system", default="b200_sm100a_calibrated")
+    ap.add_argument("--out", default="gpurun_out/perf_vs_real.json")
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--cases", nargs="*", default=None)
+    a = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank = dist.get_rank() if world > 1 else 0
+    rows = []
+    for name, model, layers, seq, mbs, mbc in CASES:
+        if a.cases and name not in a.cases:
+            continue
+        real = measure(model, layers, seq, mbs, mbc, a.steps, a.warmup)
+        if rank == 0:
+            pred = predict(model, layers, seq, mbs, mbc, world, a.system)
+            row = {"case": name, "world": world, "model": model, "layers": layers, "seq": seq, "mbs": mbs, "mbc": mbc,
+                   "pred_ms": pred["iter_ms"], "real_ms": real["iter_ms"],
+                   "time_err_pct": 100 * (pred["iter_ms"] - real["iter_ms"]) / real["iter_ms"],
+                   "pred_gib": pred["peak_gib"], "real_gib": real["peak_gib"],
+                   "mem_err_pct": 100 * (pred["peak_gib"] - real["peak_gib"]) / real["peak_gib"] if pred["peak_gib"] else None,
+                   "pred_mfu": pred["mfu"], "real_tokens_per_s": real["tokens_per_s"], "efficiency_misses": pred["miss"]}
+            rows.append(row)
+            print(f"{name:28s} n={world} time pred {row['pred_ms']:9.2f} ms real {row['real_ms']:9.2f} ms ({row['time_err_pct']:+6.2f} %)   "
+                  f"mem pred {row['pred_gib']:.2f} GiB real {row['real_gib']:.2f} GiB ({row['mem_err_pct']:+6.2f} %)", flush=True)
+    if rank == 0:
+        os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
+        json.dump({"system": a.system, "world": world, "rows": rows}, open(a.out, "w"), indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
