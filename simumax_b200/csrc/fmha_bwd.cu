@@ -13,8 +13,10 @@
 //   dQ^T leaves through TMEM -> registers -> smem [64 q][128 d] fp32 -> cp.reduce.async.bulk.tensor (add) into dq_accum.
 //
 // TMEM columns: S^T [0,64)  dP^T [64,128)  dQ^T [128,192)  dV [192,320)  dK [320,448).
-// Warp roles (320 threads): warp0 TMA producer, warp1 MMA issuer (+TMEM alloc), warps 2..5 softmax / dK epilogue,
-// warps 6..9 dQ drain / dV epilogue.
+// Warp roles (448 threads): warp0 TMA producer, warp1 MMA issuer (+TMEM alloc), warps 2..9 softmax / dK epilogue (two
+// warps share a key row: 32 query columns each, so every SM sub-partition has two softmax warps to hide latency),
+// warps 10..13 dQ drain / dV epilogue.  With causal masking CTA x processes key tiles x and n-1-x back to back, which
+// gives every CTA the same number of (key tile, query tile) pairs.
 //
 // Pre-pass: D[b,h,s] = rowsum(dO o O); post-pass: dq = bf16(dq_accum).
 // Replaces the fused-attention backward the reference times through TE / cuDNN
@@ -42,7 +44,8 @@ SMX_DEVICE void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0,
 constexpr int kBwdBKV = 128;
 constexpr int kBwdBQ = 64;
 constexpr int kBwdD = 128;
-constexpr int kBwdThreads = 320;
+constexpr int kBwdSoftmaxWarps = 8;
+constexpr int kBwdThreads = (2 + kBwdSoftmaxWarps + 4) * 32;
 constexpr int kBwdKVBytes = kBwdBKV * kBwdD * 2;      // 32 KB each for K and V
 constexpr int kBwdQBytes = kBwdBQ * kBwdD * 2;        // 16 KB each for Q_i and dO_i
 constexpr int kBwdStageBytes = 2 * kBwdQBytes;
@@ -54,6 +57,7 @@ struct FmhaBwdParams {
   int B, S_q, S_kv, H, H_kv;
   float scale;
   int causal;
+  int pair;           // causal load balancing: CTA x handles key tiles x and n-1-x
   const float* lse;   // [B, H, S_q]
   const float* dsum;  // [B, H, S_q]  rowsum(dO o O)
   __nv_bfloat16* dk;  // strides in elements
@@ -91,21 +95,21 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* dq_full = bars + 13;
   uint64_t* dq_empty = bars + 14;
   uint64_t* all_done = bars + 15;
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* acc_empty = bars + 16;
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp_idx = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
-  const int kv_tile = blockIdx.x;
   const int kv_head = blockIdx.y;
   const int batch = blockIdx.z;
   const int group = p.H / p.H_kv;
-  const int k0 = kv_tile * BKV;
   const int shift = p.S_kv - p.S_q;
   const int n_q_tiles = (p.S_q + BQ - 1) / BQ;
-  int i_begin = 0;
-  if (p.causal) i_begin = max(0, k0 - shift) / BQ;
-  const int nq_local = max(0, n_q_tiles - i_begin);
-  const int n_iter = nq_local * group;
+  const int n_kv_tiles = (p.S_kv + BKV - 1) / BKV;
+  // causal: CTA x owns key tiles x and (n-1-x) so every CTA sees the same number of (q tile, kv tile) pairs
+  const int n_cta_tiles = (p.pair && (int)blockIdx.x != n_kv_tiles - 1 - (int)blockIdx.x) ? 2 : 1;
+  auto tile_index = [&](int t) { return t == 0 ? (int)blockIdx.x : n_kv_tiles - 1 - (int)blockIdx.x; };
+  auto tile_begin = [&](int k0) { return p.causal ? max(0, k0 - shift) / BQ : 0; };
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -119,16 +123,17 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(&qdo_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_empty, 4);
+    mbar_init(s_empty, kBwdSoftmaxWarps);
     mbar_init(dp_full, 1);
-    mbar_init(dp_empty, 4);
-    mbar_init(p_full, 4);
+    mbar_init(dp_empty, kBwdSoftmaxWarps);
+    mbar_init(p_full, kBwdSoftmaxWarps);
     mbar_init(pv_done, 1);
-    mbar_init(ds_full, 4);
+    mbar_init(ds_full, kBwdSoftmaxWarps);
     mbar_init(dkq_done, 1);
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, 4);
     mbar_init(all_done, 1);
+    mbar_init(acc_empty, kBwdSoftmaxWarps + 4);
     fence_barrier_init();
   }
   if (warp_idx == 1) tmem_alloc<1>(tmem_base_ptr, 512);
@@ -142,31 +147,39 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t tmem_dv = tmem_base + 192;
   const uint32_t tmem_dk = tmem_base + 320;
 
-  auto iter_head = [&](int it) { return kv_head * group + it / nq_local; };
-  auto iter_q0 = [&](int it) { return (i_begin + it % nq_local) * BQ; };
-
   if (warp_idx == 0) {
     // ============================ TMA producer ============================
-    if (lane == 0 && n_iter > 0) {
-      mbar_arrive_expect_tx(kv_full, 2 * kBwdKVBytes);
-#pragma unroll
-      for (int c = 0; c < D / 64; ++c) {
-        bwd_tma_load_4d(&tmap_k, kv_full, sK + c * (BKV * 128), c * 64, k0, kv_head, batch);
-        bwd_tma_load_4d(&tmap_v, kv_full, sV + c * (BKV * 128), c * 64, k0, kv_head, batch);
-      }
-      for (int it = 0; it < n_iter; ++it) {
-        const int st = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(&qdo_empty[st], ph ^ 1, 21);
-        uint8_t* sQ = sQdO + st * kBwdStageBytes;
-        uint8_t* sdO = sQ + kBwdQBytes;
-        mbar_arrive_expect_tx(&qdo_full[st], kBwdStageBytes);
-        const int head = iter_head(it), q0 = iter_q0(it);
+    if (lane == 0) {
+      int g_base = 0, tw = 0;
+      for (int t = 0; t < n_cta_tiles; ++t) {
+        const int k0 = tile_index(t) * BKV;
+        const int i_begin = tile_begin(k0);
+        const int nq_local = max(0, n_q_tiles - i_begin);
+        const int n_iter = nq_local * group;
+        if (n_iter == 0) continue;
+        if (tw > 0) mbar_wait(all_done, (tw - 1) & 1, 20);      // previous tile's MMAs are done with K / V
+        mbar_arrive_expect_tx(kv_full, 2 * kBwdKVBytes);
 #pragma unroll
         for (int c = 0; c < D / 64; ++c) {
-          bwd_tma_load_4d(&tmap_q, &qdo_full[st], sQ + c * (BQ * 128), c * 64, q0, head, batch);
-          bwd_tma_load_4d(&tmap_do, &qdo_full[st], sdO + c * (BQ * 128), c * 64, q0, head, batch);
+          bwd_tma_load_4d(&tmap_k, kv_full, sK + c * (BKV * 128), c * 64, k0, kv_head, batch);
+          bwd_tma_load_4d(&tmap_v, kv_full, sV + c * (BKV * 128), c * 64, k0, kv_head, batch);
         }
+        for (int it = 0; it < n_iter; ++it) {
+          const int g = g_base + it;
+          const int st = g & 1;
+          mbar_wait(&qdo_empty[st], ((g >> 1) & 1) ^ 1, 21);
+          uint8_t* sQ = sQdO + st * kBwdStageBytes;
+          uint8_t* sdO = sQ + kBwdQBytes;
+          mbar_arrive_expect_tx(&qdo_full[st], kBwdStageBytes);
+          const int head = kv_head * group + it / nq_local, q0 = (i_begin + it % nq_local) * BQ;
+#pragma unroll
+          for (int c = 0; c < D / 64; ++c) {
+            bwd_tma_load_4d(&tmap_q, &qdo_full[st], sQ + c * (BQ * 128), c * 64, q0, head, batch);
+            bwd_tma_load_4d(&tmap_do, &qdo_full[st], sdO + c * (BQ * 128), c * 64, q0, head, batch);
+          }
+        }
+        g_base += n_iter;
+        ++tw;
       }
     }
   } else if (warp_idx == 1) {
@@ -174,10 +187,10 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     constexpr uint32_t idesc_s = make_idesc(1, 1, 0, 0, BKV, BQ);    // K (K-major) x Q (K-major)      -> S^T[128, 64]
     constexpr uint32_t idesc_dv = make_idesc(1, 1, 0, 1, BKV, D);    // P^T (K-major) x dO (MN-major)  -> dV[128, 128]
     constexpr uint32_t idesc_dq = make_idesc(1, 1, 1, 1, D, BQ);     // K (MN-major) x dS^T (MN-major) -> dQ^T[128, 64]
-    auto issue_s = [&](int it) {       // S^T(it) = K Q^T
-      const int st = it & 1;
-      mbar_wait(&qdo_full[st], (it >> 1) & 1, 22);
-      if (it > 0) mbar_wait(s_empty, (it - 1) & 1, 23);
+    auto issue_s = [&](int g) {       // S^T(g) = K Q^T
+      const int st = g & 1;
+      mbar_wait(&qdo_full[st], (g >> 1) & 1, 22);
+      if (g > 0) mbar_wait(s_empty, (g - 1) & 1, 23);
       tcgen05_fence_after();
       if (elect_one()) {
         uint8_t* sQ = sQdO + st * kBwdStageBytes;
@@ -191,9 +204,9 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       __syncwarp();
     };
-    auto issue_dp = [&](int it) {      // dP^T(it) = V dO^T
-      const int st = it & 1;
-      if (it > 0) mbar_wait(dp_empty, (it - 1) & 1, 24);
+    auto issue_dp = [&](int g) {      // dP^T(g) = V dO^T
+      const int st = g & 1;
+      if (g > 0) mbar_wait(dp_empty, (g - 1) & 1, 24);
       tcgen05_fence_after();
       if (elect_one()) {
         uint8_t* sdO = sQdO + st * kBwdStageBytes + kBwdQBytes;
@@ -207,178 +220,205 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       __syncwarp();
     };
-    if (n_iter > 0) {
-      mbar_wait(kv_full, 0, 25);
-      issue_s(0);
-      issue_dp(0);
-    }
-    for (int it = 0; it < n_iter; ++it) {
-      const int st = it & 1;
-      uint8_t* sQ = sQdO + st * kBwdStageBytes;
-      uint8_t* sdO = sQ + kBwdQBytes;
-      if (it + 1 < n_iter) issue_s(it + 1);
-      // dV += P^T dO
-      mbar_wait(p_full, it & 1, 26);
-      tcgen05_fence_after();
-      if (elect_one()) {
-        const uint64_t a0 = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
-        const uint64_t b0 = make_smem_desc_sw128(smem_u32(sdO), BQ * 128, 1024);
+    int g_base = 0, tw = 0;
+    for (int t = 0; t < n_cta_tiles; ++t) {
+      const int k0 = tile_index(t) * BKV;
+      const int n_iter = max(0, n_q_tiles - tile_begin(k0)) * group;
+      if (n_iter == 0) continue;
+      mbar_wait(kv_full, tw & 1, 25);
+      issue_s(g_base);
+      issue_dp(g_base);
+      for (int it = 0; it < n_iter; ++it) {
+        const int g = g_base + it;
+        const int st = g & 1;
+        uint8_t* sQ = sQdO + st * kBwdStageBytes;
+        uint8_t* sdO = sQ + kBwdQBytes;
+        if (it + 1 < n_iter) issue_s(g + 1);
+        // dV += P^T dO
+        mbar_wait(p_full, g & 1, 26);
+        if (it == 0 && tw > 0) mbar_wait(acc_empty, (tw - 1) & 1, 36);   // previous tile's dK / dV have been drained
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t a0 = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
+          const uint64_t b0 = make_smem_desc_sw128(smem_u32(sdO), BQ * 128, 1024);
 #pragma unroll
-        for (int k = 0; k < BQ / 16; ++k)
-          umma_f16<1>(tmem_dv, a0 + k * 2, b0 + k * ((16 * 128) >> 4), idesc_dv, (it > 0 || k > 0) ? 1u : 0u);
-        umma_commit<1>(pv_done);
+          for (int k = 0; k < BQ / 16; ++k)
+            umma_f16<1>(tmem_dv, a0 + k * 2, b0 + k * ((16 * 128) >> 4), idesc_dv, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit<1>(pv_done);
+        }
+        __syncwarp();
+        if (it + 1 < n_iter) issue_dp(g + 1);
+        // dK += dS^T Q ;  dQ^T = K^T dS^T
+        mbar_wait(ds_full, g & 1, 27);
+        if (g > 0) mbar_wait(dq_empty, (g - 1) & 1, 28);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint64_t a0 = make_smem_desc_sw128(smem_u32(sdS), 16, 1024);
+          const uint64_t b0 = make_smem_desc_sw128(smem_u32(sQ), BQ * 128, 1024);
+#pragma unroll
+          for (int k = 0; k < BQ / 16; ++k)
+            umma_f16<1>(tmem_dk, a0 + k * 2, b0 + k * ((16 * 128) >> 4), idesc_dv, (it > 0 || k > 0) ? 1u : 0u);
+          const uint64_t ak = make_smem_desc_sw128(smem_u32(sK), BKV * 128, 1024);
+          const uint64_t bs = make_smem_desc_sw128(smem_u32(sdS), BKV * 128, 1024);
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k)
+            umma_f16<1>(tmem_dq, ak + k * ((16 * 128) >> 4), bs + k * ((16 * 128) >> 4), idesc_dq, k > 0 ? 1u : 0u);
+          umma_commit<1>(dq_full);
+          umma_commit<1>(dkq_done);
+          umma_commit<1>(&qdo_empty[st]);
+          if (it + 1 == n_iter) umma_commit<1>(all_done);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      if (it + 1 < n_iter) issue_dp(it + 1);
-      // dK += dS^T Q ;  dQ^T = K^T dS^T
-      mbar_wait(ds_full, it & 1, 27);
-      if (it > 0) mbar_wait(dq_empty, (it - 1) & 1, 28);
-      tcgen05_fence_after();
-      if (elect_one()) {
-        const uint64_t a0 = make_smem_desc_sw128(smem_u32(sdS), 16, 1024);
-        const uint64_t b0 = make_smem_desc_sw128(smem_u32(sQ), BQ * 128, 1024);
-#pragma unroll
-        for (int k = 0; k < BQ / 16; ++k)
-          umma_f16<1>(tmem_dk, a0 + k * 2, b0 + k * ((16 * 128) >> 4), idesc_dv, (it > 0 || k > 0) ? 1u : 0u);
-        const uint64_t ak = make_smem_desc_sw128(smem_u32(sK), BKV * 128, 1024);
-        const uint64_t bs = make_smem_desc_sw128(smem_u32(sdS), BKV * 128, 1024);
-#pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)
-          umma_f16<1>(tmem_dq, ak + k * ((16 * 128) >> 4), bs + k * ((16 * 128) >> 4), idesc_dq, k > 0 ? 1u : 0u);
-        umma_commit<1>(dq_full);
-        umma_commit<1>(dkq_done);
-        umma_commit<1>(&qdo_empty[st]);
-        if (it + 1 == n_iter) umma_commit<1>(all_done);
-      }
-      __syncwarp();
+      g_base += n_iter;
+      ++tw;
     }
-  } else if (warp_idx < 6) {
-    // ============================ softmax / dS (one key row per thread) ============================
+  } else if (warp_idx < 2 + kBwdSoftmaxWarps) {
+    // ============== softmax / dS: one key row per thread, the 64 query columns split over two warps ==============
     const int quad = warp_idx % 4;
+    const int half = (warp_idx - 2) / 4;
+    const int col0 = half * 32;
     const int row_in_tile = quad * 32 + lane;
-    const int kv_row = k0 + row_in_tile;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
-    const int tid = threadIdx.x - 64;     // 0..127
+    const int tid = threadIdx.x - 64;     // 0..255
     const float c_log2 = p.scale * 1.4426950408889634f;
-    for (int it = 0; it < n_iter; ++it) {
-      const int head = iter_head(it), q0 = iter_q0(it);
-      {
-        // stage lse (log2 units) and D for the 64 query columns of this tile
-        const int qi = q0 + (tid & 63);
-        const long long off = ((long long)batch * p.H + head) * p.S_q + qi;
-        float* dst = (tid < 64 ? sLse : sDsum) + (it & 1) * 64 + (tid & 63);
-        float v;
-        if (tid < 64) {
-          v = (qi < p.S_q) ? p.lse[off] * 1.4426950408889634f : INFINITY;
-          if (!(v > -INFINITY)) v = INFINITY;
-        } else {
-          v = (qi < p.S_q) ? p.dsum[off] : 0.f;
+    int g_base = 0, tw = 0;
+    for (int t = 0; t < n_cta_tiles; ++t) {
+      const int k0 = tile_index(t) * BKV;
+      const int kv_row = k0 + row_in_tile;
+      const int i_begin = tile_begin(k0);
+      const int nq_local = max(0, n_q_tiles - i_begin);
+      const int n_iter = nq_local * group;
+      for (int it = 0; it < n_iter; ++it) {
+        const int g = g_base + it;
+        const int head = kv_head * group + it / nq_local, q0 = (i_begin + it % nq_local) * BQ;
+        if (tid < 128) {
+          // stage lse (log2 units) and D for the 64 query columns of this tile
+          const int qi = q0 + (tid & 63);
+          const long long off = ((long long)batch * p.H + head) * p.S_q + qi;
+          float* dst = (tid < 64 ? sLse : sDsum) + (g & 1) * 64 + (tid & 63);
+          float v;
+          if (tid < 64) {
+            v = (qi < p.S_q) ? p.lse[off] * 1.4426950408889634f : INFINITY;
+            if (!(v > -INFINITY)) v = INFINITY;
+          } else {
+            v = (qi < p.S_q) ? p.dsum[off] : 0.f;
+          }
+          *dst = v;
         }
-        *dst = v;
-      }
-      named_bar_sync(1, 128);
-      const float* lse2 = sLse + (it & 1) * 64;
-      const float* dsum = sDsum + (it & 1) * 64;
-      mbar_wait(s_full, it & 1, 29);
-      tcgen05_fence_after();
-      uint32_t r[64];
-      {
-        uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
-        uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
-        tmem_ld_32x32b_x32(tmem_s + lane_addr, r0);
-        tmem_ld_32x32b_x32(tmem_s + lane_addr + 32, r1);
+        named_bar_sync(1, kBwdSoftmaxWarps * 32);
+        const float4* lse4 = reinterpret_cast<const float4*>(sLse + (g & 1) * 64 + col0);
+        const float4* dsum4 = reinterpret_cast<const float4*>(sDsum + (g & 1) * 64 + col0);
+        mbar_wait(s_full, g & 1, 29);
+        tcgen05_fence_after();
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_addr + col0, r);
         tmem_ld_wait();
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);
-      const bool need_mask = (p.causal && (k0 + BKV - 1 > q0 + shift)) || (k0 + BKV > p.S_kv);
-      float pr[64];
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty);
+        const bool need_mask = (p.causal && (k0 + BKV - 1 > q0 + shift)) || (k0 + BKV > p.S_kv);
+        float pr[32];
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        float e = exp2f(__uint_as_float(r[i]) * c_log2 - lse2[i]);
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 l = lse4[i4];
+          pr[4 * i4 + 0] = exp2f(__uint_as_float(r[4 * i4 + 0]) * c_log2 - l.x);
+          pr[4 * i4 + 1] = exp2f(__uint_as_float(r[4 * i4 + 1]) * c_log2 - l.y);
+          pr[4 * i4 + 2] = exp2f(__uint_as_float(r[4 * i4 + 2]) * c_log2 - l.z);
+          pr[4 * i4 + 3] = exp2f(__uint_as_float(r[4 * i4 + 3]) * c_log2 - l.w);
+        }
         if (need_mask) {
-          const bool ok = (kv_row < p.S_kv) && (!p.causal || kv_row <= q0 + i + shift);
-          e = ok ? e : 0.f;
-        }
-        pr[i] = e;
-      }
-      if (it > 0) mbar_wait(pv_done, (it - 1) & 1, 30);     // dV(it-1) has finished reading the P^T tile
-      {
-        uint8_t* prow = sP + row_in_tile * 128;
 #pragma unroll
-        for (int c16 = 0; c16 < 8; ++c16) {
-          uint4 pk;
-          pk.x = pack_bf16x2(pr[c16 * 8 + 0], pr[c16 * 8 + 1]);
-          pk.y = pack_bf16x2(pr[c16 * 8 + 2], pr[c16 * 8 + 3]);
-          pk.z = pack_bf16x2(pr[c16 * 8 + 4], pr[c16 * 8 + 5]);
-          pk.w = pack_bf16x2(pr[c16 * 8 + 6], pr[c16 * 8 + 7]);
-          *reinterpret_cast<uint4*>(prow + ((c16 ^ (row_in_tile & 7)) << 4)) = pk;
+          for (int i = 0; i < 32; ++i) {
+            const bool ok = (kv_row < p.S_kv) && (!p.causal || kv_row <= q0 + col0 + i + shift);
+            pr[i] = ok ? pr[i] : 0.f;
+          }
         }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-      // dS^T = P^T o (dP^T - D) * scale
-      mbar_wait(dp_full, it & 1, 31);
-      tcgen05_fence_after();
-      {
-        uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
-        uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
-        tmem_ld_32x32b_x32(tmem_dp + lane_addr, r0);
-        tmem_ld_32x32b_x32(tmem_dp + lane_addr + 32, r1);
+        if (g > 0) mbar_wait(pv_done, (g - 1) & 1, 30);     // dV(g-1) has finished reading the P^T tile
+        {
+          uint8_t* prow = sP + row_in_tile * 128;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 pk;
+            pk.x = pack_bf16x2(pr[c * 8 + 0], pr[c * 8 + 1]);
+            pk.y = pack_bf16x2(pr[c * 8 + 2], pr[c * 8 + 3]);
+            pk.z = pack_bf16x2(pr[c * 8 + 4], pr[c * 8 + 5]);
+            pk.w = pack_bf16x2(pr[c * 8 + 6], pr[c * 8 + 7]);
+            *reinterpret_cast<uint4*>(prow + (((half * 4 + c) ^ (row_in_tile & 7)) << 4)) = pk;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        // dS^T = P^T o (dP^T - D) * scale
+        mbar_wait(dp_full, g & 1, 31);
+        tcgen05_fence_after();
+        tmem_ld_32x32b_x32(tmem_dp + lane_addr + col0, r);
         tmem_ld_wait();
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dp_empty);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dp_empty);
 #pragma unroll
-      for (int i = 0; i < 64; ++i) pr[i] = pr[i] * (__uint_as_float(r[i]) - dsum[i]) * p.scale;
-      if (it > 0) mbar_wait(dkq_done, (it - 1) & 1, 32);    // dK/dQ(it-1) have finished reading the dS^T tile
-      {
-        uint8_t* drow = sdS + row_in_tile * 128;
-#pragma unroll
-        for (int c16 = 0; c16 < 8; ++c16) {
-          uint4 pk;
-          pk.x = pack_bf16x2(pr[c16 * 8 + 0], pr[c16 * 8 + 1]);
-          pk.y = pack_bf16x2(pr[c16 * 8 + 2], pr[c16 * 8 + 3]);
-          pk.z = pack_bf16x2(pr[c16 * 8 + 4], pr[c16 * 8 + 5]);
-          pk.w = pack_bf16x2(pr[c16 * 8 + 6], pr[c16 * 8 + 7]);
-          *reinterpret_cast<uint4*>(drow + ((c16 ^ (row_in_tile & 7)) << 4)) = pk;
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 dsm = dsum4[i4];
+          pr[4 * i4 + 0] *= (__uint_as_float(r[4 * i4 + 0]) - dsm.x) * p.scale;
+          pr[4 * i4 + 1] *= (__uint_as_float(r[4 * i4 + 1]) - dsm.y) * p.scale;
+          pr[4 * i4 + 2] *= (__uint_as_float(r[4 * i4 + 2]) - dsm.z) * p.scale;
+          pr[4 * i4 + 3] *= (__uint_as_float(r[4 * i4 + 3]) - dsm.w) * p.scale;
         }
+        if (g > 0) mbar_wait(dkq_done, (g - 1) & 1, 32);    // dK/dQ(g-1) have finished reading the dS^T tile
+        {
+          uint8_t* drow = sdS + row_in_tile * 128;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 pk;
+            pk.x = pack_bf16x2(pr[c * 8 + 0], pr[c * 8 + 1]);
+            pk.y = pack_bf16x2(pr[c * 8 + 2], pr[c * 8 + 3]);
+            pk.z = pack_bf16x2(pr[c * 8 + 4], pr[c * 8 + 5]);
+            pk.w = pack_bf16x2(pr[c * 8 + 6], pr[c * 8 + 7]);
+            *reinterpret_cast<uint4*>(drow + (((half * 4 + c) ^ (row_in_tile & 7)) << 4)) = pk;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ds_full);
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ds_full);
-    }
-    // ---- dK epilogue (rows = keys)
-    if (n_iter > 0) {
-      mbar_wait(all_done, 0, 33);
-      tcgen05_fence_after();
-    }
-    const bool row_ok = kv_row < p.S_kv;
-    __nv_bfloat16* out = p.dk + batch * p.dk_sb + (long long)(row_ok ? kv_row : 0) * p.dk_ss + kv_head * p.dk_sh;
-#pragma unroll 1
-    for (int c = 0; c < D / 32; ++c) {
-      uint32_t o[32];
+      // ---- dK epilogue (rows = keys; this warp writes head-dim columns [half*64, half*64+64))
       if (n_iter > 0) {
-        tmem_ld_32x32b_x32(tmem_dk + lane_addr + c * 32, o);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0u;
+        mbar_wait(all_done, tw & 1, 33);
+        tcgen05_fence_after();
       }
-      if (row_ok) {
-        uint4* dst = reinterpret_cast<uint4*>(out + c * 32);
+      const bool row_ok = kv_row < p.S_kv;
+      __nv_bfloat16* out = p.dk + batch * p.dk_sb + (long long)(row_ok ? kv_row : 0) * p.dk_ss + kv_head * p.dk_sh + half * 64;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        if (n_iter > 0) {
+          tmem_ld_32x32b_x32(tmem_dk + lane_addr + half * 64 + c * 32, o);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(o[8 * i]), __uint_as_float(o[8 * i + 1]));
-          v.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]), __uint_as_float(o[8 * i + 3]));
-          v.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]), __uint_as_float(o[8 * i + 5]));
-          v.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]), __uint_as_float(o[8 * i + 7]));
-          dst[i] = v;
+          for (int i = 0; i < 32; ++i) o[i] = 0u;
         }
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(out + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(o[8 * i]), __uint_as_float(o[8 * i + 1]));
+            v.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]), __uint_as_float(o[8 * i + 3]));
+            v.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]), __uint_as_float(o[8 * i + 5]));
+            v.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]), __uint_as_float(o[8 * i + 7]));
+            dst[i] = v;
+          }
+        }
+      }
+      if (n_iter > 0) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+        g_base += n_iter;
+        ++tw;
       }
     }
   } else {
@@ -386,66 +426,81 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int quad = warp_idx % 4;
     const int d_idx = quad * 32 + lane;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
-    const int tid = threadIdx.x - 192;    // 0..127
-    for (int it = 0; it < n_iter; ++it) {
-      const int head = iter_head(it), q0 = iter_q0(it);
-      mbar_wait(dq_full, it & 1, 34);
-      tcgen05_fence_after();
-      uint32_t r[64];
-      {
-        uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
-        uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
-        tmem_ld_32x32b_x32(tmem_dq + lane_addr, r0);
-        tmem_ld_32x32b_x32(tmem_dq + lane_addr + 32, r1);
-        tmem_ld_wait();
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dq_empty);
-      // the previous tile's bulk reduce must have finished reading the staging buffer
-      if (tid == 0) tma_store_wait_read<0>();
-      named_bar_sync(2, 128);
+    const int tid = threadIdx.x - (2 + kBwdSoftmaxWarps) * 32;    // 0..127
+    int g_base = 0, tw = 0;
+    for (int t = 0; t < n_cta_tiles; ++t) {
+      const int k0 = tile_index(t) * BKV;
+      const int i_begin = tile_begin(k0);
+      const int nq_local = max(0, n_q_tiles - i_begin);
+      const int n_iter = nq_local * group;
+      for (int it = 0; it < n_iter; ++it) {
+        const int g = g_base + it;
+        const int head = kv_head * group + it / nq_local, q0 = (i_begin + it % nq_local) * BQ;
+        mbar_wait(dq_full, g & 1, 34);
+        tcgen05_fence_after();
+        uint32_t r[64];
+        {
+          uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+          uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+          tmem_ld_32x32b_x32(tmem_dq + lane_addr, r0);
+          tmem_ld_32x32b_x32(tmem_dq + lane_addr + 32, r1);
+          tmem_ld_wait();
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_empty);
+        // the previous tile's bulk reduce must have finished reading the staging buffer
+        if (tid == 0) tma_store_wait_read<0>();
+        named_bar_sync(2, 128);
 #pragma unroll
-      for (int i = 0; i < 64; ++i) sDq[i * D + d_idx] = __uint_as_float(r[i]);
-      fence_proxy_async_smem();
-      named_bar_sync(3, 128);
-      if (tid == 0) {
-        bwd_tma_reduce_add_4d(&tmap_dq, sDq, 0, q0, head, batch);
-        tma_store_commit();
+        for (int i = 0; i < 64; ++i) sDq[i * D + d_idx] = __uint_as_float(r[i]);
+        fence_proxy_async_smem();
+        named_bar_sync(3, 128);
+        if (tid == 0) {
+          bwd_tma_reduce_add_4d(&tmap_dq, sDq, 0, q0, head, batch);
+          tma_store_commit();
+        }
+      }
+      // ---- dV epilogue (rows = keys)
+      if (n_iter > 0) {
+        mbar_wait(all_done, tw & 1, 35);
+        tcgen05_fence_after();
+      }
+      const int kv_row = k0 + d_idx;
+      const bool row_ok = kv_row < p.S_kv;
+      __nv_bfloat16* out = p.dv + batch * p.dv_sb + (long long)(row_ok ? kv_row : 0) * p.dv_ss + kv_head * p.dv_sh;
+#pragma unroll 1
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t o[32];
+        if (n_iter > 0) {
+          tmem_ld_32x32b_x32(tmem_dv + lane_addr + c * 32, o);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = 0u;
+        }
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(out + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 v;
+            v.x = pack_bf16x2(__uint_as_float(o[8 * i]), __uint_as_float(o[8 * i + 1]));
+            v.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]), __uint_as_float(o[8 * i + 3]));
+            v.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]), __uint_as_float(o[8 * i + 5]));
+            v.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]), __uint_as_float(o[8 * i + 7]));
+            dst[i] = v;
+          }
+        }
+      }
+      if (n_iter > 0) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+        g_base += n_iter;
+        ++tw;
       }
     }
     if (tid == 0) tma_store_wait_all<0>();
-    // ---- dV epilogue (rows = keys)
-    if (n_iter > 0) {
-      mbar_wait(all_done, 0, 35);
-      tcgen05_fence_after();
-    }
-    const int kv_row = k0 + d_idx;
-    const bool row_ok = kv_row < p.S_kv;
-    __nv_bfloat16* out = p.dv + batch * p.dv_sb + (long long)(row_ok ? kv_row : 0) * p.dv_ss + kv_head * p.dv_sh;
-#pragma unroll 1
-    for (int c = 0; c < D / 32; ++c) {
-      uint32_t o[32];
-      if (n_iter > 0) {
-        tmem_ld_32x32b_x32(tmem_dv + lane_addr + c * 32, o);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0u;
-      }
-      if (row_ok) {
-        uint4* dst = reinterpret_cast<uint4*>(out + c * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(o[8 * i]), __uint_as_float(o[8 * i + 1]));
-          v.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]), __uint_as_float(o[8 * i + 3]));
-          v.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]), __uint_as_float(o[8 * i + 5]));
-          v.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]), __uint_as_float(o[8 * i + 7]));
-          dst[i] = v;
-        }
-      }
-    }
   }
 
   tcgen05_fence_before();
@@ -570,7 +625,9 @@ int smx_fmha_bwd(const void* q, const void* k, const void* v, const void* o, con
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  dim3 grid((S_kv + kBwdBKV - 1) / kBwdBKV, H_kv, B);
+  const int n_kv_tiles = (S_kv + kBwdBKV - 1) / kBwdBKV;
+  p.pair = (causal && n_kv_tiles > 1) ? 1 : 0;
+  dim3 grid(p.pair ? (n_kv_tiles + 1) / 2 : n_kv_tiles, H_kv, B);
   fmha_bwd_kernel<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(tq, tk, tv, tdo, tdq, p);
   {
     const long long rows = (long long)B * S_q * H;
