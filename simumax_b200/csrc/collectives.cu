@@ -83,6 +83,14 @@ SMX_DEVICE uint4 multimem_ld_reduce_bf16x8(const void* mc) {
                : "memory");
   return v;
 }
+SMX_DEVICE uint4 multimem_ld_reduce_f32x4(const void* mc) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
 SMX_DEVICE void multimem_st_v4(void* mc, uint4 v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z),
                "r"(v.w)
@@ -118,6 +126,36 @@ SMX_DEVICE uint4 pack_bf16x8(const float (&acc)[8]) {
   return r;
 }
 
+// 16-byte granule reductions, bf16x8 (fp32 accumulate) or f32x4
+template <bool F32>
+SMX_DEVICE uint4 multimem_ld_reduce16(const void* mc) {
+  if constexpr (F32) return multimem_ld_reduce_f32x4(mc);
+  else return multimem_ld_reduce_bf16x8(mc);
+}
+template <bool F32>
+SMX_DEVICE uint4 reduce16_peers(const PeerPtrs& pp, long long byte_off) {
+  uint4 v[kMaxRanks];
+#pragma unroll
+  for (int s = 0; s < kMaxRanks; ++s)
+    if (s < pp.world) v[s] = ld_v4(reinterpret_cast<const char*>(pp.data[(pp.rank + s) % pp.world]) + byte_off);
+  if constexpr (F32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < kMaxRanks; ++s)
+      if (s < pp.world) {
+        acc.x += __uint_as_float(v[s].x); acc.y += __uint_as_float(v[s].y);
+        acc.z += __uint_as_float(v[s].z); acc.w += __uint_as_float(v[s].w);
+      }
+    return make_uint4(__float_as_uint(acc.x), __float_as_uint(acc.y), __float_as_uint(acc.z), __float_as_uint(acc.w));
+  } else {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int s = 0; s < kMaxRanks; ++s)
+      if (s < pp.world) acc_bf16x8(acc, v[s]);
+    return pack_bf16x8(acc);
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // Symmetric buffer layout (bytes): [ region A : in ][ region B : out ] -- offsets passed by the host.
 // All sizes are multiples of 16 bytes.
@@ -149,7 +187,8 @@ __global__ void __launch_bounds__(512) all_gather_kernel(PeerPtrs pp, long long 
   cta_barrier_all_ranks(pp, epoch + 1);
 }
 
-// reduce_scatter (bf16 sum): out <- sum_r in_r[rank * shard .. (rank+1) * shard)
+// reduce_scatter (sum; bf16 with fp32 accumulation, or fp32): out <- sum_r in_r[rank * shard .. (rank+1) * shard)
+template <bool F32>
 __global__ void __launch_bounds__(512) reduce_scatter_kernel(PeerPtrs pp, long long in_off, long long out_off,
                                                             long long shard_bytes, uint32_t epoch, int use_nvls) {
   cta_barrier_all_ranks(pp, epoch);
@@ -160,24 +199,16 @@ __global__ void __launch_bounds__(512) reduce_scatter_kernel(PeerPtrs pp, long l
   if (use_nvls && pp.mc_data) {
     const char* mc = reinterpret_cast<const char*>(pp.mc_data) + src_off;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += stride)
-      st_v4(dst + i * 16, multimem_ld_reduce_bf16x8(mc + i * 16));
+      st_v4(dst + i * 16, multimem_ld_reduce16<F32>(mc + i * 16));
   } else {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += stride) {
-      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      uint4 v[kMaxRanks];
-#pragma unroll
-      for (int s = 0; s < kMaxRanks; ++s)
-        if (s < pp.world) v[s] = ld_v4(reinterpret_cast<const char*>(pp.data[(pp.rank + s) % pp.world]) + src_off + i * 16);
-#pragma unroll
-      for (int s = 0; s < kMaxRanks; ++s)
-        if (s < pp.world) acc_bf16x8(acc, v[s]);
-      st_v4(dst + i * 16, pack_bf16x8(acc));
-    }
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += stride)
+      st_v4(dst + i * 16, reduce16_peers<F32>(pp, src_off + i * 16));
   }
   cta_barrier_all_ranks(pp, epoch + 1);
 }
 
-// all_reduce (bf16 sum), result written to out on every rank
+// all_reduce (sum), result written to out on every rank
+template <bool F32>
 __global__ void __launch_bounds__(512) all_reduce_kernel(PeerPtrs pp, long long in_off, long long out_off,
                                                         long long total_bytes, uint32_t epoch, int use_nvls) {
   cta_barrier_all_ranks(pp, epoch);
@@ -191,18 +222,10 @@ __global__ void __launch_bounds__(512) all_reduce_kernel(PeerPtrs pp, long long 
     const char* mc_in = reinterpret_cast<const char*>(pp.mc_data) + in_off;
     char* mc_out = reinterpret_cast<char*>(pp.mc_data) + out_off;
     for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi; i += stride)
-      multimem_st_v4(mc_out + i * 16, multimem_ld_reduce_bf16x8(mc_in + i * 16));
+      multimem_st_v4(mc_out + i * 16, multimem_ld_reduce16<F32>(mc_in + i * 16));
   } else {
     for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi; i += stride) {
-      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      uint4 v[kMaxRanks];
-#pragma unroll
-      for (int s = 0; s < kMaxRanks; ++s)
-        if (s < pp.world) v[s] = ld_v4(reinterpret_cast<const char*>(pp.data[(pp.rank + s) % pp.world]) + in_off + i * 16);
-#pragma unroll
-      for (int s = 0; s < kMaxRanks; ++s)
-        if (s < pp.world) acc_bf16x8(acc, v[s]);
-      const uint4 r = pack_bf16x8(acc);
+      const uint4 r = reduce16_peers<F32>(pp, in_off + i * 16);
 #pragma unroll 1
       for (int s = 0; s < pp.world; ++s)
         st_v4(reinterpret_cast<char*>(pp.data[(pp.rank + s) % pp.world]) + out_off + i * 16, r);
@@ -266,17 +289,23 @@ int smx_all_gather(void* const* data_ptrs, void* const* flag_ptrs, void* mc, int
   return (int)cudaGetLastError();
 }
 int smx_reduce_scatter(void* const* data_ptrs, void* const* flag_ptrs, void* mc, int rank, int world, long long in_off,
-                       long long out_off, long long shard_bytes, unsigned epoch, int use_nvls, int ctas, void* stream) {
+                       long long out_off, long long shard_bytes, unsigned epoch, int use_nvls, int ctas, void* stream,
+                       int f32) {
   if (world > smx::kMaxRanks || shard_bytes % 16) return -40;
-  smx::reduce_scatter_kernel<<<ctas, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      make_pp(data_ptrs, flag_ptrs, mc, rank, world), in_off, out_off, shard_bytes, epoch, use_nvls);
+  auto pp = make_pp(data_ptrs, flag_ptrs, mc, rank, world);
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  if (f32) smx::reduce_scatter_kernel<true><<<ctas, 512, 0, st>>>(pp, in_off, out_off, shard_bytes, epoch, use_nvls);
+  else smx::reduce_scatter_kernel<false><<<ctas, 512, 0, st>>>(pp, in_off, out_off, shard_bytes, epoch, use_nvls);
   return (int)cudaGetLastError();
 }
 int smx_all_reduce(void* const* data_ptrs, void* const* flag_ptrs, void* mc, int rank, int world, long long in_off,
-                   long long out_off, long long total_bytes, unsigned epoch, int use_nvls, int ctas, void* stream) {
+                   long long out_off, long long total_bytes, unsigned epoch, int use_nvls, int ctas, void* stream,
+                   int f32) {
   if (world > smx::kMaxRanks || total_bytes % 16) return -40;
-  smx::all_reduce_kernel<<<ctas, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      make_pp(data_ptrs, flag_ptrs, mc, rank, world), in_off, out_off, total_bytes, epoch, use_nvls);
+  auto pp = make_pp(data_ptrs, flag_ptrs, mc, rank, world);
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  if (f32) smx::all_reduce_kernel<true><<<ctas, 512, 0, st>>>(pp, in_off, out_off, total_bytes, epoch, use_nvls);
+  else smx::all_reduce_kernel<false><<<ctas, 512, 0, st>>>(pp, in_off, out_off, total_bytes, epoch, use_nvls);
   return (int)cudaGetLastError();
 }
 int smx_all_to_all(void* const* data_ptrs, void* const* flag_ptrs, int rank, int world, long long in_off,

@@ -289,23 +289,30 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int i_begin = tile_begin(k0);
       const int nq_local = max(0, n_q_tiles - i_begin);
       const int n_iter = nq_local * group;
+      // lse (log2 units) and D*scale of the 64 query columns are staged in smem one iteration ahead: threads 0..127 keep
+      // the next iteration's value in a register across the current iteration, so the global-load latency is hidden.
+      auto load_stat = [&](int it_) -> float {
+        const int head_ = kv_head * group + it_ / nq_local, q0_ = (i_begin + it_ % nq_local) * BQ;
+        const int qi = q0_ + (tid & 63);
+        const long long off = ((long long)batch * p.H + head_) * p.S_q + qi;
+        float v;
+        if (tid < 64) {
+          v = (qi < p.S_q) ? p.lse[off] * 1.4426950408889634f : INFINITY;
+          if (!(v > -INFINITY)) v = INFINITY;
+        } else {
+          v = (qi < p.S_q) ? p.dsum[off] * p.scale : 0.f;
+        }
+        return v;
+      };
+      float stat_next = 0.f;
+      if (tid < 128 && n_iter > 0) {
+        // first iteration of this tile: nothing was prefetched yet
+        ((tid < 64 ? sLse : sDsum) + (g_base & 1) * 64)[tid & 63] = load_stat(0);
+      }
       for (int it = 0; it < n_iter; ++it) {
         const int g = g_base + it;
-        const int head = kv_head * group + it / nq_local, q0 = (i_begin + it % nq_local) * BQ;
-        if (tid < 128) {
-          // stage lse (log2 units) and D for the 64 query columns of this tile
-          const int qi = q0 + (tid & 63);
-          const long long off = ((long long)batch * p.H + head) * p.S_q + qi;
-          float* dst = (tid < 64 ? sLse : sDsum) + (g & 1) * 64 + (tid & 63);
-          float v;
-          if (tid < 64) {
-            v = (qi < p.S_q) ? p.lse[off] * 1.4426950408889634f : INFINITY;
-            if (!(v > -INFINITY)) v = INFINITY;
-          } else {
-            v = (qi < p.S_q) ? p.dsum[off] : 0.f;
-          }
-          *dst = v;
-        }
+        const int q0 = (i_begin + it % nq_local) * BQ;
+        if (tid < 128 && it + 1 < n_iter) stat_next = load_stat(it + 1);
         named_bar_sync(1, kBwdSoftmaxWarps * 32);
         const float4* lse4 = reinterpret_cast<const float4*>(sLse + (g & 1) * 64 + col0);
         const float4* dsum4 = reinterpret_cast<const float4*>(sDsum + (g & 1) * 64 + col0);
@@ -361,10 +368,10 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
         for (int i4 = 0; i4 < 8; ++i4) {
           const float4 dsm = dsum4[i4];
-          pr[4 * i4 + 0] *= (__uint_as_float(r[4 * i4 + 0]) - dsm.x) * p.scale;
-          pr[4 * i4 + 1] *= (__uint_as_float(r[4 * i4 + 1]) - dsm.y) * p.scale;
-          pr[4 * i4 + 2] *= (__uint_as_float(r[4 * i4 + 2]) - dsm.z) * p.scale;
-          pr[4 * i4 + 3] *= (__uint_as_float(r[4 * i4 + 3]) - dsm.w) * p.scale;
+          pr[4 * i4 + 0] *= fmaf(__uint_as_float(r[4 * i4 + 0]), p.scale, -dsm.x);      // (dP - D) * scale, D pre-scaled
+          pr[4 * i4 + 1] *= fmaf(__uint_as_float(r[4 * i4 + 1]), p.scale, -dsm.y);
+          pr[4 * i4 + 2] *= fmaf(__uint_as_float(r[4 * i4 + 2]), p.scale, -dsm.z);
+          pr[4 * i4 + 3] *= fmaf(__uint_as_float(r[4 * i4 + 3]), p.scale, -dsm.w);
         }
         if (g > 0) mbar_wait(dkq_done, (g - 1) & 1, 32);    // dK/dQ(g-1) have finished reading the dS^T tile
         {
@@ -382,6 +389,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(ds_full);
+        if (tid < 128 && it + 1 < n_iter) ((tid < 64 ? sLse : sDsum) + ((g + 1) & 1) * 64)[tid & 63] = stat_next;
       }
       // ---- dK epilogue (rows = keys; this warp writes head-dim columns [half*64, half*64+64))
       if (n_iter > 0) {

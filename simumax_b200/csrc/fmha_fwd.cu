@@ -38,7 +38,9 @@ struct FmhaCfg {
   static constexpr int kVBytes = kFmhaBlockKV * D_V * 2;
   static constexpr int kPBytes = kFmhaBlockQ * kFmhaBlockKV * 2;
   static constexpr int kStageBytes = kKBytes + kVBytes;
-  static constexpr int kSmemBytes = kQBytes + kPBytes + kFmhaStages * kStageBytes + 1024 + 256;
+  // no alignment slack: the dynamic window of a kernel without static smem starts 1024-byte aligned (checked at run
+  // time), and the slack would push two co-resident CTAs (2 x 113.25 KB + 2 x 1 KB reserved) over the 228 KB of an SM
+  static constexpr int kSmemBytes = kQBytes + kPBytes + kFmhaStages * kStageBytes + 256;
   static constexpr int kTmemCols = 256;  // S: 64 columns, O: D_V (<=128) columns
 };
 
@@ -58,7 +60,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   using Cfg = FmhaCfg<D_QK, D_V>;
   constexpr int BQ = kFmhaBlockQ, BKV = kFmhaBlockKV;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u)) {
+    printf("simumax_b200: fmha_fwd dynamic smem base %u is not 1024-byte aligned\n", smem_u32(smem_raw));
+    __trap();
+  }
   uint8_t* sQ = smem;
   uint8_t* sP = sQ + Cfg::kQBytes;
   uint8_t* sKV = sP + Cfg::kPBytes;
@@ -206,21 +212,21 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);
       const int k0 = j * BKV;
-      float mx = -INFINITY;
       const bool need_mask = (p.causal && (k0 + BKV - 1 > q0 + causal_shift)) || (k0 + BKV > p.S_kv);
       if (need_mask) {
         const int limit = p.causal ? min(row + causal_shift, p.S_kv - 1) : p.S_kv - 1;
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          float v = __uint_as_float(r[i]);
-          if (k0 + i > limit) v = -INFINITY;
-          r[i] = __float_as_uint(v);
-          mx = fmaxf(mx, v);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        for (int i = 0; i < 64; ++i)
+          if (k0 + i > limit) r[i] = 0xff800000u;   // -inf
       }
+      // four independent max chains (a single 64-long dependent chain is pure latency with one warp per scheduler)
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mx4[j] = fmaxf(mx4[j], __uint_as_float(r[i + j]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       // lazy rescale: only move the reference max when it grew by more than 2^8 in the exp2 domain
       float m_new = m_used;
       bool grow = (mx > m_used) && ((mx - m_used) * c_log2 > 8.f || m_used == -INFINITY);
@@ -247,7 +253,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       m_used = m_new;
       const float mc = (m_used == -INFINITY) ? 0.f : m_used * c_log2;
-      float sum = 0.f;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
       // P row -> bf16 -> 128B-swizzled K-major smem tile [128 rows][64 kv]
       uint8_t* prow = sP + row_in_tile * 128;
 #pragma unroll
@@ -256,7 +262,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           e[i] = exp2f(__uint_as_float(r[c16 * 8 + i]) * c_log2 - mc);
-          sum += e[i];
+          sum4[i & 3] += e[i];
         }
         uint4 pk;
         pk.x = pack_bf16x2(e[0], e[1]);
@@ -265,7 +271,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         pk.w = pack_bf16x2(e[6], e[7]);
         *reinterpret_cast<uint4*>(prow + ((c16 ^ (row_in_tile & 7)) << 4)) = pk;
       }
-      l += sum;
+      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tcgen05_fence_before();
       __syncwarp();

@@ -34,6 +34,7 @@ def _fn(name, argtypes):
 _PTRS = _c.POINTER(_c.c_void_p)
 _SIG_COLL = [_PTRS, _PTRS, _c.c_void_p, _c.c_int, _c.c_int, _c.c_longlong, _c.c_longlong, _c.c_longlong, _c.c_uint,
              _c.c_int, _c.c_int, _c.c_void_p]
+_SIG_RED = _SIG_COLL + [_c.c_int]
 _SIG_A2A = [_PTRS, _PTRS, _c.c_int, _c.c_int, _c.c_longlong, _c.c_longlong, _c.c_longlong, _c.c_uint, _c.c_int, _c.c_void_p]
 _SIG_PUT = [_PTRS, _PTRS, _c.c_int, _c.c_int, _c.c_int, _c.c_longlong, _c.c_longlong, _c.c_longlong, _c.c_int, _c.c_void_p]
 
@@ -85,28 +86,47 @@ class SymmetricWorkspace:
         self.epoch = (self.epoch + 2) & 0x7FFFFFFF or 1
         return e
 
-    def _coll(self, name, nbytes, use_nvls, ctas):
-        rc = _fn(name, _SIG_COLL)(self.data_ptrs, self.flag_ptrs, self.multicast_ptr if self.has_nvls else None,
-                                  self.rank, self.world, 0, self.in_bytes, nbytes, self._next_epoch(),
-                                  1 if (use_nvls and self.has_nvls) else 0, min(ctas, MAX_CTAS), self._stream())
+    def _coll(self, name, nbytes, use_nvls, ctas, in_off=None, out_off=None, f32=None):
+        """``in_off`` / ``out_off`` are byte offsets into the symmetric buffer (defaults: the in / out regions)."""
+        in_off = 0 if in_off is None else in_off
+        out_off = self.in_bytes if out_off is None else out_off
+        assert in_off % 16 == 0 and out_off % 16 == 0 and nbytes % 16 == 0
+        args = [self.data_ptrs, self.flag_ptrs, self.multicast_ptr if self.has_nvls else None, self.rank, self.world,
+                in_off, out_off, nbytes, self._next_epoch(), 1 if (use_nvls and self.has_nvls) else 0,
+                min(ctas, MAX_CTAS), self._stream()]
+        if f32 is None:
+            rc = _fn(name, _SIG_COLL)(*args)
+        else:
+            rc = _fn(name, _SIG_RED)(*args, 1 if f32 else 0)
         _lib.check(rc, name)
         _lib.count_launch()
 
+    def view(self, byte_off: int, dtype, numel: int) -> torch.Tensor:
+        """Typed view of an arbitrary range of the local symmetric buffer."""
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        assert byte_off % 16 == 0 and byte_off + nbytes <= self.in_bytes + self.out_bytes
+        return self.data[byte_off:byte_off + nbytes].view(dtype)
+
     # ---- collectives (operate in place on the workspace regions)
-    def all_gather(self, shard_bytes: int, use_nvls: bool = True, ctas: int = 32):
+    def all_gather(self, shard_bytes: int, use_nvls: bool = True, ctas: int = 32, in_off=None, out_off=None):
         """out[r*shard:(r+1)*shard] on every rank <- in[:shard] of rank r."""
-        assert shard_bytes <= self.in_bytes and shard_bytes * self.world <= self.out_bytes
-        self._coll("smx_all_gather", shard_bytes, use_nvls, ctas)
+        if in_off is None and out_off is None:
+            assert shard_bytes <= self.in_bytes and shard_bytes * self.world <= self.out_bytes
+        self._coll("smx_all_gather", shard_bytes, use_nvls, ctas, in_off, out_off)
 
-    def reduce_scatter(self, shard_bytes: int, use_nvls: bool = True, ctas: int = 32):
-        """out[:shard] <- sum over ranks of in[rank*shard:(rank+1)*shard]   (bf16)."""
-        assert shard_bytes * self.world <= self.in_bytes and shard_bytes <= self.out_bytes
-        self._coll("smx_reduce_scatter", shard_bytes, use_nvls, ctas)
+    def reduce_scatter(self, shard_bytes: int, use_nvls: bool = True, ctas: int = 32, in_off=None, out_off=None,
+                       dtype=torch.bfloat16):
+        """out[:shard] <- sum over ranks of in[rank*shard:(rank+1)*shard]   (bf16 with fp32 accumulation, or fp32)."""
+        if in_off is None and out_off is None:
+            assert shard_bytes * self.world <= self.in_bytes and shard_bytes <= self.out_bytes
+        self._coll("smx_reduce_scatter", shard_bytes, use_nvls, ctas, in_off, out_off, f32=(dtype == torch.float32))
 
-    def all_reduce(self, total_bytes: int, use_nvls: bool = True, ctas: int = 32):
-        """out[:total] <- sum over ranks of in[:total]   (bf16)."""
-        assert total_bytes <= self.in_bytes and total_bytes <= self.out_bytes
-        self._coll("smx_all_reduce", total_bytes, use_nvls, ctas)
+    def all_reduce(self, total_bytes: int, use_nvls: bool = True, ctas: int = 32, in_off=None, out_off=None,
+                   dtype=torch.bfloat16):
+        """out[:total] <- sum over ranks of in[:total]   (bf16 or fp32)."""
+        if in_off is None and out_off is None:
+            assert total_bytes <= self.in_bytes and total_bytes <= self.out_bytes
+        self._coll("smx_all_reduce", total_bytes, use_nvls, ctas, in_off, out_off, f32=(dtype == torch.float32))
 
     def all_to_all(self, chunk_bytes: int, ctas: int = 32):
         """out[src*chunk:(src+1)*chunk] of rank dst <- in[dst*chunk:(dst+1)*chunk] of rank src."""

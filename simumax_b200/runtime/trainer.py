@@ -57,8 +57,9 @@ class LlamaDims:
 class _Flat:
     """Carves named views out of one flat buffer (Megatron-style contiguous param / grad buffers)."""
 
-    def __init__(self, numel, dtype, device):
-        self.buf = torch.empty(numel, dtype=dtype, device=device)
+    def __init__(self, numel, dtype, device, buf=None):
+        self.buf = torch.empty(numel, dtype=dtype, device=device) if buf is None else buf
+        assert self.buf.numel() == numel and self.buf.dtype == dtype
         self.off = 0
 
     def take(self, *shape):
@@ -73,7 +74,7 @@ class _Flat:
 class LlamaTrainer:
     def __init__(self, dims: LlamaDims, micro_batch: int, seq_len: int, dp_group: Optional[dist.ProcessGroup] = None,
                  lr: float = 1e-4, weight_decay: float = 0.1, betas=(0.9, 0.95), max_grad_norm: float = 1.0,
-                 attention_bwd: str = "auto", seed: int = 1234, device=None):
+                 attention_bwd: str = "auto", seed: int = 1234, device=None, comm: str = "auto"):
         self.d = dims
         self.B, self.S = micro_batch, seq_len
         self.T = micro_batch * seq_len
@@ -87,9 +88,30 @@ class LlamaTrainer:
         P = d.total_numel()
         pad = (-P) % (self.world * 1024)
         self.P, self.Ppad = P, P + pad
-        # ---- parameters (bf16) and fp32 main grads, identical layouts
-        self.params = _Flat(self.Ppad, torch.bfloat16, dev)
-        self.grads = _Flat(self.Ppad, torch.float32, dev)
+        # ---- parameters (bf16) and fp32 main grads, identical layouts.  With data parallelism both live in one
+        # symmetric (peer-mapped) allocation so the ZeRO-1 reduce-scatter / all-gather run as our own NVLink kernels.
+        self.shard = self.Ppad // self.world
+        self.ws, self.comm = None, "none"
+        p_buf = g_buf = None
+        if self.world > 1:
+            self.comm = "nccl" if comm == "nccl" else "smx"
+            if self.comm == "smx":
+                try:
+                    from ..parallel.symm import SymmetricWorkspace
+                    self._off_p, self._off_g = 0, self.Ppad * 2
+                    self._off_gs = self._off_g + self.Ppad * 4
+                    self._off_sc = self._off_gs + self.shard * 4
+                    self.ws = SymmetricWorkspace(self._off_sc + 512, 256, group=dp_group)
+                    p_buf = self.ws.view(self._off_p, torch.bfloat16, self.Ppad)
+                    g_buf = self.ws.view(self._off_g, torch.float32, self.Ppad)
+                except Exception as e:                      # no peer access / symmetric memory: NCCL baseline path
+                    if comm == "smx":
+                        raise
+                    import warnings
+                    warnings.warn(f"in-kernel collectives unavailable ({type(e).__name__}: {e}); using NCCL")
+                    self.ws, self.comm, p_buf, g_buf = None, "nccl", None, None
+        self.params = _Flat(self.Ppad, torch.bfloat16, dev, p_buf)
+        self.grads = _Flat(self.Ppad, torch.float32, dev, g_buf)
         self.w, self.g = self._carve(self.params), self._carve(self.grads)
         gen = torch.Generator(device=dev).manual_seed(seed)
         self.params.buf.normal_(0.0, 0.02, generator=gen)
@@ -99,13 +121,18 @@ class LlamaTrainer:
         self.w["final_norm"].fill_(1.0)
         self.grads.buf.zero_()
         # ---- ZeRO-1 optimizer shard
-        self.shard = self.Ppad // self.world
         lo = self.rank * self.shard
         self.master = self.params.buf[lo:lo + self.shard].float()
         self.m = torch.zeros(self.shard, dtype=torch.float32, device=dev)
         self.v = torch.zeros(self.shard, dtype=torch.float32, device=dev)
-        self.grad_shard = torch.empty(self.shard, dtype=torch.float32, device=dev) if self.world > 1 else None
-        self.sqnorm = torch.zeros(1, dtype=torch.float32, device=dev)
+        if self.ws is not None:
+            self.grad_shard = self.ws.view(self._off_gs, torch.float32, self.shard)
+            self.sqnorm = self.ws.view(self._off_sc, torch.float32, 4)[:1]       # all-reduced in place (16-byte granule)
+            self.sqnorm_out = self.ws.view(self._off_sc + 256, torch.float32, 4)[:1]
+        else:
+            self.grad_shard = torch.empty(self.shard, dtype=torch.float32, device=dev) if self.world > 1 else None
+            self.sqnorm = torch.zeros(1, dtype=torch.float32, device=dev)
+            self.sqnorm_out = self.sqnorm
         # ---- static activation storage
         T, H, F, L = self.T, d.hidden, d.ffn, d.layers
         bf = dict(dtype=torch.bfloat16, device=dev)
@@ -258,20 +285,33 @@ class LlamaTrainer:
         the updated bf16 params."""
         self.step_count += 1
         b1, b2 = self.betas
-        if self.world > 1:
-            dist.reduce_scatter_tensor(self.grad_shard, self.grads.buf, op=dist.ReduceOp.AVG, group=self.group)
+        lo = self.rank * self.shard
+        if self.world > 1 and self.ws is not None:
+            # pull-reduce my slice of every peer's fp32 main grads over NVLink (multimem.ld_reduce when NVLS is up)
+            self.ws.reduce_scatter(self.shard * 4, in_off=self._off_g, out_off=self._off_gs, dtype=torch.float32, ctas=64)
+            gsh = self.grad_shard
+        elif self.world > 1:
+            dist.reduce_scatter_tensor(self.grad_shard, self.grads.buf, op=dist.ReduceOp.SUM, group=self.group)
             gsh = self.grad_shard
         else:
             gsh = self.grads.buf
         self.sqnorm.zero_()
         E.sqnorm(gsh, out=self.sqnorm)
-        if self.world > 1:
+        if self.ws is not None:
+            self.ws.view(self._off_sc, torch.float32, 4)[1:].zero_()
+            self.ws.all_reduce(16, in_off=self._off_sc, out_off=self._off_sc + 256, dtype=torch.float32, ctas=1)
+        elif self.world > 1:
             dist.all_reduce(self.sqnorm, group=self.group)
-        lo = self.rank * self.shard
+        # grads hold the SUM over ranks of per-rank means -> prescale by 1/world inside the fused optimizer kernel
         E.adamw_(self.master, self.m, self.v, gsh, self.params.buf[lo:lo + self.shard], self.lr, b1, b2, 1e-8, self.wd,
-                 self.step_count, sqnorm_t=self.sqnorm, max_norm=self.max_norm, zero_grad=(self.world == 1))
+                 self.step_count, sqnorm_t=self.sqnorm_out, max_norm=self.max_norm, grad_prescale=1.0 / self.world,
+                 zero_grad=(self.world == 1))
         if self.world > 1:
-            dist.all_gather_into_tensor(self.params.buf, self.params.buf[lo:lo + self.shard], group=self.group)
+            if self.ws is not None:
+                # push my updated bf16 shard into every peer's parameter buffer (multimem.st when NVLS is up)
+                self.ws.all_gather(self.shard * 2, in_off=self._off_p + lo * 2, out_off=self._off_p, ctas=64)
+            else:
+                dist.all_gather_into_tensor(self.params.buf, self.params.buf[lo:lo + self.shard], group=self.group)
             self.grads.buf.zero_()
 
     def run_microbatches(self, device_batches: List[Tuple[torch.Tensor, torch.Tensor]]) -> torch.Tensor:

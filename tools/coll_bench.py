@@ -55,6 +55,14 @@ def main():
         ws.input(torch.bfloat16, n).copy_(x); ws.all_reduce(n * 2, use_nvls=nvls); torch.cuda.synchronize()
         ref = x.float().clone(); dist.all_reduce(ref)
         ok[f"all_reduce_{tag}"] = bool(torch.allclose(ws.output(torch.bfloat16, n).float(), ref, atol=0.1, rtol=0.02))
+        # fp32 reductions (ZeRO-1 main-grad path)
+        xf = x.float()
+        ws.input(torch.float32, n).copy_(xf); ws.reduce_scatter(shard * 4, use_nvls=nvls, dtype=torch.float32); torch.cuda.synchronize()
+        ref = torch.empty(shard, device="cuda", dtype=torch.float32); dist.reduce_scatter_tensor(ref, xf.clone())
+        ok[f"reduce_scatter_f32_{tag}"] = bool(torch.allclose(ws.output(torch.float32, shard), ref, atol=1e-4, rtol=1e-5))
+        ws.input(torch.float32, n).copy_(xf); ws.all_reduce(n * 4, use_nvls=nvls, dtype=torch.float32); torch.cuda.synchronize()
+        ref = xf.clone(); dist.all_reduce(ref)
+        ok[f"all_reduce_f32_{tag}"] = bool(torch.allclose(ws.output(torch.float32, n), ref, atol=1e-4, rtol=1e-5))
     ws.input(torch.bfloat16, n).copy_(x); ws.all_to_all(shard * 2); torch.cuda.synchronize()
     ref = torch.empty(n, device="cuda", dtype=torch.bfloat16); dist.all_to_all_single(ref, x.contiguous())
     ok["all_to_all_p2p"] = bool(torch.equal(ws.output(torch.bfloat16, n), ref))
