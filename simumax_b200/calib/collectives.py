@@ -212,6 +212,46 @@ def measure_burst(total_bytes: int = 32 << 20, ops_per_window: int = 20, keep: i
     return out
 
 
+def measure_p2p_overlap(total_bytes: int = 64 << 20, gemms: int = 8) -> dict:
+    """Pipeline send/recv the way a 1F1B schedule issues it: NCCL ``isend/irecv`` to the ring neighbours on a side
+    stream while the main stream runs GEMMs.  Reports the p2p time alone, the GEMM time alone, and both overlapped
+    (so the model's ``p2p`` efficiency and the compute slowdown under communication are both visible)."""
+    import torch
+    import torch.distributed as dist
+    from ..ops.gemm import gemm
+    world, rank = dist.get_world_size(), dist.get_rank()
+    a = torch.randn(6144, 6144, device="cuda").bfloat16()
+    b = torch.randn(6144, 6144, device="cuda").bfloat16()
+    c = torch.empty(6144, 6144, device="cuda", dtype=torch.bfloat16)
+    src = torch.empty(total_bytes // 2, device="cuda", dtype=torch.bfloat16).normal_()
+    dst = torch.empty_like(src)
+    side = torch.cuda.Stream()
+
+    def compute():
+        for _ in range(gemms):
+            gemm(a, b, "TN", out=c)
+
+    def p2p():
+        reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, src, (rank + 1) % world),
+                                       dist.P2POp(dist.irecv, dst, (rank - 1) % world)])
+        for r in reqs:
+            r.wait()
+
+    def both():
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            p2p()
+        compute()
+        torch.cuda.current_stream().wait_stream(side)
+
+    out = {"world": world, "bytes": total_bytes}
+    for name, fn in (("gemm_only_us", compute), ("p2p_only_us", p2p), ("overlapped_us", both)):
+        out[name] = _timed(fn, 5, dist, torch)
+    out["p2p_GBps_alone"] = total_bytes / out["p2p_only_us"] / 1e3
+    out["exposed_us"] = max(0.0, out["overlapped_us"] - out["gemm_only_us"])
+    return out
+
+
 def fixed_latency_from_burst(burst_by_world: Dict[int, dict], fits_by_world: Dict[int, Dict[str, Dict[str, float]]],
                              which: str = "smx", spread_us: float = 25.0) -> Dict[str, dict]:
     """fixed_us = burst-measured time - what the fitted line predicts; one scalar per op when the group sizes agree
@@ -257,6 +297,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     res = sweep(max_bytes=a.max_bytes)
     res["burst"] = measure_burst()
+    res["p2p_overlap"] = measure_p2p_overlap()
     if dist.get_rank() == 0:
         res["fit_smx"] = fit_all(res, which="smx")
         res["fit_nccl"] = fit_all(res, which="nccl")

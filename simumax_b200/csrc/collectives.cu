@@ -187,28 +187,49 @@ __global__ void __launch_bounds__(512) all_gather_kernel(PeerPtrs pp, long long 
   cta_barrier_all_ranks(pp, epoch + 1);
 }
 
+// Sum granules [lo, hi) (16 B each, at byte offset src_off in every rank's buffer) and hand each result to `emit(i, v)`.
+// Remote loads have microseconds of latency, so every thread keeps U granules x world peers in flight.
+template <bool F32, int U, typename Emit>
+SMX_DEVICE void reduce_granules(const PeerPtrs& pp, int use_nvls, long long src_off, long long lo, long long hi, Emit emit) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long first = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (use_nvls && pp.mc_data) {
+    const char* mc = reinterpret_cast<const char*>(pp.mc_data) + src_off;
+    for (long long i = first; i < hi; i += stride * U) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i + u * stride < hi) v[u] = multimem_ld_reduce16<F32>(mc + (i + u * stride) * 16);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i + u * stride < hi) emit(i + u * stride, v[u]);
+    }
+  } else {
+    for (long long i = first; i < hi; i += stride * U) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i + u * stride < hi) v[u] = reduce16_peers<F32>(pp, src_off + (i + u * stride) * 16);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i + u * stride < hi) emit(i + u * stride, v[u]);
+    }
+  }
+}
+
 // reduce_scatter (sum; bf16 with fp32 accumulation, or fp32): out <- sum_r in_r[rank * shard .. (rank+1) * shard)
-template <bool F32>
+template <bool F32, int U>
 __global__ void __launch_bounds__(512) reduce_scatter_kernel(PeerPtrs pp, long long in_off, long long out_off,
                                                             long long shard_bytes, uint32_t epoch, int use_nvls) {
   cta_barrier_all_ranks(pp, epoch);
-  const long long n16 = shard_bytes / 16;
-  const long long src_off = in_off + (long long)pp.rank * shard_bytes;
   char* dst = reinterpret_cast<char*>(pp.data[pp.rank]) + out_off;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  if (use_nvls && pp.mc_data) {
-    const char* mc = reinterpret_cast<const char*>(pp.mc_data) + src_off;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += stride)
-      st_v4(dst + i * 16, multimem_ld_reduce16<F32>(mc + i * 16));
-  } else {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += stride)
-      st_v4(dst + i * 16, reduce16_peers<F32>(pp, src_off + i * 16));
-  }
+  reduce_granules<F32, U>(pp, use_nvls, in_off + (long long)pp.rank * shard_bytes, 0, shard_bytes / 16,
+                          [&](long long i, uint4 v) { st_v4(dst + i * 16, v); });
   cta_barrier_all_ranks(pp, epoch + 1);
 }
 
-// all_reduce (sum), result written to out on every rank
-template <bool F32>
+// all_reduce (sum), result written to out on every rank: each rank reduces its slice and broadcasts it
+template <bool F32, int U>
 __global__ void __launch_bounds__(512) all_reduce_kernel(PeerPtrs pp, long long in_off, long long out_off,
                                                         long long total_bytes, uint32_t epoch, int use_nvls) {
   cta_barrier_all_ranks(pp, epoch);
@@ -217,19 +238,15 @@ __global__ void __launch_bounds__(512) all_reduce_kernel(PeerPtrs pp, long long 
   const long long per = (n16_total + pp.world - 1) / pp.world;
   const long long lo = per * pp.rank;
   const long long hi = min(n16_total, lo + per);
-  const long long stride = (long long)gridDim.x * blockDim.x;
   if (use_nvls && pp.mc_data) {
-    const char* mc_in = reinterpret_cast<const char*>(pp.mc_data) + in_off;
     char* mc_out = reinterpret_cast<char*>(pp.mc_data) + out_off;
-    for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi; i += stride)
-      multimem_st_v4(mc_out + i * 16, multimem_ld_reduce16<F32>(mc_in + i * 16));
+    reduce_granules<F32, U>(pp, 1, in_off, lo, hi, [&](long long i, uint4 v) { multimem_st_v4(mc_out + i * 16, v); });
   } else {
-    for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi; i += stride) {
-      const uint4 r = reduce16_peers<F32>(pp, in_off + i * 16);
+    reduce_granules<F32, U>(pp, 0, in_off, lo, hi, [&](long long i, uint4 v) {
 #pragma unroll 1
       for (int s = 0; s < pp.world; ++s)
-        st_v4(reinterpret_cast<char*>(pp.data[(pp.rank + s) % pp.world]) + out_off + i * 16, r);
-    }
+        st_v4(reinterpret_cast<char*>(pp.data[(pp.rank + s) % pp.world]) + out_off + i * 16, v);
+    });
   }
   cta_barrier_all_ranks(pp, epoch + 1);
 }
@@ -294,8 +311,12 @@ int smx_reduce_scatter(void* const* data_ptrs, void* const* flag_ptrs, void* mc,
   if (world > smx::kMaxRanks || shard_bytes % 16) return -40;
   auto pp = make_pp(data_ptrs, flag_ptrs, mc, rank, world);
   auto st = reinterpret_cast<cudaStream_t>(stream);
-  if (f32) smx::reduce_scatter_kernel<true><<<ctas, 512, 0, st>>>(pp, in_off, out_off, shard_bytes, epoch, use_nvls);
-  else smx::reduce_scatter_kernel<false><<<ctas, 512, 0, st>>>(pp, in_off, out_off, shard_bytes, epoch, use_nvls);
+#define SMX_RS(F, U) smx::reduce_scatter_kernel<F, U><<<ctas, 512, 0, st>>>(pp, in_off, out_off, shard_bytes, epoch, use_nvls)
+  // loads in flight per thread = U (NVLS) or U * world (P2P): deeper unroll for small groups
+  if (world <= 2) { if (f32) SMX_RS(true, 8); else SMX_RS(false, 8); }
+  else if (world <= 4) { if (f32) SMX_RS(true, 4); else SMX_RS(false, 4); }
+  else { if (f32) SMX_RS(true, 2); else SMX_RS(false, 2); }
+#undef SMX_RS
   return (int)cudaGetLastError();
 }
 int smx_all_reduce(void* const* data_ptrs, void* const* flag_ptrs, void* mc, int rank, int world, long long in_off,
@@ -304,8 +325,11 @@ int smx_all_reduce(void* const* data_ptrs, void* const* flag_ptrs, void* mc, int
   if (world > smx::kMaxRanks || total_bytes % 16) return -40;
   auto pp = make_pp(data_ptrs, flag_ptrs, mc, rank, world);
   auto st = reinterpret_cast<cudaStream_t>(stream);
-  if (f32) smx::all_reduce_kernel<true><<<ctas, 512, 0, st>>>(pp, in_off, out_off, total_bytes, epoch, use_nvls);
-  else smx::all_reduce_kernel<false><<<ctas, 512, 0, st>>>(pp, in_off, out_off, total_bytes, epoch, use_nvls);
+#define SMX_AR(F, U) smx::all_reduce_kernel<F, U><<<ctas, 512, 0, st>>>(pp, in_off, out_off, total_bytes, epoch, use_nvls)
+  if (world <= 2) { if (f32) SMX_AR(true, 8); else SMX_AR(false, 8); }
+  else if (world <= 4) { if (f32) SMX_AR(true, 4); else SMX_AR(false, 4); }
+  else { if (f32) SMX_AR(true, 2); else SMX_AR(false, 2); }
+#undef SMX_AR
   return (int)cudaGetLastError();
 }
 int smx_all_to_all(void* const* data_ptrs, void* const* flag_ptrs, int rank, int world, long long in_off,

@@ -39,6 +39,12 @@ SMX_DEVICE void bwd_tma_reduce_add_4d(const CUtensorMap* m, const void* smem_src
       "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+SMX_DEVICE void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 SMX_DEVICE void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 constexpr int kBwdBKV = 128;
@@ -49,21 +55,31 @@ constexpr int kBwdThreads = (2 + kBwdSoftmaxWarps + 4) * 32;
 constexpr int kBwdKVBytes = kBwdBKV * kBwdD * 2;      // 32 KB each for K and V
 constexpr int kBwdQBytes = kBwdBQ * kBwdD * 2;        // 16 KB each for Q_i and dO_i
 constexpr int kBwdStageBytes = 2 * kBwdQBytes;
+constexpr int kBwdStages = 3;                      // Q/dO ring: a load issued when iteration g-1 retires lands before g+2 needs it
 constexpr int kBwdPBytes = kBwdBKV * kBwdBQ * 2;      // 16 KB each for P^T and dS^T
 constexpr int kBwdDqBytes = kBwdBQ * kBwdD * 4;       // 32 KB fp32 staging for the dQ reduce
-constexpr int kBwdSmemBytes = 2 * kBwdKVBytes + 2 * kBwdStageBytes + 2 * kBwdPBytes + kBwdDqBytes + 2 * 2 * 64 * 4 + 256 + 1024;
+// no alignment slack: a kernel without static smem gets a 1024-byte aligned dynamic window (checked at run time)
+constexpr int kBwdSmemBytes = 2 * kBwdKVBytes + kBwdStages * kBwdStageBytes + 2 * kBwdPBytes + kBwdDqBytes + 2 * kBwdStages * 64 * 4 + 256;
 
 struct FmhaBwdParams {
   int B, S_q, S_kv, H, H_kv;
   float scale;
   int causal;
   int pair;           // causal load balancing: CTA x handles key tiles x and n-1-x
-  const float* lse;   // [B, H, S_q]
-  const float* dsum;  // [B, H, S_q]  rowsum(dO o O)
+  const float* lse2;  // [B, H, S_pad]  lse * log2(e)   (+inf in the padding and where the row had no keys)
+  const float* dsum;  // [B, H, S_pad]  rowsum(dO o O) * scale   (0 in the padding);  S_pad = ceil(S_q / 64) * 64
+  long long s_pad;
+  long long* trace;   // optional [3 roles][32 iterations][16 events] clock64 stamps of CTA (0,0,0); nullptr = off
   __nv_bfloat16* dk;  // strides in elements
   __nv_bfloat16* dv;
   long long dk_sb, dk_ss, dk_sh, dv_sb, dv_ss, dv_sh;
 };
+
+#define SMX_TRACE(role, g, ev)                                                                             \
+  do {                                                                                                  \
+    if (p.trace && (g) < 32 && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)     \
+      p.trace[((role) * 32 + (g)) * 16 + (ev)] = clock64();                                             \
+  } while (0)
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -71,19 +87,23 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 const __grid_constant__ CUtensorMap tmap_dq, const FmhaBwdParams p) {
   constexpr int BKV = kBwdBKV, BQ = kBwdBQ, D = kBwdD;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u)) {
+    printf("simumax_b200: fmha_bwd dynamic smem base %u is not 1024-byte aligned\n", smem_u32(smem_raw));
+    __trap();
+  }
   uint8_t* sK = smem;
   uint8_t* sV = sK + kBwdKVBytes;
   uint8_t* sQdO = sV + kBwdKVBytes;                    // [2 stages][Q 16 KB | dO 16 KB]
-  uint8_t* sP = sQdO + 2 * kBwdStageBytes;
+  uint8_t* sP = sQdO + kBwdStages * kBwdStageBytes;
   uint8_t* sdS = sP + kBwdPBytes;
   float* sDq = reinterpret_cast<float*>(sdS + kBwdPBytes);
   float* sLse = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sDq) + kBwdDqBytes);   // [2][64]
-  float* sDsum = sLse + 2 * 64;                                                            // [2][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDsum + 2 * 64);
+  float* sDsum = sLse + kBwdStages * 64;                                                            // [2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDsum + kBwdStages * 64);
   uint64_t* kv_full = bars;            // 1
-  uint64_t* qdo_full = bars + 1;       // [2]
-  uint64_t* qdo_empty = bars + 3;      // [2]
+  uint64_t* qdo_full = bars + 17;      // [kBwdStages]
+  uint64_t* qdo_empty = bars + 17 + kBwdStages;
   uint64_t* s_full = bars + 5;
   uint64_t* s_empty = bars + 6;
   uint64_t* dp_full = bars + 7;
@@ -96,7 +116,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* dq_empty = bars + 14;
   uint64_t* all_done = bars + 15;
   uint64_t* acc_empty = bars + 16;
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 17);
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 17 + 2 * kBwdStages);
 
   const int warp_idx = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -118,7 +138,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tma_prefetch_desc(&tmap_do);
     tma_prefetch_desc(&tmap_dq);
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kBwdStages; ++i) {
       mbar_init(&qdo_full[i], 1);
       mbar_init(&qdo_empty[i], 1);
     }
@@ -166,12 +186,15 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         for (int it = 0; it < n_iter; ++it) {
           const int g = g_base + it;
-          const int st = g & 1;
-          mbar_wait(&qdo_empty[st], ((g >> 1) & 1) ^ 1, 21);
+          const int st = g % kBwdStages;
+          mbar_wait(&qdo_empty[st], ((g / kBwdStages) & 1) ^ 1, 21);
           uint8_t* sQ = sQdO + st * kBwdStageBytes;
           uint8_t* sdO = sQ + kBwdQBytes;
-          mbar_arrive_expect_tx(&qdo_full[st], kBwdStageBytes);
+          mbar_arrive_expect_tx(&qdo_full[st], kBwdStageBytes + 2 * 64 * 4);
           const int head = kv_head * group + it / nq_local, q0 = (i_begin + it % nq_local) * BQ;
+          const long long stat_off = ((long long)batch * p.H + head) * p.s_pad + q0;
+          bulk_load_1d(sLse + st * 64, p.lse2 + stat_off, 64 * 4, &qdo_full[st]);
+          bulk_load_1d(sDsum + st * 64, p.dsum + stat_off, 64 * 4, &qdo_full[st]);
 #pragma unroll
           for (int c = 0; c < D / 64; ++c) {
             bwd_tma_load_4d(&tmap_q, &qdo_full[st], sQ + c * (BQ * 128), c * 64, q0, head, batch);
@@ -187,35 +210,44 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     constexpr uint32_t idesc_s = make_idesc(1, 1, 0, 0, BKV, BQ);    // K (K-major) x Q (K-major)      -> S^T[128, 64]
     constexpr uint32_t idesc_dv = make_idesc(1, 1, 0, 1, BKV, D);    // P^T (K-major) x dO (MN-major)  -> dV[128, 128]
     constexpr uint32_t idesc_dq = make_idesc(1, 1, 1, 1, D, BQ);     // K (MN-major) x dS^T (MN-major) -> dQ^T[128, 64]
+    // every UMMA smem descriptor is a constant plus (stage * stage_stride): build them once, the issue loop is then
+    // two 64-bit adds per MMA (issue latency of this single thread is on the critical path: 32 MMAs per iteration)
+    const uint64_t kK_km = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+    const uint64_t kV_km = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
+    const uint64_t kK_mn = make_smem_desc_sw128(smem_u32(sK), BKV * 128, 1024);
+    const uint64_t kP_km = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
+    const uint64_t kdS_km = make_smem_desc_sw128(smem_u32(sdS), 16, 1024);
+    const uint64_t kdS_mn = make_smem_desc_sw128(smem_u32(sdS), BKV * 128, 1024);
+    const uint64_t kQ_km = make_smem_desc_sw128(smem_u32(sQdO), 16, 1024);
+    const uint64_t kQ_mn = make_smem_desc_sw128(smem_u32(sQdO), BQ * 128, 1024);
+    const uint64_t kdO_km = make_smem_desc_sw128(smem_u32(sQdO + kBwdQBytes), 16, 1024);
+    const uint64_t kdO_mn = make_smem_desc_sw128(smem_u32(sQdO + kBwdQBytes), BQ * 128, 1024);
+    constexpr uint64_t kStageStep = kBwdStageBytes >> 4;
     auto issue_s = [&](int g) {       // S^T(g) = K Q^T
-      const int st = g & 1;
-      mbar_wait(&qdo_full[st], (g >> 1) & 1, 22);
+      const int st = g % kBwdStages;
+      mbar_wait(&qdo_full[st], (g / kBwdStages) & 1, 22);
       if (g > 0) mbar_wait(s_empty, (g - 1) & 1, 23);
       tcgen05_fence_after();
       if (elect_one()) {
-        uint8_t* sQ = sQdO + st * kBwdStageBytes;
+        const uint64_t b0 = kQ_km + st * kStageStep;
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint64_t a = make_smem_desc_sw128(smem_u32(sK + (k / 4) * (BKV * 128)), 16, 1024) + (k % 4) * 2;
-          const uint64_t b = make_smem_desc_sw128(smem_u32(sQ + (k / 4) * (BQ * 128)), 16, 1024) + (k % 4) * 2;
-          umma_f16<1>(tmem_s, a, b, idesc_s, k > 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < D / 16; ++k)
+          umma_f16<1>(tmem_s, kK_km + ((k / 4) * ((BKV * 128) >> 4) + (k % 4) * 2), b0 + ((k / 4) * ((BQ * 128) >> 4) + (k % 4) * 2),
+                      idesc_s, k > 0 ? 1u : 0u);
         umma_commit<1>(s_full);
       }
       __syncwarp();
     };
     auto issue_dp = [&](int g) {      // dP^T(g) = V dO^T
-      const int st = g & 1;
+      const int st = g % kBwdStages;
       if (g > 0) mbar_wait(dp_empty, (g - 1) & 1, 24);
       tcgen05_fence_after();
       if (elect_one()) {
-        uint8_t* sdO = sQdO + st * kBwdStageBytes + kBwdQBytes;
+        const uint64_t b0 = kdO_km + st * kStageStep;
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint64_t a = make_smem_desc_sw128(smem_u32(sV + (k / 4) * (BKV * 128)), 16, 1024) + (k % 4) * 2;
-          const uint64_t b = make_smem_desc_sw128(smem_u32(sdO + (k / 4) * (BQ * 128)), 16, 1024) + (k % 4) * 2;
-          umma_f16<1>(tmem_dp, a, b, idesc_s, k > 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < D / 16; ++k)
+          umma_f16<1>(tmem_dp, kV_km + ((k / 4) * ((BKV * 128) >> 4) + (k % 4) * 2), b0 + ((k / 4) * ((BQ * 128) >> 4) + (k % 4) * 2),
+                      idesc_s, k > 0 ? 1u : 0u);
         umma_commit<1>(dp_full);
       }
       __syncwarp();
@@ -230,45 +262,49 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       issue_dp(g_base);
       for (int it = 0; it < n_iter; ++it) {
         const int g = g_base + it;
-        const int st = g & 1;
+        const int st = g % kBwdStages;
         uint8_t* sQ = sQdO + st * kBwdStageBytes;
         uint8_t* sdO = sQ + kBwdQBytes;
+        SMX_TRACE(0, g, 0);
         if (it + 1 < n_iter) issue_s(g + 1);
+        SMX_TRACE(0, g, 1);
         // dV += P^T dO
         mbar_wait(p_full, g & 1, 26);
+        SMX_TRACE(0, g, 2);
         if (it == 0 && tw > 0) mbar_wait(acc_empty, (tw - 1) & 1, 36);   // previous tile's dK / dV have been drained
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint64_t a0 = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
-          const uint64_t b0 = make_smem_desc_sw128(smem_u32(sdO), BQ * 128, 1024);
+          const uint64_t b0 = kdO_mn + st * kStageStep;
 #pragma unroll
           for (int k = 0; k < BQ / 16; ++k)
-            umma_f16<1>(tmem_dv, a0 + k * 2, b0 + k * ((16 * 128) >> 4), idesc_dv, (it > 0 || k > 0) ? 1u : 0u);
+            umma_f16<1>(tmem_dv, kP_km + k * 2, b0 + k * ((16 * 128) >> 4), idesc_dv, (it > 0 || k > 0) ? 1u : 0u);
           umma_commit<1>(pv_done);
         }
         __syncwarp();
+        SMX_TRACE(0, g, 3);
         if (it + 1 < n_iter) issue_dp(g + 1);
+        SMX_TRACE(0, g, 4);
         // dK += dS^T Q ;  dQ^T = K^T dS^T
         mbar_wait(ds_full, g & 1, 27);
+        SMX_TRACE(0, g, 5);
         if (g > 0) mbar_wait(dq_empty, (g - 1) & 1, 28);
+        SMX_TRACE(0, g, 6);
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint64_t a0 = make_smem_desc_sw128(smem_u32(sdS), 16, 1024);
-          const uint64_t b0 = make_smem_desc_sw128(smem_u32(sQ), BQ * 128, 1024);
+          const uint64_t b0 = kQ_mn + st * kStageStep;
 #pragma unroll
           for (int k = 0; k < BQ / 16; ++k)
-            umma_f16<1>(tmem_dk, a0 + k * 2, b0 + k * ((16 * 128) >> 4), idesc_dv, (it > 0 || k > 0) ? 1u : 0u);
-          const uint64_t ak = make_smem_desc_sw128(smem_u32(sK), BKV * 128, 1024);
-          const uint64_t bs = make_smem_desc_sw128(smem_u32(sdS), BKV * 128, 1024);
+            umma_f16<1>(tmem_dk, kdS_km + k * 2, b0 + k * ((16 * 128) >> 4), idesc_dv, (it > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k)
-            umma_f16<1>(tmem_dq, ak + k * ((16 * 128) >> 4), bs + k * ((16 * 128) >> 4), idesc_dq, k > 0 ? 1u : 0u);
+            umma_f16<1>(tmem_dq, kK_mn + k * ((16 * 128) >> 4), kdS_mn + k * ((16 * 128) >> 4), idesc_dq, k > 0 ? 1u : 0u);
           umma_commit<1>(dq_full);
           umma_commit<1>(dkq_done);
           umma_commit<1>(&qdo_empty[st]);
           if (it + 1 == n_iter) umma_commit<1>(all_done);
         }
         __syncwarp();
+        SMX_TRACE(0, g, 7);
       }
       g_base += n_iter;
       ++tw;
@@ -289,38 +325,23 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int i_begin = tile_begin(k0);
       const int nq_local = max(0, n_q_tiles - i_begin);
       const int n_iter = nq_local * group;
-      // lse (log2 units) and D*scale of the 64 query columns are staged in smem one iteration ahead: threads 0..127 keep
-      // the next iteration's value in a register across the current iteration, so the global-load latency is hidden.
-      auto load_stat = [&](int it_) -> float {
-        const int head_ = kv_head * group + it_ / nq_local, q0_ = (i_begin + it_ % nq_local) * BQ;
-        const int qi = q0_ + (tid & 63);
-        const long long off = ((long long)batch * p.H + head_) * p.S_q + qi;
-        float v;
-        if (tid < 64) {
-          v = (qi < p.S_q) ? p.lse[off] * 1.4426950408889634f : INFINITY;
-          if (!(v > -INFINITY)) v = INFINITY;
-        } else {
-          v = (qi < p.S_q) ? p.dsum[off] * p.scale : 0.f;
-        }
-        return v;
-      };
-      float stat_next = 0.f;
-      if (tid < 128 && n_iter > 0) {
-        // first iteration of this tile: nothing was prefetched yet
-        ((tid < 64 ? sLse : sDsum) + (g_base & 1) * 64)[tid & 63] = load_stat(0);
-      }
       for (int it = 0; it < n_iter; ++it) {
         const int g = g_base + it;
         const int q0 = (i_begin + it % nq_local) * BQ;
-        if (tid < 128 && it + 1 < n_iter) stat_next = load_stat(it + 1);
-        named_bar_sync(1, kBwdSoftmaxWarps * 32);
-        const float4* lse4 = reinterpret_cast<const float4*>(sLse + (g & 1) * 64 + col0);
-        const float4* dsum4 = reinterpret_cast<const float4*>(sDsum + (g & 1) * 64 + col0);
+        // per-column statistics ride on the same transaction barrier as Q / dO (bulk copies issued by the producer)
+        const int st = g % kBwdStages;
+        const float4* lse4 = reinterpret_cast<const float4*>(sLse + st * 64 + col0);
+        const float4* dsum4 = reinterpret_cast<const float4*>(sDsum + st * 64 + col0);
+        if (warp_idx == 2) SMX_TRACE(1, g, 0);
+        mbar_wait(&qdo_full[st], (g / kBwdStages) & 1, 37);
+        if (warp_idx == 2) SMX_TRACE(1, g, 1);
         mbar_wait(s_full, g & 1, 29);
+        if (warp_idx == 2) SMX_TRACE(1, g, 2);
         tcgen05_fence_after();
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_s + lane_addr + col0, r);
         tmem_ld_wait();
+        if (warp_idx == 2) SMX_TRACE(1, g, 3);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty);
@@ -341,7 +362,9 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             pr[i] = ok ? pr[i] : 0.f;
           }
         }
+        if (warp_idx == 2) SMX_TRACE(1, g, 4);
         if (g > 0) mbar_wait(pv_done, (g - 1) & 1, 30);     // dV(g-1) has finished reading the P^T tile
+        if (warp_idx == 2) SMX_TRACE(1, g, 5);
         {
           uint8_t* prow = sP + row_in_tile * 128;
 #pragma unroll
@@ -357,11 +380,14 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
+        if (warp_idx == 2) SMX_TRACE(1, g, 6);
         // dS^T = P^T o (dP^T - D) * scale
         mbar_wait(dp_full, g & 1, 31);
+        if (warp_idx == 2) SMX_TRACE(1, g, 7);
         tcgen05_fence_after();
         tmem_ld_32x32b_x32(tmem_dp + lane_addr + col0, r);
         tmem_ld_wait();
+        if (warp_idx == 2) SMX_TRACE(1, g, 8);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dp_empty);
@@ -373,7 +399,9 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           pr[4 * i4 + 2] *= fmaf(__uint_as_float(r[4 * i4 + 2]), p.scale, -dsm.z);
           pr[4 * i4 + 3] *= fmaf(__uint_as_float(r[4 * i4 + 3]), p.scale, -dsm.w);
         }
+        if (warp_idx == 2) SMX_TRACE(1, g, 9);
         if (g > 0) mbar_wait(dkq_done, (g - 1) & 1, 32);    // dK/dQ(g-1) have finished reading the dS^T tile
+        if (warp_idx == 2) SMX_TRACE(1, g, 10);
         {
           uint8_t* drow = sdS + row_in_tile * 128;
 #pragma unroll
@@ -389,7 +417,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(ds_full);
-        if (tid < 128 && it + 1 < n_iter) ((tid < 64 ? sLse : sDsum) + ((g + 1) & 1) * 64)[tid & 63] = stat_next;
+        if (warp_idx == 2) SMX_TRACE(1, g, 11);
       }
       // ---- dK epilogue (rows = keys; this warp writes head-dim columns [half*64, half*64+64))
       if (n_iter > 0) {
@@ -444,7 +472,9 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int it = 0; it < n_iter; ++it) {
         const int g = g_base + it;
         const int head = kv_head * group + it / nq_local, q0 = (i_begin + it % nq_local) * BQ;
+        if (quad == 2) SMX_TRACE(2, g, 0);
         mbar_wait(dq_full, g & 1, 34);
+        if (quad == 2) SMX_TRACE(2, g, 1);
         tcgen05_fence_after();
         uint32_t r[64];
         {
@@ -458,8 +488,10 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(dq_empty);
         // the previous tile's bulk reduce must have finished reading the staging buffer
+        if (quad == 2) SMX_TRACE(2, g, 2);
         if (tid == 0) tma_store_wait_read<0>();
         named_bar_sync(2, 128);
+        if (quad == 2) SMX_TRACE(2, g, 3);
 #pragma unroll
         for (int i = 0; i < 64; ++i) sDq[i * D + d_idx] = __uint_as_float(r[i]);
         fence_proxy_async_smem();
@@ -468,6 +500,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           bwd_tma_reduce_add_4d(&tmap_dq, sDq, 0, q0, head, batch);
           tma_store_commit();
         }
+        if (quad == 2) SMX_TRACE(2, g, 4);
       }
       // ---- dV epilogue (rows = keys)
       if (n_iter > 0) {
@@ -519,17 +552,25 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
-// D[b,h,s] = sum_d dO[b,s,h,d] * O[b,s,h,d]   (one warp per (b,s,h) row of 128)
+// Per-row statistics for the main kernel, one warp per (b, h, s) row incl. the padding rows s in [S, S_pad):
+//   dsum[b,h,s] = scale * sum_d dO[b,s,h,d] * O[b,s,h,d]      (0 in the padding)
+//   lse2[b,h,s] = lse[b,h,s] * log2(e)                         (+inf in the padding and for rows without keys)
 __global__ void fmha_bwd_dsum_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
-                                     float* __restrict__ dsum, int B, int S, int H, int D, long long o_sb, long long o_ss,
+                                     const float* __restrict__ lse, float* __restrict__ dsum, float* __restrict__ lse2,
+                                     int B, int S, int S_pad, int H, int D, float scale, long long o_sb, long long o_ss,
                                      long long o_sh, long long do_sb, long long do_ss, long long do_sh) {
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / 32;
   const int lane = threadIdx.x % 32;
-  const long long total = (long long)B * S * H;
+  const long long total = (long long)B * S_pad * H;
   if (warp >= total) return;
   const int h = warp % H;
-  const int s = (warp / H) % S;
-  const int b = warp / ((long long)H * S);
+  const int s = (warp / H) % S_pad;
+  const int b = warp / ((long long)H * S_pad);
+  const long long out = ((long long)b * H + h) * S_pad + s;
+  if (s >= S) {
+    if (lane == 0) { dsum[out] = 0.f; lse2[out] = INFINITY; }
+    return;
+  }
   const __nv_bfloat16* po = o + b * o_sb + s * o_ss + h * o_sh;
   const __nv_bfloat16* pd = d_o + b * do_sb + s * do_ss + h * do_sh;
   float acc = 0.f;
@@ -545,7 +586,11 @@ __global__ void fmha_bwd_dsum_kernel(const __nv_bfloat16* __restrict__ o, const 
     }
   }
   acc = warp_sum(acc);
-  if (lane == 0) dsum[((long long)b * H + h) * S + s] = acc;
+  if (lane == 0) {
+    dsum[out] = acc * scale;
+    const float l = lse[((long long)b * H + h) * S + s];
+    lse2[out] = (l > -INFINITY) ? l * 1.4426950408889634f : INFINITY;
+  }
 }
 
 // dq[b,s,h,:] = bf16(dq_accum[b,s,h,:])   (dq strided, accum contiguous [B,S,H,D])
@@ -588,12 +633,13 @@ inline int bwd_make_tmap_4d(CUtensorMap* out, CUtensorMapDataType dt, CUtensorMa
 
 extern "C" {
 
-// Workspace: dsum [B,H,S_q] fp32 and dq_accum [B,S_q,H,128] fp32 (both provided by the caller; dq_accum is zeroed here).
+// Workspace: stats [2, B, H, S_pad] fp32 (S_pad = ceil(S_q/64)*64: scaled row sums, then lse in log2 units) and
+// dq_accum [B,S_q,H,128] fp32, both provided by the caller; dq_accum is zeroed here.
 // All of q,k,v,o,do,dq,dk,dv are "bshd" views with element strides (last dim contiguous, 16B aligned).
 int smx_fmha_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse, void* dq,
                  void* dk, void* dv, float* dsum, float* dq_accum, int B, int S_q, int S_kv, int H, int H_kv, int d,
                  const long long* strides /* 8 x (sb, ss, sh): q k v o do dq dk dv */, float scale, int causal,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, long long* trace) {
   using namespace smx;
   if (d != kBwdD) return -31;
   if (H % H_kv) return -30;
@@ -601,6 +647,8 @@ int smx_fmha_bwd(const void* q, const void* k, const void* v, const void* o, con
   const long long* so = strides + 9; const long long* sdo = strides + 12; const long long* sdq = strides + 15;
   const long long* sdk = strides + 18; const long long* sdv = strides + 21;
   CUtensorMap tq, tk, tv, tdo, tdq;
+  const long long s_pad = (S_q + kBwdBQ - 1) / kBwdBQ * kBwdBQ;
+  float* lse2 = dsum + (long long)B * H * s_pad;
   const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const auto SW = CU_TENSOR_MAP_SWIZZLE_128B;
   int rc = bwd_make_tmap_4d(&tq, BF, SW, q, d, S_q, H, B, sq[1] * 2, sq[2] * 2, sq[0] * 2, 64, kBwdBQ);
@@ -617,15 +665,16 @@ int smx_fmha_bwd(const void* q, const void* k, const void* v, const void* o, con
   cudaError_t e = cudaMemsetAsync(dq_accum, 0, (size_t)B * S_q * H * d * sizeof(float), stream);
   if (e != cudaSuccess) return (int)e;
   {
-    const long long rows = (long long)B * S_q * H;
+    const long long rows = (long long)B * s_pad * H;
     const int threads = 256;
     const long long blocks = (rows * 32 + threads - 1) / threads;
     fmha_bwd_dsum_kernel<<<(unsigned)blocks, threads, 0, stream>>>(
-        (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, dsum, B, S_q, H, d, so[0], so[1], so[2], sdo[0], sdo[1], sdo[2]);
+        (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, lse, dsum, lse2, B, S_q, (int)s_pad, H, d, scale, so[0], so[1],
+        so[2], sdo[0], sdo[1], sdo[2]);
   }
   FmhaBwdParams p;
   p.B = B; p.S_q = S_q; p.S_kv = S_kv; p.H = H; p.H_kv = H_kv; p.scale = scale; p.causal = causal;
-  p.lse = lse; p.dsum = dsum; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
+  p.lse2 = lse2; p.dsum = dsum; p.s_pad = s_pad; p.trace = trace; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
   p.dk_sb = sdk[0]; p.dk_ss = sdk[1]; p.dk_sh = sdk[2]; p.dv_sb = sdv[0]; p.dv_ss = sdv[1]; p.dv_sh = sdv[2];
   static bool attr_set = false;
   if (!attr_set) {

@@ -138,6 +138,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // ============================ MMA issuer ============================
     constexpr uint32_t idesc_s = make_idesc(1, 1, 0, 0, BQ, BKV);   // Q (K-major) x K (K-major) -> S[128, 64]
     constexpr uint32_t idesc_o = make_idesc(1, 1, 0, 1, BQ, D_V);   // P (K-major) x V (MN-major) -> O[128, D_V]
+    // constant UMMA descriptors (+ stage * stride): the single issuing thread's latency is on the critical path
+    const uint64_t kQ_km = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+    const uint64_t kP_km = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
+    const uint64_t kK_km = make_smem_desc_sw128(smem_u32(sKV), 16, 1024);
+    const uint64_t kV_mn = make_smem_desc_sw128(smem_u32(sKV + Cfg::kKBytes), BKV * 128, 1024);
+    constexpr uint64_t kStageStep = Cfg::kStageBytes >> 4;
     mbar_wait(q_full, 0, 2);
     int stage = 0;
     uint32_t phase = 0;
@@ -146,13 +152,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (j > 0) mbar_wait(s_empty, (j - 1) & 1, 3);
       tcgen05_fence_after();
       if (elect_one()) {
-        uint8_t* sK = sKV + st * Cfg::kStageBytes;
+        const uint64_t b0 = kK_km + st * kStageStep;
 #pragma unroll
-        for (int k = 0; k < D_QK / 16; ++k) {
-          const uint64_t a = make_smem_desc_sw128(smem_u32(sQ + (k / 4) * (BQ * 128)), 16, 1024) + (k % 4) * 2;
-          const uint64_t b = make_smem_desc_sw128(smem_u32(sK + (k / 4) * (BKV * 128)), 16, 1024) + (k % 4) * 2;
-          umma_f16<1>(tmem_s, a, b, idesc_s, k > 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < D_QK / 16; ++k)
+          umma_f16<1>(tmem_s, kQ_km + ((k / 4) * ((BQ * 128) >> 4) + (k % 4) * 2), b0 + ((k / 4) * ((BKV * 128) >> 4) + (k % 4) * 2),
+                      idesc_s, k > 0 ? 1u : 0u);
         umma_commit<1>(s_full);
       }
       __syncwarp();
@@ -174,12 +178,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_wait(p_full, j & 1, 6);
       tcgen05_fence_after();
       if (elect_one()) {
-        uint8_t* sV = sKV + stage * Cfg::kStageBytes + Cfg::kKBytes;
-        const uint64_t a0 = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
-        const uint64_t b0 = make_smem_desc_sw128(smem_u32(sV), BKV * 128, 1024);
+        const uint64_t b0 = kV_mn + stage * kStageStep;
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k)
-          umma_f16<1>(tmem_o, a0 + k * 2, b0 + k * ((16 * 128) >> 4), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          umma_f16<1>(tmem_o, kP_km + k * 2, b0 + k * ((16 * 128) >> 4), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit<1>(pv_done);
         umma_commit<1>(&kv_empty[stage]);
       }

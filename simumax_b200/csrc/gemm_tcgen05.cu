@@ -106,21 +106,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     m_blk = first_m + in_group % gsz;
     n_blk = in_group / gsz;
   };
+  // Work list = full tiles for the rounds that fill every CTA, then the tiles of the last partial round cut into
+  // `tail_split` column slices (64-column granularity) so that the tail occupies (almost) all CTAs for a fraction of
+  // a round instead of a few CTAs for a whole one.  No cross-CTA reduction is needed: slices own disjoint columns.
+  const int full_tiles = (num_tiles / (int)gridDim.x) * (int)gridDim.x;
+  const int tail_tiles = num_tiles - full_tiles;
+  int tail_split = 1;
+  if (tail_tiles > 0) {
+    if (BLOCK_N >= 256 && tail_tiles * 4 <= (int)gridDim.x) tail_split = 4;
+    else if (BLOCK_N >= 128 && tail_tiles * 2 <= (int)gridDim.x) tail_split = 2;
+  }
+  const int num_work = full_tiles + tail_tiles * tail_split;
+  auto work_coords = [&](int w, int& g, int& m0, int& n0, int& n_eff) {
+    int t = w, part = 0;
+    n_eff = BLOCK_N;
+    if (w >= full_tiles) {
+      const int j = w - full_tiles;
+      t = full_tiles + j / tail_split;
+      part = j % tail_split;
+      n_eff = BLOCK_N / tail_split;
+    }
+    int m_blk, n_blk;
+    tile_coords(t, g, m_blk, n_blk);
+    m0 = m_blk * kBlockM;
+    n0 = n_blk * BLOCK_N + part * n_eff;
+  };
 
   if (warp_idx == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int g, m_blk, n_blk;
-        tile_coords(t, g, m_blk, n_blk);
-        const int m0 = m_blk * kBlockM, n0 = n_blk * BLOCK_N;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        int g, m0, n0, n_eff;
+        work_coords(w, g, m0, n0, n_eff);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kABytes + n_eff * kRowBytes);
           const int k0 = kb * BLOCK_K;
           if constexpr (!A_MN) {
             tma_load_3d(&tmap_a, &full_bar[stage], sa, k0, m0, g);
@@ -130,10 +154,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               tma_load_3d(&tmap_a, &full_bar[stage], sa + c * kMnChunkBytes, m0 + c * 64, k0, g);
           }
           if constexpr (!B_MN) {
-            tma_load_3d(&tmap_b, &full_bar[stage], sb, k0, n0, g);
+            // K-major B: box = 64 rows, so a work item loads exactly the n_eff rows it multiplies
+            for (int c = 0; c < n_eff / 64; ++c)
+              tma_load_3d(&tmap_b, &full_bar[stage], sb + c * (64 * kRowBytes), k0, n0 + c * 64, g);
           } else {
-#pragma unroll
-            for (int c = 0; c < BLOCK_N / 64; ++c)
+            for (int c = 0; c < n_eff / 64; ++c)
               tma_load_3d(&tmap_b, &full_bar[stage], sb + c * kMnChunkBytes, n0 + c * 64, k0, g);
           }
           if (++stage == kStages) {
@@ -146,7 +171,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp_idx == 1) {
     // ============================ MMA issuer ============================
     constexpr uint32_t kFmt = (ELEM_BYTES == 2) ? 1u /*bf16*/ : 0u /*e4m3*/;
-    constexpr uint32_t idesc = make_idesc(kFmt, kFmt, A_MN ? 1u : 0u, B_MN ? 1u : 0u, kBlockM, BLOCK_N);
     // descriptor start-address advance (in 16 B units) per UMMA_K step
     constexpr uint32_t a_kstep = A_MN ? (UMMA_K * kRowBytes) >> 4 : (UMMA_K * ELEM_BYTES) >> 4;
     constexpr uint32_t b_kstep = B_MN ? (UMMA_K * kRowBytes) >> 4 : (UMMA_K * ELEM_BYTES) >> 4;
@@ -154,7 +178,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int n_eff = (w >= full_tiles) ? BLOCK_N / tail_split : BLOCK_N;
+      const uint32_t idesc = make_idesc(kFmt, kFmt, A_MN ? 1u : 0u, B_MN ? 1u : 0u, kBlockM, n_eff);
       mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + as * BLOCK_N;
@@ -191,16 +217,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const bool vec_ok = OUT_F32 ? (p.ldc % 4 == 0) : (p.ldc % 8 == 0);
     int as = 0;
     uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      int g, m_blk, n_blk;
-      tile_coords(t, g, m_blk, n_blk);
-      const int row = m_blk * kBlockM + q * 32 + lane;
-      const int n0 = n_blk * BLOCK_N;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      int g, m0, n0, n_eff;
+      work_coords(w, g, m0, n0, n_eff);
+      const int row = m0 + q * 32 + lane;
       mbar_wait(&tmem_full_bar[as], aphase);
       tcgen05_fence_after();
       OutT* c_row = c_base + (long long)g * p.c_batch_stride + (long long)row * p.ldc;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = 0; c < n_eff / 32; ++c) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BLOCK_N + c * 32;
         tmem_ld_32x32b_x32(taddr, r);
@@ -320,9 +345,15 @@ int pick_block_n(int G, int M, int N, int num_sms) {
   for (int i = 0; i < 3; ++i) {
     int bn = cands[i];
     long long tiles = (long long)G * m_tiles * ((N + bn - 1) / bn);
-    long long waves = (tiles + num_sms - 1) / num_sms;
+    long long ctas = tiles < num_sms ? tiles : num_sms;
+    long long full = tiles / ctas, tail = tiles - full * ctas;
+    int split = 1;                                   // mirrors the kernel's tail slicing
+    if (tail > 0) {
+      if (bn >= 256 && tail * 4 <= ctas) split = 4;
+      else if (bn >= 128 && tail * 2 <= ctas) split = 2;
+    }
     // per-tile cost ~ bn columns of MMA + a fixed prologue/epilogue-exposure term
-    long long cost = waves * (bn + 24);
+    long long cost = full * (bn + 24) + (tail > 0 ? bn / split + 24 : 0);
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
       best = bn;
@@ -352,7 +383,7 @@ int smx_gemm(const void* A, const void* B, void* C, int G, int M, int N, int K, 
   if (!a_mn) rc = smx::make_tmap_3d(&ta, dt, A, K, M, G, lda * eb, a_bs * eb, block_k, smx::kBlockM);
   else       rc = smx::make_tmap_3d(&ta, dt, A, M, K, G, lda * eb, a_bs * eb, 64, block_k);
   if (rc) return rc;
-  if (!b_mn) rc = smx::make_tmap_3d(&tb, dt, B, K, N, G, ldb * eb, b_bs * eb, block_k, block_n);
+  if (!b_mn) rc = smx::make_tmap_3d(&tb, dt, B, K, N, G, ldb * eb, b_bs * eb, block_k, 64);   // loaded in 64-row slices
   else       rc = smx::make_tmap_3d(&tb, dt, B, N, K, G, ldb * eb, b_bs * eb, 64, block_k);
   if (rc) return rc;
   smx::GemmParams p;

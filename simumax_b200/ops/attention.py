@@ -75,7 +75,7 @@ def _bwd_fn():
     if _bwd is None:
         f = _lib.lib().smx_fmha_bwd
         f.restype = _c.c_int
-        f.argtypes = [_c.c_void_p] * 11 + [_c.c_int] * 6 + [_c.c_void_p, _c.c_float, _c.c_int, _c.c_void_p]
+        f.argtypes = [_c.c_void_p] * 11 + [_c.c_int] * 6 + [_c.c_void_p, _c.c_float, _c.c_int, _c.c_void_p, _c.c_void_p]
         _bwd = f
     return _bwd
 
@@ -88,7 +88,7 @@ def _bwd_workspace(device, B, S_q, H, D):
     key = (device, B, S_q, H, D)
     ws = _bwd_ws.get(key)
     if ws is None:
-        ws = (torch.empty(B, H, S_q, device=device, dtype=torch.float32),
+        ws = (torch.empty(2, B, H, (S_q + 63) // 64 * 64, device=device, dtype=torch.float32),
               torch.empty(B, S_q, H, D, device=device, dtype=torch.float32))
         _bwd_ws.clear()
         _bwd_ws[key] = ws
@@ -97,7 +97,7 @@ def _bwd_workspace(device, B, S_q, H, D):
 
 def fmha_bwd(d_o: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, lse: torch.Tensor,
              dq: Optional[torch.Tensor] = None, dk: Optional[torch.Tensor] = None, dv: Optional[torch.Tensor] = None,
-             causal: bool = True, scale: Optional[float] = None):
+             causal: bool = True, scale: Optional[float] = None, trace: Optional[torch.Tensor] = None):
     """Backward of :func:`fmha_fwd` (csrc/fmha_bwd.cu; head dim 128). All tensors are bshd views; dq/dk/dv may be
     slices of a packed d_qkv buffer. Returns (dq, dk, dv)."""
     B, S_q, H, D = q.shape
@@ -118,7 +118,7 @@ def fmha_bwd(d_o: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tenso
     rc = _bwd_fn()(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(), dq.data_ptr(),
                    dk.data_ptr(), dv.data_ptr(), dsum.data_ptr(), acc.data_ptr(), B, S_q, S_kv, H, H_kv, D,
                    _c.cast(strides, _c.c_void_p), float(scale), 1 if causal else 0,
-                   torch.cuda.current_stream(q.device).cuda_stream)
+                   torch.cuda.current_stream(q.device).cuda_stream, trace.data_ptr() if trace is not None else None)
     _lib.check(rc, f"fmha_bwd B{B} S{S_q}x{S_kv} H{H}/{H_kv} d{D}")
     _lib.count_launch(3)
     return dq, dk, dv
