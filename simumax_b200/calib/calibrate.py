@@ -31,11 +31,27 @@ def _nominal_tflops(template: dict) -> Dict[str, float]:
     return {op: v["tflops"] for op, v in template["accelerator"]["op"].items()}
 
 
+def foreign_gpu_processes(device_index: int = 0) -> List[str]:
+    """PIDs of other processes holding a context on the GPU we are about to time (calibration on a shared GPU is
+    meaningless; reference test_ce_permute_efficiency.py:62-92 refuses to run in that case)."""
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-compute-apps=pid,used_memory", "--format=csv,noheader", "-i", str(device_index)],
+                             capture_output=True, text=True, timeout=20).stdout
+    except Exception:
+        return []
+    mine = str(os.getpid())
+    return [l.strip() for l in out.splitlines() if l.strip() and l.split(",")[0].strip() != mine]
+
+
 def run_ops(out_path: str, supplement: Optional[str] = None, limit_per_op: Optional[int] = None,
-            workloads=None, log=print) -> dict:
+            workloads=None, log=print, allow_shared_gpu: bool = False) -> dict:
     """GPU part: returns {"ops": {op: {key: {...}}}, "bandwidth": {...}, "meta": {...}}."""
     import torch
     from . import measure
+    others = foreign_gpu_processes(torch.cuda.current_device())
+    if others and not allow_shared_gpu:
+        raise RuntimeError(f"GPU is in use by other processes {others}; calibrate on an idle GPU (or pass --allow-shared-gpu)")
     template = b200_template()
     requests = collect_requests(workloads or DEFAULT_WORKLOADS)
     have = {}
@@ -109,6 +125,7 @@ def main(argv=None):
     o.add_argument("--out", default="gpurun_out/calib_ops.json")
     o.add_argument("--supplement", default=None)
     o.add_argument("--limit-per-op", type=int, default=None)
+    o.add_argument("--allow-shared-gpu", action="store_true")
     m = sub.add_parser("merge", help="write the system config (no GPU needed)")
     m.add_argument("--ops", default=None)
     m.add_argument("--coll", nargs="*", default=[])
@@ -120,7 +137,7 @@ def main(argv=None):
     s = sub.add_parser("shapes", help="list the shapes the default workloads need (CPU)")
     a = ap.parse_args(argv)
     if a.cmd == "ops":
-        run_ops(a.out, a.supplement, a.limit_per_op)
+        run_ops(a.out, a.supplement, a.limit_per_op, allow_shared_gpu=a.allow_shared_gpu)
     elif a.cmd == "merge":
         sysj = merge(a.ops, a.coll, a.out, a.base, a.name, a.coll_impl, a.measured_peaks)
         print(f"wrote {a.out}: " + ", ".join(f"{op}:{len(v.get('accurate_efficient_factor') or {})}" for op, v in sysj["accelerator"]["op"].items()))

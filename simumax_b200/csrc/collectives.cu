@@ -218,8 +218,10 @@ SMX_DEVICE void reduce_granules(const PeerPtrs& pp, int use_nvls, long long src_
 }
 
 // reduce_scatter (sum; bf16 with fp32 accumulation, or fp32): out <- sum_r in_r[rank * shard .. (rank+1) * shard)
+// 256 threads: (256 x <=128 regs) fits next to a resident 192-thread GEMM CTA, so an overlapped reduce-scatter does not
+// evict compute CTAs from their SMs
 template <bool F32, int U>
-__global__ void __launch_bounds__(512) reduce_scatter_kernel(PeerPtrs pp, long long in_off, long long out_off,
+__global__ void __launch_bounds__(256) reduce_scatter_kernel(PeerPtrs pp, long long in_off, long long out_off,
                                                             long long shard_bytes, uint32_t epoch, int use_nvls) {
   cta_barrier_all_ranks(pp, epoch);
   char* dst = reinterpret_cast<char*>(pp.data[pp.rank]) + out_off;
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(512) reduce_scatter_kernel(PeerPtrs pp, long l
 
 // all_reduce (sum), result written to out on every rank: each rank reduces its slice and broadcasts it
 template <bool F32, int U>
-__global__ void __launch_bounds__(512) all_reduce_kernel(PeerPtrs pp, long long in_off, long long out_off,
+__global__ void __launch_bounds__(256) all_reduce_kernel(PeerPtrs pp, long long in_off, long long out_off,
                                                         long long total_bytes, uint32_t epoch, int use_nvls) {
   cta_barrier_all_ranks(pp, epoch);
   const long long n16_total = total_bytes / 16;
@@ -311,7 +313,7 @@ int smx_reduce_scatter(void* const* data_ptrs, void* const* flag_ptrs, void* mc,
   if (world > smx::kMaxRanks || shard_bytes % 16) return -40;
   auto pp = make_pp(data_ptrs, flag_ptrs, mc, rank, world);
   auto st = reinterpret_cast<cudaStream_t>(stream);
-#define SMX_RS(F, U) smx::reduce_scatter_kernel<F, U><<<ctas, 512, 0, st>>>(pp, in_off, out_off, shard_bytes, epoch, use_nvls)
+#define SMX_RS(F, U) smx::reduce_scatter_kernel<F, U><<<ctas, 256, 0, st>>>(pp, in_off, out_off, shard_bytes, epoch, use_nvls)
   // loads in flight per thread = U (NVLS) or U * world (P2P): deeper unroll for small groups
   if (world <= 2) { if (f32) SMX_RS(true, 8); else SMX_RS(false, 8); }
   else if (world <= 4) { if (f32) SMX_RS(true, 4); else SMX_RS(false, 4); }
@@ -325,7 +327,7 @@ int smx_all_reduce(void* const* data_ptrs, void* const* flag_ptrs, void* mc, int
   if (world > smx::kMaxRanks || total_bytes % 16) return -40;
   auto pp = make_pp(data_ptrs, flag_ptrs, mc, rank, world);
   auto st = reinterpret_cast<cudaStream_t>(stream);
-#define SMX_AR(F, U) smx::all_reduce_kernel<F, U><<<ctas, 512, 0, st>>>(pp, in_off, out_off, total_bytes, epoch, use_nvls)
+#define SMX_AR(F, U) smx::all_reduce_kernel<F, U><<<ctas, 256, 0, st>>>(pp, in_off, out_off, total_bytes, epoch, use_nvls)
   if (world <= 2) { if (f32) SMX_AR(true, 8); else SMX_AR(false, 8); }
   else if (world <= 4) { if (f32) SMX_AR(true, 4); else SMX_AR(false, 4); }
   else { if (f32) SMX_AR(true, 2); else SMX_AR(false, 2); }

@@ -111,20 +111,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // a round instead of a few CTAs for a whole one.  No cross-CTA reduction is needed: slices own disjoint columns.
   const int full_tiles = (num_tiles / (int)gridDim.x) * (int)gridDim.x;
   const int tail_tiles = num_tiles - full_tiles;
-  int tail_split = 1;
+  int split_log2 = 0;       // tail tiles are cut into 1, 2 or 4 column slices
   if (tail_tiles > 0) {
-    if (BLOCK_N >= 256 && tail_tiles * 4 <= (int)gridDim.x) tail_split = 4;
-    else if (BLOCK_N >= 128 && tail_tiles * 2 <= (int)gridDim.x) tail_split = 2;
+    if (BLOCK_N >= 256 && tail_tiles * 4 <= (int)gridDim.x) split_log2 = 2;
+    else if (BLOCK_N >= 128 && tail_tiles * 2 <= (int)gridDim.x) split_log2 = 1;
   }
+  const int tail_split = 1 << split_log2;
   const int num_work = full_tiles + tail_tiles * tail_split;
   auto work_coords = [&](int w, int& g, int& m0, int& n0, int& n_eff) {
     int t = w, part = 0;
     n_eff = BLOCK_N;
     if (w >= full_tiles) {
       const int j = w - full_tiles;
-      t = full_tiles + j / tail_split;
-      part = j % tail_split;
-      n_eff = BLOCK_N / tail_split;
+      t = full_tiles + (j >> split_log2);
+      part = j & (tail_split - 1);
+      n_eff = BLOCK_N >> split_log2;
     }
     int m_blk, n_blk;
     tile_coords(t, g, m_blk, n_blk);
@@ -155,11 +156,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           if constexpr (!B_MN) {
             // K-major B: box = 64 rows, so a work item loads exactly the n_eff rows it multiplies
-            for (int c = 0; c < n_eff / 64; ++c)
-              tma_load_3d(&tmap_b, &full_bar[stage], sb + c * (64 * kRowBytes), k0, n0 + c * 64, g);
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 64; ++c)
+              if (c * 64 < n_eff) tma_load_3d(&tmap_b, &full_bar[stage], sb + c * (64 * kRowBytes), k0, n0 + c * 64, g);
           } else {
-            for (int c = 0; c < n_eff / 64; ++c)
-              tma_load_3d(&tmap_b, &full_bar[stage], sb + c * kMnChunkBytes, n0 + c * 64, k0, g);
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 64; ++c)
+              if (c * 64 < n_eff) tma_load_3d(&tmap_b, &full_bar[stage], sb + c * kMnChunkBytes, n0 + c * 64, k0, g);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -179,7 +182,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int as = 0;
     uint32_t aphase = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-      const int n_eff = (w >= full_tiles) ? BLOCK_N / tail_split : BLOCK_N;
+      const int n_eff = (w >= full_tiles) ? (BLOCK_N >> split_log2) : BLOCK_N;
       const uint32_t idesc = make_idesc(kFmt, kFmt, A_MN ? 1u : 0u, B_MN ? 1u : 0u, kBlockM, n_eff);
       mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
       tcgen05_fence_after();

@@ -62,6 +62,11 @@ class _Flat:
         assert self.buf.numel() == numel and self.buf.dtype == dtype
         self.off = 0
 
+    def align(self, multiple: int) -> int:
+        """Skip to the next multiple (bucket boundary); returns the new offset."""
+        self.off = (self.off + multiple - 1) // multiple * multiple
+        return self.off
+
     def take(self, *shape):
         n = 1
         for s in shape:
@@ -85,9 +90,19 @@ class LlamaTrainer:
         self.lr, self.wd, self.betas, self.max_norm = lr, weight_decay, betas, max_grad_norm
         self.step_count = 0
         d, dev = dims, self.device
-        P = d.total_numel()
-        pad = (-P) % (self.world * 1024)
-        self.P, self.Ppad = P, P + pad
+        # ZeRO-1 buckets: embedding | one per layer | final norm + LM head.  Every bucket is padded to a multiple of
+        # world * 1024 elements so each rank owns an equal, 16-byte aligned slice of every bucket; a bucket's grads can
+        # be reduce-scattered as soon as its layer's backward is done (overlap with the rest of the backward pass).
+        self._balign = self.world * 1024
+        up = lambda n: (n + self._balign - 1) // self._balign * self._balign
+        sizes = [up(d.vocab * d.hidden)] + [up(d.layer_numel())] * d.layers + [up(d.hidden + d.vocab * d.hidden)]
+        self.buckets = []                      # (flat offset, padded size)
+        off = 0
+        for sz in sizes:
+            self.buckets.append((off, sz))
+            off += sz
+        self.P, self.Ppad = d.total_numel(), off
+        self.shard_off = [b_lo // self.world for b_lo, _ in self.buckets]      # offsets inside the local shard arrays
         # ---- parameters (bf16) and fp32 main grads, identical layouts.  With data parallelism both live in one
         # symmetric (peer-mapped) allocation so the ZeRO-1 reduce-scatter / all-gather run as our own NVLink kernels.
         self.shard = self.Ppad // self.world
@@ -120,9 +135,8 @@ class LlamaTrainer:
                 t.fill_(1.0)
         self.w["final_norm"].fill_(1.0)
         self.grads.buf.zero_()
-        # ---- ZeRO-1 optimizer shard
-        lo = self.rank * self.shard
-        self.master = self.params.buf[lo:lo + self.shard].float()
+        # ---- ZeRO-1 optimizer shard = concatenation of this rank's slice of every bucket
+        self.master = torch.cat([self._my_slice(self.params.buf, b) for b in range(len(self.buckets))]).float()
         self.m = torch.zeros(self.shard, dtype=torch.float32, device=dev)
         self.v = torch.zeros(self.shard, dtype=torch.float32, device=dev)
         if self.ws is not None:
@@ -160,6 +174,19 @@ class LlamaTrainer:
         self.loss_acc = torch.zeros(1, dtype=torch.float32, device=dev)
         self.attention_bwd = self._pick_attention_bwd(attention_bwd)
         self.debug_hook = None       # callable(layer_index, trainer) invoked after each layer's backward
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.world > 1 else None
+        self._ag_events = [None] * len(self.buckets)      # params of bucket b are valid on the main stream after this
+        self._rs_launched = [False] * len(self.buckets)
+        self.overlap = self.world > 1
+
+    def _my_slice(self, flat_buf: torch.Tensor, b: int) -> torch.Tensor:
+        lo, sz = self.buckets[b]
+        per = sz // self.world
+        return flat_buf[lo + self.rank * per: lo + (self.rank + 1) * per]
+
+    def _shard_slice(self, arr: torch.Tensor, b: int) -> torch.Tensor:
+        per = self.buckets[b][1] // self.world
+        return arr[self.shard_off[b]: self.shard_off[b] + per]
 
     # ------------------------------------------------------------------------------------------
     def _carve(self, flat: _Flat):
@@ -167,12 +194,14 @@ class LlamaTrainer:
         H, F = d.hidden, d.ffn
         out = {"embed": flat.take(d.vocab, H), "ln1": [], "wqkv": [], "wo": [], "ln2": [], "wfc1": [], "wfc2": []}
         for _ in range(d.layers):
+            flat.align(self._balign)
             out["ln1"].append(flat.take(H))
             out["wqkv"].append(flat.take(d.qkv_out, H))
             out["wo"].append(flat.take(H, d.heads * d.head_dim))
             out["ln2"].append(flat.take(H))
             out["wfc1"].append(flat.take(2 * F, H))
             out["wfc2"].append(flat.take(H, F))
+        flat.align(self._balign)
         out["final_norm"] = flat.take(H)
         out["lm_head"] = flat.take(d.vocab, H)
         return out
@@ -211,8 +240,10 @@ class LlamaTrainer:
     def forward(self, tokens: torch.Tensor, targets: torch.Tensor, loss_scale: float) -> torch.Tensor:
         d, a, w = self.d, self.act, self.w
         L = d.layers
+        self._wait_params(0)
         torch.index_select(w["embed"], 0, tokens, out=a["x"][0])
         for i in range(L):
+            self._wait_params(1 + i)
             x = a["x"][i]
             E.rmsnorm_fwd(x, w["ln1"][i], d.eps, out=a["h1"][i], rstd=a["rstd1"][i])
             gemm(a["h1"][i], w["wqkv"][i], "TN", out=a["qkv"][i])
@@ -227,18 +258,23 @@ class LlamaTrainer:
             E.swiglu_fwd(a["u"][i], out=a["g"][i])
             gemm(a["g"][i], w["wfc2"][i], "TN", out=self.tmp_h)
             E.add(a["x2"][i], self.tmp_h, out=a["x"][i + 1])
+        self._wait_params(L + 1)
         E.rmsnorm_fwd(a["x"][L], w["final_norm"], d.eps, out=a["xf"], rstd=a["rstdf"])
         gemm(a["xf"], w["lm_head"], "TN", out=self.logits)
         loss_rows = E.cross_entropy_(self.logits, targets, grad_scale=loss_scale)      # logits now hold dlogits
         return loss_rows
 
-    def backward(self, tokens: torch.Tensor) -> None:
+    def backward(self, tokens: torch.Tensor, last_microbatch: bool = False) -> None:
+        """``last_microbatch``: the gradients are final after this pass, so each bucket's reduce-scatter is launched on
+        the communication stream the moment its layer is done."""
         d, a, w, g = self.d, self.act, self.w, self.g
         L = d.layers
+        rs = self._launch_rs if (last_microbatch and self.overlap) else (lambda b: None)
         dl = self.logits
         gemm(dl, a["xf"], "NT", out=g["lm_head"], accumulate=True)
         gemm(dl, w["lm_head"], "NN", out=self.tmp_h)
         E.rmsnorm_bwd(a["x"][L], w["final_norm"], self.tmp_h, a["rstdf"], g["final_norm"], dx=self.dx)
+        rs(L + 1)
         for i in reversed(range(L)):
             dx3 = self.dx
             # MLP
@@ -258,7 +294,9 @@ class LlamaTrainer:
             E.rmsnorm_bwd(a["x"][i], w["ln1"][i], self.tmp_h, a["rstd1"][i], g["ln1"][i], dx=dx3, accumulate_dx=True)
             if self.debug_hook is not None:
                 self.debug_hook(i, self)
+            rs(1 + i)
         g["embed"].index_add_(0, tokens, self.dx.float())
+        rs(0)
 
     def _attention_backward(self, i: int) -> None:
         d, a = self.d, self.act
@@ -280,18 +318,41 @@ class LlamaTrainer:
             dq.copy_(qa.grad.permute(0, 2, 1, 3)); dk.copy_(ka.grad.permute(0, 2, 1, 3)); dv.copy_(va.grad.permute(0, 2, 1, 3))
 
     # ------------------------------------------------------------------------------------------
+    def _wait_params(self, b: int) -> None:
+        ev = self._ag_events[b]
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def _launch_rs(self, b: int) -> None:
+        """Reduce-scatter bucket ``b`` (fp32 sum) into this rank's grad shard on the communication stream, then clear it."""
+        if self.world == 1 or self._rs_launched[b]:
+            return
+        self._rs_launched[b] = True
+        lo, sz = self.buckets[b]
+        per = sz // self.world
+        self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.comm_stream):
+            if self.ws is not None:
+                # pull-reduce my slice of every peer's main grads over NVLink (multimem.ld_reduce when NVLS is up)
+                self.ws.reduce_scatter(per * 4, in_off=self._off_g + lo * 4, out_off=self._off_gs + self.shard_off[b] * 4,
+                                       dtype=torch.float32, ctas=64)
+            else:
+                dist.reduce_scatter_tensor(self._shard_slice(self.grad_shard, b), self.grads.buf[lo:lo + sz],
+                                           op=dist.ReduceOp.SUM, group=self.group)
+            self.grads.buf[lo:lo + sz].zero_()
+
     def optimizer_step(self) -> None:
-        """ZeRO-1: reduce-scatter fp32 main grads, clip by global norm, fused AdamW on the local shard, all-gather
-        the updated bf16 params."""
+        """ZeRO-1: (bucketed, overlapped) reduce-scatter of the fp32 main grads, clip by global norm, fused AdamW on the
+        local shard, bucketed all-gather of the updated bf16 params that the next forward waits on layer by layer."""
         self.step_count += 1
         b1, b2 = self.betas
-        lo = self.rank * self.shard
-        if self.world > 1 and self.ws is not None:
-            # pull-reduce my slice of every peer's fp32 main grads over NVLink (multimem.ld_reduce when NVLS is up)
-            self.ws.reduce_scatter(self.shard * 4, in_off=self._off_g, out_off=self._off_gs, dtype=torch.float32, ctas=64)
-            gsh = self.grad_shard
-        elif self.world > 1:
-            dist.reduce_scatter_tensor(self.grad_shard, self.grads.buf, op=dist.ReduceOp.SUM, group=self.group)
+        main = torch.cuda.current_stream(self.device)
+        nb = len(self.buckets)
+        if self.world > 1:
+            for b in reversed(range(nb)):
+                self._launch_rs(b)                       # whatever the backward pass did not launch already
+            main.wait_stream(self.comm_stream)
+            self._rs_launched = [False] * nb
             gsh = self.grad_shard
         else:
             gsh = self.grads.buf
@@ -303,25 +364,44 @@ class LlamaTrainer:
         elif self.world > 1:
             dist.all_reduce(self.sqnorm, group=self.group)
         # grads hold the SUM over ranks of per-rank means -> prescale by 1/world inside the fused optimizer kernel
-        E.adamw_(self.master, self.m, self.v, gsh, self.params.buf[lo:lo + self.shard], self.lr, b1, b2, 1e-8, self.wd,
-                 self.step_count, sqnorm_t=self.sqnorm_out, max_norm=self.max_norm, grad_prescale=1.0 / self.world,
-                 zero_grad=(self.world == 1))
-        if self.world > 1:
-            if self.ws is not None:
-                # push my updated bf16 shard into every peer's parameter buffer (multimem.st when NVLS is up)
-                self.ws.all_gather(self.shard * 2, in_off=self._off_p + lo * 2, out_off=self._off_p, ctas=64)
-            else:
-                dist.all_gather_into_tensor(self.params.buf, self.params.buf[lo:lo + self.shard], group=self.group)
-            self.grads.buf.zero_()
+        if self.world == 1:
+            E.adamw_(self.master, self.m, self.v, gsh, self.params.buf, self.lr, b1, b2, 1e-8, self.wd, self.step_count,
+                     sqnorm_t=self.sqnorm_out, max_norm=self.max_norm, zero_grad=True)
+            return
+        for b in range(nb):                              # forward order: the first layers' params are gathered first
+            lo, sz = self.buckets[b]
+            per = sz // self.world
+            E.adamw_(self._shard_slice(self.master, b), self._shard_slice(self.m, b), self._shard_slice(self.v, b),
+                     self._shard_slice(gsh, b), self._my_slice(self.params.buf, b), self.lr, b1, b2, 1e-8, self.wd,
+                     self.step_count, sqnorm_t=self.sqnorm_out, max_norm=self.max_norm, grad_prescale=1.0 / self.world,
+                     zero_grad=False)
+            self.comm_stream.wait_stream(main)
+            with torch.cuda.stream(self.comm_stream):
+                if self.ws is not None:
+                    # push my updated bf16 slice into every peer's parameter buffer (multimem.st when NVLS is up)
+                    self.ws.all_gather(per * 2, in_off=self._off_p + (lo + self.rank * per) * 2, out_off=self._off_p + lo * 2,
+                                       ctas=32)
+                else:
+                    dist.all_gather_into_tensor(self.params.buf[lo:lo + sz], self._my_slice(self.params.buf, b),
+                                                group=self.group)
+                ev = torch.cuda.Event()
+                ev.record(self.comm_stream)
+                self._ag_events[b] = ev
+
+    def synchronize(self) -> None:
+        """Wait for outstanding parameter all-gathers (call before reading ``params`` from the host)."""
+        if self.comm_stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+        torch.cuda.synchronize(self.device)
 
     def run_microbatches(self, device_batches: List[Tuple[torch.Tensor, torch.Tensor]]) -> torch.Tensor:
         n = len(device_batches)
         self.loss_acc.zero_()
         scale = 1.0 / (n * self.T)
-        for tok, tgt in device_batches:
+        for i, (tok, tgt) in enumerate(device_batches):
             rows = self.forward(tok, tgt, loss_scale=scale)
             self.loss_acc += rows.sum() * scale
-            self.backward(tok)
+            self.backward(tok, last_microbatch=(i == n - 1))
         self.optimizer_step()
         return self.loss_acc
 
@@ -330,11 +410,11 @@ class LlamaTrainer:
         n = len(host_batches)
         self.loss_acc.zero_()
         scale = 1.0 / (n * self.T)
-        for tok_h, tgt_h in host_batches:
+        for i, (tok_h, tgt_h) in enumerate(host_batches):
             self.tok_dev.copy_(tok_h.view(-1), non_blocking=True)
             self.tgt_dev.copy_(tgt_h.view(-1), non_blocking=True)
             rows = self.forward(self.tok_dev, self.tgt_dev, loss_scale=scale)
             self.loss_acc += rows.sum() * scale
-            self.backward(self.tok_dev)
+            self.backward(self.tok_dev, last_microbatch=(i == n - 1))
         self.optimizer_step()
         return float(self.loss_acc.item())
