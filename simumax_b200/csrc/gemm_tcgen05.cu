@@ -355,8 +355,9 @@ int pick_block_n(int G, int M, int N, int num_sms) {
       if (bn >= 256 && tail * 4 <= ctas) split = 4;
       else if (bn >= 128 && tail * 2 <= ctas) split = 2;
     }
-    // per-tile cost ~ bn columns of MMA + a fixed prologue/epilogue-exposure term
-    long long cost = full * (bn + 24) + (tail > 0 ? bn / split + 24 : 0);
+    // per-tile cost follows the shared-memory roofline of an SS MMA: (A bytes + B bytes) per k-step ~ 128 + bn,
+    // plus a fixed prologue / epilogue-exposure term
+    long long cost = full * (128 + bn + 16) + (tail > 0 ? 128 + bn / split + 16 : 0);
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
       best = bn;
