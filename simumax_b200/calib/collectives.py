@@ -97,7 +97,7 @@ def _timed(fn, iters, dist, torch, warm=3):
     return float(t)
 
 
-def sweep(sizes: Optional[List[int]] = None, max_bytes: int = 256 << 20, ctas_options=(16, 32, 64)) -> dict:
+def sweep(sizes: Optional[List[int]] = None, max_bytes: int = 256 << 20, ctas_options=(32, 64, 128)) -> dict:
     """Run inside an initialised NCCL process group. Returns {"world", "nvls", "impl": {op: {"sizes", "times_us"}}}."""
     import torch
     import torch.distributed as dist

@@ -298,7 +298,7 @@ static smx::PeerPtrs make_pp(void* const* data_ptrs, void* const* flag_ptrs, voi
   return pp;
 }
 
-int smx_coll_max_ctas() { return 64; }
+int smx_coll_max_ctas() { return 128; }
 
 int smx_all_gather(void* const* data_ptrs, void* const* flag_ptrs, void* mc, int rank, int world, long long in_off,
                    long long out_off, long long shard_bytes, unsigned epoch, int use_nvls, int ctas, void* stream) {

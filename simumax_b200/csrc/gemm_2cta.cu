@@ -1,0 +1,323 @@
+// 2-CTA (cta_group::2) persistent tcgen05 GEMM for sm_100a: a CTA pair (cluster of 2, same TPC) owns one 256 x 256 output
+// tile.  Each CTA stages its own 128 rows of A and only HALF of B (128 of the 256 N rows); the leader CTA's single MMA
+// thread issues tcgen05.mma.cta_group::2 (M = 256), which reads A from both CTAs' shared memory and the two halves of B,
+// and leaves rows [0,128) of the accumulator in the leader's TMEM and rows [128,256) in the peer's.
+//
+// Why: an SS MMA is shared-memory-bandwidth bound: a 1-CTA 128x256x16 step reads 12 KB per 64 math
+// clocks, over the ~128 B/clk port; the pair reads 4 KB (A) + 4 KB (half B) per CTA for the same math per SM.
+//
+// Pipeline (per CTA unless noted):
+//   warp0 lane0  TMA producer     waits local empty[s]; leader: arrive.expect_tx(2 x stage bytes) on its full[s];
+//                                 peer: remote arrive on the leader's full[s]; both: cp.async.bulk.tensor...cta_group::2
+//                                 whose complete_tx lands on the LEADER's full[s] (peer bit of the barrier address cleared)
+//   warp1 lane0  MMA issuer       leader only: waits full[s], 4 x tcgen05.mma.cta_group::2, tcgen05.commit multicast to
+//                                 empty[s] of both CTAs (and to tmem_full[a] of both after the last k-block)
+//   warps 2..5   epilogue         wait local tmem_full[a]; TMEM -> registers -> global (bf16 / fp32, optional +=);
+//                                 arrive on the LEADER's tmem_empty[a] (count 8 = 4 warps x 2 CTAs)
+//
+// All four operand layouts (TN / NN / NT / TT) as in gemm_tcgen05.cu; bf16 inputs.
+#include "sm100_common.cuh"
+
+namespace smx {
+
+constexpr int k2BlockM = 256;       // per pair (128 per CTA)
+constexpr int k2BlockN = 256;       // per pair (each CTA stages 128 rows of B)
+constexpr int k2RowBytes = 128;
+constexpr int k2Threads = 192;
+constexpr int k2ABytes = 128 * k2RowBytes;           // 16 KB
+constexpr int k2BBytes = 128 * k2RowBytes;           // 16 KB (half of B)
+constexpr int k2StageBytes = k2ABytes + k2BBytes;    // 32 KB
+constexpr int k2Stages = 6;
+constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;       // clears the CTA-rank bit of a shared::cluster address (-> CTA 0 of the pair)
+
+struct Gemm2Params {
+  int G, M, N, K;
+  int m_tiles, n_tiles;      // 256 x 256 tiles per group
+  long long ldc, c_batch_stride;
+  float alpha;
+  int accumulate;
+};
+
+template <bool A_MN, bool B_MN, bool OUT_F32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
+gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 void* __restrict__ c_ptr, const Gemm2Params p) {
+  constexpr int BLOCK_K = 64, UMMA_K = 16, kKSteps = BLOCK_K / UMMA_K;
+  constexpr uint32_t kMnChunkBytes = BLOCK_K * k2RowBytes;      // 8 KB: one 64-wide MN chunk of an MN-major tile
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + k2Stages * k2StageBytes);
+  uint64_t* empty_bar = full_bar + k2Stages;
+  uint64_t* tmem_full_bar = empty_bar + k2Stages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < k2Stages; ++i) {
+      mbar_init(&full_bar[i], 2);      // leader's own arrive.expect_tx + the peer's remote arrive
+      mbar_init(&empty_bar[i], 1);     // one multicast tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 8);  // 4 epilogue warps in each of the 2 CTAs (only the leader's copy is waited on)
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) tmem_alloc<2>(tmem_base_ptr, 512);
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  const int tiles_per_group = p.m_tiles * p.n_tiles;
+  const int num_tiles = tiles_per_group * p.G;
+  const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  // grouped rasterisation: 4 (256-row) M-tiles down before the next N-tile
+  auto tile_coords = [&](int t, int& g, int& m_blk, int& n_blk) {
+    g = t / tiles_per_group;
+    int r = t - g * tiles_per_group;
+    constexpr int kGroupM = 4;
+    int width = kGroupM * p.n_tiles;
+    int group_id = r / width;
+    int first_m = group_id * kGroupM;
+    int gsz = min(p.m_tiles - first_m, kGroupM);
+    int in_group = r - group_id * width;
+    m_blk = first_m + in_group % gsz;
+    n_blk = in_group / gsz;
+  };
+
+  if (warp_idx == 0) {
+    // ============================ TMA producer (both CTAs) ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        int g, m_blk, n_blk;
+        tile_coords(t, g, m_blk, n_blk);
+        const int m0 = m_blk * k2BlockM + (int)cta_rank * 128;     // my rows of A / of the output
+        const int n0 = n_blk * k2BlockN + (int)cta_rank * 128;     // my half of B
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 41);
+          uint8_t* sa = smem + stage * k2StageBytes;
+          uint8_t* sb = sa + k2ABytes;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * k2StageBytes);
+          else mbar_arrive_cluster(&full_bar[stage], 0);
+          const uint32_t bar = smem_u32(&full_bar[stage]) & kPeerBitMask;     // bytes are counted on the leader's barrier
+          const int k0 = kb * BLOCK_K;
+          if constexpr (!A_MN) {
+            tma_load_3d_2sm(&tmap_a, bar, sa, k0, m0, g);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tma_load_3d_2sm(&tmap_a, bar, sa + c * kMnChunkBytes, m0 + c * 64, k0, g);
+          }
+          if constexpr (!B_MN) {
+            tma_load_3d_2sm(&tmap_b, bar, sb, k0, n0, g);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tma_load_3d_2sm(&tmap_b, bar, sb + c * kMnChunkBytes, n0 + c * 64, k0, g);
+          }
+          if (++stage == k2Stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ============================ MMA issuer (leader CTA only) ============================
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc(1u, 1u, A_MN ? 1u : 0u, B_MN ? 1u : 0u, k2BlockM, k2BlockN);
+      constexpr uint32_t a_kstep = A_MN ? (UMMA_K * k2RowBytes) >> 4 : (UMMA_K * 2) >> 4;
+      constexpr uint32_t b_kstep = B_MN ? (UMMA_K * k2RowBytes) >> 4 : (UMMA_K * 2) >> 4;
+      const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smem), A_MN ? kMnChunkBytes : 16, 1024);
+      const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem + k2ABytes), B_MN ? kMnChunkBytes : 16, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        mbar_wait(&tmem_empty_bar[as], aphase ^ 1, 42);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + as * k2BlockN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 43);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint64_t a_desc = a_desc0 + (uint64_t)stage * (k2StageBytes >> 4);
+            const uint64_t b_desc = b_desc0 + (uint64_t)stage * (k2StageBytes >> 4);
+#pragma unroll
+            for (int k = 0; k < kKSteps; ++k)
+              umma_f16<2>(tmem_d, a_desc + k * a_kstep, b_desc + k * b_kstep, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit<2>(&empty_bar[stage]);                       // frees the stage in both CTAs
+            if (kb == num_k_blocks - 1) umma_commit<2>(&tmem_full_bar[as]);   // accumulator ready in both CTAs
+          }
+          __syncwarp();
+          if (++stage == k2Stages) { stage = 0; phase ^= 1; }
+        }
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else {
+    // ============================ epilogue (both CTAs, own 128 rows) ============================
+    const int q = warp_idx % 4;
+    using OutT = typename std::conditional<OUT_F32, float, __nv_bfloat16>::type;
+    OutT* c_base = reinterpret_cast<OutT*>(c_ptr);
+    const bool vec_ok = OUT_F32 ? (p.ldc % 4 == 0) : (p.ldc % 8 == 0);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      int g, m_blk, n_blk;
+      tile_coords(t, g, m_blk, n_blk);
+      const int row = m_blk * k2BlockM + (int)cta_rank * 128 + q * 32 + lane;
+      const int n0 = n_blk * k2BlockN;
+      mbar_wait(&tmem_full_bar[as], aphase, 44);
+      tcgen05_fence_after();
+      OutT* c_row = c_base + (long long)g * p.c_batch_stride + (long long)row * p.ldc;
+#pragma unroll 1
+      for (int c = 0; c < k2BlockN / 32; ++c) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * k2BlockN + c * 32;
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row < p.M && col0 < p.N) {
+          if (vec_ok && col0 + 32 <= p.N) {
+            if constexpr (OUT_F32) {
+              float4* dst = reinterpret_cast<float4*>(c_row + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 v = make_float4(__uint_as_float(r[4 * j]) * p.alpha, __uint_as_float(r[4 * j + 1]) * p.alpha,
+                                       __uint_as_float(r[4 * j + 2]) * p.alpha, __uint_as_float(r[4 * j + 3]) * p.alpha);
+                if (p.accumulate) {
+                  float4 o = dst[j];
+                  v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                }
+                dst[j] = v;
+              }
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(c_row + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[8 * j + e]) * p.alpha;
+                if (p.accumulate) {
+                  uint4 o = dst[j];
+                  const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&o);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    float2 of = __bfloat1622float2(ob[e]);
+                    f[2 * e] += of.x;
+                    f[2 * e + 1] += of.y;
+                  }
+                }
+                uint4 v;
+                v.x = pack_bf16x2(f[0], f[1]);
+                v.y = pack_bf16x2(f[2], f[3]);
+                v.z = pack_bf16x2(f[4], f[5]);
+                v.w = pack_bf16x2(f[6], f[7]);
+                dst[j] = v;
+              }
+            }
+          } else {
+            for (int j = 0; j < 32; ++j) {
+              if (col0 + j < p.N) {
+                float v = __uint_as_float(r[j]) * p.alpha;
+                if constexpr (OUT_F32) {
+                  if (p.accumulate) v += c_row[col0 + j];
+                  c_row[col0 + j] = v;
+                } else {
+                  if (p.accumulate) v += __bfloat162float(c_row[col0 + j]);
+                  c_row[col0 + j] = __float2bfloat16(v);
+                }
+              }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty_bar[as]);
+        else mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();          // nobody may still be reading the peer's smem / signalling its barriers
+  if (warp_idx == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<2>(tmem_base, 512);
+  }
+}
+
+}  // namespace smx
+
+namespace {
+
+template <bool A_MN, bool B_MN, bool OUT_F32>
+int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const smx::Gemm2Params& p, int num_sms,
+                cudaStream_t stream) {
+  auto kern = smx::gemm_2cta_kernel<A_MN, B_MN, OUT_F32>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smx::k2SmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int tiles = p.G * p.m_tiles * p.n_tiles;
+  const int max_pairs = num_sms / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  kern<<<2 * pairs, smx::k2Threads, smx::k2SmemBytes, stream>>>(ta, tb, C, p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+// Same contract as smx_gemm (bf16 inputs only).  Returns -12 when the problem is not worth a 256 x 256 pair tile.
+int smx_gemm_2cta(const void* A, const void* B, void* C, int G, int M, int N, int K, int a_mn, int b_mn, int out_f32,
+                  int accumulate, float alpha, long long lda, long long ldb, long long ldc, long long a_bs,
+                  long long b_bs, long long c_bs, int num_sms, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (G <= 0 || M <= 0 || N <= 0 || K <= 0) return 0;
+  if (M < 256 || N < 256) return -12;
+  const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn) rc = smx::make_tmap_3d(&ta, dt, A, K, M, G, lda * 2, a_bs * 2, 64, 128);
+  else       rc = smx::make_tmap_3d(&ta, dt, A, M, K, G, lda * 2, a_bs * 2, 64, 64);
+  if (rc) return rc;
+  if (!b_mn) rc = smx::make_tmap_3d(&tb, dt, B, K, N, G, ldb * 2, b_bs * 2, 64, 128);
+  else       rc = smx::make_tmap_3d(&tb, dt, B, N, K, G, ldb * 2, b_bs * 2, 64, 64);
+  if (rc) return rc;
+  smx::Gemm2Params p;
+  p.G = G; p.M = M; p.N = N; p.K = K;
+  p.m_tiles = (M + smx::k2BlockM - 1) / smx::k2BlockM;
+  p.n_tiles = (N + smx::k2BlockN - 1) / smx::k2BlockN;
+  p.ldc = ldc; p.c_batch_stride = c_bs; p.alpha = alpha; p.accumulate = accumulate;
+  if (!a_mn && !b_mn) return out_f32 ? launch_2cta<false, false, true>(ta, tb, C, p, num_sms, stream)
+                                     : launch_2cta<false, false, false>(ta, tb, C, p, num_sms, stream);
+  if (!a_mn && b_mn)  return out_f32 ? launch_2cta<false, true, true>(ta, tb, C, p, num_sms, stream)
+                                     : launch_2cta<false, true, false>(ta, tb, C, p, num_sms, stream);
+  if (a_mn && b_mn)   return out_f32 ? launch_2cta<true, true, true>(ta, tb, C, p, num_sms, stream)
+                                     : launch_2cta<true, true, false>(ta, tb, C, p, num_sms, stream);
+  return out_f32 ? launch_2cta<true, false, true>(ta, tb, C, p, num_sms, stream)
+                 : launch_2cta<true, false, false>(ta, tb, C, p, num_sms, stream);
+}
+
+}  // extern "C"

@@ -37,6 +37,21 @@ def _fn():
     return f
 
 
+def _fn2():
+    f = _lib.lib().smx_gemm_2cta
+    if not getattr(f, "_configured", False):
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 8 + [ctypes.c_float] + \
+            [ctypes.c_longlong] * 6 + [ctypes.c_int, ctypes.c_void_p]
+        f._configured = True
+    return f
+
+
+def _two_cta_default() -> bool:
+    import os
+    return os.environ.get("SMX_GEMM_2CTA", "0") == "1"
+
+
 def _as3d(t: torch.Tensor) -> torch.Tensor:
     return t if t.dim() == 3 else t.unsqueeze(0)
 
@@ -62,7 +77,7 @@ def _tma_ready(t3: torch.Tensor) -> torch.Tensor:
 
 def gemm(a: torch.Tensor, b: torch.Tensor, layout: str = "TN", out: torch.Tensor | None = None,
          out_dtype: torch.dtype | None = None, accumulate: bool = False, alpha: float = 1.0,
-         block_n: int = 0, sm_limit: int = 0) -> torch.Tensor:
+         block_n: int = 0, sm_limit: int = 0, two_cta: bool | None = None) -> torch.Tensor:
     """out (+)= alpha * op(a) @ op(b).  2-D inputs = one GEMM, 3-D inputs = grouped GEMM over dim 0.
 
     The innermost dimension of every operand must be contiguous; row strides only need 16-byte
@@ -105,6 +120,19 @@ def gemm(a: torch.Tensor, b: torch.Tensor, layout: str = "TN", out: torch.Tensor
     nsm = _num_sms(a.device.index if a.device.index is not None else torch.cuda.current_device())
     if sm_limit:
         nsm = min(nsm, sm_limit)
+    if two_cta is None:
+        two_cta = _two_cta_default()
+    if two_cta and dtype == 0 and M >= 256 and N >= 256 and block_n == 0:
+        # CTA-pair kernel (csrc/gemm_2cta.cu): 256 x 256 tiles, B split across the pair
+        rc = _fn2()(a3.data_ptr(), b3.data_ptr(), out3.data_ptr(), G, M, N, K, a_mn, b_mn,
+                    1 if out3.dtype == torch.float32 else 0, 1 if accumulate else 0, float(alpha),
+                    a3.stride(1), b3.stride(1), out3.stride(1),
+                    a3.stride(0) if G > 1 else 0, b3.stride(0) if G > 1 else 0, out3.stride(0) if G > 1 else 0, nsm, stream)
+        _lib.check(rc, f"gemm_2cta[{layout}] G{G} M{M} N{N} K{K}")
+        _lib.count_launch()
+        if out.dim() == 3 and squeeze and out is out3:
+            return out3[0]
+        return out
     rc = _fn()(a3.data_ptr(), b3.data_ptr(), out3.data_ptr(), G, M, N, K, a_mn, b_mn, dtype,
                1 if out3.dtype == torch.float32 else 0, 1 if accumulate else 0, float(alpha),
                a3.stride(1), b3.stride(1), out3.stride(1),

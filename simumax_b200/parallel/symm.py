@@ -18,7 +18,7 @@ import torch.distributed as dist
 from ..ops import _lib
 
 _c = ctypes
-MAX_CTAS = 64
+MAX_CTAS = 128
 MAX_RANKS = 8
 
 

@@ -85,11 +85,11 @@ def main():
         row = {"bytes": total}
         variants = [("p2p", False)] + ([("nvls", True)] if ws.has_nvls else [])
         for tag, nv in variants:
-            for ctas in (16, 32, 64):
+            for ctas in (32, 64, 128):
                 t = timed(lambda: ws.all_gather(shard_b, use_nvls=nv, ctas=ctas), iters); row[f"ag_{tag}_c{ctas}_GBps"] = shard_b * world * f / t / 1e6
                 t = timed(lambda: ws.reduce_scatter(shard_b, use_nvls=nv, ctas=ctas), iters); row[f"rs_{tag}_c{ctas}_GBps"] = shard_b * world * f / t / 1e6
                 t = timed(lambda: ws.all_reduce(total, use_nvls=nv, ctas=ctas), iters); row[f"ar_{tag}_c{ctas}_GBps"] = total * 2 * f / t / 1e6
-        for ctas in (16, 32, 64):
+        for ctas in (32, 64, 128):
             t = timed(lambda: ws.all_to_all(shard_b, ctas=ctas), iters); row[f"a2a_p2p_c{ctas}_GBps"] = shard_b * world * f / t / 1e6
         t = timed(lambda: dist.all_gather_into_tensor(nccl_out[:sh_el * world], nccl_in[:sh_el]), iters); row["ag_nccl_GBps"] = shard_b * world * f / t / 1e6
         t = timed(lambda: dist.reduce_scatter_tensor(nccl_out[:sh_el], nccl_in[:sh_el * world]), iters); row["rs_nccl_GBps"] = shard_b * world * f / t / 1e6
