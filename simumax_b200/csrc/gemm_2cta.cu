@@ -98,21 +98,42 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     n_blk = in_group / gsz;
   };
 
+  // Work list: full 256 x 256 tiles for the rounds that occupy every pair, then the tiles of the last partial round cut
+  // into two 128-column slices when that lets the tail fit in (about) half a round (same idea as gemm_tcgen05.cu).
+  const int full_tiles = (num_tiles / num_pairs) * num_pairs;
+  const int tail_tiles = num_tiles - full_tiles;
+  const int split_log2 = (tail_tiles > 0 && tail_tiles * 2 <= num_pairs) ? 1 : 0;
+  const int num_work = full_tiles + (tail_tiles << split_log2);
+  auto work_coords = [&](int w, int& g, int& m_blk, int& n_base, int& n_eff) {
+    int t = w, part = 0;
+    n_eff = k2BlockN;
+    if (w >= full_tiles) {
+      const int j = w - full_tiles;
+      t = full_tiles + (j >> split_log2);
+      part = j & ((1 << split_log2) - 1);
+      n_eff = k2BlockN >> split_log2;
+    }
+    int n_blk;
+    tile_coords(t, g, m_blk, n_blk);
+    n_base = n_blk * k2BlockN + part * n_eff;
+  };
+
   if (warp_idx == 0) {
     // ============================ TMA producer (both CTAs) ============================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = pair; t < num_tiles; t += num_pairs) {
-        int g, m_blk, n_blk;
-        tile_coords(t, g, m_blk, n_blk);
+      for (int w = pair; w < num_work; w += num_pairs) {
+        int g, m_blk, n_base, n_eff;
+        work_coords(w, g, m_blk, n_base, n_eff);
+        const int half = n_eff >> 1;                               // B rows staged by each CTA (128 or 64)
         const int m0 = m_blk * k2BlockM + (int)cta_rank * 128;     // my rows of A / of the output
-        const int n0 = n_blk * k2BlockN + (int)cta_rank * 128;     // my half of B
+        const int n0 = n_base + (int)cta_rank * half;              // my half of B
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 41);
           uint8_t* sa = smem + stage * k2StageBytes;
           uint8_t* sb = sa + k2ABytes;
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * k2StageBytes);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (k2ABytes + half * k2RowBytes));
           else mbar_arrive_cluster(&full_bar[stage], 0);
           const uint32_t bar = smem_u32(&full_bar[stage]) & kPeerBitMask;     // bytes are counted on the leader's barrier
           const int k0 = kb * BLOCK_K;
@@ -123,10 +144,13 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int c = 0; c < 2; ++c) tma_load_3d_2sm(&tmap_a, bar, sa + c * kMnChunkBytes, m0 + c * 64, k0, g);
           }
           if constexpr (!B_MN) {
-            tma_load_3d_2sm(&tmap_b, bar, sb, k0, n0, g);
+#pragma unroll
+            for (int c = 0; c < 2; ++c)      // 64-row boxes
+              if (c * 64 < half) tma_load_3d_2sm(&tmap_b, bar, sb + c * (64 * k2RowBytes), k0, n0 + c * 64, g);
           } else {
 #pragma unroll
-            for (int c = 0; c < 2; ++c) tma_load_3d_2sm(&tmap_b, bar, sb + c * kMnChunkBytes, n0 + c * 64, k0, g);
+            for (int c = 0; c < 2; ++c)
+              if (c * 64 < half) tma_load_3d_2sm(&tmap_b, bar, sb + c * kMnChunkBytes, n0 + c * 64, k0, g);
           }
           if (++stage == k2Stages) { stage = 0; phase ^= 1; }
         }
@@ -135,7 +159,6 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp_idx == 1) {
     // ============================ MMA issuer (leader CTA only) ============================
     if (leader) {
-      constexpr uint32_t idesc = make_idesc(1u, 1u, A_MN ? 1u : 0u, B_MN ? 1u : 0u, k2BlockM, k2BlockN);
       constexpr uint32_t a_kstep = A_MN ? (UMMA_K * k2RowBytes) >> 4 : (UMMA_K * 2) >> 4;
       constexpr uint32_t b_kstep = B_MN ? (UMMA_K * k2RowBytes) >> 4 : (UMMA_K * 2) >> 4;
       const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smem), A_MN ? kMnChunkBytes : 16, 1024);
@@ -144,7 +167,9 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int t = pair; t < num_tiles; t += num_pairs) {
+      for (int w = pair; w < num_work; w += num_pairs) {
+        const int n_eff = (w >= full_tiles) ? (k2BlockN >> split_log2) : k2BlockN;
+        const uint32_t idesc = make_idesc(1u, 1u, A_MN ? 1u : 0u, B_MN ? 1u : 0u, k2BlockM, n_eff);
         mbar_wait(&tmem_empty_bar[as], aphase ^ 1, 42);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + as * k2BlockN;
@@ -175,16 +200,15 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const bool vec_ok = OUT_F32 ? (p.ldc % 4 == 0) : (p.ldc % 8 == 0);
     int as = 0;
     uint32_t aphase = 0;
-    for (int t = pair; t < num_tiles; t += num_pairs) {
-      int g, m_blk, n_blk;
-      tile_coords(t, g, m_blk, n_blk);
+    for (int w = pair; w < num_work; w += num_pairs) {
+      int g, m_blk, n0, n_eff;
+      work_coords(w, g, m_blk, n0, n_eff);
       const int row = m_blk * k2BlockM + (int)cta_rank * 128 + q * 32 + lane;
-      const int n0 = n_blk * k2BlockN;
       mbar_wait(&tmem_full_bar[as], aphase, 44);
       tcgen05_fence_after();
       OutT* c_row = c_base + (long long)g * p.c_batch_stride + (long long)row * p.ldc;
 #pragma unroll 1
-      for (int c = 0; c < k2BlockN / 32; ++c) {
+      for (int c = 0; c < n_eff / 32; ++c) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * k2BlockN + c * 32;
         tmem_ld_32x32b_x32(taddr, r);
@@ -278,8 +302,27 @@ int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const smx
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
+  // A persistent grid must be fully co-resident: ask the driver how many CTA pairs fit at once (GPCs with an odd
+  // number of usable TPC slots make this smaller than num_sms / 2; oversubscribing would run a second serial wave).
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms & ~1, 1, 1);
+    cfg.blockDim = dim3(smx::k2Threads, 1, 1);
+    cfg.dynamicSmemBytes = smx::k2SmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    max_clusters = (e == cudaSuccess && n > 0) ? n : num_sms / 2;
+    if (e != cudaSuccess) (void)cudaGetLastError();
+    if (getenv("SMX_GEMM_VERBOSE")) fprintf(stderr, "simumax_b200: gemm_2cta max active clusters = %d (rc %d)\n", n, (int)e);
+  }
   const int tiles = p.G * p.m_tiles * p.n_tiles;
-  const int max_pairs = num_sms / 2;
+  int max_pairs = num_sms / 2 < max_clusters ? num_sms / 2 : max_clusters;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   kern<<<2 * pairs, smx::k2Threads, smx::k2SmemBytes, stream>>>(ta, tb, C, p);
   return (int)cudaGetLastError();
@@ -302,7 +345,7 @@ int smx_gemm_2cta(const void* A, const void* B, void* C, int G, int M, int N, in
   if (!a_mn) rc = smx::make_tmap_3d(&ta, dt, A, K, M, G, lda * 2, a_bs * 2, 64, 128);
   else       rc = smx::make_tmap_3d(&ta, dt, A, M, K, G, lda * 2, a_bs * 2, 64, 64);
   if (rc) return rc;
-  if (!b_mn) rc = smx::make_tmap_3d(&tb, dt, B, K, N, G, ldb * 2, b_bs * 2, 64, 128);
+  if (!b_mn) rc = smx::make_tmap_3d(&tb, dt, B, K, N, G, ldb * 2, b_bs * 2, 64, 64);
   else       rc = smx::make_tmap_3d(&tb, dt, B, N, K, G, ldb * 2, b_bs * 2, 64, 64);
   if (rc) return rc;
   smx::Gemm2Params p;

@@ -72,7 +72,9 @@ SMX_DEVICE void mbar_arrive_cluster(uint64_t* bar, uint32_t cta_rank) {
   asm volatile(
       "{\n\t.reg .b32 remote;\n\t"
       "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remote];\n\t}" ::"r"(smem_u32(bar)),
+      // plain arrive: an explicit .release.cluster lowers to MEMBAR.ALL.GPU + ERRBAR per call (seen in SASS / ncu as
+      // 'stall_membar' on the producer thread); the callers only signal and order TMEM/TMA traffic by other means
+      "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t}" ::"r"(smem_u32(bar)),
       "r"(cta_rank)
       : "memory");
 }

@@ -49,7 +49,7 @@ def _fn2():
 
 def _two_cta_default() -> bool:
     import os
-    return os.environ.get("SMX_GEMM_2CTA", "0") == "1"
+    return os.environ.get("SMX_GEMM_2CTA", "1") == "1"
 
 
 def _as3d(t: torch.Tensor) -> torch.Tensor:

@@ -87,3 +87,27 @@ def test_gemm_fp8():
     out = gemm(a, b, "TN", alpha=0.5)
     ref = 0.5 * (a.float() @ b.float().t())
     torch.testing.assert_close(out.float(), ref, atol=1e-1, rtol=2e-2)
+
+
+@pytest.mark.parametrize("layout", ["TN", "NN", "NT", "TT"])
+@pytest.mark.parametrize("shape", [(256, 256, 64), (512, 768, 320), (1000, 520, 200), (2048, 4096, 512), (4096, 4096 + 256, 192)])
+@pytest.mark.parametrize("mode", ["bf16", "f32_accumulate"])
+def test_gemm_cta_pair_kernel(layout, shape, mode):
+    """cta_group::2 kernel (256 x 256 pair tiles, tail round sliced) against fp32 torch, every layout."""
+    from simumax_b200.ops.gemm import gemm
+    torch.manual_seed(11)
+    M, N, K = shape
+    a = torch.randn((K, M) if layout in ("NT", "TT") else (M, K), device="cuda").bfloat16()
+    b = torch.randn((K, N) if layout in ("NN", "NT") else (N, K), device="cuda").bfloat16()
+    af = a.float().t() if layout in ("NT", "TT") else a.float()
+    bf = b.float() if layout in ("NN", "NT") else b.float().t()
+    ref = af @ bf
+    if mode == "bf16":
+        out = gemm(a, b, layout, two_cta=True)
+        torch.testing.assert_close(out.float(), ref, atol=2e-2 * ref.abs().max().item(), rtol=2e-2)
+        one = gemm(a, b, layout, two_cta=False)
+        torch.testing.assert_close(out.float(), one.float(), atol=1e-2 * ref.abs().max().item(), rtol=1e-2)
+    else:
+        c = torch.full((M, N), 0.5, device="cuda", dtype=torch.float32)
+        gemm(a, b, layout, out=c, accumulate=True, two_cta=True)
+        torch.testing.assert_close(c, ref + 0.5, atol=1e-3 * ref.abs().max().item(), rtol=1e-4)
