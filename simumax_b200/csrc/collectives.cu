@@ -281,6 +281,11 @@ __global__ void __launch_bounds__(512) p2p_put_kernel(PeerPtrs pp, int dst_rank,
     st_v4(dst + i * 16, ld_nc_v4(src + i * 16));
 }
 
+// cross-rank barrier only (one CTA): everything enqueued before it on every rank's stream is complete and visible
+__global__ void __launch_bounds__(32) rank_barrier_kernel(PeerPtrs pp, uint32_t epoch) {
+  cta_barrier_all_ranks(pp, epoch);
+}
+
 }  // namespace smx
 
 extern "C" {
@@ -332,6 +337,12 @@ int smx_all_reduce(void* const* data_ptrs, void* const* flag_ptrs, void* mc, int
   else if (world <= 4) { if (f32) SMX_AR(true, 4); else SMX_AR(false, 4); }
   else { if (f32) SMX_AR(true, 2); else SMX_AR(false, 2); }
 #undef SMX_AR
+  return (int)cudaGetLastError();
+}
+int smx_rank_barrier(void* const* data_ptrs, void* const* flag_ptrs, int rank, int world, unsigned epoch, void* stream) {
+  if (world > smx::kMaxRanks) return -40;
+  smx::rank_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(make_pp(data_ptrs, flag_ptrs, nullptr, rank, world),
+                                                                              epoch);
   return (int)cudaGetLastError();
 }
 int smx_all_to_all(void* const* data_ptrs, void* const* flag_ptrs, int rank, int world, long long in_off,

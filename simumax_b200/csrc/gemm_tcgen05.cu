@@ -44,7 +44,17 @@ struct GemmParams {
   long long c_batch_stride;  // elements
   float alpha;
   int accumulate;
+  // Fused GEMM -> reduce-scatter epilogue (rs_world > 1, fp32 output): row block [r * rs_rows, (r+1) * rs_rows) of the
+  // product belongs to rank r and is summed into that rank's buffer with red.global.add.v4.f32 straight from the
+  // epilogue registers (peer-mapped memory over NVLink), tile by tile while later tiles are still being multiplied.
+  int rs_world, rs_rows;
+  float* rs_out[8];
 };
+
+SMX_DEVICE void red_add_v4_f32_sys(float* dst, float4 v) {
+  asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 
 template <int BLOCK_N, bool A_MN, bool B_MN, bool OUT_F32, int ELEM_BYTES>
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -235,7 +245,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tmem_ld_wait();
         const int col0 = n0 + c * 32;
         if (row < p.M && col0 < p.N) {
-          if (vec_ok && col0 + 32 <= p.N) {
+          if (OUT_F32 && p.rs_world > 1) {
+            if constexpr (OUT_F32) {
+              const int owner = row / p.rs_rows;
+              float* dst = p.rs_out[owner] + (long long)(row - owner * p.rs_rows) * p.ldc + col0;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (col0 + 4 * j + 4 <= p.N)
+                  red_add_v4_f32_sys(dst + 4 * j, make_float4(__uint_as_float(r[4 * j]) * p.alpha, __uint_as_float(r[4 * j + 1]) * p.alpha,
+                                                              __uint_as_float(r[4 * j + 2]) * p.alpha, __uint_as_float(r[4 * j + 3]) * p.alpha));
+            }
+          } else if (vec_ok && col0 + 32 <= p.N) {
             if constexpr (OUT_F32) {
               float4* dst = reinterpret_cast<float4*>(c_row + col0);
 #pragma unroll
@@ -368,7 +388,22 @@ int pick_block_n(int G, int M, int N, int num_sms) {
 
 }  // namespace
 
+namespace {
+int g_rs_world = 1;
+float* g_rs_out[8] = {nullptr};
+}  // namespace
+
 extern "C" {
+
+// Arms the fused reduce-scatter epilogue for the NEXT smx_gemm call (fp32 output, G == 1): out_ptrs[r] is rank r's
+// [M / world, N] fp32 buffer as mapped in this process (symmetric memory); the caller zeroes the buffers beforehand and
+// runs a cross-rank barrier afterwards.
+int smx_gemm_arm_reduce_scatter(void* const* out_ptrs, int world) {
+  if (world < 1 || world > 8) return -14;
+  g_rs_world = world;
+  for (int i = 0; i < world; ++i) g_rs_out[i] = reinterpret_cast<float*>(out_ptrs[i]);
+  return 0;
+}
 
 // dtype: 0 = bf16 inputs, 1 = fp8 e4m3 inputs.  a_mn / b_mn: operand stored MN-major ([K, MN] row-major).
 // lda / ldb / ldc and batch strides are in elements.  Returns 0 on success (cudaError / negative on failure).
@@ -395,6 +430,14 @@ int smx_gemm(const void* A, const void* B, void* C, int G, int M, int N, int K, 
   p.m_tiles = (M + smx::kBlockM - 1) / smx::kBlockM;
   p.n_tiles = (N + block_n - 1) / block_n;
   p.ldc = ldc; p.c_batch_stride = c_bs; p.alpha = alpha; p.accumulate = accumulate;
+  p.rs_world = 1; p.rs_rows = M;
+  for (int i = 0; i < 8; ++i) p.rs_out[i] = nullptr;
+  if (g_rs_world > 1) {
+    if (!out_f32 || G != 1 || N % 4 || M % g_rs_world) return -13;
+    p.rs_world = g_rs_world; p.rs_rows = M / g_rs_world;
+    for (int i = 0; i < g_rs_world; ++i) p.rs_out[i] = g_rs_out[i];
+    g_rs_world = 1;      // one-shot: applies to this launch only
+  }
   if (dtype == 0) {
     if (!a_mn && !b_mn) return out_f32 ? launch_bn<false, false, true, 2>(block_n, ta, tb, C, p, num_sms, stream)
                                        : launch_bn<false, false, false, 2>(block_n, ta, tb, C, p, num_sms, stream);

@@ -136,6 +136,17 @@ class SymmetricWorkspace:
         _lib.check(rc, "smx_all_to_all")
         _lib.count_launch()
 
+    def barrier(self):
+        """Device-side barrier across the group on the current stream (flag exchange over NVLink, no NCCL)."""
+        rc = _fn("smx_rank_barrier", [_PTRS, _PTRS, _c.c_int, _c.c_int, _c.c_uint, _c.c_void_p])(
+            self.data_ptrs, self.flag_ptrs, self.rank, self.world, self._next_epoch(), self._stream())
+        _lib.check(rc, "smx_rank_barrier")
+        _lib.count_launch()
+
+    def peer_ptrs(self, byte_off: int = 0):
+        """ctypes array of every rank's mapping of ``buffer + byte_off`` (for kernels that write to peers directly)."""
+        return (_c.c_void_p * MAX_RANKS)(*[(int(p) + byte_off) for p in self._hd.buffer_ptrs] + [0] * (MAX_RANKS - self.world))
+
     def put(self, dst_rank: int, nbytes: int, ctas: int = 16):
         """One-sided copy in[:nbytes] -> out[:nbytes] of ``dst_rank`` (pipeline send); caller orders with events."""
         rc = _fn("smx_p2p_put", _SIG_PUT)(self.data_ptrs, self.flag_ptrs, self.rank, self.world, dst_rank, 0,

@@ -36,3 +36,13 @@ def test_zero1_step_smx_matches_nccl():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     assert json.loads(line)["ok"], line
+
+
+@pytest.mark.timeout(300)
+def test_fused_gemm_reduce_scatter():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29535", os.path.join(ROOT, "tools", "fused_check.py")]
+    r = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0 and "FUSED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -1,0 +1,67 @@
+"""Fused GEMM + reduce-scatter vs (GEMM, then NCCL reduce_scatter), under torchrun on >= 2 GPUs: correctness + time."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+from simumax_b200.ops.gemm import gemm
+from simumax_b200.parallel.fused import gemm_reduce_scatter
+from simumax_b200.parallel.symm import SymmetricWorkspace
+
+
+def timed(fn, iters=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0")); torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    res = {"world": world, "cases": []}
+    ok = True
+    for (M, N, Kfull) in [(4096, 4096, 4096), (4096, 8192, 28672), (8192, 4096, 14336)]:
+        K = Kfull // world                      # row-parallel linear: each rank holds a K shard
+        torch.manual_seed(10 + rank)
+        x = torch.randn(M, K, device="cuda").bfloat16() * 0.5
+        w = torch.randn(N, K, device="cuda").bfloat16() * 0.5
+        ws = SymmetricWorkspace(256, M // world * N * 4 + 256)
+        out = gemm_reduce_scatter(x, w, ws, "TN").clone()
+        full = torch.empty(M, N, device="cuda", dtype=torch.float32)
+        gemm(x, w, "TN", out=full)
+        ref = torch.empty(M // world, N, device="cuda", dtype=torch.float32)
+        dist.reduce_scatter_tensor(ref, full)
+        err = ((out - ref).abs().max() / ref.abs().max()).item()
+        good = err < 1e-3
+        ok &= good
+        t_fused = timed(lambda: gemm_reduce_scatter(x, w, ws, "TN"))
+        def unfused():
+            gemm(x, w, "TN", out=full)
+            dist.reduce_scatter_tensor(ref, full)
+        t_unf = timed(unfused)
+        t_gemm = timed(lambda: gemm(x, w, "TN", out=full))
+        flops = 2.0 * M * N * K
+        nv_bytes = (world - 1) / world * M * N * 4
+        roof_ms = max(flops / 1.67e15, nv_bytes / 900e9) * 1e3
+        row = {"M": M, "N": N, "K_per_rank": K, "rel_err": err, "fused_ms": t_fused, "gemm_then_nccl_rs_ms": t_unf, "gemm_only_ms": t_gemm,
+               "roofline_ms": roof_ms, "fused_fraction_of_roofline": roof_ms / t_fused}
+        res["cases"].append(row)
+        if rank == 0:
+            print(row, flush=True)
+        del ws
+    res["ok"] = bool(ok)
+    if rank == 0:
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump(res, open(f"gpurun_out/fused_gemm_rs_{world}.json", "w"), indent=1)
+        print("FUSED_OK" if ok else "FUSED_MISMATCH")
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
