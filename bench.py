@@ -107,6 +107,7 @@ def predicted(model: str, n_gpus: int, seq: int, mbs: int, mbc: int):
         st = StrategyConfig.init_from_config_file(get_simu_strategy_config("tp1_pp1_dp8_mbs1"))
         st.world_size, st.tp_size, st.pp_size = n_gpus, 1, 1
         st.seq_len, st.micro_batch_size, st.micro_batch_num = seq, mbs, mbc
+        st.dp_overlap_model = True      # the runtime overlaps ZeRO-1 collectives with backward / next forward
         p = PerfLLM()
         p.configure(strategy_config=st, model_config=get_simu_model_config(model), system_config=sys_path)
         import contextlib

@@ -233,6 +233,10 @@ class StrategyConfig(Config):
     use_fused_grad_accumulation: bool = True
     cross_entropy_loss_fusion: bool = False
     overlap_grad_reduce: bool = True
+    # extension (reference charges DP collectives as fully exposed, perf_llm.py:1570): when True the bucketed ZeRO-1
+    # reduce-scatter hides behind the last micro-batch's backward and the all-gather behind the next forward
+    dp_overlap_model: bool = False
+    dp_overlap_efficiency: float = 0.5      # fraction of the overlappable collective time that is actually hidden
 
     te_version: Optional[str] = None
     te_dummy_wgrad_min_version: str = "2.3.0"

@@ -363,6 +363,14 @@ class PerfLLM(PerfBase):
             res["dp_comm_num_gather"] = 2 if is_moe else 1
             res["dp_comm_time"] = total
             res["dp_comm_exposed_time"] = total
+            if details and getattr(s, "dp_overlap_model", False) and group_size > 1 and n_rs > 0 and n_ag > 0:
+                # overlap extension: each collective is exposed only past the compute it can hide behind, and never
+                # less than its last bucket (which has nothing left to overlap with)
+                fwd_t, bwd_t = self._compute_single_batch_fwd_bwd_time(model_name)
+                eta = float(getattr(s, "dp_overlap_efficiency", 0.5))    # overlapped kernels share SMs / HBM with the GEMMs
+                rs_t, ag_t = details["reduce_scatter_time"], details["all_gather_time"]
+                exposed = max(rs_t - eta * min(rs_t, bwd_t), rs_t / n_rs) + max(ag_t - eta * min(ag_t, fwd_t), ag_t / n_ag)
+                res["dp_comm_exposed_time"] = min(total, exposed)
             if details:
                 res["details"] = details
             return res

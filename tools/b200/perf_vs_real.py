@@ -41,6 +41,7 @@ def predict(model, layers, seq, mbs, mbc, world, system):
     st = StrategyConfig.init_from_config_file(get_simu_strategy_config("tp1_pp1_dp8_mbs1"))
     st.world_size, st.tp_size, st.pp_size = world, 1, 1
     st.seq_len, st.micro_batch_size, st.micro_batch_num = seq, mbs, mbc
+    st.dp_overlap_model = True      # the runtime overlaps ZeRO-1 collectives with backward / next forward
     p = PerfLLM()
     with contextlib.redirect_stdout(io.StringIO()):
         p.configure(strategy_config=st, model_config=get_simu_model_config(model), system_config=get_simu_system_config(system))
