@@ -23,6 +23,10 @@ DEFAULT_WORKLOADS: List[Tuple[str, str, dict, dict]] = [
     ("llama3-70b", "tp4_pp1_dp2_mbs1", {"layer_num": 12}, {}),
     ("deepseekv2", "ep8_pp1_dp8_mbs1", {"layer_num": 4}, {}),
     ("deepseekv2", "ep4_pp2_dp4_mbs1", {"layer_num": 4}, {}),
+    # shapes of the predicted-vs-measured cases (tools/b200/perf_vs_real.py): bigger micro-batch, longer sequence, 70B widths at tp1
+    ("llama3-8b", "tp1_pp1_dp8_mbs1", {"layer_num": 16}, {"micro_batch_size": 2}),
+    ("llama3-8b", "tp1_pp1_dp8_mbs1", {"layer_num": 16}, {"seq_len": 8192}),
+    ("llama3-70b", "tp1_pp1_dp8_mbs1", {"layer_num": 4}, {}),
 ]
 
 

@@ -281,6 +281,33 @@ __global__ void __launch_bounds__(512) p2p_put_kernel(PeerPtrs pp, int dst_rank,
     st_v4(dst + i * 16, ld_nc_v4(src + i * 16));
 }
 
+// Chunked all-gather for the fused all-gather -> GEMM: CTA b pushes row chunk b of the local shard into every rank's
+// gathered buffer and then raises flag[rank * gridDim.x + b] = epoch on every rank (st.release.sys after a system
+// fence), so a consumer kernel can start on a chunk the moment it has landed.  No entry barrier: the consumer side is
+// protected by the flags, the producer side by the caller's stream order (the previous consumer has finished).
+__global__ void __launch_bounds__(512) all_gather_chunked_kernel(PeerPtrs pp, long long in_off, long long out_off,
+                                                                long long flag_off, long long shard_bytes, uint32_t epoch) {
+  const long long chunk = shard_bytes / gridDim.x;            // bytes per CTA (multiple of 16 by construction)
+  const long long n16 = chunk / 16;
+  const char* src = reinterpret_cast<const char*>(pp.data[pp.rank]) + in_off + (long long)blockIdx.x * chunk;
+  const long long dst_off = out_off + (long long)pp.rank * shard_bytes + (long long)blockIdx.x * chunk;
+  for (long long i = threadIdx.x; i < n16; i += blockDim.x) {
+    const uint4 v = ld_nc_v4(src + i * 16);
+#pragma unroll 1
+    for (int s = 0; s < pp.world; ++s) {
+      const int peer = (pp.rank + s) % pp.world;
+      st_v4(reinterpret_cast<char*>(pp.data[peer]) + dst_off + i * 16, v);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < (unsigned)pp.world) {
+    uint32_t* flag = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(pp.data[threadIdx.x]) + flag_off) +
+                     (long long)pp.rank * gridDim.x + blockIdx.x;
+    st_release_sys(flag, epoch);
+  }
+}
+
 // cross-rank barrier only (one CTA): everything enqueued before it on every rank's stream is complete and visible
 __global__ void __launch_bounds__(32) rank_barrier_kernel(PeerPtrs pp, uint32_t epoch) {
   cta_barrier_all_ranks(pp, epoch);
@@ -343,6 +370,14 @@ int smx_rank_barrier(void* const* data_ptrs, void* const* flag_ptrs, int rank, i
   if (world > smx::kMaxRanks) return -40;
   smx::rank_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(make_pp(data_ptrs, flag_ptrs, nullptr, rank, world),
                                                                               epoch);
+  return (int)cudaGetLastError();
+}
+int smx_all_gather_chunked(void* const* data_ptrs, void* const* flag_ptrs, int rank, int world, long long in_off,
+                           long long out_off, long long flag_off, long long shard_bytes, unsigned epoch, int chunks,
+                           void* stream) {
+  if (world > smx::kMaxRanks || chunks <= 0 || shard_bytes % (16LL * chunks)) return -40;
+  smx::all_gather_chunked_kernel<<<chunks, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      make_pp(data_ptrs, flag_ptrs, nullptr, rank, world), in_off, out_off, flag_off, shard_bytes, epoch);
   return (int)cudaGetLastError();
 }
 int smx_all_to_all(void* const* data_ptrs, void* const* flag_ptrs, int rank, int world, long long in_off,

@@ -49,6 +49,12 @@ struct GemmParams {
   // epilogue registers (peer-mapped memory over NVLink), tile by tile while later tiles are still being multiplied.
   int rs_world, rs_rows;
   float* rs_out[8];
+  // Fused all-gather -> GEMM prologue (ag_flags != nullptr): A is a gathered buffer that peers fill chunk by chunk over
+  // NVLink while this kernel runs; ag_flags[row / ag_rows_per_flag] >= ag_epoch means those rows have landed.  M-tiles
+  // are visited starting at ag_first_m_blk (this rank's own rows) so the MMAs start before any remote byte arrives.
+  const uint32_t* ag_flags;
+  int ag_rows_per_flag, ag_first_m_blk;
+  uint32_t ag_epoch;
 };
 
 SMX_DEVICE void red_add_v4_f32_sys(float* dst, float4 v) {
@@ -115,6 +121,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int in_group = r - group_id * width;
     m_blk = first_m + in_group % gsz;
     n_blk = in_group / gsz;
+    if (p.ag_flags) {
+      m_blk += p.ag_first_m_blk;
+      if (m_blk >= p.m_tiles) m_blk -= p.m_tiles;
+    }
   };
   // Work list = full tiles for the rounds that fill every CTA, then the tiles of the last partial round cut into
   // `tail_split` column slices (64-column granularity) so that the tail occupies (almost) all CTAs for a fraction of
@@ -151,6 +161,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
         int g, m0, n0, n_eff;
         work_coords(w, g, m0, n0, n_eff);
+        if (p.ag_flags) {
+          // gathered operand: wait until every row of this M-tile has been delivered (flags are written with
+          // st.release.sys by the gather kernel of the owning rank), then order the TMA (async proxy) reads after it
+          const int last_row = min(m0 + kBlockM, p.M) - 1;
+          const uint64_t t0 = global_timer_ns();
+          for (int f = m0 / p.ag_rows_per_flag; f <= last_row / p.ag_rows_per_flag; ++f) {
+            uint32_t v;
+            do {
+              asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ag_flags + f) : "memory");
+              if ((int32_t)(v - p.ag_epoch) < 0 && global_timer_ns() - t0 > 20000000000ull) {
+                printf("simumax_b200: all-gather GEMM timed out waiting for rows of flag %d (have %u want %u)\n", f, v, p.ag_epoch);
+                __trap();
+              }
+            } while ((int32_t)(v - p.ag_epoch) < 0);
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
@@ -391,6 +418,9 @@ int pick_block_n(int G, int M, int N, int num_sms) {
 namespace {
 int g_rs_world = 1;
 float* g_rs_out[8] = {nullptr};
+const uint32_t* g_ag_flags = nullptr;
+int g_ag_rows = 1, g_ag_first = 0;
+uint32_t g_ag_epoch = 0;
 }  // namespace
 
 extern "C" {
@@ -402,6 +432,15 @@ int smx_gemm_arm_reduce_scatter(void* const* out_ptrs, int world) {
   if (world < 1 || world > 8) return -14;
   g_rs_world = world;
   for (int i = 0; i < world; ++i) g_rs_out[i] = reinterpret_cast<float*>(out_ptrs[i]);
+  return 0;
+}
+
+// Arms the fused all-gather prologue for the NEXT smx_gemm call: A must be the gathered buffer; flags[i] >= epoch means
+// rows [i * rows_per_flag, (i+1) * rows_per_flag) are in place.  first_m_blk = index of the first 128-row tile to visit.
+int smx_gemm_arm_all_gather(const void* flags, int rows_per_flag, int first_m_blk, unsigned epoch) {
+  if (rows_per_flag <= 0) return -15;
+  g_ag_flags = reinterpret_cast<const uint32_t*>(flags);
+  g_ag_rows = rows_per_flag; g_ag_first = first_m_blk; g_ag_epoch = epoch;
   return 0;
 }
 
@@ -430,6 +469,8 @@ int smx_gemm(const void* A, const void* B, void* C, int G, int M, int N, int K, 
   p.m_tiles = (M + smx::kBlockM - 1) / smx::kBlockM;
   p.n_tiles = (N + block_n - 1) / block_n;
   p.ldc = ldc; p.c_batch_stride = c_bs; p.alpha = alpha; p.accumulate = accumulate;
+  p.ag_flags = g_ag_flags; p.ag_rows_per_flag = g_ag_rows; p.ag_first_m_blk = g_ag_first; p.ag_epoch = g_ag_epoch;
+  g_ag_flags = nullptr;        // one-shot
   p.rs_world = 1; p.rs_rows = M;
   for (int i = 0; i < 8; ++i) p.rs_out[i] = nullptr;
   if (g_rs_world > 1) {

@@ -47,3 +47,62 @@ def gemm_reduce_scatter(a: torch.Tensor, b: torch.Tensor, ws: SymmetricWorkspace
     _lib.count_launch()
     ws.barrier()                                   # all peers' adds have landed
     return out
+
+
+def allgather_gemm(x_shard: torch.Tensor, w: torch.Tensor, ws: SymmetricWorkspace, layout: str = "TN", chunks: int = 8,
+                   out: torch.Tensor | None = None, comm_stream: torch.cuda.Stream | None = None) -> torch.Tensor:
+    """y[M, N] = all_gather(x_shard over ranks)[M, K] @ w^T   (column-parallel linear forward with sequence parallelism,
+    reference cost model dense_module.py:351-416) with the gather overlapped into the GEMM.
+
+    A chunked push all-gather runs on ``comm_stream`` (every CTA pushes one row chunk of the local shard to all peers and
+    raises a per-chunk flag); the GEMM starts immediately on this rank's own rows and its TMA producer waits on the flag
+    of each remote row block only when it gets there -- communication of chunk *c* overlaps the MMAs of the chunks that
+    arrived earlier.  Workspace layout: [x_shard | 4 KiB flags | gathered x (world x shard)]."""
+    assert layout == "TN" and x_shard.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x_shard.is_contiguous()
+    world, rank = ws.world, ws.rank
+    ms, K = x_shard.shape
+    N = w.shape[0]
+    M = ms * world
+    assert ms % (chunks * 1) == 0 and (ms // chunks) * K * 2 % 16 == 0 and world * chunks * 4 <= 4096
+    shard_bytes = ms * K * 2
+    flag_off = (shard_bytes + 255) // 256 * 256
+    xg_off = flag_off + 4096
+    assert xg_off + world * shard_bytes <= ws.in_bytes + ws.out_bytes, "symmetric workspace too small"
+    main = torch.cuda.current_stream(x_shard.device)
+    comm = comm_stream or getattr(ws, "_ag_stream", None)
+    if comm is None:
+        comm = ws._ag_stream = torch.cuda.Stream(device=x_shard.device)
+    if not getattr(ws, "_ag_ready", False):
+        ws.view(flag_off, torch.int32, 1024).zero_()
+        ws._ag_epoch = 0
+        ws._ag_ready = True
+        ws.barrier()
+    ws._ag_epoch += 1
+    epoch = ws._ag_epoch
+    xg = ws.view(xg_off, torch.bfloat16, M * K).view(M, K)
+    comm.wait_stream(main)
+    with torch.cuda.stream(comm):
+        ws.view(0, torch.bfloat16, ms * K).view(ms, K).copy_(x_shard)
+        ws.barrier()                      # every rank is done reading the previous gathered buffer
+        f = _lib.lib().smx_all_gather_chunked
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.POINTER(ctypes.c_void_p)] * 2 + [ctypes.c_int] * 2 + [ctypes.c_longlong] * 4 + [ctypes.c_uint, ctypes.c_int,
+                                                                                                         ctypes.c_void_p]
+        _lib.check(f(ws.data_ptrs, ws.flag_ptrs, rank, world, 0, xg_off, flag_off, shard_bytes, epoch, chunks,
+                     torch.cuda.current_stream(x_shard.device).cuda_stream), "all_gather_chunked")
+        _lib.count_launch()
+    y = torch.empty(M, N, device=x_shard.device, dtype=torch.bfloat16) if out is None else out
+    lib = _lib.lib()
+    arm = lib.smx_gemm_arm_all_gather
+    arm.restype = ctypes.c_int
+    arm.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint]
+    flags = ws.view(flag_off, torch.int32, 1024)
+    _lib.check(arm(flags.data_ptr(), ms // chunks, rank * ms // 128, epoch), "arm_all_gather")
+    a3, b3 = _tma_ready(_as3d(xg)), _tma_ready(_as3d(w))
+    nsm = _num_sms(x_shard.device.index if x_shard.device.index is not None else torch.cuda.current_device())
+    rc = _fn()(a3.data_ptr(), b3.data_ptr(), y.data_ptr(), 1, M, N, K, 0, 0, 0, 0, 0, 1.0, a3.stride(1), b3.stride(1), y.stride(0),
+               0, 0, 0, 0, nsm, main.cuda_stream)
+    _lib.check(rc, f"allgather_gemm M{M} N{N} K{K} world{world}")
+    _lib.count_launch()
+    main.wait_stream(comm)                # the gather kernel itself must be complete before the workspace is reused
+    return y
