@@ -49,7 +49,7 @@ def gemm_reduce_scatter(a: torch.Tensor, b: torch.Tensor, ws: SymmetricWorkspace
     return out
 
 
-def allgather_gemm(x_shard: torch.Tensor, w: torch.Tensor, ws: SymmetricWorkspace, layout: str = "TN", chunks: int = 8,
+def allgather_gemm(x_shard: torch.Tensor, w: torch.Tensor, ws: SymmetricWorkspace, layout: str = "TN", chunks: int = 32,
                    out: torch.Tensor | None = None, comm_stream: torch.cuda.Stream | None = None) -> torch.Tensor:
     """y[M, N] = all_gather(x_shard over ranks)[M, K] @ w^T   (column-parallel linear forward with sequence parallelism,
     reference cost model dense_module.py:351-416) with the gather overlapped into the GEMM.
