@@ -115,8 +115,8 @@ def measure_sdp(req: ShapeRequest, backward: bool) -> Dict[str, float]:
     if not backward:
         ms = _time(lambda i: fmha_fwd(*sets[i % ring][:3], causal=True, out=sets[i % ring][3], lse=sets[i % ring][4]))
     else:
-        if Dqk != 128 or Dv != 128:
-            raise NotImplementedError("fmha_bwd supports head dim 128")
+        if Dqk not in (128, 192) or Dv != 128:
+            raise NotImplementedError("fmha_bwd supports qk head dim 128 / 192 with v head dim 128")
         for s in sets:
             fmha_fwd(s[0], s[1], s[2], causal=True, out=s[3], lse=s[4])
             s.append(_rand((B, S, H, Dv)))

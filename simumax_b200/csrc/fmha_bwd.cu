@@ -54,12 +54,33 @@ constexpr int kBwdSoftmaxWarps = 8;
 constexpr int kBwdThreads = (2 + kBwdSoftmaxWarps + 4) * 32;
 constexpr int kBwdKVBytes = kBwdBKV * kBwdD * 2;      // 32 KB each for K and V
 constexpr int kBwdQBytes = kBwdBQ * kBwdD * 2;        // 16 KB each for Q_i and dO_i
-constexpr int kBwdStageBytes = 2 * kBwdQBytes;
-constexpr int kBwdStages = 3;                      // Q/dO ring: a load issued when iteration g-1 retires lands before g+2 needs it
+constexpr int kBwdStageBytesUnused = 2 * kBwdQBytes;
+constexpr int kBwdStagesUnused = 3;                      // Q/dO ring: a load issued when iteration g-1 retires lands before g+2 needs it
 constexpr int kBwdPBytes = kBwdBKV * kBwdBQ * 2;      // 16 KB each for P^T and dS^T
 constexpr int kBwdDqBytes = kBwdBQ * kBwdD * 4;       // 32 KB fp32 staging for the dQ reduce
-// no alignment slack: a kernel without static smem gets a 1024-byte aligned dynamic window (checked at run time)
-constexpr int kBwdSmemBytes = 2 * kBwdKVBytes + kBwdStages * kBwdStageBytes + 2 * kBwdPBytes + kBwdDqBytes + 2 * kBwdStages * 64 * 4 + 256;
+// Per head-dim configuration.  DQK = 128 is the software-pipelined fast path.  DQK = 192 (MLA: qk 192 / v 128) needs a
+// 192-column dK accumulator, so dQ^T (two M=128 blocks, the second one half empty) has to alias the S^T / dP^T columns:
+// S^T(g+1) / dP^T(g+1) can then only be issued after dQ^T(g) has been drained (no look-ahead), and shared memory only has
+// room for a 2-deep Q/dO ring.
+template <int DQK>
+struct BwdCfg {
+  static constexpr int kKBytes = kBwdBKV * DQK * 2;
+  static constexpr int kVBytes = kBwdBKV * kBwdD * 2;
+  static constexpr int kQBytes = kBwdBQ * DQK * 2;
+  static constexpr int kdOBytes = kBwdBQ * kBwdD * 2;
+  static constexpr int kStageBytes = kQBytes + kdOBytes;
+  static constexpr bool kLookahead = (DQK == 128);
+  static constexpr int kStages = kLookahead ? 3 : 2;
+  static constexpr int kDqBlocks = (DQK + 127) / 128;
+  static constexpr int kTmS = 0, kTmDp = 64;
+  static constexpr int kTmDq0 = kLookahead ? 128 : 0;     // block 1 (DQK = 192) lives at kTmDp
+  static constexpr int kTmDv = kLookahead ? 192 : 128;
+  static constexpr int kTmDk = kLookahead ? 320 : 256;
+  // no alignment slack: a kernel without static smem gets a 1024-byte aligned dynamic window (checked at run time)
+  static constexpr int kSmemBytes = kKBytes + kVBytes + kStages * kStageBytes + 2 * kBwdPBytes + kBwdDqBytes + 2 * kStages * 64 * 4 + 256;
+  static_assert(kSmemBytes <= 227 * 1024, "fmha_bwd shared memory budget");
+  static_assert(kTmDk + DQK <= 512, "fmha_bwd TMEM budget");
+};
 
 struct FmhaBwdParams {
   int B, S_q, S_kv, H, H_kv;
@@ -81,11 +102,13 @@ struct FmhaBwdParams {
       p.trace[((role) * 32 + (g)) * 16 + (ev)] = clock64();                                             \
   } while (0)
 
+template <int DQK>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                 const __grid_constant__ CUtensorMap tmap_dq, const FmhaBwdParams p) {
-  constexpr int BKV = kBwdBKV, BQ = kBwdBQ, D = kBwdD;
+  using Cfg = BwdCfg<DQK>;
+  constexpr int BKV = kBwdBKV, BQ = kBwdBQ, D = kBwdD;      // D = head dim of V / dO / dV
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u)) {
@@ -93,17 +116,17 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     __trap();
   }
   uint8_t* sK = smem;
-  uint8_t* sV = sK + kBwdKVBytes;
-  uint8_t* sQdO = sV + kBwdKVBytes;                    // [2 stages][Q 16 KB | dO 16 KB]
-  uint8_t* sP = sQdO + kBwdStages * kBwdStageBytes;
+  uint8_t* sV = sK + Cfg::kKBytes;
+  uint8_t* sQdO = sV + Cfg::kVBytes;                    // [2 stages][Q 16 KB | dO 16 KB]
+  uint8_t* sP = sQdO + Cfg::kStages * Cfg::kStageBytes;
   uint8_t* sdS = sP + kBwdPBytes;
   float* sDq = reinterpret_cast<float*>(sdS + kBwdPBytes);
   float* sLse = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sDq) + kBwdDqBytes);   // [2][64]
-  float* sDsum = sLse + kBwdStages * 64;                                                            // [2][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDsum + kBwdStages * 64);
+  float* sDsum = sLse + Cfg::kStages * 64;                                                            // [2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDsum + Cfg::kStages * 64);
   uint64_t* kv_full = bars;            // 1
-  uint64_t* qdo_full = bars + 17;      // [kBwdStages]
-  uint64_t* qdo_empty = bars + 17 + kBwdStages;
+  uint64_t* qdo_full = bars + 17;      // [Cfg::kStages]
+  uint64_t* qdo_empty = bars + 17 + Cfg::kStages;
   uint64_t* s_full = bars + 5;
   uint64_t* s_empty = bars + 6;
   uint64_t* dp_full = bars + 7;
@@ -116,7 +139,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* dq_empty = bars + 14;
   uint64_t* all_done = bars + 15;
   uint64_t* acc_empty = bars + 16;
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 17 + 2 * kBwdStages);
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 17 + 2 * Cfg::kStages);
 
   const int warp_idx = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -138,7 +161,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tma_prefetch_desc(&tmap_do);
     tma_prefetch_desc(&tmap_dq);
     mbar_init(kv_full, 1);
-    for (int i = 0; i < kBwdStages; ++i) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
       mbar_init(&qdo_full[i], 1);
       mbar_init(&qdo_empty[i], 1);
     }
@@ -161,11 +184,11 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_ptr;
-  const uint32_t tmem_s = tmem_base;
-  const uint32_t tmem_dp = tmem_base + 64;
-  const uint32_t tmem_dq = tmem_base + 128;
-  const uint32_t tmem_dv = tmem_base + 192;
-  const uint32_t tmem_dk = tmem_base + 320;
+  const uint32_t tmem_s = tmem_base + Cfg::kTmS;
+  const uint32_t tmem_dp = tmem_base + Cfg::kTmDp;
+  const uint32_t tmem_dq = tmem_base + Cfg::kTmDq0;      // dQ^T block b sits at tmem_dq + 64 * b
+  const uint32_t tmem_dv = tmem_base + Cfg::kTmDv;
+  const uint32_t tmem_dk = tmem_base + Cfg::kTmDk;
 
   if (warp_idx == 0) {
     // ============================ TMA producer ============================
@@ -178,28 +201,26 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int n_iter = nq_local * group;
         if (n_iter == 0) continue;
         if (tw > 0) mbar_wait(all_done, (tw - 1) & 1, 20);      // previous tile's MMAs are done with K / V
-        mbar_arrive_expect_tx(kv_full, 2 * kBwdKVBytes);
+        mbar_arrive_expect_tx(kv_full, Cfg::kKBytes + Cfg::kVBytes);
 #pragma unroll
-        for (int c = 0; c < D / 64; ++c) {
-          bwd_tma_load_4d(&tmap_k, kv_full, sK + c * (BKV * 128), c * 64, k0, kv_head, batch);
-          bwd_tma_load_4d(&tmap_v, kv_full, sV + c * (BKV * 128), c * 64, k0, kv_head, batch);
-        }
+        for (int c = 0; c < DQK / 64; ++c) bwd_tma_load_4d(&tmap_k, kv_full, sK + c * (BKV * 128), c * 64, k0, kv_head, batch);
+#pragma unroll
+        for (int c = 0; c < D / 64; ++c) bwd_tma_load_4d(&tmap_v, kv_full, sV + c * (BKV * 128), c * 64, k0, kv_head, batch);
         for (int it = 0; it < n_iter; ++it) {
           const int g = g_base + it;
-          const int st = g % kBwdStages;
-          mbar_wait(&qdo_empty[st], ((g / kBwdStages) & 1) ^ 1, 21);
-          uint8_t* sQ = sQdO + st * kBwdStageBytes;
-          uint8_t* sdO = sQ + kBwdQBytes;
-          mbar_arrive_expect_tx(&qdo_full[st], kBwdStageBytes + 2 * 64 * 4);
+          const int st = g % Cfg::kStages;
+          mbar_wait(&qdo_empty[st], ((g / Cfg::kStages) & 1) ^ 1, 21);
+          uint8_t* sQ = sQdO + st * Cfg::kStageBytes;
+          uint8_t* sdO = sQ + Cfg::kQBytes;
+          mbar_arrive_expect_tx(&qdo_full[st], Cfg::kStageBytes + 2 * 64 * 4);
           const int head = kv_head * group + it / nq_local, q0 = (i_begin + it % nq_local) * BQ;
           const long long stat_off = ((long long)batch * p.H + head) * p.s_pad + q0;
           bulk_load_1d(sLse + st * 64, p.lse2 + stat_off, 64 * 4, &qdo_full[st]);
           bulk_load_1d(sDsum + st * 64, p.dsum + stat_off, 64 * 4, &qdo_full[st]);
 #pragma unroll
-          for (int c = 0; c < D / 64; ++c) {
-            bwd_tma_load_4d(&tmap_q, &qdo_full[st], sQ + c * (BQ * 128), c * 64, q0, head, batch);
-            bwd_tma_load_4d(&tmap_do, &qdo_full[st], sdO + c * (BQ * 128), c * 64, q0, head, batch);
-          }
+          for (int c = 0; c < DQK / 64; ++c) bwd_tma_load_4d(&tmap_q, &qdo_full[st], sQ + c * (BQ * 128), c * 64, q0, head, batch);
+#pragma unroll
+          for (int c = 0; c < D / 64; ++c) bwd_tma_load_4d(&tmap_do, &qdo_full[st], sdO + c * (BQ * 128), c * 64, q0, head, batch);
         }
         g_base += n_iter;
         ++tw;
@@ -209,6 +230,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // ============================ MMA issuer ============================
     constexpr uint32_t idesc_s = make_idesc(1, 1, 0, 0, BKV, BQ);    // K (K-major) x Q (K-major)      -> S^T[128, 64]
     constexpr uint32_t idesc_dv = make_idesc(1, 1, 0, 1, BKV, D);    // P^T (K-major) x dO (MN-major)  -> dV[128, 128]
+    constexpr uint32_t idesc_dk = make_idesc(1, 1, 0, 1, BKV, DQK);  // dS^T (K-major) x Q (MN-major)  -> dK[128, DQK]
     constexpr uint32_t idesc_dq = make_idesc(1, 1, 1, 1, D, BQ);     // K (MN-major) x dS^T (MN-major) -> dQ^T[128, 64]
     // every UMMA smem descriptor is a constant plus (stage * stage_stride): build them once, the issue loop is then
     // two 64-bit adds per MMA (issue latency of this single thread is on the critical path: 32 MMAs per iteration)
@@ -220,18 +242,19 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint64_t kdS_mn = make_smem_desc_sw128(smem_u32(sdS), BKV * 128, 1024);
     const uint64_t kQ_km = make_smem_desc_sw128(smem_u32(sQdO), 16, 1024);
     const uint64_t kQ_mn = make_smem_desc_sw128(smem_u32(sQdO), BQ * 128, 1024);
-    const uint64_t kdO_km = make_smem_desc_sw128(smem_u32(sQdO + kBwdQBytes), 16, 1024);
-    const uint64_t kdO_mn = make_smem_desc_sw128(smem_u32(sQdO + kBwdQBytes), BQ * 128, 1024);
-    constexpr uint64_t kStageStep = kBwdStageBytes >> 4;
+    const uint64_t kdO_km = make_smem_desc_sw128(smem_u32(sQdO + Cfg::kQBytes), 16, 1024);
+    const uint64_t kdO_mn = make_smem_desc_sw128(smem_u32(sQdO + Cfg::kQBytes), BQ * 128, 1024);
+    constexpr uint64_t kStageStep = Cfg::kStageBytes >> 4;
     auto issue_s = [&](int g) {       // S^T(g) = K Q^T
-      const int st = g % kBwdStages;
-      mbar_wait(&qdo_full[st], (g / kBwdStages) & 1, 22);
+      const int st = g % Cfg::kStages;
+      mbar_wait(&qdo_full[st], (g / Cfg::kStages) & 1, 22);
       if (g > 0) mbar_wait(s_empty, (g - 1) & 1, 23);
+      if (!Cfg::kLookahead && g > 0) mbar_wait(dq_empty, (g - 1) & 1, 38);     // dQ^T(g-1) aliases the S^T / dP^T columns
       tcgen05_fence_after();
       if (elect_one()) {
         const uint64_t b0 = kQ_km + st * kStageStep;
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k)
+        for (int k = 0; k < DQK / 16; ++k)
           umma_f16<1>(tmem_s, kK_km + ((k / 4) * ((BKV * 128) >> 4) + (k % 4) * 2), b0 + ((k / 4) * ((BQ * 128) >> 4) + (k % 4) * 2),
                       idesc_s, k > 0 ? 1u : 0u);
         umma_commit<1>(s_full);
@@ -239,7 +262,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       __syncwarp();
     };
     auto issue_dp = [&](int g) {      // dP^T(g) = V dO^T
-      const int st = g % kBwdStages;
+      const int st = g % Cfg::kStages;
       if (g > 0) mbar_wait(dp_empty, (g - 1) & 1, 24);
       tcgen05_fence_after();
       if (elect_one()) {
@@ -258,15 +281,22 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int n_iter = max(0, n_q_tiles - tile_begin(k0)) * group;
       if (n_iter == 0) continue;
       mbar_wait(kv_full, tw & 1, 25);
-      issue_s(g_base);
-      issue_dp(g_base);
+      if constexpr (Cfg::kLookahead) {
+        issue_s(g_base);
+        issue_dp(g_base);
+      }
       for (int it = 0; it < n_iter; ++it) {
         const int g = g_base + it;
-        const int st = g % kBwdStages;
-        uint8_t* sQ = sQdO + st * kBwdStageBytes;
-        uint8_t* sdO = sQ + kBwdQBytes;
+        const int st = g % Cfg::kStages;
+        uint8_t* sQ = sQdO + st * Cfg::kStageBytes;
+        uint8_t* sdO = sQ + Cfg::kQBytes;
         SMX_TRACE(0, g, 0);
-        if (it + 1 < n_iter) issue_s(g + 1);
+        if constexpr (Cfg::kLookahead) {
+          if (it + 1 < n_iter) issue_s(g + 1);
+        } else {
+          issue_s(g);          // waits for dQ^T(g-1) to be drained (aliased columns)
+          issue_dp(g);
+        }
         SMX_TRACE(0, g, 1);
         // dV += P^T dO
         mbar_wait(p_full, g & 1, 26);
@@ -282,22 +312,30 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         __syncwarp();
         SMX_TRACE(0, g, 3);
-        if (it + 1 < n_iter) issue_dp(g + 1);
+        if constexpr (Cfg::kLookahead) {
+          if (it + 1 < n_iter) issue_dp(g + 1);
+        }
         SMX_TRACE(0, g, 4);
         // dK += dS^T Q ;  dQ^T = K^T dS^T
         mbar_wait(ds_full, g & 1, 27);
         SMX_TRACE(0, g, 5);
-        if (g > 0) mbar_wait(dq_empty, (g - 1) & 1, 28);
+        if (Cfg::kLookahead && g > 0) mbar_wait(dq_empty, (g - 1) & 1, 28);
         SMX_TRACE(0, g, 6);
         tcgen05_fence_after();
         if (elect_one()) {
           const uint64_t b0 = kQ_mn + st * kStageStep;
 #pragma unroll
           for (int k = 0; k < BQ / 16; ++k)
-            umma_f16<1>(tmem_dk, kdS_km + k * 2, b0 + k * ((16 * 128) >> 4), idesc_dv, (it > 0 || k > 0) ? 1u : 0u);
+            umma_f16<1>(tmem_dk, kdS_km + k * 2, b0 + k * ((16 * 128) >> 4), idesc_dk, (it > 0 || k > 0) ? 1u : 0u);
+          // dQ^T block b = rows [128 b, 128 b + 128) of K^T (for DQK = 192 the upper half of block 1 reads past the K
+          // tile into the V tile: finite garbage in TMEM lanes 64..127 that the drain drops)
 #pragma unroll
-          for (int k = 0; k < BKV / 16; ++k)
-            umma_f16<1>(tmem_dq, kK_mn + k * ((16 * 128) >> 4), kdS_mn + k * ((16 * 128) >> 4), idesc_dq, k > 0 ? 1u : 0u);
+          for (int b = 0; b < Cfg::kDqBlocks; ++b) {
+#pragma unroll
+            for (int k = 0; k < BKV / 16; ++k)
+              umma_f16<1>(tmem_dq + 64 * b, kK_mn + b * ((2 * BKV * 128) >> 4) + k * ((16 * 128) >> 4),
+                          kdS_mn + k * ((16 * 128) >> 4), idesc_dq, k > 0 ? 1u : 0u);
+          }
           umma_commit<1>(dq_full);
           umma_commit<1>(dkq_done);
           umma_commit<1>(&qdo_empty[st]);
@@ -329,11 +367,11 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int g = g_base + it;
         const int q0 = (i_begin + it % nq_local) * BQ;
         // per-column statistics ride on the same transaction barrier as Q / dO (bulk copies issued by the producer)
-        const int st = g % kBwdStages;
+        const int st = g % Cfg::kStages;
         const float4* lse4 = reinterpret_cast<const float4*>(sLse + st * 64 + col0);
         const float4* dsum4 = reinterpret_cast<const float4*>(sDsum + st * 64 + col0);
         if (warp_idx == 2) SMX_TRACE(1, g, 0);
-        mbar_wait(&qdo_full[st], (g / kBwdStages) & 1, 37);
+        mbar_wait(&qdo_full[st], (g / Cfg::kStages) & 1, 37);
         if (warp_idx == 2) SMX_TRACE(1, g, 1);
         mbar_wait(s_full, g & 1, 29);
         if (warp_idx == 2) SMX_TRACE(1, g, 2);
@@ -425,12 +463,12 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tcgen05_fence_after();
       }
       const bool row_ok = kv_row < p.S_kv;
-      __nv_bfloat16* out = p.dk + batch * p.dk_sb + (long long)(row_ok ? kv_row : 0) * p.dk_ss + kv_head * p.dk_sh + half * 64;
+      __nv_bfloat16* out = p.dk + batch * p.dk_sb + (long long)(row_ok ? kv_row : 0) * p.dk_ss + kv_head * p.dk_sh + half * (DQK / 2);
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < DQK / 64; ++c) {
         uint32_t o[32];
         if (n_iter > 0) {
-          tmem_ld_32x32b_x32(tmem_dk + lane_addr + half * 64 + c * 32, o);
+          tmem_ld_32x32b_x32(tmem_dk + lane_addr + half * (DQK / 2) + c * 32, o);
           tmem_ld_wait();
         } else {
 #pragma unroll
@@ -476,29 +514,35 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mbar_wait(dq_full, g & 1, 34);
         if (quad == 2) SMX_TRACE(2, g, 1);
         tcgen05_fence_after();
-        uint32_t r[64];
-        {
-          uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
-          uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
-          tmem_ld_32x32b_x32(tmem_dq + lane_addr, r0);
-          tmem_ld_32x32b_x32(tmem_dq + lane_addr + 32, r1);
-          tmem_ld_wait();
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(dq_empty);
-        // the previous tile's bulk reduce must have finished reading the staging buffer
-        if (quad == 2) SMX_TRACE(2, g, 2);
-        if (tid == 0) tma_store_wait_read<0>();
-        named_bar_sync(2, 128);
-        if (quad == 2) SMX_TRACE(2, g, 3);
+#pragma unroll 1
+        for (int b = 0; b < Cfg::kDqBlocks; ++b) {
+          uint32_t r[64];
+          {
+            uint32_t (&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+            uint32_t (&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+            tmem_ld_32x32b_x32(tmem_dq + 64 * b + lane_addr, r0);
+            tmem_ld_32x32b_x32(tmem_dq + 64 * b + lane_addr + 32, r1);
+            tmem_ld_wait();
+          }
+          if (b + 1 == Cfg::kDqBlocks) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_empty);
+          }
+          // the previous bulk reduce must have finished reading the staging buffer
+          if (quad == 2) SMX_TRACE(2, g, 2);
+          if (tid == 0) tma_store_wait_read<0>();
+          named_bar_sync(2, 128);
+          if (quad == 2) SMX_TRACE(2, g, 3);
 #pragma unroll
-        for (int i = 0; i < 64; ++i) sDq[i * D + d_idx] = __uint_as_float(r[i]);
-        fence_proxy_async_smem();
-        named_bar_sync(3, 128);
-        if (tid == 0) {
-          bwd_tma_reduce_add_4d(&tmap_dq, sDq, 0, q0, head, batch);
-          tma_store_commit();
+          for (int i = 0; i < 64; ++i) sDq[i * D + d_idx] = __uint_as_float(r[i]);
+          fence_proxy_async_smem();
+          named_bar_sync(3, 128);
+          if (tid == 0) {
+            // box = 128 head-dim columns starting at 128 b; columns past DQK are out of bounds and dropped by TMA
+            bwd_tma_reduce_add_4d(&tmap_dq, sDq, 128 * b, q0, head, batch);
+            tma_store_commit();
+          }
         }
         if (quad == 2) SMX_TRACE(2, g, 4);
       }
@@ -641,7 +685,7 @@ int smx_fmha_bwd(const void* q, const void* k, const void* v, const void* o, con
                  const long long* strides /* 8 x (sb, ss, sh): q k v o do dq dk dv */, float scale, int causal,
                  cudaStream_t stream, long long* trace) {
   using namespace smx;
-  if (d != kBwdD) return -31;
+  if (d != 128 && d != 192) return -31;      // d = qk head dim; v head dim is 128
   if (H % H_kv) return -30;
   const long long* sq = strides; const long long* sk = strides + 3; const long long* sv = strides + 6;
   const long long* so = strides + 9; const long long* sdo = strides + 12; const long long* sdq = strides + 15;
@@ -655,9 +699,9 @@ int smx_fmha_bwd(const void* q, const void* k, const void* v, const void* o, con
   if (rc) return rc;
   rc = bwd_make_tmap_4d(&tk, BF, SW, k, d, S_kv, H_kv, B, sk[1] * 2, sk[2] * 2, sk[0] * 2, 64, kBwdBKV);
   if (rc) return rc;
-  rc = bwd_make_tmap_4d(&tv, BF, SW, v, d, S_kv, H_kv, B, sv[1] * 2, sv[2] * 2, sv[0] * 2, 64, kBwdBKV);
+  rc = bwd_make_tmap_4d(&tv, BF, SW, v, kBwdD, S_kv, H_kv, B, sv[1] * 2, sv[2] * 2, sv[0] * 2, 64, kBwdBKV);
   if (rc) return rc;
-  rc = bwd_make_tmap_4d(&tdo, BF, SW, d_o, d, S_q, H, B, sdo[1] * 2, sdo[2] * 2, sdo[0] * 2, 64, kBwdBQ);
+  rc = bwd_make_tmap_4d(&tdo, BF, SW, d_o, kBwdD, S_q, H, B, sdo[1] * 2, sdo[2] * 2, sdo[0] * 2, 64, kBwdBQ);
   if (rc) return rc;
   rc = bwd_make_tmap_4d(&tdq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_NONE, dq_accum, d, S_q, H, B,
                         (uint64_t)H * d * 4, (uint64_t)d * 4, (uint64_t)S_q * H * d * 4, kBwdD, kBwdBQ);
@@ -669,7 +713,7 @@ int smx_fmha_bwd(const void* q, const void* k, const void* v, const void* o, con
     const int threads = 256;
     const long long blocks = (rows * 32 + threads - 1) / threads;
     fmha_bwd_dsum_kernel<<<(unsigned)blocks, threads, 0, stream>>>(
-        (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, lse, dsum, lse2, B, S_q, (int)s_pad, H, d, scale, so[0], so[1],
+        (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, lse, dsum, lse2, B, S_q, (int)s_pad, H, kBwdD, scale, so[0], so[1],
         so[2], sdo[0], sdo[1], sdo[2]);
   }
   FmhaBwdParams p;
@@ -678,14 +722,17 @@ int smx_fmha_bwd(const void* q, const void* k, const void* v, const void* o, con
   p.dk_sb = sdk[0]; p.dk_ss = sdk[1]; p.dk_sh = sdk[2]; p.dv_sb = sdv[0]; p.dv_ss = sdv[1]; p.dv_sh = sdv[2];
   static bool attr_set = false;
   if (!attr_set) {
-    e = cudaFuncSetAttribute(fmha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes);
+    e = cudaFuncSetAttribute(fmha_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<128>::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(fmha_bwd_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdCfg<192>::kSmemBytes);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int n_kv_tiles = (S_kv + kBwdBKV - 1) / kBwdBKV;
   p.pair = (causal && n_kv_tiles > 1) ? 1 : 0;
   dim3 grid(p.pair ? (n_kv_tiles + 1) / 2 : n_kv_tiles, H_kv, B);
-  fmha_bwd_kernel<<<grid, kBwdThreads, kBwdSmemBytes, stream>>>(tq, tk, tv, tdo, tdq, p);
+  if (d == 128) fmha_bwd_kernel<128><<<grid, kBwdThreads, BwdCfg<128>::kSmemBytes, stream>>>(tq, tk, tv, tdo, tdq, p);
+  else fmha_bwd_kernel<192><<<grid, kBwdThreads, BwdCfg<192>::kSmemBytes, stream>>>(tq, tk, tv, tdo, tdq, p);
   {
     const long long rows = (long long)B * S_q * H;
     const long long n = rows * (d / 8);

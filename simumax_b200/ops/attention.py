@@ -102,8 +102,8 @@ def fmha_bwd(d_o: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tenso
     slices of a packed d_qkv buffer. Returns (dq, dk, dv)."""
     B, S_q, H, D = q.shape
     _, S_kv, H_kv, _ = k.shape
-    if D != 128 or v.shape[-1] != 128:
-        raise NotImplementedError("fmha_bwd: head dim 128 only")
+    if D not in (128, 192) or v.shape[-1] != 128:
+        raise NotImplementedError("fmha_bwd: qk head dim 128 or 192 (MLA) with v head dim 128")
     if scale is None:
         scale = 1.0 / math.sqrt(D)
     dq = torch.empty_like(q) if dq is None else dq

@@ -79,3 +79,26 @@ def test_fmha_bwd(cfg, causal):
         assert torch.isfinite(got.float()).all(), name
         assert err < 2e-2, (name, err.item())
         torch.testing.assert_close(got.float(), ref, atol=5e-2 * ref.abs().max().item(), rtol=0)
+
+
+@pytest.mark.parametrize("causal", [True, False])
+@pytest.mark.parametrize("cfg", [(1, 256, 2, 2), (2, 512, 4, 4), (1, 200, 4, 2), (1, 1024, 8, 8)])
+def test_fmha_bwd_mla(cfg, causal):
+    """MLA head dims (qk 192 / v 128): the backward variant without S/dP look-ahead (dQ^T aliases their TMEM columns)."""
+    from simumax_b200.ops.attention import fmha_bwd, fmha_fwd
+    torch.manual_seed(5)
+    B, S, H, Hk = cfg
+    q = torch.randn(B, S, H, 192, device="cuda").bfloat16()
+    k = torch.randn(B, S, Hk, 192, device="cuda").bfloat16()
+    v = torch.randn(B, S, Hk, 128, device="cuda").bfloat16()
+    d_o = torch.randn(B, S, H, 128, device="cuda").bfloat16()
+    scale = 1.0 / math.sqrt(192)
+    o, lse = fmha_fwd(q, k, v, causal=causal, scale=scale)
+    dq, dk, dv = fmha_bwd(d_o, q, k, v, o, lse, causal=causal, scale=scale)
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    ro, _ = _ref(qf, kf, vf, causal, scale)
+    ro.backward(d_o.float())
+    for name, got, ref in (("dq", dq, qf.grad), ("dk", dk, kf.grad), ("dv", dv, vf.grad)):
+        assert torch.isfinite(got.float()).all(), name
+        err = (got.float() - ref).norm() / ref.norm()
+        assert err < 2e-2, (name, err.item())
