@@ -147,3 +147,47 @@ def gemm(a: torch.Tensor, b: torch.Tensor, layout: str = "TN", out: torch.Tensor
 
 def gemm_flops(M: int, N: int, K: int, G: int = 1) -> float:
     return 2.0 * G * M * N * K
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# MXFP8 (block-scaled fp8): e4m3 payload + one UE8M0 (power-of-two) scale per 32 consecutive K elements of each row
+# ------------------------------------------------------------------------------------------------------------------
+def mxfp8_quantize(x: torch.Tensor):
+    """x [rows, K] (K % 32 == 0) -> (payload e4m3 [rows, K], scales uint8 [rows, K / 32]);  x ~= payload * 2^(scale - 127)."""
+    rows, K = x.shape
+    assert K % 32 == 0
+    xb = x.float().view(rows, K // 32, 32)
+    amax = xb.abs().amax(dim=-1).clamp_min(1e-30)
+    e = torch.ceil(torch.log2(amax / 448.0)).clamp(-127, 127)
+    q = (xb / torch.exp2(e)[..., None]).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).view(rows, K)
+    return q.contiguous(), (e + 127).to(torch.uint8).contiguous()
+
+
+def mxfp8_dequantize(q: torch.Tensor, scales: torch.Tensor) -> torch.Tensor:
+    rows, K = q.shape
+    return (q.float().view(rows, K // 32, 32) * torch.exp2(scales.float() - 127.0)[..., None]).view(rows, K)
+
+
+def gemm_mxfp8(a: torch.Tensor, sfa: torch.Tensor, b: torch.Tensor, sfb: torch.Tensor, out: torch.Tensor | None = None,
+               out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """out[M, N] = dequant(a, sfa)[M, K] @ dequant(b, sfb)[N, K]^T with the scaling done inside tcgen05
+    (``kind::mxf8f6f4.block_scale``, csrc/gemm_mxfp8.cu).  K must be a multiple of 128."""
+    assert a.dtype == torch.float8_e4m3fn and b.dtype == torch.float8_e4m3fn and sfa.dtype == torch.uint8 and sfb.dtype == torch.uint8
+    M, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K and K % 128 == 0 and sfa.shape == (M, K // 32) and sfb.shape == (N, K // 32)
+    assert a.stride(1) == 1 and b.stride(1) == 1 and sfa.is_contiguous() and sfb.is_contiguous()
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=out_dtype)
+    f = _lib.lib().smx_gemm_mxfp8
+    if not getattr(f, "_configured", False):
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int] * 4 + [ctypes.c_longlong] * 5 + [ctypes.c_int, ctypes.c_void_p]
+        f._configured = True
+    nsm = _num_sms(a.device.index if a.device.index is not None else torch.cuda.current_device())
+    rc = f(a.data_ptr(), b.data_ptr(), out.data_ptr(), sfa.data_ptr(), sfb.data_ptr(), M, N, K,
+           1 if out.dtype == torch.float32 else 0, a.stride(0), b.stride(0), out.stride(0), sfa.stride(0), sfb.stride(0), nsm,
+           torch.cuda.current_stream(a.device).cuda_stream)
+    _lib.check(rc, f"gemm_mxfp8 M{M} N{N} K{K}")
+    _lib.count_launch()
+    return out

@@ -111,3 +111,23 @@ def test_gemm_cta_pair_kernel(layout, shape, mode):
         c = torch.full((M, N), 0.5, device="cuda", dtype=torch.float32)
         gemm(a, b, layout, out=c, accumulate=True, two_cta=True)
         torch.testing.assert_close(c, ref + 0.5, atol=1e-3 * ref.abs().max().item(), rtol=1e-4)
+
+
+@pytest.mark.parametrize("shape", [(128, 256, 128), (200, 300, 384), (1024, 768, 1024), (4096, 512, 2048)])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_gemm_mxfp8_block_scaled(shape, out_dtype):
+    """tcgen05 kind::mxf8f6f4.block_scale: result must equal the matmul of the dequantised operands; every 32-block gets
+    a different power-of-two magnitude so a misplaced scale factor cannot go unnoticed."""
+    from simumax_b200.ops.gemm import gemm_mxfp8, mxfp8_dequantize, mxfp8_quantize
+    torch.manual_seed(13)
+    M, N, K = shape
+    x = torch.randn(M, K, device="cuda") * torch.exp2(torch.randint(-6, 6, (M, K // 32), device="cuda").float()).repeat_interleave(32, 1)
+    w = torch.randn(N, K, device="cuda") * torch.exp2(torch.randint(-6, 6, (N, K // 32), device="cuda").float()).repeat_interleave(32, 1)
+    qa, sa = mxfp8_quantize(x)
+    qb, sb = mxfp8_quantize(w)
+    ref = mxfp8_dequantize(qa, sa) @ mxfp8_dequantize(qb, sb).t()
+    out = gemm_mxfp8(qa, sa, qb, sb, out_dtype=out_dtype)
+    tol = 2e-5 if out_dtype == torch.float32 else 1e-2
+    assert ((out.float() - ref).abs().max() / ref.abs().max()).item() < tol
+    # and the quantisation itself is faithful to the unquantised product to fp8 precision
+    assert ((ref - x @ w.t()).norm() / (x @ w.t()).norm()).item() < 6e-2
