@@ -59,6 +59,10 @@ def measure_matmul(req: ShapeRequest, fp8: bool = False) -> Dict[str, float]:
     m_eff = b * m if layout in ("TN", "NN") else m          # batch folds into rows for activations
     k_eff = k if layout in ("TN", "NN") else b * k
     dt = torch.float8_e4m3fn if fp8 else torch.bfloat16
+    if fp8:
+        # fp8 tensor-core operands must be K-major: dgrad / wgrad multiply pre-transposed fp8 copies (what TE's
+        # Float8Tensor keeps around); the transposition itself belongs to the quantiser op, not to the GEMM key
+        layout = "TN"
     a_shape = {"TN": (m_eff, k_eff), "NN": (m_eff, k_eff), "NT": (k_eff, m_eff), "TT": (k_eff, m_eff)}[layout]
     b_shape = {"TN": (n, k_eff), "NN": (k_eff, n), "NT": (k_eff, n), "TT": (n, k_eff)}[layout]
     per_set = (a_shape[0] * a_shape[1] + b_shape[0] * b_shape[1]) * (1 if fp8 else 2) + m_eff * n * out_dtype.itemsize
@@ -77,7 +81,15 @@ def measure_group_matmul(req: ShapeRequest, fp8: bool = False) -> Dict[str, floa
     ng, M, N, K = (req.geti(x) for x in ("ng", "M", "N", "K"))
     stage = req.fields["stage"]
     dt = torch.float8_e4m3fn if fp8 else torch.bfloat16
-    if stage == "fwd":            # y[g, M, N] = x[g, M, K] w[g, N, K]^T
+    if fp8 and stage != "fwd":     # K-major operands only (see measure_matmul): same flops through the TN kernel
+        if stage == "bwd_grad_act":
+            M, N, K, stage = M, K, N, "fwd"                 # dx[g, M, K] = dy[g, M, N] w^T[g, K, N]^T
+        else:
+            ng, M, N, K = ng, N, K, M                       # dw[g, N, K] = dy^T[g, N, M] x^T[g, K, M]^T
+            stage = "fwd_f32"
+    if stage == "fwd_f32":
+        a_shape, b_shape, layout, out_shape, out_dtype, acc = (ng, M, K), (ng, N, K), "TN", (ng, M, N), torch.float32, True
+    elif stage == "fwd":            # y[g, M, N] = x[g, M, K] w[g, N, K]^T
         a_shape, b_shape, layout, out_shape, out_dtype, acc = (ng, M, K), (ng, N, K), "TN", (ng, M, N), torch.bfloat16, False
     elif stage == "bwd_grad_act":  # dx[g, M, K] = dy[g, M, N] w[g, N, K]
         a_shape, b_shape, layout, out_shape, out_dtype, acc = (ng, M, N), (ng, N, K), "NN", (ng, M, K), torch.bfloat16, False

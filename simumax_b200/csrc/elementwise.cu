@@ -450,6 +450,28 @@ static inline int grid_for(long long work_items, int threads, int cap = 148 * 16
 }
 #define SMX_STREAM reinterpret_cast<cudaStream_t>(stream)
 
+namespace smx {
+// out[i] = sum_s slots[s * n + i]   (bf16 in, fp32 accumulate, bf16 out): the owner-side half of the fused GEMM + reduce-scatter
+__global__ void sum_slots_kernel(const __nv_bfloat16* __restrict__ slots, __nv_bfloat16* __restrict__ out, long long n, int nslots) {
+  const long long i8 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8;
+  if (i8 >= n) return;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int s = 0; s < nslots; ++s) {
+    const uint4 v = *reinterpret_cast<const uint4*>(slots + (long long)s * n + i8);
+    const __nv_bfloat162* p2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(p2[j]);
+      acc[2 * j] += f.x;
+      acc[2 * j + 1] += f.y;
+    }
+  }
+  uint4 r;
+  r.x = pack_bf16x2(acc[0], acc[1]); r.y = pack_bf16x2(acc[2], acc[3]); r.z = pack_bf16x2(acc[4], acc[5]); r.w = pack_bf16x2(acc[6], acc[7]);
+  *reinterpret_cast<uint4*>(out + i8) = r;
+}
+}  // namespace smx
+
 extern "C" {
 
 int smx_rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, long long rows, int H, float eps,
@@ -532,6 +554,14 @@ int smx_add(const void* a, const void* b, void* y, long long n, void* stream) {
 int smx_copy(const void* src, void* dst, long long nbytes, void* stream) {
   if (nbytes % 16) return -20;
   smx::copy_kernel<<<grid_for(nbytes / 16, 256, 148 * 8), 256, 0, SMX_STREAM>>>((const uint4*)src, (uint4*)dst, nbytes / 16);
+  return (int)cudaGetLastError();
+}
+
+int smx_sum_slots(const void* slots, void* out, long long n, int nslots, void* stream) {
+  if (n % 8) return -50;
+  const long long threads = n / 8;
+  smx::sum_slots_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(slots), reinterpret_cast<__nv_bfloat16*>(out), n, nslots);
   return (int)cudaGetLastError();
 }
 

@@ -48,6 +48,7 @@ struct GemmParams {
   // product belongs to rank r and is summed into that rank's buffer with red.global.add.v4.f32 straight from the
   // epilogue registers (peer-mapped memory over NVLink), tile by tile while later tiles are still being multiplied.
   int rs_world, rs_rows;
+  int rs_rank;               // bf16 output: this rank's slot index in the owner's [world][rs_rows, N] staging buffer
   float* rs_out[8];
   // Fused all-gather -> GEMM prologue (ag_flags != nullptr): A is a gathered buffer that peers fill chunk by chunk over
   // NVLink while this kernel runs; ag_flags[row / ag_rows_per_flag] >= ag_epoch means those rows have landed.  M-tiles
@@ -264,6 +265,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_wait(&tmem_full_bar[as], aphase);
       tcgen05_fence_after();
       OutT* c_row = c_base + (long long)g * p.c_batch_stride + (long long)row * p.ldc;
+      if constexpr (!OUT_F32) {
+        if (p.rs_world > 1 && row < p.M) {
+          // fused reduce-scatter, bf16 flavour: plain 16-byte stores of my partial tile into slot `rs_rank` of the owning
+          // rank's staging buffer (peer-mapped memory); the owner sums the `world` slots afterwards
+          const int owner = row / p.rs_rows;
+          c_row = reinterpret_cast<OutT*>(p.rs_out[owner]) + ((long long)p.rs_rank * p.rs_rows + (row - owner * p.rs_rows)) * p.ldc;
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < n_eff / 32; ++c) {
         uint32_t r[32];
@@ -416,7 +425,7 @@ int pick_block_n(int G, int M, int N, int num_sms) {
 }  // namespace
 
 namespace {
-int g_rs_world = 1;
+int g_rs_world = 1, g_rs_rank = 0;
 float* g_rs_out[8] = {nullptr};
 const uint32_t* g_ag_flags = nullptr;
 int g_ag_rows = 1, g_ag_first = 0;
@@ -428,9 +437,9 @@ extern "C" {
 // Arms the fused reduce-scatter epilogue for the NEXT smx_gemm call (fp32 output, G == 1): out_ptrs[r] is rank r's
 // [M / world, N] fp32 buffer as mapped in this process (symmetric memory); the caller zeroes the buffers beforehand and
 // runs a cross-rank barrier afterwards.
-int smx_gemm_arm_reduce_scatter(void* const* out_ptrs, int world) {
+int smx_gemm_arm_reduce_scatter(void* const* out_ptrs, int world, int rank) {
   if (world < 1 || world > 8) return -14;
-  g_rs_world = world;
+  g_rs_world = world; g_rs_rank = rank;
   for (int i = 0; i < world; ++i) g_rs_out[i] = reinterpret_cast<float*>(out_ptrs[i]);
   return 0;
 }
@@ -471,11 +480,11 @@ int smx_gemm(const void* A, const void* B, void* C, int G, int M, int N, int K, 
   p.ldc = ldc; p.c_batch_stride = c_bs; p.alpha = alpha; p.accumulate = accumulate;
   p.ag_flags = g_ag_flags; p.ag_rows_per_flag = g_ag_rows; p.ag_first_m_blk = g_ag_first; p.ag_epoch = g_ag_epoch;
   g_ag_flags = nullptr;        // one-shot
-  p.rs_world = 1; p.rs_rows = M;
+  p.rs_world = 1; p.rs_rows = M; p.rs_rank = 0;
   for (int i = 0; i < 8; ++i) p.rs_out[i] = nullptr;
   if (g_rs_world > 1) {
-    if (!out_f32 || G != 1 || N % 4 || M % g_rs_world) return -13;
-    p.rs_world = g_rs_world; p.rs_rows = M / g_rs_world;
+    if (G != 1 || N % 8 || M % g_rs_world || accumulate) return -13;
+    p.rs_world = g_rs_world; p.rs_rows = M / g_rs_world; p.rs_rank = g_rs_rank;
     for (int i = 0; i < g_rs_world; ++i) p.rs_out[i] = g_rs_out[i];
     g_rs_world = 1;      // one-shot: applies to this launch only
   }

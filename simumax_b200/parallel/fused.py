@@ -17,36 +17,58 @@ from .symm import SymmetricWorkspace
 
 
 def gemm_reduce_scatter(a: torch.Tensor, b: torch.Tensor, ws: SymmetricWorkspace, layout: str = "TN", out_off: int | None = None,
-                        alpha: float = 1.0) -> torch.Tensor:
-    """out_r[M/world, N] (fp32, in the symmetric buffer at ``out_off``) = sum over ranks of (op(a) @ op(b))[r-th row block].
+                        alpha: float = 1.0, mode: str = "slots", out: torch.Tensor | None = None) -> torch.Tensor:
+    """out_r[M/world, N] = sum over ranks of (op(a) @ op(b))[r-th row block].
 
-    a / b are this rank's operands (K already sharded by the caller).  Returns this rank's output view; it is complete
-    when the call returns control to the stream (a device-side cross-rank barrier closes the op)."""
+    a / b are this rank's operands (K already sharded by the caller).  Two epilogue flavours:
+
+    * ``mode="slots"`` (default, bf16): every rank stores its partial tile with plain 16-byte stores into slot ``rank`` of
+      the owner's ``[world][M/world, N]`` staging buffer (peer-mapped memory); after the closing device-side barrier the
+      owner sums the slots (fp32 accumulate) into a local bf16 tensor.  NVLink carries bf16 once, no atomics.
+    * ``mode="red"`` (fp32): tiles are added into the owner's fp32 buffer with ``red.global.add.v4.f32`` -- single pass,
+      but 16-byte remote atomics are much slower than stores on NVLink (kept for comparison).
+    """
     a_mn, b_mn = _LAYOUTS[layout]
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     a3, b3 = _tma_ready(_as3d(a)), _tma_ready(_as3d(b))
     M, K = (a3.shape[2], a3.shape[1]) if a_mn else (a3.shape[1], a3.shape[2])
     N = b3.shape[2] if b_mn else b3.shape[1]
     world = ws.world
-    assert M % world == 0 and N % 4 == 0
+    assert M % world == 0 and N % 8 == 0
     out_off = ws.in_bytes if out_off is None else out_off
     rows = M // world
-    out = ws.view(out_off, torch.float32, rows * N).view(rows, N)
-    out.zero_()
-    ws.barrier()                                   # every rank's buffer is cleared before anybody adds into it
     lib = _lib.lib()
     arm = lib.smx_gemm_arm_reduce_scatter
     arm.restype = ctypes.c_int
-    arm.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
-    _lib.check(arm(ws.peer_ptrs(out_off), world), "arm_reduce_scatter")
+    arm.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int]
     stream = torch.cuda.current_stream(a.device).cuda_stream
     nsm = _num_sms(a.device.index if a.device.index is not None else torch.cuda.current_device())
-    rc = _fn()(a3.data_ptr(), b3.data_ptr(), out.data_ptr(), 1, M, N, K, a_mn, b_mn, 0, 1, 0, float(alpha),
+    if mode == "red":
+        res = ws.view(out_off, torch.float32, rows * N).view(rows, N)
+        res.zero_()
+        ws.barrier()                               # every rank's buffer is cleared before anybody adds into it
+        _lib.check(arm(ws.peer_ptrs(out_off), world, ws.rank), "arm_reduce_scatter")
+        rc = _fn()(a3.data_ptr(), b3.data_ptr(), res.data_ptr(), 1, M, N, K, a_mn, b_mn, 0, 1, 0, float(alpha),
+                   a3.stride(1), b3.stride(1), N, 0, 0, 0, 0, nsm, stream)
+        _lib.check(rc, f"gemm_reduce_scatter[red,{layout}] M{M} N{N} K{K} world{world}")
+        _lib.count_launch()
+        ws.barrier()                               # all peers' adds have landed
+        return res
+    slots = ws.view(out_off, torch.bfloat16, world * rows * N)
+    ws.barrier()                                   # every owner has finished summing the previous call's slots
+    _lib.check(arm(ws.peer_ptrs(out_off), world, ws.rank), "arm_reduce_scatter")
+    rc = _fn()(a3.data_ptr(), b3.data_ptr(), slots.data_ptr(), 1, M, N, K, a_mn, b_mn, 0, 0, 0, float(alpha),
                a3.stride(1), b3.stride(1), N, 0, 0, 0, 0, nsm, stream)
-    _lib.check(rc, f"gemm_reduce_scatter[{layout}] M{M} N{N} K{K} world{world}")
+    _lib.check(rc, f"gemm_reduce_scatter[slots,{layout}] M{M} N{N} K{K} world{world}")
     _lib.count_launch()
-    ws.barrier()                                   # all peers' adds have landed
-    return out
+    ws.barrier()                                   # every peer's stores into my slots have landed
+    res = torch.empty(rows, N, device=a.device, dtype=torch.bfloat16) if out is None else out
+    f = lib.smx_sum_slots
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]
+    _lib.check(f(slots.data_ptr(), res.data_ptr(), rows * N, world, stream), "sum_slots")
+    _lib.count_launch()
+    return res
 
 
 def allgather_gemm(x_shard: torch.Tensor, w: torch.Tensor, ws: SymmetricWorkspace, layout: str = "TN", chunks: int = 32,
