@@ -27,7 +27,7 @@ constexpr int k2Threads = 192;
 constexpr int k2ABytes = 128 * k2RowBytes;           // 16 KB
 constexpr int k2BBytes = 128 * k2RowBytes;           // 16 KB (half of B)
 constexpr int k2StageBytes = k2ABytes + k2BBytes;    // 32 KB
-constexpr int k2Stages = 6;
+constexpr int k2Stages = 7;
 constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;       // clears the CTA-rank bit of a shared::cluster address (-> CTA 0 of the pair)
 
@@ -37,6 +37,10 @@ struct Gemm2Params {
   long long ldc, c_batch_stride;
   float alpha;
   int accumulate;
+  // fused all-gather prologue (see gemm_tcgen05.cu): flags[row / ag_rows_per_flag] >= ag_epoch <=> those rows of A landed
+  const uint32_t* ag_flags;
+  int ag_rows_per_flag, ag_first_m_blk;
+  uint32_t ag_epoch;
 };
 
 template <bool A_MN, bool B_MN, bool OUT_F32>
@@ -96,6 +100,10 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int in_group = r - group_id * width;
     m_blk = first_m + in_group % gsz;
     n_blk = in_group / gsz;
+    if (p.ag_flags) {
+      m_blk += p.ag_first_m_blk;
+      if (m_blk >= p.m_tiles) m_blk -= p.m_tiles;
+    }
   };
 
   // Work list: full 256 x 256 tiles for the rounds that occupy every pair, then the tiles of the last partial round cut
@@ -129,6 +137,22 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int half = n_eff >> 1;                               // B rows staged by each CTA (128 or 64)
         const int m0 = m_blk * k2BlockM + (int)cta_rank * 128;     // my rows of A / of the output
         const int n0 = n_base + (int)cta_rank * half;              // my half of B
+        if (p.ag_flags) {
+          // gathered A: wait until my 128 rows of this tile have been delivered by their owner's gather kernel
+          const int last_row = min(m0 + 128, p.M) - 1;
+          const uint64_t t0 = global_timer_ns();
+          for (int f = m0 / p.ag_rows_per_flag; f <= last_row / p.ag_rows_per_flag; ++f) {
+            uint32_t v;
+            do {
+              asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.ag_flags + f) : "memory");
+              if ((int32_t)(v - p.ag_epoch) < 0 && global_timer_ns() - t0 > 20000000000ull) {
+                printf("simumax_b200: all-gather GEMM (2-CTA) timed out on flag %d (have %u want %u)\n", f, v, p.ag_epoch);
+                __trap();
+              }
+            } while ((int32_t)(v - p.ag_epoch) < 0);
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 41);
           uint8_t* sa = smem + stage * k2StageBytes;
@@ -330,7 +354,21 @@ int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const smx
 
 }  // namespace
 
+namespace {
+const uint32_t* g2_ag_flags = nullptr;
+int g2_ag_rows = 1, g2_ag_first = 0;
+uint32_t g2_ag_epoch = 0;
+}  // namespace
+
 extern "C" {
+
+// Arms the fused all-gather prologue for the NEXT smx_gemm_2cta call; first_m_blk counts 256-row pair tiles.
+int smx_gemm_2cta_arm_all_gather(const void* flags, int rows_per_flag, int first_m_blk, unsigned epoch) {
+  if (rows_per_flag <= 0) return -15;
+  g2_ag_flags = reinterpret_cast<const uint32_t*>(flags);
+  g2_ag_rows = rows_per_flag; g2_ag_first = first_m_blk; g2_ag_epoch = epoch;
+  return 0;
+}
 
 // Same contract as smx_gemm (bf16 inputs only).  Returns -12 when the problem is not worth a 256 x 256 pair tile.
 int smx_gemm_2cta(const void* A, const void* B, void* C, int G, int M, int N, int K, int a_mn, int b_mn, int out_f32,
@@ -353,6 +391,8 @@ int smx_gemm_2cta(const void* A, const void* B, void* C, int G, int M, int N, in
   p.m_tiles = (M + smx::k2BlockM - 1) / smx::k2BlockM;
   p.n_tiles = (N + smx::k2BlockN - 1) / smx::k2BlockN;
   p.ldc = ldc; p.c_batch_stride = c_bs; p.alpha = alpha; p.accumulate = accumulate;
+  p.ag_flags = g2_ag_flags; p.ag_rows_per_flag = g2_ag_rows; p.ag_first_m_blk = g2_ag_first; p.ag_epoch = g2_ag_epoch;
+  g2_ag_flags = nullptr;        // one-shot
   if (!a_mn && !b_mn) return out_f32 ? launch_2cta<false, false, true>(ta, tb, C, p, num_sms, stream)
                                      : launch_2cta<false, false, false>(ta, tb, C, p, num_sms, stream);
   if (!a_mn && b_mn)  return out_f32 ? launch_2cta<false, true, true>(ta, tb, C, p, num_sms, stream)

@@ -115,15 +115,25 @@ def allgather_gemm(x_shard: torch.Tensor, w: torch.Tensor, ws: SymmetricWorkspac
         _lib.count_launch()
     y = torch.empty(M, N, device=x_shard.device, dtype=torch.bfloat16) if out is None else out
     lib = _lib.lib()
-    arm = lib.smx_gemm_arm_all_gather
-    arm.restype = ctypes.c_int
-    arm.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint]
     flags = ws.view(flag_off, torch.int32, 1024)
-    _lib.check(arm(flags.data_ptr(), ms // chunks, rank * ms // 128, epoch), "arm_all_gather")
     a3, b3 = _tma_ready(_as3d(xg)), _tma_ready(_as3d(w))
     nsm = _num_sms(x_shard.device.index if x_shard.device.index is not None else torch.cuda.current_device())
-    rc = _fn()(a3.data_ptr(), b3.data_ptr(), y.data_ptr(), 1, M, N, K, 0, 0, 0, 0, 0, 1.0, a3.stride(1), b3.stride(1), y.stride(0),
-               0, 0, 0, 0, nsm, main.cuda_stream)
+    pair_ok = M >= 256 and N >= 256 and (rank * ms) % 256 == 0
+    if pair_ok:                           # CTA-pair kernel: first tile index counts 256-row tiles
+        from ..ops.gemm import _fn2
+        arm = lib.smx_gemm_2cta_arm_all_gather
+        arm.restype = ctypes.c_int
+        arm.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint]
+        _lib.check(arm(flags.data_ptr(), ms // chunks, rank * ms // 256, epoch), "arm_all_gather_2cta")
+        rc = _fn2()(a3.data_ptr(), b3.data_ptr(), y.data_ptr(), 1, M, N, K, 0, 0, 0, 0, 1.0, a3.stride(1), b3.stride(1), y.stride(0),
+                    0, 0, 0, nsm, main.cuda_stream)
+    else:
+        arm = lib.smx_gemm_arm_all_gather
+        arm.restype = ctypes.c_int
+        arm.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint]
+        _lib.check(arm(flags.data_ptr(), ms // chunks, rank * ms // 128, epoch), "arm_all_gather")
+        rc = _fn()(a3.data_ptr(), b3.data_ptr(), y.data_ptr(), 1, M, N, K, 0, 0, 0, 0, 0, 1.0, a3.stride(1), b3.stride(1), y.stride(0),
+                   0, 0, 0, 0, nsm, main.cuda_stream)
     _lib.check(rc, f"allgather_gemm M{M} N{N} K{K} world{world}")
     _lib.count_launch()
     main.wait_stream(comm)                # the gather kernel itself must be complete before the workspace is reused

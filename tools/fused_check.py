@@ -74,7 +74,7 @@ def main():
         xg = torch.empty(M, K, device="cuda", dtype=torch.bfloat16)
         dist.all_gather_into_tensor(xg, xs)
         ref = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-        gemm(xg, w, "TN", out=ref, two_cta=False)
+        gemm(xg, w, "TN", out=ref)
         torch.cuda.synchronize()
         err = ((y.float() - ref.float()).abs().max() / ref.float().abs().max()).item()
         good = err < 1e-3
@@ -83,9 +83,9 @@ def main():
         t_fused = timed(lambda: allgather_gemm(xs, w, ws, out=yb))
         def unfused():
             dist.all_gather_into_tensor(xg, xs)
-            gemm(xg, w, "TN", out=ref, two_cta=False)
+            gemm(xg, w, "TN", out=ref)
         t_unf = timed(unfused)
-        t_gemm = timed(lambda: gemm(xg, w, "TN", out=ref, two_cta=False))
+        t_gemm = timed(lambda: gemm(xg, w, "TN", out=ref))
         roof_ms = max(2.0 * M * N * K / 1.67e15, (world - 1) / world * M * K * 2 / 900e9) * 1e3
         row = {"op": "allgather_gemm", "M": M, "N": N, "K": K, "rel_err": err, "fused_ms": t_fused, "nccl_ag_then_gemm_ms": t_unf,
                "gemm_only_ms": t_gemm, "roofline_ms": roof_ms, "fused_fraction_of_roofline": roof_ms / t_fused}
