@@ -172,6 +172,83 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_bwd_kernel(const __nv_bfloat1
 }
 
 // ----------------------------------------------------------------------------------------------
+// Owner-side half of the fused GEMM -> reduce-scatter (gemm_2cta.cu, RS epilogue), fused with what follows a row-parallel
+// linear in a transformer block:   x2 = residual + sum_s slots[s];   h = rmsnorm(x2) * gamma.
+// The kernel itself waits (thread 0 of every CTA, ld.acquire.sys) until this rank's completion counter says that every
+// CTA of every rank's GEMM has landed its stores -- no separate barrier launch.  One CTA per row.
+// ----------------------------------------------------------------------------------------------
+template <int THREADS, int VPT>
+__global__ void __launch_bounds__(THREADS) rs_consume_kernel(const __nv_bfloat16* __restrict__ slots, int nslots,
+                                                            long long slot_stride, const __nv_bfloat16* __restrict__ residual,
+                                                            __nv_bfloat16* __restrict__ sum_out,
+                                                            const __nv_bfloat16* __restrict__ gamma,
+                                                            __nv_bfloat16* __restrict__ normed, float* __restrict__ rstd,
+                                                            int H, float eps, const uint32_t* counter, uint32_t target) {
+  __shared__ float red[32];
+  if (counter != nullptr) {
+    if (threadIdx.x == 0) {
+      const uint64_t t0 = global_timer_ns();
+      uint32_t v;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if ((int32_t)(v - target) < 0 && global_timer_ns() - t0 > 20000000000ull) {
+          printf("simumax_b200: reduce-scatter consumer timed out (counter %u, want %u)\n", v, target);
+          __trap();
+        }
+      } while ((int32_t)(v - target) < 0);
+    }
+    __syncthreads();
+  }
+  const long long row = blockIdx.x;
+  float v[VPT][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * THREADS + threadIdx.x) * 8;
+    if (c < H) {
+      if (residual) load8(residual + row * H + c, v[i]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+      }
+      for (int s = 0; s < nslots; ++s) {
+        float t[8];
+        load8(slots + s * slot_stride + row * H + c, t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] += t[j];
+      }
+      // round to bf16 first: the normalisation must see exactly the residual stream that is stored (and re-read in backward)
+      bf16x8 r;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r.v[j] = __floats2bfloat162_rn(v[i][2 * j], v[i][2 * j + 1]);
+      if (sum_out) *reinterpret_cast<bf16x8*>(sum_out + row * H + c) = r;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(r.v[j]);
+        v[i][2 * j] = f.x;
+        v[i][2 * j + 1] = f.y;
+        ss += f.x * f.x + f.y * f.y;
+      }
+    }
+  }
+  if (gamma == nullptr) return;
+  ss = block_sum<THREADS>(ss, red);
+  const float r = rsqrtf(ss / H + eps);
+  if (threadIdx.x == 0 && rstd) rstd[row] = r;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * THREADS + threadIdx.x) * 8;
+    if (c < H) {
+      float g[8], o[8];
+      load8(gamma + c, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = v[i][j] * r * g[j];
+      store8(normed + row * H + c, o);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // SwiGLU: y = silu(a) * b with [a | b] = x[:, :F], x[:, F:]
 // ----------------------------------------------------------------------------------------------
 __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long rows,
@@ -482,6 +559,24 @@ int smx_rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, long
   else if (H <= 8192) smx::rmsnorm_fwd_kernel<512, 2><<<(unsigned)rows, 512, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (bf16*)y, rstd, H, eps);
   else if (H <= 16384) smx::rmsnorm_fwd_kernel<512, 4><<<(unsigned)rows, 512, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (bf16*)y, rstd, H, eps);
   else return -21;
+  return (int)cudaGetLastError();
+}
+
+// slots: [nslots][rows, H] bf16 (this rank's staging buffer).  residual / sum_out / gamma (+ normed, rstd) / counter optional.
+int smx_rs_consume(const void* slots, int nslots, long long rows, int H, const void* residual, void* sum_out,
+                   const void* gamma, void* normed, float* rstd, float eps, const void* counter, unsigned target,
+                   void* stream) {
+  if (H % 8) return -20;
+  if (gamma && !normed) return -22;
+  const long long ss = rows * H;
+#define SMX_RSC(T, V) smx::rs_consume_kernel<T, V><<<(unsigned)rows, T, 0, SMX_STREAM>>>((const bf16*)slots, nslots, ss, \
+    (const bf16*)residual, (bf16*)sum_out, (const bf16*)gamma, (bf16*)normed, rstd, H, eps, (const uint32_t*)counter, target)
+  if (H <= 2048) SMX_RSC(256, 1);
+  else if (H <= 4096) SMX_RSC(256, 2);
+  else if (H <= 8192) SMX_RSC(512, 2);
+  else if (H <= 16384) SMX_RSC(512, 4);
+  else return -21;
+#undef SMX_RSC
   return (int)cudaGetLastError();
 }
 

@@ -27,8 +27,20 @@ constexpr int k2Threads = 192;
 constexpr int k2ABytes = 128 * k2RowBytes;           // 16 KB
 constexpr int k2BBytes = 128 * k2RowBytes;           // 16 KB (half of B)
 constexpr int k2StageBytes = k2ABytes + k2BBytes;    // 32 KB
-constexpr int k2Stages = 7;
-constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256;
+constexpr int k2Stages = 7;          // plain GEMM
+constexpr int k2StagesRS = 6;        // fused reduce-scatter epilogue: one stage is traded for the store staging buffers
+constexpr int k2StgWarpBytes = 32 * 128;                   // staging tile per epilogue warp: 32 rows x 64 bf16, 128B-swizzled
+constexpr int k2SmemBytesFor(int stages, bool rs) {
+  return rs ? stages * k2StageBytes + 1024 + 1024 + 4 * k2StgWarpBytes : stages * k2StageBytes + 1024 + 256;
+}
+struct RsMaps {
+  CUtensorMap m[8];          // [owner]: my slot in that rank's staging buffer as a [rs_rows, N] bf16 tensor, box 64 x 32
+};
+struct NoMaps {
+  int unused;
+};
+template <bool RS> struct RsArg { using type = NoMaps; };
+template <> struct RsArg<true> { using type = RsMaps; };
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;       // clears the CTA-rank bit of a shared::cluster address (-> CTA 0 of the pair)
 
 struct Gemm2Params {
@@ -41,14 +53,23 @@ struct Gemm2Params {
   const uint32_t* ag_flags;
   int ag_rows_per_flag, ag_first_m_blk;
   uint32_t ag_epoch;
+  // fused reduce-scatter epilogue (RS kernels only): row block [o * rs_rows, (o+1) * rs_rows) of the product belongs to
+  // rank o; my partial tile goes into slot `rs_rank` of o's [world][rs_rows, N] bf16 staging buffer (peer-mapped memory)
+  // through 128B-swizzled shared memory and TMA tensor stores.  The last CTA to finish adds 1 to rs_counter[r] on every rank.
+  int rs_world, rs_rank, rs_rows;
+  uint32_t* rs_counter[8];
+  uint32_t* rs_ticket;       // local, zero-initialised CTA ticket (last CTA signals)
 };
 
-template <bool A_MN, bool B_MN, bool OUT_F32>
+template <bool A_MN, bool B_MN, bool OUT_F32, bool RS = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 void* __restrict__ c_ptr, const Gemm2Params p) {
+                 void* __restrict__ c_ptr, const Gemm2Params p,
+                 const __grid_constant__ typename RsArg<RS>::type rs_maps) {
   constexpr int BLOCK_K = 64, UMMA_K = 16, kKSteps = BLOCK_K / UMMA_K;
   constexpr uint32_t kMnChunkBytes = BLOCK_K * k2RowBytes;      // 8 KB: one 64-wide MN chunk of an MN-major tile
+  constexpr int k2Stages = RS ? k2StagesRS : smx::k2Stages;     // shadows the namespace constant inside the kernel
+  static_assert(!(RS && OUT_F32), "the reduce-scatter epilogue stores bf16 partial tiles");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -100,7 +121,7 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int in_group = r - group_id * width;
     m_blk = first_m + in_group % gsz;
     n_blk = in_group / gsz;
-    if (p.ag_flags) {
+    if (p.ag_flags || RS) {       // rotated start: own rows first (all-gather) / the next rank's rows first (reduce-scatter)
       m_blk += p.ag_first_m_blk;
       if (m_blk >= p.m_tiles) m_blk -= p.m_tiles;
     }
@@ -231,6 +252,44 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_wait(&tmem_full_bar[as], aphase, 44);
       tcgen05_fence_after();
       OutT* c_row = c_base + (long long)g * p.c_batch_stride + (long long)row * p.ldc;
+      if constexpr (RS) {
+        // ---- fused reduce-scatter: TMEM -> bf16 -> 128B-swizzled smem tile (32 rows x 64 columns per warp) -> one TMA
+        // tensor store per chunk into slot `rs_rank` of the owner's staging buffer (the tensor map clips the M / N edges).
+        const uint32_t stg_warp = smem_u32(smem) + k2Stages * k2StageBytes + 1024 + q * k2StgWarpBytes;
+        const uint32_t stg_row = stg_warp + lane * 128;
+        const int row0 = m_blk * k2BlockM + (int)cta_rank * 128 + q * 32;      // first row of this warp (one owner per warp)
+        const int owner = min(row0 / p.rs_rows, p.rs_world - 1);
+        const int slot_row0 = row0 - owner * p.rs_rows;
+#pragma unroll 1
+        for (int c = 0; c < n_eff / 64; ++c) {
+          uint32_t r0[32], r1[32];
+          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * k2BlockN + c * 64;
+          tmem_ld_32x32b_x32(taddr, r0);
+          tmem_ld_32x32b_x32(taddr + 32, r1);
+          tmem_ld_wait();
+          if (lane == 0) tma_store_wait_read<0>();      // the previous store has finished reading the staging tile
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            st_shared_v4(stg_row + ((j ^ (lane & 7)) << 4),
+                         pack_bf16x2(__uint_as_float(r0[8 * j]) * p.alpha, __uint_as_float(r0[8 * j + 1]) * p.alpha),
+                         pack_bf16x2(__uint_as_float(r0[8 * j + 2]) * p.alpha, __uint_as_float(r0[8 * j + 3]) * p.alpha),
+                         pack_bf16x2(__uint_as_float(r0[8 * j + 4]) * p.alpha, __uint_as_float(r0[8 * j + 5]) * p.alpha),
+                         pack_bf16x2(__uint_as_float(r0[8 * j + 6]) * p.alpha, __uint_as_float(r0[8 * j + 7]) * p.alpha));
+            st_shared_v4(stg_row + (((4 + j) ^ (lane & 7)) << 4),
+                         pack_bf16x2(__uint_as_float(r1[8 * j]) * p.alpha, __uint_as_float(r1[8 * j + 1]) * p.alpha),
+                         pack_bf16x2(__uint_as_float(r1[8 * j + 2]) * p.alpha, __uint_as_float(r1[8 * j + 3]) * p.alpha),
+                         pack_bf16x2(__uint_as_float(r1[8 * j + 4]) * p.alpha, __uint_as_float(r1[8 * j + 5]) * p.alpha),
+                         pack_bf16x2(__uint_as_float(r1[8 * j + 6]) * p.alpha, __uint_as_float(r1[8 * j + 7]) * p.alpha));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M) {
+            tma_store_3d_addr(&rs_maps.m[owner], stg_warp, n0 + c * 64, slot_row0, 0);
+            tma_store_commit();
+          }
+        }
+      } else
 #pragma unroll 1
       for (int c = 0; c < n_eff / 32; ++c) {
         uint32_t r[32];
@@ -302,6 +361,30 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
+    if constexpr (RS) {
+      // every store of this CTA has landed at its owner -> one release-increment on every rank's completion counter
+      if (lane == 0) {
+        tma_store_wait_all<0>();
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps
+      if (warp_idx == 2) {
+        // last CTA of the grid (ticket) announces this rank's completion: +1 on every rank's counter, release at system scope
+        uint32_t last = 0;
+        if (lane == 0) {
+          __threadfence();
+          uint32_t t;
+          asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(p.rs_ticket) : "memory");
+          last = (t == gridDim.x - 1) ? 1u : 0u;
+          if (last) *p.rs_ticket = 0;                       // self-resetting: the next launch starts from zero
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && lane < p.rs_world) {
+          __threadfence_system();
+          asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p.rs_counter[lane]), "r"(1u) : "memory");
+        }
+      }
+    }
   }
 
   tcgen05_fence_before();
@@ -316,13 +399,15 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 namespace {
 
-template <bool A_MN, bool B_MN, bool OUT_F32>
+template <bool A_MN, bool B_MN, bool OUT_F32, bool RS = false>
 int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const smx::Gemm2Params& p, int num_sms,
-                cudaStream_t stream) {
-  auto kern = smx::gemm_2cta_kernel<A_MN, B_MN, OUT_F32>;
+                cudaStream_t stream, int* grid_out = nullptr,
+                const typename smx::RsArg<RS>::type& maps = typename smx::RsArg<RS>::type()) {
+  auto kern = smx::gemm_2cta_kernel<A_MN, B_MN, OUT_F32, RS>;
+  constexpr int kSmem = smx::k2SmemBytesFor(RS ? smx::k2StagesRS : smx::k2Stages, RS);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smx::k2SmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -333,7 +418,7 @@ int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const smx
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(num_sms & ~1, 1, 1);
     cfg.blockDim = dim3(smx::k2Threads, 1, 1);
-    cfg.dynamicSmemBytes = smx::k2SmemBytes;
+    cfg.dynamicSmemBytes = kSmem;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -348,7 +433,8 @@ int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const smx
   const int tiles = p.G * p.m_tiles * p.n_tiles;
   int max_pairs = num_sms / 2 < max_clusters ? num_sms / 2 : max_clusters;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  kern<<<2 * pairs, smx::k2Threads, smx::k2SmemBytes, stream>>>(ta, tb, C, p);
+  if (grid_out) *grid_out = 2 * pairs;
+  kern<<<2 * pairs, smx::k2Threads, kSmem, stream>>>(ta, tb, C, p, maps);
   return (int)cudaGetLastError();
 }
 
@@ -393,6 +479,9 @@ int smx_gemm_2cta(const void* A, const void* B, void* C, int G, int M, int N, in
   p.ldc = ldc; p.c_batch_stride = c_bs; p.alpha = alpha; p.accumulate = accumulate;
   p.ag_flags = g2_ag_flags; p.ag_rows_per_flag = g2_ag_rows; p.ag_first_m_blk = g2_ag_first; p.ag_epoch = g2_ag_epoch;
   g2_ag_flags = nullptr;        // one-shot
+  p.rs_world = 1; p.rs_rank = 0; p.rs_rows = M;
+  for (int i = 0; i < 8; ++i) p.rs_counter[i] = nullptr;
+  p.rs_ticket = nullptr;
   if (!a_mn && !b_mn) return out_f32 ? launch_2cta<false, false, true>(ta, tb, C, p, num_sms, stream)
                                      : launch_2cta<false, false, false>(ta, tb, C, p, num_sms, stream);
   if (!a_mn && b_mn)  return out_f32 ? launch_2cta<false, true, true>(ta, tb, C, p, num_sms, stream)
@@ -401,6 +490,48 @@ int smx_gemm_2cta(const void* A, const void* B, void* C, int G, int M, int N, in
                                      : launch_2cta<true, true, false>(ta, tb, C, p, num_sms, stream);
   return out_f32 ? launch_2cta<true, false, true>(ta, tb, C, p, num_sms, stream)
                  : launch_2cta<true, false, false>(ta, tb, C, p, num_sms, stream);
+}
+
+
+// Fused GEMM -> reduce-scatter (tensor-parallel row-linear forward / column-linear dgrad with sequence parallelism):
+// C_partial = alpha * op(A) op(B) is never materialised locally; row block o of it is stored into slot `rank` of rank o's
+// staging buffer slot_ptrs[o] ([world][M / world, N] bf16, peer-mapped) from the epilogue, and every CTA finally adds 1 to
+// counter_ptrs[r] on every rank r is incremented once per rank and call (by the last CTA to finish, `ticket` is a local
+// zero-initialised word), so a consumer may read its slots once its own counter has advanced by `world`.
+// Layouts TN (b_mn = 0) and NN (b_mn = 1); returns -12 when the problem is too small for pair tiles, -13 on bad shapes.
+int smx_gemm_2cta_reduce_scatter(const void* A, const void* B, void* const* slot_ptrs, void* const* counter_ptrs, void* ticket,
+                                 int world, int rank, int M, int N, int K, int b_mn, float alpha, long long lda,
+                                 long long ldb, int num_sms, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (M < 256 || N < 256) return -12;
+  if (world < 1 || world > 8 || M % world || N % 8 || (M / world) % 128) return -13;
+  const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap ta, tb;
+  int rc = smx::make_tmap_3d(&ta, dt, A, K, M, 1, lda * 2, 0, 64, 128);
+  if (rc) return rc;
+  if (!b_mn) rc = smx::make_tmap_3d(&tb, dt, B, K, N, 1, ldb * 2, 0, 64, 64);
+  else       rc = smx::make_tmap_3d(&tb, dt, B, N, K, 1, ldb * 2, 0, 64, 64);
+  if (rc) return rc;
+  smx::Gemm2Params p;
+  p.G = 1; p.M = M; p.N = N; p.K = K;
+  p.m_tiles = (M + smx::k2BlockM - 1) / smx::k2BlockM;
+  p.n_tiles = (N + smx::k2BlockN - 1) / smx::k2BlockN;
+  p.ldc = N; p.c_batch_stride = 0; p.alpha = alpha; p.accumulate = 0;
+  p.ag_flags = nullptr; p.ag_rows_per_flag = 1; p.ag_epoch = 0;
+  p.rs_world = world; p.rs_rank = rank; p.rs_rows = M / world;
+  p.rs_ticket = reinterpret_cast<uint32_t*>(ticket);
+  // start with the rows of the next rank and finish with my own, so every owner's NVLink ingress sees one source at a time
+  p.ag_first_m_blk = (int)(((long long)((rank + 1) % world) * p.rs_rows) / smx::k2BlockM);
+  smx::RsMaps maps;
+  for (int i = 0; i < 8; ++i) {
+    p.rs_counter[i] = i < world ? reinterpret_cast<uint32_t*>(counter_ptrs[i]) : nullptr;
+    const int o = i < world ? i : 0;       // unused entries replicate owner 0 (never dereferenced)
+    char* slot = reinterpret_cast<char*>(slot_ptrs[o]) + (long long)rank * p.rs_rows * N * 2;
+    rc = smx::make_tmap_3d(&maps.m[i], dt, slot, N, p.rs_rows, 1, (uint64_t)N * 2, (uint64_t)p.rs_rows * N * 2, 64, 32);
+    if (rc) return rc;
+  }
+  return b_mn ? launch_2cta<false, true, false, true>(ta, tb, nullptr, p, num_sms, stream, nullptr, maps)
+              : launch_2cta<false, false, false, true>(ta, tb, nullptr, p, num_sms, stream, nullptr, maps);
 }
 
 }  // extern "C"

@@ -16,11 +16,87 @@ from ..ops.gemm import _LAYOUTS, _as3d, _fn, _num_sms, _tma_ready
 from .symm import SymmetricWorkspace
 
 
+_RS_COUNTER_WORD, _RS_TICKET_WORD = 0, 1        # user signal words of the workspace used by the TMA-store flavour
+
+
+class RsHandle:
+    """An in-flight fused GEMM -> reduce-scatter: this rank's ``[world][rows, N]`` slot buffer and the counter value that
+    means "every rank's stores have landed"."""
+
+    def __init__(self, ws, slots, rows, n, target):
+        self.ws, self.slots, self.rows, self.n, self.target = ws, slots, rows, n, target
+
+    def consume(self, residual: torch.Tensor | None = None, out: torch.Tensor | None = None, gamma: torch.Tensor | None = None,
+                normed: torch.Tensor | None = None, rstd: torch.Tensor | None = None, eps: float = 1e-5) -> torch.Tensor:
+        """out = (residual +) sum of the slots; with ``gamma`` also ``normed = rmsnorm(out) * gamma`` (and ``rstd``) -- one
+        kernel that itself waits on the completion counter (no barrier launch)."""
+        ws, rows, n = self.ws, self.rows, self.n
+        if out is None:
+            out = torch.empty(rows, n, device=self.slots.device, dtype=torch.bfloat16)
+        f = _lib.lib().smx_rs_consume
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_int] + [ctypes.c_void_p] * 5 + [
+            ctypes.c_float, ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p]
+        ptr = lambda t: None if t is None else t.data_ptr()
+        if gamma is not None and normed is None:
+            normed = torch.empty_like(out)
+        _lib.check(f(self.slots.data_ptr(), ws.world, rows, n, ptr(residual), out.data_ptr(), ptr(gamma), ptr(normed), ptr(rstd),
+                     float(eps), ws.user_flag(_RS_COUNTER_WORD).data_ptr(), self.target & 0xFFFFFFFF,
+                     torch.cuda.current_stream(out.device).cuda_stream), "rs_consume")
+        _lib.count_launch()
+        return out
+
+
+def gemm_reduce_scatter_launch(a: torch.Tensor, b: torch.Tensor, ws: SymmetricWorkspace, layout: str = "TN",
+                               slot_off: int | None = None, alpha: float = 1.0) -> RsHandle:
+    """Launch the CTA-pair GEMM whose epilogue TMA-stores every partial tile (bf16, through 128B-swizzled shared memory) into
+    slot ``rank`` of the owning rank's staging buffer; returns a handle whose ``consume`` sums the slots.
+
+    Two slot buffers (``2 * world * rows * N * 2`` bytes from ``slot_off``) alternate between calls, so a rank that runs
+    ahead never overwrites slots its peer has not summed yet: launch -> consume -> launch ... is the only ordering rule.
+    Layouts: TN (``b`` is [N, K]) and NN (``b`` is [K, N])."""
+    a_mn, b_mn = _LAYOUTS[layout]
+    assert not a_mn, "A must be K-major (row-major [M, K]) for the fused reduce-scatter GEMM"
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    a3, b3 = _tma_ready(_as3d(a)), _tma_ready(_as3d(b))
+    M, K = a3.shape[1], a3.shape[2]
+    N = b3.shape[2] if b_mn else b3.shape[1]
+    world = ws.world
+    rows = M // world
+    slot_off = ws.in_bytes if slot_off is None else slot_off
+    one = world * rows * N * 2
+    assert slot_off % 256 == 0 and slot_off + 2 * one <= ws.in_bytes + ws.out_bytes, "symmetric workspace too small for 2 slot buffers"
+    calls = getattr(ws, "_rs_calls", 0)
+    if calls == 0:
+        ws.user_flag(_RS_COUNTER_WORD).zero_()
+        ws.user_flag(_RS_TICKET_WORD).zero_()
+        ws.barrier()                                   # nobody increments a counter that is still being cleared
+    ws._rs_calls = calls + 1
+    off = slot_off + (calls & 1) * one
+    f = _lib.lib().smx_gemm_2cta_reduce_scatter
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p,
+                  ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                  ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]
+    nsm = _num_sms(a.device.index if a.device.index is not None else torch.cuda.current_device())
+    rc = f(a3.data_ptr(), b3.data_ptr(), ws.peer_ptrs(off), ws.user_flag_ptrs(_RS_COUNTER_WORD),
+           ws.user_flag(_RS_TICKET_WORD).data_ptr(), world, ws.rank, M, N, K, b_mn, float(alpha), a3.stride(1), b3.stride(1), nsm,
+           torch.cuda.current_stream(a.device).cuda_stream)
+    _lib.check(rc, f"gemm_reduce_scatter[tma,{layout}] M{M} N{N} K{K} world{world}")
+    _lib.count_launch()
+    slots = ws.view(off, torch.bfloat16, world * rows * N)
+    return RsHandle(ws, slots, rows, N, (calls + 1) * world)
+
+
 def gemm_reduce_scatter(a: torch.Tensor, b: torch.Tensor, ws: SymmetricWorkspace, layout: str = "TN", out_off: int | None = None,
                         alpha: float = 1.0, mode: str = "slots", out: torch.Tensor | None = None) -> torch.Tensor:
     """out_r[M/world, N] = sum over ranks of (op(a) @ op(b))[r-th row block].
 
-    a / b are this rank's operands (K already sharded by the caller).  Two epilogue flavours:
+    a / b are this rank's operands (K already sharded by the caller).  Epilogue flavours:
+
+    * ``mode="tma"``: CTA-pair GEMM, tiles leave through shared memory and TMA tensor stores (full NVLink packets), the
+      consumer waits on a completion counter -- see :func:`gemm_reduce_scatter_launch`.  ``out_off`` must leave room for two
+      slot buffers.
 
     * ``mode="slots"`` (default, bf16): every rank stores its partial tile with plain 16-byte stores into slot ``rank`` of
       the owner's ``[world][M/world, N]`` staging buffer (peer-mapped memory); after the closing device-side barrier the
@@ -28,6 +104,8 @@ def gemm_reduce_scatter(a: torch.Tensor, b: torch.Tensor, ws: SymmetricWorkspace
     * ``mode="red"`` (fp32): tiles are added into the owner's fp32 buffer with ``red.global.add.v4.f32`` -- single pass,
       but 16-byte remote atomics are much slower than stores on NVLink (kept for comparison).
     """
+    if mode == "tma":
+        return gemm_reduce_scatter_launch(a, b, ws, layout, out_off, alpha).consume(out=out)
     a_mn, b_mn = _LAYOUTS[layout]
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     a3, b3 = _tma_ready(_as3d(a)), _tma_ready(_as3d(b))

@@ -20,6 +20,8 @@ from ..ops import _lib
 _c = ctypes
 MAX_CTAS = 128
 MAX_RANKS = 8
+USER_FLAG_BASE = MAX_CTAS * MAX_RANKS      # first int32 word of the signal buffer that the collectives do not use
+USER_FLAG_WORDS = 256
 
 
 def _fn(name, argtypes):
@@ -54,7 +56,7 @@ class SymmetricWorkspace:
         except Exception:
             pass
         self.data = symm_mem.empty(self.in_bytes + self.out_bytes, dtype=torch.uint8, device=self.device)
-        self.flags = symm_mem.empty(MAX_CTAS * MAX_RANKS, dtype=torch.int32, device=self.device)
+        self.flags = symm_mem.empty(MAX_CTAS * MAX_RANKS + USER_FLAG_WORDS, dtype=torch.int32, device=self.device)
         self.flags.zero_()
         self._hd = symm_mem.rendezvous(self.data, self.group.group_name)
         self._hf = symm_mem.rendezvous(self.flags, self.group.group_name)
@@ -146,6 +148,16 @@ class SymmetricWorkspace:
     def peer_ptrs(self, byte_off: int = 0):
         """ctypes array of every rank's mapping of ``buffer + byte_off`` (for kernels that write to peers directly)."""
         return (_c.c_void_p * MAX_RANKS)(*[(int(p) + byte_off) for p in self._hd.buffer_ptrs] + [0] * (MAX_RANKS - self.world))
+
+    def user_flag_ptrs(self, word: int):
+        """ctypes array of every rank's mapping of user signal word ``word`` (fused kernels' completion counters)."""
+        assert 0 <= word < USER_FLAG_WORDS
+        off = (USER_FLAG_BASE + word) * 4
+        return (_c.c_void_p * MAX_RANKS)(*[(int(p) + off) for p in self._hf.buffer_ptrs] + [0] * (MAX_RANKS - self.world))
+
+    def user_flag(self, word: int) -> torch.Tensor:
+        """Local view (1 element, int32) of user signal word ``word``."""
+        return self.flags[USER_FLAG_BASE + word: USER_FLAG_BASE + word + 1]
 
     def put(self, dst_rank: int, nbytes: int, ctas: int = 16):
         """One-sided copy in[:nbytes] -> out[:nbytes] of ``dst_rank`` (pipeline send); caller orders with events."""

@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
 from simumax_b200.ops.gemm import gemm
-from simumax_b200.parallel.fused import allgather_gemm, gemm_reduce_scatter
+from simumax_b200.ops import elementwise as E
+from simumax_b200.parallel.fused import allgather_gemm, gemm_reduce_scatter, gemm_reduce_scatter_launch
 from simumax_b200.parallel.symm import SymmetricWorkspace
 
 
@@ -30,34 +31,62 @@ def main():
         torch.manual_seed(10 + rank)
         x = torch.randn(M, K, device="cuda").bfloat16() * 0.5
         w = torch.randn(N, K, device="cuda").bfloat16() * 0.5
-        ws = SymmetricWorkspace(256, M * N * 4 + 256)
+        ws = SymmetricWorkspace(1024, M * N * 4 + 1024)
         full = torch.empty(M, N, device="cuda", dtype=torch.float32)
         gemm(x, w, "TN", out=full)
         ref = torch.empty(M // world, N, device="cuda", dtype=torch.float32)
         dist.reduce_scatter_tensor(ref, full)
-        out = gemm_reduce_scatter(x, w, ws, "TN").float()
+        scale = ref.abs().max()
+        out = gemm_reduce_scatter(x, w, ws, "TN", mode="slots").float()
         out_red = gemm_reduce_scatter(x, w, ws, "TN", mode="red").clone()
+        torch.cuda.synchronize(); dist.barrier()
+        # TMA-store epilogue (CTA-pair kernel), TN and NN, then the fused consumer: residual add + RMSNorm in the same kernel
+        out_tma = gemm_reduce_scatter(x, w, ws, "TN", mode="tma").float()
+        wT = w.t().contiguous()
+        out_tma_nn = gemm_reduce_scatter(x, wT, ws, "NN", mode="tma").float()
+        resid = torch.randn(M // world, N, device="cuda").bfloat16()
+        gamma = (1.0 + 0.1 * torch.randn(N, device="cuda")).bfloat16()
+        normed = torch.empty(M // world, N, device="cuda", dtype=torch.bfloat16)
+        rstd = torch.empty(M // world, device="cuda", dtype=torch.float32)
+        x2 = gemm_reduce_scatter_launch(x, w, ws, "TN").consume(residual=resid, gamma=gamma, normed=normed, rstd=rstd)
         torch.cuda.synchronize()
-        err = ((out - ref).abs().max() / ref.abs().max()).item()
-        err_red = ((out_red - ref).abs().max() / ref.abs().max()).item()
-        good = err < 2e-2 and err_red < 1e-3
+        x2_ref = (resid.float() + ref).bfloat16().float()
+        rstd_ref = torch.rsqrt((x2.float() ** 2).mean(-1) + 1e-5)
+        normed_ref = x2.float() * rstd_ref[:, None] * gamma.float()
+        err = ((out - ref).abs().max() / scale).item()
+        err_red = ((out_red - ref).abs().max() / scale).item()
+        err_tma = ((out_tma - ref).abs().max() / scale).item()
+        err_tma_nn = ((out_tma_nn - ref).abs().max() / scale).item()
+        err_x2 = ((x2.float() - x2_ref).abs().max() / scale).item()
+        err_norm = ((normed.float() - normed_ref).abs().max() / normed_ref.abs().max()).item()
+        err_rstd = ((rstd - rstd_ref).abs().max() / rstd_ref.abs().max()).item()
+        good = err < 2e-2 and err_red < 1e-3 and err_tma < 2e-2 and err_tma_nn < 2e-2 and err_x2 < 2e-2 and err_norm < 2e-2 and err_rstd < 1e-3
         ok &= good
         ob = torch.empty(M // world, N, device="cuda", dtype=torch.bfloat16)
-        t_fused = timed(lambda: gemm_reduce_scatter(x, w, ws, "TN", out=ob))
-        t_red = timed(lambda: gemm_reduce_scatter(x, w, ws, "TN", mode="red"))
+        t_tma = timed(lambda: gemm_reduce_scatter(x, w, ws, "TN", mode="tma", out=ob))
+        t_tma_norm = timed(lambda: gemm_reduce_scatter_launch(x, w, ws, "TN").consume(residual=resid, out=ob, gamma=gamma, normed=normed,
+                                                                                       rstd=rstd))
+        t_fused = timed(lambda: gemm_reduce_scatter(x, w, ws, "TN", mode="slots", out=ob))
         fb = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
         rb = torch.empty(M // world, N, device="cuda", dtype=torch.bfloat16)
         def unfused():
             gemm(x, w, "TN", out=fb)
             dist.reduce_scatter_tensor(rb, fb)
         t_unf = timed(unfused)
+        def unfused_norm():
+            unfused()
+            E.add(resid, rb, out=ob)
+            E.rmsnorm_fwd(ob, gamma, 1e-5, out=normed, rstd=rstd)
+        t_unf_norm = timed(unfused_norm)
         t_gemm = timed(lambda: gemm(x, w, "TN", out=fb))
         flops = 2.0 * M * N * K
         nv_bytes = (world - 1) / world * M * N * 2
         roof_ms = max(flops / 1.67e15, nv_bytes / 900e9) * 1e3
-        row = {"op": "gemm_reduce_scatter", "M": M, "N": N, "K_per_rank": K, "rel_err": err, "rel_err_red": err_red, "fused_ms": t_fused,
-               "fused_red_fp32_ms": t_red, "gemm_then_nccl_rs_ms": t_unf, "gemm_only_ms": t_gemm,
-               "roofline_ms": roof_ms, "fused_fraction_of_roofline": roof_ms / t_fused}
+        row = {"op": "gemm_reduce_scatter", "M": M, "N": N, "K_per_rank": K, "rel_err_tma": err_tma, "rel_err_tma_nn": err_tma_nn,
+               "rel_err_slots": err, "rel_err_red": err_red, "rel_err_x2": err_x2, "rel_err_normed": err_norm, "rel_err_rstd": err_rstd,
+               "fused_tma_ms": t_tma, "fused_tma_add_rmsnorm_ms": t_tma_norm, "fused_slots_v2_ms": t_fused,
+               "gemm_then_nccl_rs_ms": t_unf, "gemm_nccl_rs_add_rmsnorm_ms": t_unf_norm, "gemm_only_ms": t_gemm,
+               "roofline_ms": roof_ms, "fused_fraction_of_roofline": roof_ms / t_tma}
         res["cases"].append(row)
         if rank == 0:
             print(row, flush=True)
