@@ -387,6 +387,77 @@ __global__ void __launch_bounds__(THREADS) cross_entropy_fwd_bwd_kernel(__nv_bfl
   }
 }
 
+// Vocab-parallel cross-entropy (tensor-parallel LM head, Megatron vocab_parallel_cross_entropy): every rank holds V_local
+// columns [v0, v0 + V_local) of the logits.  Phase 1 writes per-row (max, sum exp(x - max), target logit or 0, has_target) of
+// the local shard; the tiny [rows, 4] fp32 statistics are all-gathered over the TP group; phase 2 combines the `world`
+// statistics per row, emits the loss and overwrites the local logits with their gradient -- each logit is read twice and
+// written once, exactly like the single-rank fused kernel.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) ce_vp_stats_kernel(const __nv_bfloat16* __restrict__ logits,
+                                                             const long long* __restrict__ targets, float4* __restrict__ stats,
+                                                             int V, long long ld, long long v0) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  const __nv_bfloat16* z = logits + row * ld;
+  const int nvec = V / 8;
+  float m = -INFINITY, s = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += THREADS) {
+    float f[8];
+    load8(z + i * 8, f);
+    float lm = f[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) lm = fmaxf(lm, f[j]);
+    const float nm = fmaxf(m, lm);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += __expf(f[j] - nm);
+    s = s * __expf(m - nm) + acc;
+    m = nm;
+  }
+  const float gm = block_max<THREADS>(m, red);
+  s = (m == -INFINITY) ? 0.f : s * __expf(m - gm);
+  const float gs = block_sum<THREADS>(s, red);
+  if (threadIdx.x == 0) {
+    const long long t = targets[row] - v0;
+    const bool mine = t >= 0 && t < V;
+    stats[row] = make_float4(gm, gs, mine ? __bfloat162float(z[t]) : 0.f, mine ? 1.f : 0.f);
+  }
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) ce_vp_grad_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restrict__ targets,
+                                                            const float4* __restrict__ all_stats, int world, long long rows,
+                                                            float* __restrict__ loss, int V, long long ld, long long v0,
+                                                            float grad_scale) {
+  const long long row = blockIdx.x;
+  __nv_bfloat16* z = logits + row * ld;
+  float gm = -INFINITY;
+  for (int r = 0; r < world; ++r) gm = fmaxf(gm, all_stats[r * rows + row].x);
+  float gs = 0.f, tl = 0.f, has = 0.f;
+  for (int r = 0; r < world; ++r) {
+    const float4 st = all_stats[r * rows + row];
+    gs += st.y * __expf(st.x - gm);
+    tl += st.z;
+    has += st.w;
+  }
+  if (threadIdx.x == 0) loss[row] = has > 0.f ? gm + __logf(gs) - tl : 0.f;
+  const float inv = 1.f / gs;
+  const float sc = has > 0.f ? grad_scale : 0.f;
+  const long long tgt = targets[row] - v0;
+  const int nvec = V / 8;
+  for (int i = threadIdx.x; i < nvec; i += THREADS) {
+    float f[8];
+    load8(z + i * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float p = __expf(f[j] - gm) * inv;
+      if (i * 8 + j == tgt) p -= 1.f;
+      f[j] = p * sc;
+    }
+    store8(z + i * 8, f);
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // Optimizer: squared L2 norm of fp32 grads (per-CTA partials + one atomic), fused AdamW step on
 // flat fp32 master / m / v with bf16 model-param write-back and grad clipping scale.
@@ -615,6 +686,20 @@ int smx_cross_entropy(void* logits, const long long* targets, float* loss, long 
                       float grad_scale, int write_grad, void* stream) {
   if (ld % 8) return -20;
   smx::cross_entropy_fwd_bwd_kernel<1024><<<(unsigned)rows, 1024, 0, SMX_STREAM>>>((bf16*)logits, targets, loss, V, ld, grad_scale, write_grad);
+  return (int)cudaGetLastError();
+}
+
+int smx_ce_vp_stats(const void* logits, const long long* targets, void* stats, long long rows, int V, long long ld,
+                    long long v0, void* stream) {
+  if (V % 8 || ld % 8) return -20;
+  smx::ce_vp_stats_kernel<1024><<<(unsigned)rows, 1024, 0, SMX_STREAM>>>((const bf16*)logits, targets, (float4*)stats, V, ld, v0);
+  return (int)cudaGetLastError();
+}
+int smx_ce_vp_grad(void* logits, const long long* targets, const void* all_stats, int world, float* loss, long long rows, int V,
+                   long long ld, long long v0, float grad_scale, void* stream) {
+  if (V % 8 || ld % 8) return -20;
+  smx::ce_vp_grad_kernel<1024><<<(unsigned)rows, 1024, 0, SMX_STREAM>>>((bf16*)logits, targets, (const float4*)all_stats, world, rows,
+                                                                      loss, V, ld, v0, grad_scale);
   return (int)cudaGetLastError();
 }
 

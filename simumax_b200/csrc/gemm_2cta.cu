@@ -59,10 +59,23 @@ struct Gemm2Params {
   int rs_world, rs_rank, rs_rows;
   uint32_t* rs_counter[8];
   uint32_t* rs_ticket;       // local, zero-initialised CTA ticket (last CTA signals)
+  // in-kernel all-gather push (AG kernels): warps 6-7 of every CTA copy row chunks of this rank's shard of A (which already
+  // sits at its place in the local gathered buffer) into every peer's gathered buffer -- multimem.st through the NVLS
+  // multicast alias when there is one, plain peer stores otherwise -- and raise flag[rank * chunks + c] on every rank.
+  const uint4* ag_src;           // my shard inside my gathered buffer
+  uint4* ag_dst[8];              // every rank's mapping of those same rows in ITS gathered buffer
+  uint4* ag_mc_dst;              // multicast alias (nullptr: P2P stores)
+  uint32_t* ag_peer_flags[8];    // every rank's flags + rank * chunks
+  long long ag_chunk_vec;        // 16-byte vectors per chunk
+  int ag_chunks, ag_world, ag_rank, ag_shard_rows;
 };
 
-template <bool A_MN, bool B_MN, bool OUT_F32, bool RS = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
+SMX_DEVICE void ag_st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <bool A_MN, bool B_MN, bool OUT_F32, bool RS = false, bool AG = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads + 64, 1)
 gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  void* __restrict__ c_ptr, const Gemm2Params p,
                  const __grid_constant__ typename RsArg<RS>::type rs_maps) {
@@ -158,8 +171,8 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int half = n_eff >> 1;                               // B rows staged by each CTA (128 or 64)
         const int m0 = m_blk * k2BlockM + (int)cta_rank * 128;     // my rows of A / of the output
         const int n0 = n_base + (int)cta_rank * half;              // my half of B
-        if (p.ag_flags) {
-          // gathered A: wait until my 128 rows of this tile have been delivered by their owner's gather kernel
+        if (p.ag_flags && !(AG && m0 / p.ag_shard_rows == p.ag_rank)) {
+          // gathered A: wait until my 128 rows of this tile have been delivered by their owner's gather warps / kernel
           const int last_row = min(m0 + 128, p.M) - 1;
           const uint64_t t0 = global_timer_ns();
           for (int f = m0 / p.ag_rows_per_flag; f <= last_row / p.ag_rows_per_flag; ++f) {
@@ -237,7 +250,47 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (as == 0) aphase ^= 1;
       }
     }
-  } else {
+  } else if (AG && warp_idx >= 6) {
+    // ============================ all-gather push (both CTAs, 64 threads) ============================
+    const int gt = threadIdx.x - k2Threads;
+    for (int c = blockIdx.x; c < p.ag_chunks; c += gridDim.x) {
+      const uint4* src = p.ag_src + (long long)c * p.ag_chunk_vec;
+      for (long long i0 = 0; i0 < p.ag_chunk_vec; i0 += 64 * 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const long long i = i0 + u * 64 + gt;
+          if (i < p.ag_chunk_vec)
+            asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src + i) : "memory");
+        }
+        if (p.ag_mc_dst != nullptr) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const long long i = i0 + u * 64 + gt;
+            if (i < p.ag_chunk_vec)
+              asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p.ag_mc_dst + (long long)c * p.ag_chunk_vec + i),
+                           "r"(v[u].x), "r"(v[u].y), "r"(v[u].z), "r"(v[u].w) : "memory");
+          }
+        } else {
+#pragma unroll 1
+          for (int s = 1; s < p.ag_world; ++s) {
+            int peer = p.ag_rank - s;             // the rank that needs my rows first is my predecessor
+            if (peer < 0) peer += p.ag_world;
+            uint4* dst = p.ag_dst[peer] + (long long)c * p.ag_chunk_vec;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const long long i = i0 + u * 64 + gt;
+              if (i < p.ag_chunk_vec)
+                asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst + i), "r"(v[u].x), "r"(v[u].y), "r"(v[u].z), "r"(v[u].w) : "memory");
+            }
+          }
+        }
+      }
+      __threadfence_system();
+      asm volatile("bar.sync 2, 64;" ::: "memory");       // the two gather warps
+      if (gt < p.ag_world) ag_st_release_sys(p.ag_peer_flags[gt] + c, p.ag_epoch);
+    }
+  } else if (warp_idx < 6) {
     // ============================ epilogue (both CTAs, own 128 rows) ============================
     const int q = warp_idx % 4;
     using OutT = typename std::conditional<OUT_F32, float, __nv_bfloat16>::type;
@@ -395,15 +448,21 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
+inline void clear_ag_push(Gemm2Params& p) {
+  p.ag_src = nullptr; p.ag_mc_dst = nullptr; p.ag_chunk_vec = 0; p.ag_chunks = 0; p.ag_world = 1; p.ag_rank = 0; p.ag_shard_rows = 1 << 30;
+  for (int i = 0; i < 8; ++i) { p.ag_dst[i] = nullptr; p.ag_peer_flags[i] = nullptr; }
+}
+
 }  // namespace smx
 
 namespace {
 
-template <bool A_MN, bool B_MN, bool OUT_F32, bool RS = false>
+template <bool A_MN, bool B_MN, bool OUT_F32, bool RS = false, bool AG = false>
 int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const smx::Gemm2Params& p, int num_sms,
                 cudaStream_t stream, int* grid_out = nullptr,
                 const typename smx::RsArg<RS>::type& maps = typename smx::RsArg<RS>::type()) {
-  auto kern = smx::gemm_2cta_kernel<A_MN, B_MN, OUT_F32, RS>;
+  auto kern = smx::gemm_2cta_kernel<A_MN, B_MN, OUT_F32, RS, AG>;
+  constexpr int kThreads = smx::k2Threads + (AG ? 64 : 0);
   constexpr int kSmem = smx::k2SmemBytesFor(RS ? smx::k2StagesRS : smx::k2Stages, RS);
   static bool attr_set = false;
   if (!attr_set) {
@@ -417,7 +476,7 @@ int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const smx
   if (max_clusters == 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(num_sms & ~1, 1, 1);
-    cfg.blockDim = dim3(smx::k2Threads, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = kSmem;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -434,7 +493,7 @@ int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, void* C, const smx
   int max_pairs = num_sms / 2 < max_clusters ? num_sms / 2 : max_clusters;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   if (grid_out) *grid_out = 2 * pairs;
-  kern<<<2 * pairs, smx::k2Threads, kSmem, stream>>>(ta, tb, C, p, maps);
+  kern<<<2 * pairs, kThreads, kSmem, stream>>>(ta, tb, C, p, maps);
   return (int)cudaGetLastError();
 }
 
@@ -482,6 +541,7 @@ int smx_gemm_2cta(const void* A, const void* B, void* C, int G, int M, int N, in
   p.rs_world = 1; p.rs_rank = 0; p.rs_rows = M;
   for (int i = 0; i < 8; ++i) p.rs_counter[i] = nullptr;
   p.rs_ticket = nullptr;
+  smx::clear_ag_push(p);
   if (!a_mn && !b_mn) return out_f32 ? launch_2cta<false, false, true>(ta, tb, C, p, num_sms, stream)
                                      : launch_2cta<false, false, false>(ta, tb, C, p, num_sms, stream);
   if (!a_mn && b_mn)  return out_f32 ? launch_2cta<false, true, true>(ta, tb, C, p, num_sms, stream)
@@ -518,6 +578,7 @@ int smx_gemm_2cta_reduce_scatter(const void* A, const void* B, void* const* slot
   p.n_tiles = (N + smx::k2BlockN - 1) / smx::k2BlockN;
   p.ldc = N; p.c_batch_stride = 0; p.alpha = alpha; p.accumulate = 0;
   p.ag_flags = nullptr; p.ag_rows_per_flag = 1; p.ag_epoch = 0;
+  smx::clear_ag_push(p);
   p.rs_world = world; p.rs_rank = rank; p.rs_rows = M / world;
   p.rs_ticket = reinterpret_cast<uint32_t*>(ticket);
   // start with the rows of the next rank and finish with my own, so every owner's NVLink ingress sees one source at a time
@@ -532,6 +593,54 @@ int smx_gemm_2cta_reduce_scatter(const void* A, const void* B, void* const* slot
   }
   return b_mn ? launch_2cta<false, true, false, true>(ta, tb, nullptr, p, num_sms, stream, nullptr, maps)
               : launch_2cta<false, false, false, true>(ta, tb, nullptr, p, num_sms, stream, nullptr, maps);
+}
+
+// Fused all-gather -> GEMM in ONE kernel (column-parallel linear forward / row-parallel dgrad with sequence parallelism):
+// C[M, N] = alpha * A[M, K] op(B), A = concatenation over ranks of [M / world, K] shards.  a_ptrs[r] is rank r's mapping of
+// the gathered buffer (this rank's own rows are already in place in a_ptrs[rank]); mc_ptr its NVLS multicast alias or null;
+// flag_ptrs[r] rank r's flag array (world * chunks words, epochs only ever grow).  Warps 6-7 of every CTA push this rank's
+// rows to all peers chunk by chunk while the MMAs start on the local rows; the TMA producer waits on the flags of a remote
+// row block only when it reaches it.  Layouts TN (b_mn = 0) and NN (b_mn = 1); bf16 or fp32 output.
+int smx_gemm_2cta_all_gather(void* const* a_ptrs, void* mc_ptr, void* const* flag_ptrs, const void* B, void* C, int world,
+                             int rank, int M, int N, int K, int b_mn, int out_f32, float alpha, long long ldb, long long ldc,
+                             int chunks, unsigned epoch, int num_sms, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (M < 256 || N < 256) return -12;
+  if (world < 2 || world > 8 || M % world || (M / world) % 128 || chunks <= 0 || (M / world) % chunks) return -13;
+  const int shard_rows = M / world;
+  const long long chunk_bytes = (long long)(shard_rows / chunks) * K * 2;
+  if (chunk_bytes % 16) return -13;
+  const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap ta, tb;
+  int rc = smx::make_tmap_3d(&ta, dt, a_ptrs[rank], K, M, 1, (uint64_t)K * 2, 0, 64, 128);
+  if (rc) return rc;
+  if (!b_mn) rc = smx::make_tmap_3d(&tb, dt, B, K, N, 1, ldb * 2, 0, 64, 64);
+  else       rc = smx::make_tmap_3d(&tb, dt, B, N, K, 1, ldb * 2, 0, 64, 64);
+  if (rc) return rc;
+  smx::Gemm2Params p;
+  p.G = 1; p.M = M; p.N = N; p.K = K;
+  p.m_tiles = (M + smx::k2BlockM - 1) / smx::k2BlockM;
+  p.n_tiles = (N + smx::k2BlockN - 1) / smx::k2BlockN;
+  p.ldc = ldc; p.c_batch_stride = 0; p.alpha = alpha; p.accumulate = 0;
+  p.rs_world = 1; p.rs_rank = 0; p.rs_rows = M; p.rs_ticket = nullptr;
+  for (int i = 0; i < 8; ++i) p.rs_counter[i] = nullptr;
+  p.ag_flags = reinterpret_cast<const uint32_t*>(flag_ptrs[rank]);
+  p.ag_rows_per_flag = shard_rows / chunks;
+  p.ag_first_m_blk = (int)(((long long)rank * shard_rows) / smx::k2BlockM);     // my own rows first
+  p.ag_epoch = epoch;
+  smx::clear_ag_push(p);
+  const long long shard_bytes = (long long)shard_rows * K * 2;
+  p.ag_src = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(a_ptrs[rank]) + rank * shard_bytes);
+  p.ag_mc_dst = mc_ptr ? reinterpret_cast<uint4*>(reinterpret_cast<char*>(mc_ptr) + rank * shard_bytes) : nullptr;
+  p.ag_chunk_vec = chunk_bytes / 16; p.ag_chunks = chunks; p.ag_world = world; p.ag_rank = rank; p.ag_shard_rows = shard_rows;
+  for (int i = 0; i < world; ++i) {
+    p.ag_dst[i] = reinterpret_cast<uint4*>(reinterpret_cast<char*>(a_ptrs[i]) + rank * shard_bytes);
+    p.ag_peer_flags[i] = reinterpret_cast<uint32_t*>(flag_ptrs[i]) + (long long)rank * chunks;
+  }
+  if (!b_mn) return out_f32 ? launch_2cta<false, false, true, false, true>(ta, tb, C, p, num_sms, stream)
+                            : launch_2cta<false, false, false, false, true>(ta, tb, C, p, num_sms, stream);
+  return out_f32 ? launch_2cta<false, true, true, false, true>(ta, tb, C, p, num_sms, stream)
+                 : launch_2cta<false, true, false, false, true>(ta, tb, C, p, num_sms, stream);
 }
 
 }  // extern "C"

@@ -21,6 +21,9 @@ _SIGS = {
     "smx_swiglu_bwd": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_void_p],
     "smx_rope": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_void_p],
     "smx_cross_entropy": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_longlong, _c.c_float, _c.c_int, _c.c_void_p],
+    "smx_ce_vp_stats": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_longlong, _c.c_longlong, _c.c_void_p],
+    "smx_ce_vp_grad": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_longlong, _c.c_longlong,
+                       _c.c_float, _c.c_void_p],
     "smx_sqnorm": [_c.c_void_p, _c.c_longlong, _c.c_void_p, _c.c_void_p],
     "smx_adamw": [_c.c_void_p] * 5 + [_c.c_longlong] + [_c.c_float] * 7 + [_c.c_void_p, _c.c_float, _c.c_float, _c.c_int, _c.c_void_p],
     "smx_permute_rows": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_void_p],
@@ -131,6 +134,29 @@ def cross_entropy_(logits: torch.Tensor, targets: torch.Tensor, grad_scale: floa
     loss = torch.empty(rows, device=logits.device, dtype=torch.float32)
     _call("smx_cross_entropy", logits.data_ptr(), targets.data_ptr(), loss.data_ptr(), rows, V, logits.stride(0),
           float(grad_scale), 1 if write_grad else 0, _stream(logits))
+    return loss
+
+
+def ce_vocab_parallel_stats(logits: torch.Tensor, targets: torch.Tensor, v0: int, stats: torch.Tensor) -> torch.Tensor:
+    """Phase 1 of the vocab-parallel CE: ``stats[row] = (max, sum exp(x - max), target logit | 0, has_target)`` of this rank's
+    ``[rows, V_local]`` logits whose first column is vocabulary id ``v0`` (reference cost model: ParallelCE,
+    simumax/core/transformer/dense_module.py:2097-2215)."""
+    assert logits.dtype == torch.bfloat16 and logits.stride(-1) == 1 and logits.dim() == 2
+    assert stats.dtype == torch.float32 and stats.numel() >= logits.shape[0] * 4 and stats.is_contiguous()
+    rows, V = logits.shape
+    _call("smx_ce_vp_stats", logits.data_ptr(), targets.data_ptr(), stats.data_ptr(), rows, V, logits.stride(0), int(v0), _stream(logits))
+    return stats
+
+
+def ce_vocab_parallel_grad_(logits: torch.Tensor, targets: torch.Tensor, v0: int, all_stats: torch.Tensor, world: int,
+                            grad_scale: float = 1.0) -> torch.Tensor:
+    """Phase 2: combine the gathered ``[world, rows, 4]`` statistics, return the per-row loss and overwrite the local logits
+    with ``d loss / d logits * grad_scale``."""
+    rows, V = logits.shape
+    assert all_stats.dtype == torch.float32 and all_stats.numel() >= world * rows * 4
+    loss = torch.empty(rows, device=logits.device, dtype=torch.float32)
+    _call("smx_ce_vp_grad", logits.data_ptr(), targets.data_ptr(), all_stats.data_ptr(), world, loss.data_ptr(), rows, V,
+          logits.stride(0), int(v0), float(grad_scale), _stream(logits))
     return loss
 
 

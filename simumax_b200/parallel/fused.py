@@ -149,6 +149,55 @@ def gemm_reduce_scatter(a: torch.Tensor, b: torch.Tensor, ws: SymmetricWorkspace
     return res
 
 
+_AG_FLAG_WORD = 16            # first of world * chunks user signal words used by the single-kernel all-gather GEMM
+_AG_MAX_CHUNKS = 128
+
+
+def ag_views(ws: SymmetricWorkspace, a_off: int, M: int, K: int):
+    """(full [M, K] view, own-rows [M / world, K] view) of a gathered activation buffer at byte offset ``a_off``: producers
+    write their shard straight into the own-rows view, :func:`allgather_gemm_inkernel` fills in the rest."""
+    full = ws.view(a_off, torch.bfloat16, M * K).view(M, K)
+    ms = M // ws.world
+    return full, full[ws.rank * ms:(ws.rank + 1) * ms]
+
+
+def allgather_gemm_inkernel(ws: SymmetricWorkspace, a_off: int, M: int, K: int, w: torch.Tensor, layout: str = "TN",
+                            out: torch.Tensor | None = None, out_dtype=torch.bfloat16, alpha: float = 1.0) -> torch.Tensor:
+    """y[M, N] = gathered(A)[M, K] @ op(w) as ONE kernel: two extra warps in every CTA of the CTA-pair GEMM push this rank's
+    rows (already in place at ``a_off``) into every peer's buffer (``multimem.st`` over the NVLS multicast alias when there is
+    one) and raise per-chunk flags; the TMA producer starts on the local rows and waits on a remote block's flags only when it
+    gets there.  No separate gather kernel, no barrier, no copy.  The gathered buffer stays valid afterwards (wgrad reuses it).
+
+    Reuse rule: a buffer may be pushed into again only after every rank has passed a later cooperative call or a barrier
+    (alternate between two buffers, or use one buffer per layer plus a barrier per pass, as runtime/tp_trainer.py does)."""
+    a_mn, b_mn = _LAYOUTS[layout]
+    assert not a_mn and w.dtype == torch.bfloat16
+    world, rank = ws.world, ws.rank
+    b3 = _tma_ready(_as3d(w))
+    N = b3.shape[2] if b_mn else b3.shape[1]
+    ms = M // world
+    chunks = _AG_MAX_CHUNKS
+    while ms % chunks or ((ms // chunks) * K * 2) % 16:
+        chunks //= 2
+    assert a_off % 1024 == 0 and a_off + M * K * 2 <= ws.in_bytes + ws.out_bytes
+    ws._ag2_epoch = getattr(ws, "_ag2_epoch", 0) + 1
+    y = torch.empty(M, N, device=w.device, dtype=out_dtype) if out is None else out
+    assert y.stride(1) == 1 and y.dtype in (torch.bfloat16, torch.float32)
+    f = _lib.lib().smx_gemm_2cta_all_gather
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p,
+                  ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                  ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int, ctypes.c_uint, ctypes.c_int, ctypes.c_void_p]
+    nsm = _num_sms(w.device.index if w.device.index is not None else torch.cuda.current_device())
+    mc = (ws.multicast_ptr + a_off) if (ws.has_nvls and getattr(ws, "ag_use_nvls", True)) else None
+    rc = f(ws.peer_ptrs(a_off), mc, ws.user_flag_ptrs(_AG_FLAG_WORD), b3.data_ptr(), y.data_ptr(), world, rank, M, N, K, b_mn,
+           1 if y.dtype == torch.float32 else 0, float(alpha), b3.stride(1), y.stride(0), chunks, ws._ag2_epoch & 0x7FFFFFFF, nsm,
+           torch.cuda.current_stream(w.device).cuda_stream)
+    _lib.check(rc, f"allgather_gemm_inkernel[{layout}] M{M} N{N} K{K} world{world}")
+    _lib.count_launch()
+    return y
+
+
 def allgather_gemm(x_shard: torch.Tensor, w: torch.Tensor, ws: SymmetricWorkspace, layout: str = "TN", chunks: int = 32,
                    out: torch.Tensor | None = None, comm_stream: torch.cuda.Stream | None = None) -> torch.Tensor:
     """y[M, N] = all_gather(x_shard over ranks)[M, K] @ w^T   (column-parallel linear forward with sequence parallelism,

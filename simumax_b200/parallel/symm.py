@@ -21,7 +21,7 @@ _c = ctypes
 MAX_CTAS = 128
 MAX_RANKS = 8
 USER_FLAG_BASE = MAX_CTAS * MAX_RANKS      # first int32 word of the signal buffer that the collectives do not use
-USER_FLAG_WORDS = 256
+USER_FLAG_WORDS = 2048
 
 
 def _fn(name, argtypes):
