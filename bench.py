@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--layers", type=int, default=0, help="debug only: override layer count (marks the run invalid)")
     ap.add_argument("--attention-bwd", default="auto")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--tp", type=int, default=1, help="tensor(+sequence)-parallel size; >1 runs TPLlamaTrainer on the fused "
+                    "all-gather->GEMM / GEMM->reduce-scatter kernels (must equal --gpus: dp = 1); default = data parallel")
     return ap.parse_args()
 
 
@@ -91,7 +93,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def predicted(model: str, n_gpus: int, seq: int, mbs: int, mbc: int):
+def predicted(model: str, n_gpus: int, seq: int, mbs: int, mbc: int, tp: int = 1):
     """What our analytical model says about this exact job (dp=N, ZeRO-1, no recompute) on the calibrated config."""
     try:
         from simumax_b200 import PerfLLM
@@ -105,9 +107,11 @@ def predicted(model: str, n_gpus: int, seq: int, mbs: int, mbc: int):
             sys_path = get_simu_system_config(sys_name)
         from simumax_b200.configs import get_simu_strategy_config
         st = StrategyConfig.init_from_config_file(get_simu_strategy_config("tp1_pp1_dp8_mbs1"))
-        st.world_size, st.tp_size, st.pp_size = n_gpus, 1, 1
+        st.world_size, st.tp_size, st.pp_size = n_gpus, tp, 1
+        st.enable_sequence_parallel = tp > 1
         st.seq_len, st.micro_batch_size, st.micro_batch_num = seq, mbs, mbc
         st.dp_overlap_model = True      # the runtime overlaps ZeRO-1 collectives with backward / next forward
+        dp = n_gpus // tp
         p = PerfLLM()
         p.configure(strategy_config=st, model_config=get_simu_model_config(model), system_config=sys_path)
         import contextlib
@@ -119,7 +123,7 @@ def predicted(model: str, n_gpus: int, seq: int, mbs: int, mbc: int):
             mem = p.analysis_mem().data
         r["peak_mem"] = mem.get("peak_mem") if isinstance(mem, dict) else None
         return {"system": sys_name, "tokens_per_s": r["throughput_per_accelerator"] * n_gpus,
-                "iter_ms": mbs * mbc * n_gpus * seq / (r["throughput_per_accelerator"] * n_gpus) * 1e3,
+                "iter_ms": mbs * mbc * dp * seq / (r["throughput_per_accelerator"] * n_gpus) * 1e3,
                 "mfu": r.get("mfu"), "peak_mem": r.get("peak_mem")}
     except Exception as e:                                   # never let the model side break the measurement
         return {"error": f"{type(e).__name__}: {e}"}
@@ -200,11 +204,18 @@ def main():
     if a.layers:
         dims.layers = a.layers
     B, S, MB = a.micro_batch, a.seq_len, a.micro_batches
-    tr = LlamaTrainer(dims, B, S, dp_group=dist.group.WORLD if world > 1 else None, attention_bwd=a.attention_bwd,
-                      seed=1234)
+    tp = a.tp
+    assert tp == 1 or tp == world, "--tp must equal --gpus (the tensor-parallel runtime runs with dp = 1)"
+    dp = world // tp
+    if tp > 1:
+        from simumax_b200.runtime.tp_trainer import TPLlamaTrainer
+        tr = TPLlamaTrainer(dims, B, S, seed=1234)
+    else:
+        tr = LlamaTrainer(dims, B, S, dp_group=dist.group.WORLD if world > 1 else None, attention_bwd=a.attention_bwd,
+                          seed=1234)
     # distinct synthetic token batches per step and micro-batch, staged in pinned host memory (e2e) and on device
     n_sets = max(a.steps, 1)
-    gen = torch.Generator().manual_seed(1000 + rank)
+    gen = torch.Generator().manual_seed(1000 + (rank if tp == 1 else 0))       # TP ranks share the batch
     host = [[(torch.randint(0, mc.vocab_size, (B, S), generator=gen).pin_memory(),
               torch.randint(0, mc.vocab_size, (B, S), generator=gen).pin_memory()) for _ in range(MB)] for _ in range(n_sets)]
     dev = [[(t.cuda().view(-1), y.cuda().view(-1)) for t, y in step] for step in host]
@@ -240,28 +251,29 @@ def main():
         return ms.item(), wall_ms, clocks, _lib.launches() - l0, last
 
     dev_ms, _, clocks, launches, loss_t = timed(lambda i: tr.run_microbatches(dev[i]), "device")
-    tokens_per_step = B * S * MB * world
+    tokens_per_step = B * S * MB * dp
     value = tokens_per_step / (dev_ms / a.steps / 1e3)
     e2e = None
     if not a.skip_e2e:
         e_ms, e_wall, _, _, loss_f = timed(lambda i: tr.train_step(host[i]), "e2e")
         e2e = {"value": tokens_per_step / (max(e_ms, e_wall) / a.steps / 1e3), "unit": "tokens/s",
                "h2d_bytes_per_step": MB * 2 * B * S * 8, "d2h_bytes_per_step": 4, "ms_per_step": max(e_ms, e_wall) / a.steps,
-               "api": "LlamaTrainer.train_step(pinned host batches) -> float loss", "last_loss": loss_f}
+               "api": f"{type(tr).__name__}.train_step(pinned host batches) -> float loss", "last_loss": loss_f}
     if rank == 0:
         mem = tr.memory_bytes()
-        pred = predicted(a.model, world, S, B, MB)
+        pred = predicted(a.model, world, S, B, MB, tp)
         flops_step = None
         out = {
             "metric": "llama3_8b_train_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": value / (BASELINE_TOK_S_PER_GPU * world), "dtype": "bf16",
             "data": "synthetic random tokens, random-init weights",
-            "config": {"model": a.model, "global_batch": B * MB * world, "seq_len": S,
-                       "parallelism": f"dp{world}_zero1_tp1_pp1", "micro_batch": B, "micro_batches": MB,
+            "config": {"model": a.model, "global_batch": B * MB * dp, "seq_len": S,
+                       "parallelism": f"dp{world}_zero1_tp1_pp1" if tp == 1 else f"dp1_tp{tp}_sp_pp1 (fused AG->GEMM / GEMM->RS kernels)",
+                       "micro_batch": B, "micro_batches": MB,
                        "layers": dims.layers, "padded_vocab": dims.vocab, "params": dims.total_numel(),
                        "optimizer": "AdamW fp32 master/m/v, fp32 main grads, grad clip 1.0", "recompute": "none",
-                       "attention_bwd": tr.attention_bwd,
+                       "attention_bwd": getattr(tr, "attention_bwd", "smx"),
                        "l2": "256 MiB buffer rewritten before every step; a step touches >100 GB of weights/activations"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "predicted": pred, "memory_gb": {k: round(v / 2 ** 30, 3) for k, v in mem.items()},

@@ -46,3 +46,14 @@ def test_fused_gemm_reduce_scatter():
            "--master-port", "29535", os.path.join(ROOT, "tools", "fused_check.py")]
     r = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), capture_output=True, text=True, timeout=280)
     assert r.returncode == 0 and "FUSED_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.timeout(300)
+def test_tensor_parallel_trainer_matches_single_gpu():
+    """TP + SP training step on the fused AG->GEMM / GEMM->RS kernels vs the 1-GPU trainer with the same weights."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29536", os.path.join(ROOT, "tools", "tp_check.py")]
+    r = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0 and "TP_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -123,3 +123,54 @@ def test_add_copy():
     dst = torch.empty_like(a)
     E.copy_(dst, a)
     assert torch.equal(dst, a)
+
+
+@pytest.mark.parametrize("world,H", [(2, 1024), (4, 4096), (8, 8192)])
+def test_rs_consume_sum_residual_rmsnorm(world, H):
+    """Owner-side kernel of the fused GEMM -> reduce-scatter: slot sum (+ residual) (+ RMSNorm), no counter wait."""
+    import ctypes
+    from simumax_b200.ops import _lib
+    torch.manual_seed(3)
+    rows = 96
+    slots, resid = _r(world, rows, H), _r(rows, H)
+    gamma = (1 + 0.1 * torch.randn(H, device="cuda")).bfloat16()
+    out, normed = torch.empty_like(resid), torch.empty_like(resid)
+    rstd = torch.empty(rows, device="cuda")
+    f = _lib.lib().smx_rs_consume
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_int] + [ctypes.c_void_p] * 5 + [
+        ctypes.c_float, ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p]
+    st = torch.cuda.current_stream().cuda_stream
+    assert f(slots.data_ptr(), world, rows, H, resid.data_ptr(), out.data_ptr(), gamma.data_ptr(), normed.data_ptr(),
+             rstd.data_ptr(), 1e-5, None, 0, st) == 0
+    ref = resid.float() + slots.float().sum(0)
+    torch.testing.assert_close(out.float(), ref, atol=6e-2, rtol=2e-2)
+    x2 = out.float()                       # the norm is taken of the bf16-rounded residual stream, as stored
+    r_ref = torch.rsqrt(x2.pow(2).mean(-1) + 1e-5)
+    torch.testing.assert_close(rstd, r_ref, atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(normed.float(), x2 * r_ref[:, None] * gamma.float(), atol=3e-2, rtol=2e-2)
+    plain = torch.empty_like(resid)
+    assert f(slots.data_ptr(), world, rows, H, None, plain.data_ptr(), None, None, None, 1e-5, None, 0, st) == 0
+    torch.testing.assert_close(plain.float(), slots.float().sum(0), atol=6e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_vocab_parallel_cross_entropy(world):
+    """Two-phase vocab-parallel CE (local stats -> gathered -> loss + in-place grad) vs fp32 CE on the full vocabulary."""
+    from simumax_b200.ops import elementwise as E
+    torch.manual_seed(4)
+    rows, V = 64, 2048 * world
+    VW = V // world
+    logits = _r(rows, V, scale=2.0)
+    tgt = torch.randint(0, V, (rows,), device="cuda")
+    lf = logits.float().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lf, tgt, reduction="none")
+    ref.sum().backward()
+    shards = [logits[:, r * VW:(r + 1) * VW].contiguous() for r in range(world)]
+    stats = torch.empty(world, rows, 4, device="cuda")
+    for r in range(world):
+        E.ce_vocab_parallel_stats(shards[r], tgt, r * VW, stats[r])
+    for r in range(world):
+        loss = E.ce_vocab_parallel_grad_(shards[r], tgt, r * VW, stats, world, grad_scale=1.0)
+        torch.testing.assert_close(loss, ref.detach(), atol=2e-2, rtol=1e-2)
+        torch.testing.assert_close(shards[r].float(), lf.grad[:, r * VW:(r + 1) * VW], atol=2e-2, rtol=2e-2)

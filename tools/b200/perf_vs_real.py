@@ -33,13 +33,21 @@ CASES = [
 ]
 
 
-def predict(model, layers, seq, mbs, mbc, world, system):
+TP_CASES = [      # measured with TPLlamaTrainer: tp = world, sequence parallel, dp = 1 (every rank sees the same batch)
+    ("llama3_8b_full_s4096_tp",    "llama3-8b",  None,   4096,  1,   4),
+    ("llama3_70b_l12_s4096_tp",    "llama3-70b", 12,     4096,  1,   4),
+    ("llama3_70b_l12_s8192_tp",    "llama3-70b", 12,     8192,  1,   2),
+]
+
+
+def predict(model, layers, seq, mbs, mbc, world, system, tp=1):
     from simumax_b200 import PerfLLM
     from simumax_b200.configs import get_simu_model_config, get_simu_strategy_config, get_simu_system_config
     from simumax_b200.core.config import StrategyConfig
     from simumax_b200.core.utils import parse_bytes
     st = StrategyConfig.init_from_config_file(get_simu_strategy_config("tp1_pp1_dp8_mbs1"))
-    st.world_size, st.tp_size, st.pp_size = world, 1, 1
+    st.world_size, st.tp_size, st.pp_size = world, tp, 1
+    st.enable_sequence_parallel = tp > 1
     st.seq_len, st.micro_batch_size, st.micro_batch_num = seq, mbs, mbc
     st.dp_overlap_model = True      # the runtime overlaps ZeRO-1 collectives with backward / next forward
     p = PerfLLM()
@@ -51,12 +59,12 @@ def predict(model, layers, seq, mbs, mbc, world, system):
         p.run_estimate()
         cost, mem = p.analysis_cost().data, p.analysis_mem().data
     tok_s = cost["throughput_per_accelerator"] * world
-    return {"iter_ms": mbs * mbc * world * seq / tok_s * 1e3, "tokens_per_s": tok_s, "mfu": cost["mfu"],
+    return {"iter_ms": mbs * mbc * (world // tp) * seq / tok_s * 1e3, "tokens_per_s": tok_s, "mfu": cost["mfu"],
             "peak_gib": parse_bytes(mem["peak_mem"]) / 2 ** 30 if isinstance(mem.get("peak_mem"), str) else None,
             "miss": {k: len(v) for k, v in p.system.miss_efficiency.items()}}
 
 
-def measure(model, layers, seq, mbs, mbc, steps, warmup):
+def measure(model, layers, seq, mbs, mbc, steps, warmup, tp=1):
     import torch
     import torch.distributed as dist
     from simumax_b200.configs import get_simu_model_config
@@ -68,7 +76,11 @@ def measure(model, layers, seq, mbs, mbc, steps, warmup):
         dims.layers = layers
     world = dist.get_world_size() if dist.is_initialized() else 1
     torch.cuda.reset_peak_memory_stats()
-    tr = LlamaTrainer(dims, mbs, seq, dp_group=dist.group.WORLD if world > 1 else None)
+    if tp > 1:
+        from simumax_b200.runtime.tp_trainer import TPLlamaTrainer
+        tr = TPLlamaTrainer(dims, mbs, seq)
+    else:
+        tr = LlamaTrainer(dims, mbs, seq, dp_group=dist.group.WORLD if world > 1 else None)
     g = torch.Generator(device="cuda").manual_seed(5)
     batches = [(torch.randint(0, mc.vocab_size, (mbs * seq,), device="cuda", generator=g),
                 torch.randint(0, mc.vocab_size, (mbs * seq,), device="cuda", generator=g)) for _ in range(mbc)]
@@ -88,7 +100,7 @@ def measure(model, layers, seq, mbs, mbc, steps, warmup):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(peak, op=dist.ReduceOp.MAX)
-    out = {"iter_ms": float(ms), "tokens_per_s": mbs * mbc * world * seq / float(ms) * 1e3, "peak_gib": float(peak) / 2 ** 30}
+    out = {"iter_ms": float(ms), "tokens_per_s": mbs * mbc * (world // tp) * seq / float(ms) * 1e3, "peak_gib": float(peak) / 2 ** 30}
     del tr, batches
     gc.collect()
     torch.cuda.empty_cache()
@@ -102,6 +114,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--cases", nargs="*", default=None)
+    ap.add_argument("--tp", action="store_true", help="tensor-parallel cases (tp = world size, sequence parallel, fused kernels)")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -112,13 +125,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank = dist.get_rank() if world > 1 else 0
     rows = []
-    for name, model, layers, seq, mbs, mbc in CASES:
+    tp = world if a.tp else 1
+    for name, model, layers, seq, mbs, mbc in (TP_CASES if a.tp else CASES):
         if a.cases and name not in a.cases:
             continue
-        real = measure(model, layers, seq, mbs, mbc, a.steps, a.warmup)
+        real = measure(model, layers, seq, mbs, mbc, a.steps, a.warmup, tp)
         if rank == 0:
-            pred = predict(model, layers, seq, mbs, mbc, world, a.system)
-            row = {"case": name, "world": world, "model": model, "layers": layers, "seq": seq, "mbs": mbs, "mbc": mbc,
+            pred = predict(model, layers, seq, mbs, mbc, world, a.system, tp)
+            row = {"case": name + (str(tp) if a.tp else ""), "world": world, "tp": tp, "model": model, "layers": layers, "seq": seq, "mbs": mbs, "mbc": mbc,
                    "pred_ms": pred["iter_ms"], "real_ms": real["iter_ms"],
                    "time_err_pct": 100 * (pred["iter_ms"] - real["iter_ms"]) / real["iter_ms"],
                    "pred_gib": pred["peak_gib"], "real_gib": real["peak_gib"],
