@@ -270,6 +270,90 @@ __global__ void __launch_bounds__(512) all_to_all_kernel(PeerPtrs pp, long long 
   cta_barrier_all_ranks(pp, epoch + 1);
 }
 
+// ----------------------------------------------------------------------------------------------------------------------
+// Fused MoE dispatch = token permutation + expert-parallel all-to-all in ONE kernel (reference cost model: Permutation
+// all2all fwd/bwd, simumax/core/transformer/moe_module.py:383-423).  Row r = (d, e, c) of the capacity-padded permuted order
+// (d = destination EP rank, e = local expert on that rank, c = capacity slot) is gathered from local token row_map[r]
+// (-1 = padding -> zeros), optionally scaled (backward: the routing probability), and stored straight into rank d's receive
+// buffer at row (e * world + rank) * C + c -- expert-major [El][world * C], exactly what the grouped GEMM consumes -- so the
+// permuted copy of the activations never exists in local memory.  One warp per row, destination ranks visited from rank + 1.
+// ----------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) moe_dispatch_kernel(PeerPtrs pp, const __nv_bfloat16* __restrict__ x,
+                                                          const int* __restrict__ row_map, const float* __restrict__ row_scale,
+                                                          long long out_off, int H, int C, int El, uint32_t epoch) {
+  cta_barrier_all_ranks(pp, epoch);
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long rows_per_dst = (long long)El * C;
+  const long long total = rows_per_dst * pp.world;
+  const int vec = H / 8;
+  for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += warps) {
+    const int hop = (int)(w / rows_per_dst);
+    const int d = (pp.rank + 1 + hop) % pp.world;
+    const long long rem = w - (long long)hop * rows_per_dst;
+    const int e = (int)(rem / C), c = (int)(rem - (long long)e * C);
+    const long long r = (long long)d * rows_per_dst + rem;
+    const int src = row_map[r];
+    const float sc = (row_scale != nullptr && src >= 0) ? row_scale[r] : 1.f;
+    char* dst = reinterpret_cast<char*>(pp.data[d]) + out_off + (((long long)e * pp.world + pp.rank) * C + c) * H * 2;
+    const uint4* sp = reinterpret_cast<const uint4*>(x + (long long)(src < 0 ? 0 : src) * H);
+    // four 16-byte loads in flight per lane (a row is 8-14 KB: one load per lane per trip leaves the warp latency bound)
+    for (int i0 = lane; i0 < vec; i0 += 128) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (src >= 0 && i0 + u * 32 < vec) v[u] = ld_nc_v4(sp + i0 + u * 32);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i0 + u * 32 >= vec) continue;
+        if (row_scale != nullptr && src >= 0) {
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v[u]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 f = __bfloat1622float2(h[j]);
+            h[j] = __floats2bfloat162_rn(f.x * sc, f.y * sc);
+          }
+        }
+        st_v4(dst + (long long)(i0 + u * 32) * 16, v[u]);
+      }
+    }
+  }
+  cta_barrier_all_ranks(pp, epoch + 1);
+}
+
+// Fused MoE combine (the way back): row (e, s, c) of this rank's expert-major buffer goes to rank s at row
+// (rank * El + e) * C + c of its permuted-order buffer; the source rank then runs the local unpermute / weighted sum.
+__global__ void __launch_bounds__(512) moe_combine_kernel(PeerPtrs pp, const __nv_bfloat16* __restrict__ y, long long out_off, int H,
+                                                         int C, int El, uint32_t epoch) {
+  cta_barrier_all_ranks(pp, epoch);
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long total = (long long)El * pp.world * C;
+  const int vec = H / 8;
+  for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += warps) {
+    // enumerate (hop, e, c) so that consecutive warps of one pass write to the same destination rank
+    const long long per_dst = (long long)El * C;
+    const int hop = (int)(w / per_dst);
+    const int s = (pp.rank + 1 + hop) % pp.world;
+    const long long rem = w - (long long)hop * per_dst;
+    const int e = (int)(rem / C), c = (int)(rem - (long long)e * C);
+    const uint4* sp = reinterpret_cast<const uint4*>(y + (((long long)e * pp.world + s) * C + c) * H);
+    char* dst = reinterpret_cast<char*>(pp.data[s]) + out_off + (((long long)pp.rank * El + e) * C + c) * H * 2;
+    for (int i0 = lane; i0 < vec; i0 += 128) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * 32 < vec) v[u] = ld_nc_v4(sp + i0 + u * 32);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * 32 < vec) st_v4(dst + (long long)(i0 + u * 32) * 16, v[u]);
+    }
+  }
+  cta_barrier_all_ranks(pp, epoch + 1);
+}
+
 // point-to-point put (pipeline send): dst rank's buffer <- local buffer; flag protocol as above restricted to a pair
 __global__ void __launch_bounds__(512) p2p_put_kernel(PeerPtrs pp, int dst_rank, long long in_off, long long out_off,
                                                      long long nbytes) {
@@ -392,6 +476,22 @@ int smx_p2p_put(void* const* data_ptrs, void* const* flag_ptrs, int rank, int wo
   if (world > smx::kMaxRanks || nbytes % 16) return -40;
   smx::p2p_put_kernel<<<ctas, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       make_pp(data_ptrs, flag_ptrs, nullptr, rank, world), dst_rank, in_off, out_off, nbytes);
+  return (int)cudaGetLastError();
+}
+
+int smx_moe_dispatch(void* const* data_ptrs, void* const* flag_ptrs, int rank, int world, const void* x, const int* row_map,
+                     const float* row_scale, long long out_off, int H, int C, int El, unsigned epoch, int ctas, void* stream) {
+  if (world > smx::kMaxRanks || H % 8 || out_off % 16) return -40;
+  smx::moe_dispatch_kernel<<<ctas, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      make_pp(data_ptrs, flag_ptrs, nullptr, rank, world), reinterpret_cast<const __nv_bfloat16*>(x), row_map, row_scale, out_off, H, C, El,
+      epoch);
+  return (int)cudaGetLastError();
+}
+int smx_moe_combine(void* const* data_ptrs, void* const* flag_ptrs, int rank, int world, const void* y, long long out_off, int H,
+                    int C, int El, unsigned epoch, int ctas, void* stream) {
+  if (world > smx::kMaxRanks || H % 8 || out_off % 16) return -40;
+  smx::moe_combine_kernel<<<ctas, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      make_pp(data_ptrs, flag_ptrs, nullptr, rank, world), reinterpret_cast<const __nv_bfloat16*>(y), out_off, H, C, El, epoch);
   return (int)cudaGetLastError();
 }
 

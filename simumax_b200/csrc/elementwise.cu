@@ -564,6 +564,30 @@ __global__ void unpermute_combine_kernel(const __nv_bfloat16* __restrict__ x, __
   }
 }
 
+// d_probs[t, k] = < dy[t, :], y_perm[inv_map[t, k], :] >  (0 for dropped slots): gradient of the MoE combine weights.
+__global__ void moe_prob_grad_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y_perm,
+                                     const int* __restrict__ inv_map, float* __restrict__ d_probs, long long slots, int topk, int H) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long sidx = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); sidx < slots; sidx += warps) {
+    const int r = inv_map[sidx];
+    float acc = 0.f;
+    if (r >= 0) {
+      const __nv_bfloat16* a = dy + (sidx / topk) * H;
+      const __nv_bfloat16* b = y_perm + (long long)r * H;
+      for (int c = lane * 8; c < H; c += 256) {
+        float fa[8], fb[8];
+        load8(a + c, fa);
+        load8(b + c, fb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += fa[j] * fb[j];
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) d_probs[sidx] = acc;
+  }
+}
+
 // residual add: y = a + b (bf16) -- used by the training harness between sub-layers
 __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                            __nv_bfloat16* __restrict__ y, long long n) {
@@ -724,6 +748,13 @@ int smx_unpermute_combine(const void* x, void* out, const int* inv_map, const fl
                           int H, void* stream) {
   if (H % 8) return -20;
   smx::unpermute_combine_kernel<<<grid_for(tokens * (H / 8), 256), 256, 0, SMX_STREAM>>>((const bf16*)x, (bf16*)out, inv_map, probs, tokens, topk, H);
+  return (int)cudaGetLastError();
+}
+int smx_moe_prob_grad(const void* dy, const void* y_perm, const int* inv_map, float* d_probs, long long tokens, int topk, int H,
+                      void* stream) {
+  if (H % 8) return -20;
+  smx::moe_prob_grad_kernel<<<grid_for(tokens * topk * 32, 256), 256, 0, SMX_STREAM>>>((const bf16*)dy, (const bf16*)y_perm, inv_map, d_probs,
+                                                                                      tokens * topk, topk, H);
   return (int)cudaGetLastError();
 }
 int smx_add(const void* a, const void* b, void* y, long long n, void* stream) {

@@ -28,6 +28,7 @@ _SIGS = {
     "smx_adamw": [_c.c_void_p] * 5 + [_c.c_longlong] + [_c.c_float] * 7 + [_c.c_void_p, _c.c_float, _c.c_float, _c.c_int, _c.c_void_p],
     "smx_permute_rows": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_void_p],
     "smx_unpermute_combine": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_void_p],
+    "smx_moe_prob_grad": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_void_p],
     "smx_add": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_void_p],
     "smx_copy": [_c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_void_p],
 }
@@ -201,6 +202,15 @@ def unpermute_combine(x: torch.Tensor, inv_map: torch.Tensor, probs: Optional[to
     _call("smx_unpermute_combine", x.data_ptr(), y.data_ptr(), inv_map.data_ptr(),
           probs.data_ptr() if probs is not None else None, tokens, topk, H, _stream(x))
     return y
+
+
+def moe_prob_grad(dy: torch.Tensor, y_perm: torch.Tensor, inv_map: torch.Tensor, topk: int) -> torch.Tensor:
+    """d_probs[t, k] = <dy[t], y_perm[inv_map[t, k]]> (0 where the slot was dropped): gradient of the MoE combine weights."""
+    _bf16c(dy, "dy"); _bf16c(y_perm, "y_perm")
+    tokens, H = dy.shape
+    out = torch.empty(tokens, topk, device=dy.device, dtype=torch.float32)
+    _call("smx_moe_prob_grad", dy.data_ptr(), y_perm.data_ptr(), inv_map.data_ptr(), out.data_ptr(), tokens, topk, H, _stream(dy))
+    return out
 
 
 def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

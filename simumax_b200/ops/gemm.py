@@ -52,6 +52,14 @@ def _two_cta_default() -> bool:
     return os.environ.get("SMX_GEMM_2CTA", "1") == "1"
 
 
+def _pair_tiles_pay(M: int) -> bool:
+    """256-row pair tiles vs 128-row tiles: take the pair kernel unless its last M-tile wastes much more of the tensor core
+    (e.g. M = 320 rows per expert: 62 % useful rows in two pair tiles, 83 % in three single tiles)."""
+    util2 = M / (-(-M // 256) * 256)
+    util1 = M / (-(-M // 128) * 128)
+    return util2 >= 0.88 * util1
+
+
 def _as3d(t: torch.Tensor) -> torch.Tensor:
     return t if t.dim() == 3 else t.unsqueeze(0)
 
@@ -122,7 +130,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, layout: str = "TN", out: torch.Tensor
         nsm = min(nsm, sm_limit)
     if two_cta is None:
         two_cta = _two_cta_default()
-    if two_cta and dtype == 0 and M >= 256 and N >= 256 and block_n == 0:
+    if two_cta and dtype == 0 and M >= 256 and N >= 256 and block_n == 0 and _pair_tiles_pay(M):
         # CTA-pair kernel (csrc/gemm_2cta.cu): 256 x 256 tiles, B split across the pair
         rc = _fn2()(a3.data_ptr(), b3.data_ptr(), out3.data_ptr(), G, M, N, K, a_mn, b_mn,
                     1 if out3.dtype == torch.float32 else 0, 1 if accumulate else 0, float(alpha),

@@ -138,6 +138,34 @@ class SymmetricWorkspace:
         _lib.check(rc, "smx_all_to_all")
         _lib.count_launch()
 
+    def moe_dispatch(self, x: torch.Tensor, row_map: torch.Tensor, out_off: int, capacity: int, local_experts: int,
+                     row_scale: Optional[torch.Tensor] = None, ctas: int = 128):
+        """Fused token permutation + EP all-to-all: row (d, e, c) of the capacity-padded permuted order is gathered from local
+        token ``row_map[r]`` (-1 = padding) and stored into rank d's buffer at ``out_off`` in expert-major ``[El][world * C]``
+        order.  ``x`` may live anywhere in local memory; the destination is the symmetric buffer."""
+        H = x.shape[-1]
+        assert x.dtype == torch.bfloat16 and x.is_contiguous() and row_map.dtype == torch.int32
+        assert row_map.numel() == self.world * local_experts * capacity
+        assert out_off + self.world * local_experts * capacity * H * 2 <= self.in_bytes + self.out_bytes
+        sig = [_PTRS, _PTRS, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_int,
+               _c.c_uint, _c.c_int, _c.c_void_p]
+        rc = _fn("smx_moe_dispatch", sig)(self.data_ptrs, self.flag_ptrs, self.rank, self.world, x.data_ptr(), row_map.data_ptr(),
+                                          row_scale.data_ptr() if row_scale is not None else None, out_off, H, capacity, local_experts,
+                                          self._next_epoch(), min(ctas, MAX_CTAS), self._stream())
+        _lib.check(rc, "smx_moe_dispatch")
+        _lib.count_launch()
+
+    def moe_combine(self, y: torch.Tensor, out_off: int, capacity: int, local_experts: int, ctas: int = 128):
+        """The way back: row (e, s, c) of the local expert-major tensor ``y`` goes to rank s, row ``(rank * El + e) * C + c`` of its
+        permuted-order buffer at ``out_off``."""
+        H = y.shape[-1]
+        assert y.dtype == torch.bfloat16 and y.is_contiguous() and y.numel() == self.world * local_experts * capacity * H
+        sig = [_PTRS, _PTRS, _c.c_int, _c.c_int, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_int, _c.c_uint, _c.c_int, _c.c_void_p]
+        rc = _fn("smx_moe_combine", sig)(self.data_ptrs, self.flag_ptrs, self.rank, self.world, y.data_ptr(), out_off, H, capacity,
+                                         local_experts, self._next_epoch(), min(ctas, MAX_CTAS), self._stream())
+        _lib.check(rc, "smx_moe_combine")
+        _lib.count_launch()
+
     def barrier(self):
         """Device-side barrier across the group on the current stream (flag exchange over NVLink, no NCCL)."""
         rc = _fn("smx_rank_barrier", [_PTRS, _PTRS, _c.c_int, _c.c_int, _c.c_uint, _c.c_void_p])(

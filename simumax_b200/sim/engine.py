@@ -241,7 +241,8 @@ class Engine:
         st.t["comp"] += SCOPE_GAP_MS
         if prof is not None and mt is not None:
             mt.phase_end(rank=st.rank, ts=st.t["comp"], profile=prof, phase=phase)
-        self._emit(st, scope.name, "scope", phase, t0, st.t["comp"])
+        if scope.name:                       # anonymous wrapper scopes (p2p bundles) cost time but are not worth a trace record
+            self._emit(st, scope.name, "scope", phase, t0, st.t["comp"])
 
     # ------------------------------------------------------------------ synchronous collectives
     def _exec_coll(self, st, job: Coll, direction: str):

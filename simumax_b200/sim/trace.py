@@ -7,6 +7,7 @@ times are microseconds; matching async send/recv pairs are linked with flow arro
 from __future__ import annotations
 
 import json
+import re
 from typing import Dict, List
 
 from .engine import Event
@@ -84,5 +85,56 @@ def write_event_log(events: List[Event], path: str) -> int:
     with open(path, "w", encoding="utf-8") as fh:
         for e in events:
             gid = f" gid {e.gid}" if e.gid else ""
-            fh.write(f"{e.name}{gid} {e.phase} cost {e.end - e.start:.6f} st {e.start:.6f} ed {e.end:.6f}\n")
+            tail = (f" post {e.post:.6f}" if e.post is not None else "") + (f" order {e.order}" if e.order is not None else "")
+            fh.write(f"{e.name}{gid} {e.phase} cost {e.end - e.start:.6f} st {e.start:.6f} ed {e.end:.6f}{tail} kind {e.kind} lane {e.lane}\n")
     return len(events)
+
+
+# ------------------------------------------------------------------------------------------------
+# text log -> trace (the reference's only path: generate_tracing.py:27-54 parse_log_line, :488 process_log_file).
+# Here the structured events are the primary path; the log round trip exists so a log produced by either
+# implementation can be turned into a trace after the fact.
+# ------------------------------------------------------------------------------------------------
+_LINE = re.compile(r"rank(?P<rank>\d+)-(?P<stack>[\w-]+)\s+(?:gid\s+(?P<gid>\S+)\s+)?(?P<phase>\w+)\s+cost\s+(?P<cost>[\d.]+)\s+"
+                   r"st\s+(?P<st>[\d.]+)\s+ed\s+(?P<ed>[\d.]+)(?:\s+post\s+(?P<post>[\d.]+))?(?:\s+order\s+(?P<order>-?\d+))?"
+                   r"(?:\s+kind\s+(?P<kind>\w+)\s+lane\s+(?P<lane>\w+))?")
+_P2P = ("send_", "recv_", "async_send", "async_recv", "sync_send", "sync_recv")
+_WAIT = ("async_wait", "sync_wait")
+_LEAF_COMPUTE = ("AtomModel", "Linear", "GroupedLinear", "AttentionScore", "optimizer_step")     # leaf jobs of sim/jobs.py
+_COLL = ("all_reduce", "all_gather", "reduce_scatter", "all2all", "broadcast", "scatter", "gather", "reduce")
+
+
+def parse_log_line(line: str):
+    """One ``log.log`` line -> ``Event`` (None if it is not a job record)."""
+    m = _LINE.match(line.strip())
+    if not m:
+        return None
+    stack = m.group("stack")
+    leaf = stack.split("-")[-1]
+    if m.group("kind"):                      # written by this package: self-describing
+        kind, lane = m.group("kind"), m.group("lane")
+    elif leaf.startswith(_WAIT):             # a reference-made log: classify by the leaf name
+        kind, lane = "wait", "wait"
+    elif leaf.startswith(_P2P):
+        kind = "p2p"
+        lane = "pp_bwd" if "backward" in (m.group("gid") or "") else "pp_fwd"
+    elif leaf.startswith(_COLL):
+        kind, lane = "comm", "comm"
+    elif leaf in _LEAF_COMPUTE:
+        kind, lane = "compute", "comp"
+    else:
+        kind, lane = "scope", "comp"
+    return Event(int(m.group("rank")), f"rank{m.group('rank')}-{stack}", kind, m.group("phase"), float(m.group("st")),
+                 float(m.group("ed")), lane, gid=m.group("gid"),
+                 post=float(m.group("post")) if m.group("post") is not None else None,
+                 order=int(m.group("order")) if m.group("order") is not None else None)
+
+
+def events_from_log(log_path: str) -> List[Event]:
+    with open(log_path, "r", encoding="utf-8") as fh:
+        return [e for e in (parse_log_line(l) for l in fh if " cost " in l) if e is not None]
+
+
+def process_log_file(log_path: str, output_json_path: str) -> int:
+    """Read a simulator text log and write the Chrome-trace JSON; returns the number of trace records."""
+    return write_trace(events_from_log(log_path), output_json_path)

@@ -75,3 +75,31 @@ def test_deadlock_is_detected():
     eng.add_rank(1, [("fwd", Scope("b", [BlockingP2P("recv", "y", 1.0)]))])
     with pytest.raises(Deadlock):
         eng.run()
+
+
+def test_log_round_trip_rebuilds_the_trace(tmp_path):
+    """log.log -> process_log_file reproduces the structured trace (reference path: generate_tracing.process_log_file)."""
+    import collections
+    import contextlib
+    import io
+    import json
+
+    from simumax_b200 import PerfLLM
+    from simumax_b200.configs import get_simu_model_config, get_simu_strategy_config, get_simu_system_config
+    from simumax_b200.sim.trace import parse_log_line, process_log_file
+    p = PerfLLM()
+    with contextlib.redirect_stdout(io.StringIO()):
+        p.configure(strategy_config=get_simu_strategy_config("tp1_pp2_dp4_mbs1"), model_config=get_simu_model_config("llama3-8b"),
+                    system_config=get_simu_system_config("b200_nominal"))
+        p.model_config.layer_num = 4
+        p.run_estimate()
+        p.simulate(str(tmp_path))
+    process_log_file(str(tmp_path / "log.log"), str(tmp_path / "from_log.json"))
+    a = [r for r in json.load(open(tmp_path / "tracing_logs.json")) if r.get("ph") in ("X", "s", "f")]
+    b = [r for r in json.load(open(tmp_path / "from_log.json")) if r.get("ph") in ("X", "s", "f")]
+    key = lambda r: (r["ph"], r["tid"], r["pid"], r["name"])
+    assert len(a) == len(b) and collections.Counter(map(key, a)) == collections.Counter(map(key, b))
+    assert all(abs(x["ts"] - y["ts"]) < 1e-2 for x, y in zip(sorted(a, key=lambda r: (key(r), r["ts"])), sorted(b, key=lambda r: (key(r), r["ts"]))))
+    # a reference-made line (no kind / lane suffix) is classified by its leaf name
+    e = parse_log_line("rank4-async_wait_recv_prev gid send_recv-0-1-forward-0-pp_group:tp:0- fwd cost 30.805182 st 0.000000 ed 30.805182")
+    assert (e.kind, e.rank, e.gid) == ("wait", 4, "send_recv-0-1-forward-0-pp_group:tp:0-")
