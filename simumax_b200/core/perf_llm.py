@@ -228,7 +228,8 @@ class PerfLLM(PerfBase):
     def _new_chunk(self, layer_num, dense_layers, preprocess, postprocess, specific_name) -> StageChunk:
         return StageChunk(layer_num=layer_num, dense_layers=dense_layers, preprocess=preprocess,
                           postprocess=postprocess, model_config=self.model_config, strategy=self.strategy,
-                          system=self.system, specific_name=specific_name)
+                          system=self.system, specific_name=specific_name,
+                          block_cache=getattr(self, "_block_cache", None))
 
     def build(self):
         """Create first / middle / last stage chunks (and virtual chunks when interleaving)."""

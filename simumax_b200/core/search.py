@@ -26,6 +26,26 @@ def merge_dict(cur: dict, merged: dict) -> dict:
     return merged
 
 
+def _cached_search(fn):
+    """Run a search entry point with the block profile cache switched on (outermost call owns it; SIMU_SEARCH_CACHE=0
+    disables it for A/B runs).  Reference: the search-only CachedChunkProfile machinery, perf_llm.py:837-1379."""
+    import functools
+    import os
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        if getattr(self, "_block_cache", None) is not None or os.environ.get("SIMU_SEARCH_CACHE", "1") == "0":
+            return fn(self, *args, **kwargs)
+        from ..models.llm import BlockProfileCache
+        self._block_cache = BlockProfileCache()
+        try:
+            return fn(self, *args, **kwargs)
+        finally:
+            self.last_search_cache_stats = {"hits": self._block_cache.hits, "misses": self._block_cache.misses}
+            self._block_cache = None
+    return wrapper
+
+
 class SearchMixin:
     # ------------------------------------------------------------------ helpers
     def _peak_key(self, use_reserved_memory: bool) -> str:
@@ -69,6 +89,7 @@ class SearchMixin:
         return perf
 
     # ------------------------------------------------------------------ micro-batch searches
+    @_cached_search
     def search_max_micro_batch_size(self, micro_batch_num=None):
         """Binary search of the largest micro-batch size that fits ``accelerator.mem_gbs`` (fixed micro-batch count)."""
         left, right = 1, 2 ** 16
@@ -94,6 +115,7 @@ class SearchMixin:
             print(f"Peak cached memory: {peak / 1024 ** 3: .2f} GB")
         return left - 1, peak
 
+    @_cached_search
     def search_max_micro_batch_size_fixed_gbs(self, pp_size, dp_size, global_batch_size, memory_utils=1.0, gmi_error=6,
                                               use_reserved_memory=True, save_all=True, verbose: bool = True):
         """All (micro_batch_size, micro_batch_num) splits of a fixed global batch that fit in memory, largest first."""
@@ -125,6 +147,7 @@ class SearchMixin:
             self.strategy.micro_batch_size, self.strategy.micro_batch_num, self._search_verbose = keep
 
     # ------------------------------------------------------------------ recompute searches
+    @_cached_search
     def search_best_selective_recompute(self, use_reserved_memory, gmi_error, best_mfu=None, all_search_result=None,
                                         save_path=None):
         if self.strategy.megatron_recompute:
@@ -154,6 +177,7 @@ class SearchMixin:
                     merge_dict(cur, all_search_result)
         return best
 
+    @_cached_search
     def search_best_recompute_layer_num(self, layer_num, use_reserved_memory: bool, gmi_error: int, best_mfu,
                                         all_search_result: dict, save_path=None):
         """Binary search of the smallest number of recomputed layers per stage that fits (fewest = fastest)."""
@@ -185,6 +209,7 @@ class SearchMixin:
             self.strategy.recompute_layer_num = keep
         return best
 
+    @_cached_search
     def search_best_strategy_no_recompute(self, gmi_error, use_reserved_memory, best_mfu, all_search_result,
                                           save_path=None):
         self.strategy.recompute_granularity = None
@@ -205,6 +230,7 @@ class SearchMixin:
         return best
 
     # ------------------------------------------------------------------ parallel strategy grid
+    @_cached_search
     def search_best_parallel_strategy(self, world_size: int, gmi_error: int, micro_batch_size: int,
                                       global_batch_size: int, all_search_result: dict, tp_search_list: List = None,
                                       ep_search_list: List = None, pp_search_list: List = None, use_etp: bool = False,

@@ -157,6 +157,85 @@ def emit_block(em: Emitter, layer_idx: int, shape, use_dense: bool):
 
 
 # ------------------------------------------------------------------------------------------------
+# search-time block cache
+# ------------------------------------------------------------------------------------------------
+class BlockProfileCache:
+    """Emitted + evaluated transformer blocks, shared between layers, chunks and search candidates.
+
+    Counterpart of the reference's search cache (``CachedChunkProfile`` / ``CachedUnitRuntimeProfile``, perf_llm.py:41-252,
+    837-1379: per-unit profiles keyed by a projection of the strategy JSON).  With the flat IR a "unit" is just the list of
+    ``OpNode`` a block emits: ``evaluate()`` does not look at neighbours, so a block that was emitted and evaluated once can be
+    re-used for every layer with the same (strategy projection, model, recompute switches, input shape) by cloning the nodes
+    under new names.  The strategy projection drops the knobs that only move whole blocks around (micro-batch count, how many
+    layers are recomputed, pipeline layer split): those are captured by the per-layer recompute configs and by which blocks a
+    chunk asks for.  Only the search entry points switch it on, so result files of plain ``perf()`` runs are untouched.
+    """
+    _VOLATILE = ("micro_batch_num", "global_batch_size", "recompute_layer_num", "num_layers_in_first_pipeline_stage",
+                 "num_layers_in_last_pipeline_stage")
+
+    def __init__(self):
+        self.store: Dict[tuple, tuple] = {}
+        self.hits = 0
+        self.misses = 0
+
+    def context_key(self, cfg: ModelConfig, st: StrategyConfig, system: SystemConfig) -> tuple:
+        import json
+        sd = {k: v for k, v in st.to_dict().items() if not any(t in k for t in self._VOLATILE)}
+        return (id(system), json.dumps(cfg.to_dict(), sort_keys=True, default=str), json.dumps(sd, sort_keys=True, default=str))
+
+    def clear(self):
+        self.store.clear()
+
+
+_BOOKS = ("real_comm_bw", "miss_efficiency", "hit_efficiency")
+
+
+def _swap_books(system: SystemConfig, books):
+    """Install ``books`` (or fresh empty tables) as the system's bookkeeping dicts; returns the previous ones."""
+    from collections import OrderedDict
+    prev = tuple(getattr(system, b) for b in _BOOKS)
+    for b, v in zip(_BOOKS, books or (OrderedDict(), OrderedDict(), OrderedDict())):
+        setattr(system, b, v)
+    return prev
+
+
+def _merge_books(system: SystemConfig, delta) -> None:
+    for b, d in zip(_BOOKS, delta):
+        dst = getattr(system, b)
+        for op, entries in d.items():
+            if isinstance(entries, dict) and isinstance(dst.get(op), dict):
+                dst[op].update(entries)
+            elif isinstance(entries, dict):
+                dst[op] = dict(entries)
+            else:
+                dst[op] = entries
+
+
+def _retarget(text: str, src: int, dst: int, prefix: str) -> str:
+    return text.replace(f"{prefix}{src}", f"{prefix}{dst}", 1) if src != dst else text
+
+
+def _clone_block(nodes: List[OpNode], tree: List[tuple], src: int, dst: int, base: int):
+    """Copies of a cached block's nodes / scope records renamed from layer ``src`` to ``dst``, node indices rebased to ``base``."""
+    from copy import copy
+    out = []
+    for n in nodes:
+        m = copy(n)
+        m.name = _retarget(n.name, src, dst, "layer_")
+        m.scope = tuple(_retarget(sn, src, dst, "TransformerLayer") for sn in n.scope)
+        if isinstance(n.layer_idx, int) and n.layer_idx == src:
+            m.layer_idx = dst
+        elif isinstance(n.layer_idx, str):
+            m.layer_idx = n.layer_idx.replace(str(src), str(dst), 1) if src != dst else n.layer_idx
+        m.act = copy(n.act)                     # the lifetime walker writes cache_for_bwd_mem
+        m.recompute_status, m.recompute_done = n.recompute_status, False
+        out.append(m)
+    scopes = [(d, _retarget(disp, src, dst, "TransformerLayer"), lo + base, hi + base,
+               tuple(_retarget(sn, src, dst, "TransformerLayer") for sn in sc)) for d, disp, lo, hi, sc in tree]
+    return out, scopes
+
+
+# ------------------------------------------------------------------------------------------------
 # stage chunk
 # ------------------------------------------------------------------------------------------------
 class StageChunk:
@@ -167,7 +246,8 @@ class StageChunk:
 
     def __init__(self, layer_num: int, dense_layers: int = 0, preprocess: bool = True, postprocess: bool = True,
                  model_config: ModelConfig = None, strategy: StrategyConfig = None, system: SystemConfig = None,
-                 specific_name: str = "GPTModel_0"):
+                 specific_name: str = "GPTModel_0", block_cache: Optional[BlockProfileCache] = None):
+        self.block_cache = block_cache
         self.layer_num = layer_num
         self.dense_layers = dense_layers
         self.preprocess, self.postprocess = preprocess, postprocess
@@ -193,8 +273,49 @@ class StageChunk:
             node, shape = D.embedding(st, cfg.hidden_size, cfg.vocab_size, shape, em.name("embedding"))
             em.add(node)
         firsts = []
+        cache = self.block_cache
+        ctx = cache.context_key(cfg, st, self.system) if cache is not None else None
+        cached_nodes = set()
+        if cache is not None:                 # keep the bookkeeping order of the uncached path: ops are recorded in node order
+            for n in em.nodes:
+                evaluate(n, self.system)
+                cached_nodes.add(id(n))
         for i in range(self.layer_num):
-            shape, first_idx = emit_block(em, i, shape, use_dense=(i < self.dense_layers))
+            use_dense = i < self.dense_layers
+            if cache is None:
+                shape, first_idx = emit_block(em, i, shape, use_dense=use_dense)
+                firsts.append(first_idx)
+                continue
+            key = (ctx, use_dense, repr(st.parse_attention_recompute(i)), repr(st.parse_mlp_recompute(i)), tuple(shape))
+            hit = cache.store.get(key)
+            if hit is None:
+                cache.misses += 1
+                n0, t0 = len(em.nodes), len(em.scope_tree)
+                shape_out, first_idx = emit_block(em, i, shape, use_dense=use_dense)
+                block = em.nodes[n0:]
+                # evaluate against empty bookkeeping tables so the block's own records (efficiency hits / misses, achieved
+                # collective bandwidths) can be replayed whenever the cached block is reused
+                books = _swap_books(self.system, None)
+                for n in block:
+                    evaluate(n, self.system)
+                delta = _swap_books(self.system, books)
+                _merge_books(self.system, delta)
+                tree = [(d, disp, lo - n0, hi - n0, sc) for d, disp, lo, hi, sc in em.scope_tree[t0:]]
+                # keep pristine copies: the nodes that stay in this chunk get statuses / walker scratch written to them
+                tpl, _ = _clone_block(block, [], i, i, 0)
+                cache.store[key] = (tpl, tree, i, first_idx - n0, shape_out, delta)
+                cached_nodes.update(id(n) for n in block)
+                shape = shape_out
+            else:
+                cache.hits += 1
+                tpl, tree, src, first_rel, shape, delta = hit
+                _merge_books(self.system, delta)
+                base = len(em.nodes)
+                nodes, scopes = _clone_block(tpl, tree, src, i, base)
+                em.nodes.extend(nodes)
+                em.scope_tree.extend(scopes)
+                first_idx = base + first_rel
+                cached_nodes.update(id(n) for n in nodes)
             firsts.append(first_idx)
         if self.postprocess:
             node, shape = D.layernorm(st, cfg.hidden_size, shape, em.name("layernorm"))
@@ -210,7 +331,8 @@ class StageChunk:
         assign_recompute_status(self.nodes)
         mem, comp, cost = MemoryInfo(), ComputeInfo(), CostInfo()
         for n in self.nodes:
-            evaluate(n, self.system)
+            if id(n) not in cached_nodes:
+                evaluate(n, self.system)
             mem = mem + n.mem
             comp = comp + n.compute
             cost = cost + n.cost

@@ -31,3 +31,28 @@ def test_max_micro_batch_size():
     p = build("tp2_pp1_dp4_mbs1", "llama3-8b", "b200_nominal", 8, run=False)
     mbs, peak = p.search_max_micro_batch_size(micro_batch_num=2)
     assert mbs >= 1 and peak > 0
+
+
+def test_search_cache_is_transparent(monkeypatch):
+    """Block profile cache (reference: CachedChunkProfile, perf_llm.py:41-252) must not change a single reported number,
+    including the achieved-bandwidth / efficiency bookkeeping, and must actually be hit."""
+    import json
+
+    def run(model, strategy, layers, **kw):
+        p = build(strategy, model, "b200_nominal", layers, run=False)
+        allr = {}
+        best = p.search_best_parallel_strategy(world_size=8, gmi_error=10, micro_batch_size=1, global_batch_size=32,
+                                               all_search_result=allr, verbose=False, **kw)
+        return json.dumps([best, allr], sort_keys=True, default=str), getattr(p, "last_search_cache_stats", None)
+
+    cases = [("llama3-70b", "tp2_pp1_dp4_mbs1", 16, dict(tp_search_list=[2, 4, 8], ep_search_list=[1], pp_search_list=[1, 2],
+                                                       recompute_search_type=["no_recompute", "full_block", "selective_recompute"])),
+             ("deepseekv2", "ep8_pp1_dp8_mbs1", 6, dict(tp_search_list=[1], ep_search_list=[4, 8], pp_search_list=[1, 2],
+                                                     recompute_search_type=["no_recompute", "full_block"]))]
+    for model, strategy, layers, kw in cases:
+        monkeypatch.setenv("SIMU_SEARCH_CACHE", "0")
+        plain, stats0 = run(model, strategy, layers, **kw)
+        monkeypatch.setenv("SIMU_SEARCH_CACHE", "1")
+        cached, stats1 = run(model, strategy, layers, **kw)
+        assert stats0 is None and stats1["hits"] > stats1["misses"] > 0
+        assert plain == cached
