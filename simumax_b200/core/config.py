@@ -237,6 +237,16 @@ class StrategyConfig(Config):
     # reduce-scatter hides behind the last micro-batch's backward and the all-gather behind the next forward
     dp_overlap_model: bool = False
     dp_overlap_efficiency: float = 0.5      # fraction of the overlappable collective time that is actually hidden
+    # extensions describing this repo's runtime instead of Megatron + NCCL (all default off = reference semantics):
+    # * tp_overlap_model: the TP / SP collectives next to a GEMM run inside that GEMM (csrc/gemm_2cta.cu, AG / RS variants);
+    #   only the measured exposed fraction is charged (tools/fused_check.py: (fused - gemm) / (unfused - gemm)), the wgrad
+    #   re-gather disappears because the gathered activation is what gets saved (so LinearCol caches the full sequence)
+    # * fused_optimizer_model: one l2-norm pass + one fused AdamW pass (read grad/master/m/v, write master/m/v/bf16 param,
+    #   zero the grad) instead of Megatron's seven-kernel chain
+    tp_overlap_model: bool = False
+    tp_overlap_exposed_ag: float = 0.6
+    tp_overlap_exposed_rs: float = 0.4
+    fused_optimizer_model: bool = False
 
     te_version: Optional[str] = None
     te_dummy_wgrad_min_version: str = "2.3.0"

@@ -34,6 +34,7 @@ class CollectiveSpec:
     phase: str              # fwd | bwd_grad_act | bwd_grad_w
     group: str = "tp"       # which parallel group (tp | cp | ep | etp) -- used by the simulator
     time: float = 0.0       # filled by evaluate()
+    exposed: float = 1.0    # fraction of the collective's time that is not hidden inside the adjacent GEMM (fused kernels)
 
 
 @dataclass
@@ -126,7 +127,7 @@ def evaluate(node: OpNode, system: SystemConfig) -> OpNode:
     cost = CostInfo()
     for spec in node.comms:
         spec.time = system.compute_net_op_time(spec.op, spec.size, comm_num=spec.comm_num, net=spec.net,
-                                               comm_stage=spec.stage)
+                                               comm_stage=spec.stage) * spec.exposed
         if spec.phase == "fwd":
             cost.fwd_net_time += spec.time
         elif spec.phase == "bwd_grad_act":
@@ -162,10 +163,10 @@ def evaluate(node: OpNode, system: SystemConfig) -> OpNode:
 
 
 def comm_step(system: SystemConfig, op: str, size, comm_num: int, net: str, label: str, *, fwd: bool = True,
-              bwd: bool = True, group: str = "tp", stage: str = "unkonw") -> SimStep:
+              bwd: bool = True, group: str = "tp", stage: str = "unkonw", exposed: float = 1.0) -> SimStep:
     """Simulator collective with its own cost lookup (the replay uses slightly different collectives than the
     analytic model in a few places, e.g. reduce-scatter for the SP embedding; reference prefill() methods)."""
-    cost = system.compute_net_op_time(op, size, comm_num=comm_num, net=net, comm_stage=stage)
+    cost = system.compute_net_op_time(op, size, comm_num=comm_num, net=net, comm_stage=stage) * exposed
     return SimStep(kind="comm", name=label, fwd_cost=cost if fwd else 0.0, bwd_cost=cost if bwd else 0.0,
                    comm_op=op, group=group, comm_num=comm_num, stage=stage)
 

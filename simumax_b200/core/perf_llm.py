@@ -317,6 +317,17 @@ class PerfLLM(PerfBase):
         G = info.all_grad_bytes
         mem = lambda b: self.system.compute_mem_access_time("default", b)
         res = {"optim_time": 0, "optim_exposed_time": 0}
+        if getattr(self.strategy, "fused_optimizer_model", False):
+            # this repo's runtime (csrc/elementwise.cu: sqnorm_kernel + adamw_kernel): one pass over the grad shard for the
+            # norm, one pass that reads grad + master/m/v and writes master/m/v + the bf16 parameter and clears the grad
+            shard_grads = states / 6 if self.strategy.grad_reduce_in_bf16 else states / 3
+            res["l2_norm_after_reduce_time"] = mem(shard_grads)
+            res["adam_time"] = mem(shard_grads + states + states + (states / 3) * 0.5 + shard_grads)
+            if self.strategy.dp_size * self.strategy.cp_size > 1:
+                res["zero_grad_buffer_time"] = mem(G)            # the full main-grad buffer, after its reduce-scatter
+            total = sum(res.values())
+            res["optim_time"] = res["optim_exposed_time"] = total
+            return res
         res["zero_grad_buffer_time"] = mem(G)
         res["l2_norm_before_reduce_time"] = mem(G)
         res["mul_before_reduce_time"] = mem(2 * G) if self.strategy.dp_size * self.strategy.cp_size > 1 else 0

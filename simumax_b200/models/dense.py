@@ -19,9 +19,16 @@ def _atom(node: OpNode, name: str = "") -> SimStep:
                    bwd_cost=node.cost.bwd_grad_act_time + node.cost.bwd_grad_w_time)
 
 
-def _tp_comm(strategy, op, size, stage, phase) -> CollectiveSpec:
+def _tp_comm(strategy, op, size, stage, phase, exposed: float = 1.0) -> CollectiveSpec:
     return CollectiveSpec(op=op, size=size, comm_num=strategy.tp_size, net=strategy.tp_net, stage=stage, phase=phase,
-                          group="tp")
+                          group="tp", exposed=exposed)
+
+
+def _fused_exposure(st: StrategyConfig):
+    """(all-gather, reduce-scatter, wgrad re-gather) exposure factors of the TP collectives adjacent to a GEMM."""
+    if getattr(st, "tp_overlap_model", False) and st.enable_sequence_parallel:
+        return float(st.tp_overlap_exposed_ag), float(st.tp_overlap_exposed_rs), 0.0
+    return 1.0, 1.0, 1.0
 
 
 # ------------------------------------------------------------------------------------------------
@@ -95,8 +102,9 @@ def linear_col(st: StrategyConfig, in_features, out_features, in_shape, name, *,
     y_bytes = out_numel * e
     # activation: the (pre-all-gather) input is what gets cached; SP caches only the local 1/tp slice (bf16 only)
     cache = tokens_x_in * a_e
-    if st.enable_sequence_parallel and not st.fp8:
-        cache /= st.tp_size
+    x_ag, x_rs, x_regather = _fused_exposure(st)
+    if st.enable_sequence_parallel and not st.fp8 and x_regather > 0:
+        cache /= st.tp_size            # (fused runtime: the gathered input itself is saved, nothing is re-gathered)
     if has_cached_inputs:
         cache = 0
     node.act.activation_mem_cache = cache
@@ -120,21 +128,21 @@ def linear_col(st: StrategyConfig, in_features, out_features, in_shape, name, *,
     size = tokens_x_in * e
     if st.tp_size > 1:
         if st.enable_sequence_parallel:
-            node.comms.append(_tp_comm(st, "all_gather", size, "LinearCol_FWD_SP", "fwd"))
-            node.comms.append(_tp_comm(st, "reduce_scatter", size, "LinearCol_BWD_ACT_SP", "bwd_grad_act"))
-            node.comms.append(_tp_comm(st, "all_gather", size, "LinearCol_BWD_W_SP", "bwd_grad_w"))
+            node.comms.append(_tp_comm(st, "all_gather", size, "LinearCol_FWD_SP", "fwd", x_ag))
+            node.comms.append(_tp_comm(st, "reduce_scatter", size, "LinearCol_BWD_ACT_SP", "bwd_grad_act", x_rs))
+            node.comms.append(_tp_comm(st, "all_gather", size, "LinearCol_BWD_W_SP", "bwd_grad_w", x_regather))
         else:
             node.comms.append(_tp_comm(st, "all_reduce", size, "LinearCol_BWD_ACT_TP", "bwd_grad_act"))
 
     def sim(n: OpNode, system) -> List[SimStep]:
         steps = []
         if st.tp_size > 1 and st.enable_sequence_parallel:
-            steps.append(comm_step(system, "all_gather", size, st.tp_size, st.tp_net, "all_gather"))
+            steps.append(comm_step(system, "all_gather", size, st.tp_size, st.tp_net, "all_gather", exposed=x_ag))
         elif st.tp_size > 1:
             steps.append(comm_step(system, "all_reduce", size, st.tp_size, st.tp_net, "all_reduce", fwd=False))
         steps.append(_atom(n, "Linear"))
         if st.tp_size > 1 and st.enable_sequence_parallel:
-            steps.append(comm_step(system, "all_gather", size, st.tp_size, st.tp_net, "all_gather", fwd=False))
+            steps.append(comm_step(system, "all_gather", size, st.tp_size, st.tp_net, "all_gather", fwd=False, exposed=x_regather))
         return steps
     node.sim_steps = sim
     return node, out_shape
@@ -183,15 +191,17 @@ def linear_row(st: StrategyConfig, in_features, out_features, in_shape, name, *,
     size = out_numel_full * e
     if st.tp_size > 1:
         if st.enable_sequence_parallel:
-            node.comms.append(_tp_comm(st, "reduce_scatter", size, "LinearROW_FWD_SP", "fwd"))
-            node.comms.append(_tp_comm(st, "all_gather", size, "LinearROW_BWD_SP", "bwd_grad_act"))
+            x_ag, x_rs, _ = _fused_exposure(st)
+            node.comms.append(_tp_comm(st, "reduce_scatter", size, "LinearROW_FWD_SP", "fwd", x_rs))
+            node.comms.append(_tp_comm(st, "all_gather", size, "LinearROW_BWD_SP", "bwd_grad_act", x_ag))
         else:
             node.comms.append(_tp_comm(st, "all_reduce", size, "LinearROW_FWD_TP", "fwd"))
 
     def sim(n: OpNode, system) -> List[SimStep]:
         steps = [_atom(n, "Linear")]
         if st.tp_size > 1 and st.enable_sequence_parallel:
-            steps.append(comm_step(system, "reduce_scatter", size, st.tp_size, st.tp_net, "reduce_scatter"))
+            steps.append(comm_step(system, "reduce_scatter", size, st.tp_size, st.tp_net, "reduce_scatter",
+                                   exposed=_fused_exposure(st)[1]))
         elif st.tp_size > 1:
             steps.append(comm_step(system, "all_reduce", size, st.tp_size, st.tp_net, "all_reduce", bwd=False))
         return steps

@@ -67,3 +67,26 @@ def test_straggler_ratio():
     assert straggler_increase_ratio(1) == 1.0
     L = math.log2(8)
     assert straggler_increase_ratio(8) == pytest.approx(1 + L / (L + 1) * 0.09 * math.sqrt(L))
+
+
+def test_runtime_semantics_knobs_are_off_by_default_and_monotone():
+    """tp_overlap_model / fused_optimizer_model describe this repo's fused runtime; default off = reference semantics."""
+    from helpers import build
+
+    def run(**over):
+        p = build("tp2_pp1_dp4_mbs1", "llama3-8b", "b200_nominal", 8, **over)
+        c = p.analysis_cost().data
+        ms = lambda v: float(str(v).split()[0])
+        return (ms(c["duration_time_per_iter"]), ms(c["breakdown_result"]["intra_exposed_time"]),
+                ms(c["breakdown_result"]["optim_time"]), p.analysis_mem().data)
+
+    base = run()
+    assert run(tp_overlap_model=False, fused_optimizer_model=False)[:3] == base[:3]
+    tp = run(tp_overlap_model=True)
+    assert tp[1] < 0.7 * base[1] and tp[2] == base[2] and tp[0] < base[0]
+    opt = run(fused_optimizer_model=True)
+    assert opt[2] < 0.6 * base[2] and opt[1] == base[1]
+    # the fused runtime saves the gathered activation instead of re-gathering it for the wgrad: more cached bytes
+    from simumax_b200.core.utils import parse_bytes
+    peak = lambda d: max(parse_bytes(v["peak_mem"]) for v in d.values()) if "peak_mem" not in d else parse_bytes(d["peak_mem"])
+    assert peak(tp[3]) > peak(base[3])

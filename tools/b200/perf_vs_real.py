@@ -40,7 +40,7 @@ TP_CASES = [      # measured with TPLlamaTrainer: tp = world, sequence parallel,
 ]
 
 
-def predict(model, layers, seq, mbs, mbc, world, system, tp=1):
+def predict(model, layers, seq, mbs, mbc, world, system, tp=1, runtime_semantics=False):
     from simumax_b200 import PerfLLM
     from simumax_b200.configs import get_simu_model_config, get_simu_strategy_config, get_simu_system_config
     from simumax_b200.core.config import StrategyConfig
@@ -50,6 +50,8 @@ def predict(model, layers, seq, mbs, mbc, world, system, tp=1):
     st.enable_sequence_parallel = tp > 1
     st.seq_len, st.micro_batch_size, st.micro_batch_num = seq, mbs, mbc
     st.dp_overlap_model = True      # the runtime overlaps ZeRO-1 collectives with backward / next forward
+    # runtime semantics: TP collectives fused into the GEMMs (measured exposure), single-pass AdamW; off = what Megatron + NCCL do
+    st.tp_overlap_model = st.fused_optimizer_model = bool(runtime_semantics)
     p = PerfLLM()
     with contextlib.redirect_stdout(io.StringIO()):
         p.configure(strategy_config=st, model_config=get_simu_model_config(model), system_config=get_simu_system_config(system))
@@ -132,14 +134,17 @@ def main():
         real = measure(model, layers, seq, mbs, mbc, a.steps, a.warmup, tp)
         if rank == 0:
             pred = predict(model, layers, seq, mbs, mbc, world, a.system, tp)
+            pred_rt = predict(model, layers, seq, mbs, mbc, world, a.system, tp, runtime_semantics=True)
             row = {"case": name + (str(tp) if a.tp else ""), "world": world, "tp": tp, "model": model, "layers": layers, "seq": seq, "mbs": mbs, "mbc": mbc,
                    "pred_ms": pred["iter_ms"], "real_ms": real["iter_ms"],
                    "time_err_pct": 100 * (pred["iter_ms"] - real["iter_ms"]) / real["iter_ms"],
                    "pred_gib": pred["peak_gib"], "real_gib": real["peak_gib"],
                    "mem_err_pct": 100 * (pred["peak_gib"] - real["peak_gib"]) / real["peak_gib"] if pred["peak_gib"] else None,
+                   "pred_runtime_semantics_ms": pred_rt["iter_ms"],
+                   "time_err_runtime_semantics_pct": 100 * (pred_rt["iter_ms"] - real["iter_ms"]) / real["iter_ms"],
                    "pred_mfu": pred["mfu"], "real_tokens_per_s": real["tokens_per_s"], "efficiency_misses": pred["miss"]}
             rows.append(row)
-            print(f"{name:28s} n={world} time pred {row['pred_ms']:9.2f} ms real {row['real_ms']:9.2f} ms ({row['time_err_pct']:+6.2f} %)   "
+            print(f"{name:28s} n={world} time pred {row['pred_ms']:9.2f} ms real {row['real_ms']:9.2f} ms ({row['time_err_pct']:+6.2f} %, runtime semantics {row['time_err_runtime_semantics_pct']:+6.2f} %)   "
                   f"mem pred {row['pred_gib']:.2f} GiB real {row['real_gib']:.2f} GiB ({row['mem_err_pct']:+6.2f} %)", flush=True)
     if rank == 0:
         os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
