@@ -79,7 +79,12 @@ class _Flat:
 class LlamaTrainer:
     def __init__(self, dims: LlamaDims, micro_batch: int, seq_len: int, dp_group: Optional[dist.ProcessGroup] = None,
                  lr: float = 1e-4, weight_decay: float = 0.1, betas=(0.9, 0.95), max_grad_norm: float = 1.0,
-                 attention_bwd: str = "auto", seed: int = 1234, device=None, comm: str = "auto"):
+                 attention_bwd: str = "auto", seed: int = 1234, device=None, comm: str = "auto",
+                 first_stage: bool = True, last_stage: bool = True, in_flight: int = 1):
+        """``first_stage`` / ``last_stage`` / ``in_flight``: pipeline-stage mode (runtime/pp_trainer.py) -- the stage owns
+        ``dims.layers`` layers, the embedding only if first, final norm + LM head + loss only if last, and keeps ``in_flight``
+        sets of activations (1F1B holds several micro-batches between their forward and backward)."""
+        self.first_stage, self.last_stage = first_stage, last_stage
         self.d = dims
         self.B, self.S = micro_batch, seq_len
         self.T = micro_batch * seq_len
@@ -95,13 +100,14 @@ class LlamaTrainer:
         # be reduce-scattered as soon as its layer's backward is done (overlap with the rest of the backward pass).
         self._balign = self.world * 1024
         up = lambda n: (n + self._balign - 1) // self._balign * self._balign
-        sizes = [up(d.vocab * d.hidden)] + [up(d.layer_numel())] * d.layers + [up(d.hidden + d.vocab * d.hidden)]
+        sizes = ([up(d.vocab * d.hidden) if first_stage else 0] + [up(d.layer_numel())] * d.layers
+                 + [up(d.hidden + d.vocab * d.hidden) if last_stage else 0])
         self.buckets = []                      # (flat offset, padded size)
         off = 0
         for sz in sizes:
             self.buckets.append((off, sz))
             off += sz
-        self.P, self.Ppad = d.total_numel(), off
+        self.P, self.Ppad = off, off
         self.shard_off = [b_lo // self.world for b_lo, _ in self.buckets]      # offsets inside the local shard arrays
         # ---- parameters (bf16) and fp32 main grads, identical layouts.  With data parallelism both live in one
         # symmetric (peer-mapped) allocation so the ZeRO-1 reduce-scatter / all-gather run as our own NVLink kernels.
@@ -133,7 +139,8 @@ class LlamaTrainer:
         for name in ("ln1", "ln2"):
             for t in self.w[name]:
                 t.fill_(1.0)
-        self.w["final_norm"].fill_(1.0)
+        if last_stage:
+            self.w["final_norm"].fill_(1.0)
         self.grads.buf.zero_()
         # ---- ZeRO-1 optimizer shard = concatenation of this rank's slice of every bucket
         self.master = torch.cat([self._my_slice(self.params.buf, b) for b in range(len(self.buckets))]).float()
@@ -150,15 +157,18 @@ class LlamaTrainer:
         # ---- static activation storage
         T, H, F, L = self.T, d.hidden, d.ffn, d.layers
         bf = dict(dtype=torch.bfloat16, device=dev)
-        self.act = {
-            "x": torch.empty(L + 1, T, H, **bf), "h1": torch.empty(L, T, H, **bf), "qkv": torch.empty(L, T, d.qkv_out, **bf),
-            "o": torch.empty(L, T, d.heads * d.head_dim, **bf), "x2": torch.empty(L, T, H, **bf),
-            "h2": torch.empty(L, T, H, **bf), "u": torch.empty(L, T, 2 * F, **bf), "g": torch.empty(L, T, F, **bf),
-            "rstd1": torch.empty(L, T, dtype=torch.float32, device=dev), "rstd2": torch.empty(L, T, dtype=torch.float32, device=dev),
-            "lse": torch.empty(L, self.B, d.heads, self.S, dtype=torch.float32, device=dev),
-            "xf": torch.empty(T, H, **bf), "rstdf": torch.empty(T, dtype=torch.float32, device=dev),
-        }
-        self.logits = torch.empty(T, d.vocab, **bf)
+        def new_act():
+            return {
+                "x": torch.empty(L + 1, T, H, **bf), "h1": torch.empty(L, T, H, **bf), "qkv": torch.empty(L, T, d.qkv_out, **bf),
+                "o": torch.empty(L, T, d.heads * d.head_dim, **bf), "x2": torch.empty(L, T, H, **bf),
+                "h2": torch.empty(L, T, H, **bf), "u": torch.empty(L, T, 2 * F, **bf), "g": torch.empty(L, T, F, **bf),
+                "rstd1": torch.empty(L, T, dtype=torch.float32, device=dev), "rstd2": torch.empty(L, T, dtype=torch.float32, device=dev),
+                "lse": torch.empty(L, self.B, d.heads, self.S, dtype=torch.float32, device=dev),
+                "xf": torch.empty(T, H, **bf), "rstdf": torch.empty(T, dtype=torch.float32, device=dev),
+            }
+        self.act_slots = [new_act() for _ in range(max(1, in_flight))]
+        self.act = self.act_slots[0]
+        self.logits = torch.empty(T, d.vocab, **bf) if last_stage else None
         # backward scratch (reused by every layer)
         self.dx = torch.empty(T, H, **bf)
         self.dx_b = torch.empty(T, H, **bf)
@@ -192,7 +202,8 @@ class LlamaTrainer:
     def _carve(self, flat: _Flat):
         d = self.d
         H, F = d.hidden, d.ffn
-        out = {"embed": flat.take(d.vocab, H), "ln1": [], "wqkv": [], "wo": [], "ln2": [], "wfc1": [], "wfc2": []}
+        out = {"embed": flat.take(d.vocab if self.first_stage else 0, H), "ln1": [], "wqkv": [], "wo": [], "ln2": [], "wfc1": [],
+               "wfc2": []}
         for _ in range(d.layers):
             flat.align(self._balign)
             out["ln1"].append(flat.take(H))
@@ -202,8 +213,8 @@ class LlamaTrainer:
             out["wfc1"].append(flat.take(2 * F, H))
             out["wfc2"].append(flat.take(H, F))
         flat.align(self._balign)
-        out["final_norm"] = flat.take(H)
-        out["lm_head"] = flat.take(d.vocab, H)
+        out["final_norm"] = flat.take(H if self.last_stage else 0)
+        out["lm_head"] = flat.take(d.vocab if self.last_stage else 0, H)
         return out
 
     def _pick_attention_bwd(self, choice: str) -> str:
@@ -221,9 +232,9 @@ class LlamaTrainer:
             return "sdpa_recompute"
 
     def memory_bytes(self) -> dict:
-        act = sum(t.numel() * t.element_size() for t in self.act.values())
+        act = sum(t.numel() * t.element_size() for slot in self.act_slots for t in slot.values())
         return {"params_bf16": self.params.buf.numel() * 2, "main_grads_fp32": self.grads.buf.numel() * 4,
-                "optimizer_fp32": self.shard * 12, "activations": act, "logits": self.logits.numel() * 2,
+                "optimizer_fp32": self.shard * 12, "activations": act, "logits": self.logits.numel() * 2 if self.logits is not None else 0,
                 "torch_max_allocated": torch.cuda.max_memory_allocated(self.device)}
 
     # ------------------------------------------------------------------------------------------
@@ -237,11 +248,20 @@ class LlamaTrainer:
         v = t[..., (nq + nk) * hd:].view(B, S, nk, hd)
         return q, k, v
 
+    def use_slot(self, k: int) -> None:
+        """Select the activation set the next forward / backward works on (pipeline stages keep several in flight)."""
+        self.act = self.act_slots[k % len(self.act_slots)]
+
     def forward(self, tokens: torch.Tensor, targets: torch.Tensor, loss_scale: float) -> torch.Tensor:
+        """First stage: ``tokens`` are token ids; later stages: the [T, H] hidden states received from the previous stage.
+        Last stage: returns the per-row loss (logits then hold dlogits); earlier stages: the hidden states to send on."""
         d, a, w = self.d, self.act, self.w
         L = d.layers
         self._wait_params(0)
-        torch.index_select(w["embed"], 0, tokens, out=a["x"][0])
+        if self.first_stage:
+            torch.index_select(w["embed"], 0, tokens, out=a["x"][0])
+        elif tokens.data_ptr() != a["x"][0].data_ptr():
+            E.copy_(a["x"][0], tokens)
         for i in range(L):
             self._wait_params(1 + i)
             x = a["x"][i]
@@ -258,22 +278,28 @@ class LlamaTrainer:
             E.swiglu_fwd(a["u"][i], out=a["g"][i])
             gemm(a["g"][i], w["wfc2"][i], "TN", out=self.tmp_h)
             E.add(a["x2"][i], self.tmp_h, out=a["x"][i + 1])
+        if not self.last_stage:
+            return a["x"][L]
         self._wait_params(L + 1)
         E.rmsnorm_fwd(a["x"][L], w["final_norm"], d.eps, out=a["xf"], rstd=a["rstdf"])
         gemm(a["xf"], w["lm_head"], "TN", out=self.logits)
         loss_rows = E.cross_entropy_(self.logits, targets, grad_scale=loss_scale)      # logits now hold dlogits
         return loss_rows
 
-    def backward(self, tokens: torch.Tensor, last_microbatch: bool = False) -> None:
+    def backward(self, tokens: torch.Tensor, last_microbatch: bool = False, d_out: Optional[torch.Tensor] = None):
         """``last_microbatch``: the gradients are final after this pass, so each bucket's reduce-scatter is launched on
-        the communication stream the moment its layer is done."""
+        the communication stream the moment its layer is done.  Pipeline stages other than the last pass ``d_out`` (the
+        gradient of the hidden states they sent on); stages other than the first return the gradient to send back."""
         d, a, w, g = self.d, self.act, self.w, self.g
         L = d.layers
         rs = self._launch_rs if (last_microbatch and self.overlap) else (lambda b: None)
-        dl = self.logits
-        gemm(dl, a["xf"], "NT", out=g["lm_head"], accumulate=True)
-        gemm(dl, w["lm_head"], "NN", out=self.tmp_h)
-        E.rmsnorm_bwd(a["x"][L], w["final_norm"], self.tmp_h, a["rstdf"], g["final_norm"], dx=self.dx)
+        if self.last_stage:
+            dl = self.logits
+            gemm(dl, a["xf"], "NT", out=g["lm_head"], accumulate=True)
+            gemm(dl, w["lm_head"], "NN", out=self.tmp_h)
+            E.rmsnorm_bwd(a["x"][L], w["final_norm"], self.tmp_h, a["rstdf"], g["final_norm"], dx=self.dx)
+        elif d_out.data_ptr() != self.dx.data_ptr():
+            E.copy_(self.dx, d_out)
         rs(L + 1)
         for i in reversed(range(L)):
             dx3 = self.dx
@@ -295,8 +321,10 @@ class LlamaTrainer:
             if self.debug_hook is not None:
                 self.debug_hook(i, self)
             rs(1 + i)
-        g["embed"].index_add_(0, tokens, self.dx.float())
+        if self.first_stage:
+            g["embed"].index_add_(0, tokens, self.dx.float())
         rs(0)
+        return None if self.first_stage else self.dx
 
     def _attention_backward(self, i: int) -> None:
         d, a = self.d, self.act
@@ -365,6 +393,8 @@ class LlamaTrainer:
             dist.all_reduce(self.sqnorm, group=self.group)
         # grads hold the SUM over ranks of per-rank means -> prescale by 1/world inside the fused optimizer kernel
         if self.world == 1:
+            if getattr(self, "norm_group", None) is not None:       # pipeline stages: the clip norm spans all stages
+                dist.all_reduce(self.sqnorm_out, group=self.norm_group)
             E.adamw_(self.master, self.m, self.v, gsh, self.params.buf, self.lr, b1, b2, 1e-8, self.wd, self.step_count,
                      sqnorm_t=self.sqnorm_out, max_norm=self.max_norm, zero_grad=True)
             return
