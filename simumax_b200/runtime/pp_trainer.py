@@ -21,7 +21,7 @@ from typing import List, Optional, Tuple
 import torch
 import torch.distributed as dist
 
-from .trainer import LlamaDims, LlamaTrainer
+from .trainer import LlamaDims
 
 
 def split_layers(n_layers: int, pp: int) -> List[Tuple[int, int]]:
@@ -38,7 +38,10 @@ def split_layers(n_layers: int, pp: int) -> List[Tuple[int, int]]:
 
 class PPLlamaTrainer:
     def __init__(self, dims: LlamaDims, micro_batch: int, seq_len: int, pp_group: Optional[dist.ProcessGroup] = None,
-                 seed: int = 1234, device=None, **trainer_kw):
+                 seed: int = 1234, device=None, stage_factory=None, act_dtype=torch.bfloat16, **trainer_kw):
+        """``stage_factory(local_dims, first, last, in_flight)`` replaces the ``LlamaTrainer`` stage (the CPU / gloo test of
+        the schedule plugs in a small autograd stage); a stage needs ``T``, ``use_slot``, ``forward``, ``backward``,
+        ``optimizer_step`` and accepts a ``norm_group`` attribute."""
         assert dist.is_initialized()
         self.group = pp_group or dist.group.WORLD
         self.pp = dist.get_world_size(self.group)
@@ -49,23 +52,28 @@ class PPLlamaTrainer:
         self.lo, self.hi = split_layers(dims.layers, self.pp)[self.stage]
         local = copy(dims)
         local.layers = self.hi - self.lo
-        self.device = device or torch.device("cuda", torch.cuda.current_device())
-        # a single-rank "data-parallel group": the stage trainer runs without ZeRO sharding
-        solo = None
-        for r in self.ranks:
-            g = dist.new_group([r])
-            if r == dist.get_rank():
-                solo = g
-        self.tr = LlamaTrainer(local, micro_batch, seq_len, dp_group=solo, seed=seed + 31 * self.stage, device=self.device,
-                               first_stage=self.first, last_stage=self.last, in_flight=self.pp - self.stage, **trainer_kw)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.on_gpu = self.device.type == "cuda"
+        in_flight = self.pp - self.stage
+        if stage_factory is not None:
+            self.tr = stage_factory(local, self.first, self.last, in_flight)
+        else:
+            from .trainer import LlamaTrainer
+            # a single-rank "data-parallel group": the stage trainer runs without ZeRO sharding
+            solo = None
+            for r in self.ranks:
+                g = dist.new_group([r])
+                if r == dist.get_rank():
+                    solo = g
+            self.tr = LlamaTrainer(local, micro_batch, seq_len, dp_group=solo, seed=seed + 31 * self.stage, device=self.device,
+                                   first_stage=self.first, last_stage=self.last, in_flight=in_flight, **trainer_kw)
         self.tr.norm_group = self.group
         self.T, self.H = self.tr.T, dims.hidden
-        bf = dict(dtype=torch.bfloat16, device=self.device)
-        n = self.pp - self.stage
-        self.recv_x = [torch.empty(self.T, self.H, **bf) for _ in range(n)] if not self.first else []
+        bf = dict(dtype=act_dtype, device=self.device)
+        self.recv_x = [torch.empty(self.T, self.H, **bf) for _ in range(in_flight)] if not self.first else []
         self.recv_dx = torch.empty(self.T, self.H, **bf) if not self.last else None
         self.send_dx = torch.empty(self.T, self.H, **bf) if not self.first else None
-        self.comm_stream = torch.cuda.Stream(device=self.device)
+        self.comm_stream = torch.cuda.Stream(device=self.device) if self.on_gpu else None
         self.loss_acc = torch.zeros(1, dtype=torch.float32, device=self.device)
 
     # ------------------------------------------------------------------------------------------ weights
@@ -99,6 +107,10 @@ class PPLlamaTrainer:
             ops.append(dist.P2POp(dist.irecv, recv_next, nxt, group=self.group))
         if not ops:
             return None
+        if not self.on_gpu:                                # CPU / gloo (schedule tests): complete the exchange in place
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            return None
         main = torch.cuda.current_stream(self.device)
         self.comm_stream.wait_stream(main)                 # what we send has been produced
         with torch.cuda.stream(self.comm_stream):
@@ -118,7 +130,7 @@ class PPLlamaTrainer:
         warm = min(self.pp - self.stage - 1, M)
         scale = 1.0 / (M * self.T)
         self.loss_acc.zero_()
-        slots = len(tr.act_slots)
+        slots = self.pp - self.stage                   # activation sets in flight == receive buffers
 
         def fwd(k, x_in):
             tr.use_slot(k)
@@ -162,7 +174,8 @@ class PPLlamaTrainer:
             g = bwd(b, self.recv_dx)
             b += 1
             self._wait(self._p2p(send_prev=g))
-        torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+        if self.on_gpu:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
         tr.optimizer_step()
         dist.broadcast(self.loss_acc, src=self.ranks[-1], group=self.group)
         return self.loss_acc
