@@ -45,10 +45,13 @@ def foreign_gpu_processes(device_index: int = 0) -> List[str]:
 
 
 def run_ops(out_path: str, supplement: Optional[str] = None, limit_per_op: Optional[int] = None,
-            workloads=None, log=print, allow_shared_gpu: bool = False) -> dict:
-    """GPU part: returns {"ops": {op: {key: {...}}}, "bandwidth": {...}, "meta": {...}}."""
+            workloads=None, log=print, allow_shared_gpu: bool = False, sustained_ms: float = 0.0) -> dict:
+    """GPU part: returns {"ops": {op: {key: {...}}}, "bandwidth": {...}, "meta": {...}}.  ``sustained_ms`` > 0 times every op
+    at the steady (power-capped) clock instead of the boost clock of a short burst -- see ``measure._time``."""
     import torch
     from . import measure
+    if sustained_ms > 0:
+        measure.SUSTAINED_MS = float(sustained_ms)
     others = foreign_gpu_processes(torch.cuda.current_device())
     if others and not allow_shared_gpu:
         raise RuntimeError(f"GPU is in use by other processes {others}; calibrate on an idle GPU (or pass --allow-shared-gpu)")
@@ -67,7 +70,7 @@ def run_ops(out_path: str, supplement: Optional[str] = None, limit_per_op: Optio
     for name, rec in bw.items():
         log(f"[calib] bandwidth {name:12s} {rec['gbs']:8.1f} GB/s")
     res = {"ops": ops, "bandwidth": bw,
-           "meta": {"device": torch.cuda.get_device_name(0), "seconds": time.time() - t0,
+           "meta": {"device": torch.cuda.get_device_name(0), "seconds": time.time() - t0, "sustained_ms": measure.SUSTAINED_MS,
                     "requested": {op: len(v) for op, v in requests.items()}}}
     os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
     json.dump(res, open(out_path, "w"), indent=1)
@@ -126,6 +129,8 @@ def main(argv=None):
     o.add_argument("--supplement", default=None)
     o.add_argument("--limit-per-op", type=int, default=None)
     o.add_argument("--allow-shared-gpu", action="store_true")
+    o.add_argument("--sustained-ms", type=float, default=0.0,
+                   help="pre-heat every op for this much device time and time it over windows of a third of it (steady clock)")
     m = sub.add_parser("merge", help="write the system config (no GPU needed)")
     m.add_argument("--ops", default=None)
     m.add_argument("--coll", nargs="*", default=[])
@@ -137,7 +142,7 @@ def main(argv=None):
     s = sub.add_parser("shapes", help="list the shapes the default workloads need (CPU)")
     a = ap.parse_args(argv)
     if a.cmd == "ops":
-        run_ops(a.out, a.supplement, a.limit_per_op, allow_shared_gpu=a.allow_shared_gpu)
+        run_ops(a.out, a.supplement, a.limit_per_op, allow_shared_gpu=a.allow_shared_gpu, sustained_ms=a.sustained_ms)
     elif a.cmd == "merge":
         sysj = merge(a.ops, a.coll, a.out, a.base, a.name, a.coll_impl, a.measured_peaks)
         print(f"wrote {a.out}: " + ", ".join(f"{op}:{len(v.get('accurate_efficient_factor') or {})}" for op, v in sysj["accelerator"]["op"].items()))

@@ -27,6 +27,11 @@ DEFAULT_WORKLOADS: List[Tuple[str, str, dict, dict]] = [
     ("llama3-8b", "tp1_pp1_dp8_mbs1", {"layer_num": 16}, {"micro_batch_size": 2}),
     ("llama3-8b", "tp1_pp1_dp8_mbs1", {"layer_num": 16}, {"seq_len": 8192}),
     ("llama3-70b", "tp1_pp1_dp8_mbs1", {"layer_num": 4}, {}),
+    # tensor-parallel cases measured by TPLlamaTrainer (perf_vs_real.py --tp): 8B at tp4, 70B-l12 at tp8, 8K sequences
+    ("llama3-8b", "tp4_pp1_dp2_mbs1", {}, {}),
+    ("llama3-70b", "tp8_pp1_dp1_mbs1", {"layer_num": 12}, {}),
+    ("llama3-70b", "tp2_pp1_dp4_mbs1", {"layer_num": 12}, {"seq_len": 8192}),
+    ("llama3-70b", "tp4_pp1_dp2_mbs1", {"layer_num": 12}, {"seq_len": 8192}),
     # fp8 linears (the reference ships no fp8 numbers for B200 at all)
     ("llama3-8b", "tp1_pp1_dp8_mbs1", {}, {"fp8": True}),
     ("llama3-70b", "tp2_pp1_dp4_mbs1", {"layer_num": 12}, {"fp8": True}),

@@ -1,0 +1,99 @@
+"""Differential fuzzing of the analytical core against the unmodified reference: random (model, strategy, system) triples,
+both implementations evaluated in-process, headline numbers (iteration time, tokens/s/GPU, MFU, per-stage peak memory, the set
+of efficiency-table misses) must be identical -- or both must reject the configuration.
+
+    python tools/fuzz_vs_reference.py [n_cases] [seed]        # CPU only; needs the reference checkout (REF, default /root/reference)
+"""
+import json
+import os
+import random
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from compare_with_reference import run  # noqa: E402
+
+DENSE = ["llama3-8b", "llama3-70b", "llama2-13b", "llama2-7b", "qwen3-32b", "gpt3-175b", "aquila2-34b", "llama3-405b_padding_128"]
+MOE = ["deepseekv2", "deepseekv3", "deepseekv2-lite", "mixtral-8x7b", "deepseek-16b", "mixtral-8x1b"]
+CAP = {"moe_pad_expert_input_to_capacity": True, "capacity": 1}
+DENSE_BASE = ["tp1_pp2_dp4_mbs1", "tp2_pp1_dp4_mbs1", "tp2_pp1_dp4_mbs1_full_recompute", "tp2_pp1_dp4_mbs1_selective_recompute",
+              "tp4_pp1_dp2_mbs1", "tp8_pp1_dp1_mbs1", "tp1_pp1_dp8_mbs1"]
+MOE_BASE = ["ep8_pp1_dp8_mbs1", "ep4_pp2_dp4_mbs1", "ep4_pp2_dp4_mbs1_full_recompute", "ep4_pp2_dp4_mbs1_selective_recompute"]
+
+
+def sample(rng: random.Random):
+    moe = rng.random() < 0.4
+    model = rng.choice(MOE if moe else DENSE)
+    base = rng.choice(MOE_BASE if moe else DENSE_BASE)
+    so = {}
+    world = rng.choice([8, 16, 32, 64])
+    so["world_size"] = world
+    pp = rng.choice([1, 1, 2, 4])
+    so["pp_size"] = pp
+    if moe:
+        so["ep_size"] = rng.choice([1, 2, 4, 8])
+        so["tp_size"] = rng.choice([1, 1, 2])
+        so["etp_size"] = rng.choice([1, 1, so["tp_size"]])
+    else:
+        so["tp_size"] = rng.choice([1, 2, 4, 8])
+        if rng.random() < 0.25:
+            so["cp_size"] = 2
+            so["cp_a2a_mode"] = rng.choice(["sync_cp", "async_cp"])
+    so["enable_sequence_parallel"] = so["tp_size"] > 1 and rng.random() < 0.8
+    so["seq_len"] = rng.choice([2048, 4096, 8192, 16384])
+    so["micro_batch_size"] = rng.choice([1, 1, 2])
+    so["micro_batch_num"] = rng.choice([pp, 2 * pp, 4 * pp, 8, 16])
+    if rng.random() < 0.15:
+        so["fp8"] = True
+    if rng.random() < 0.2:
+        so["zero_state"] = 0
+    if rng.random() < 0.3:
+        so["te_version"] = rng.choice(["2.1.0", "2.8.0", "2.11.0"])
+    if rng.random() < 0.3:
+        so["cross_entropy_loss_fusion"] = True
+    if moe and rng.random() < 0.5:
+        so["dispatch_probs"] = True
+    if rng.random() < 0.25:
+        so["enable_recompute"] = rng.random() < 0.5
+    if rng.random() < 0.2:
+        so["recompute_layer_num"] = rng.choice([1, 2, 3])
+    if rng.random() < 0.15:
+        so["use_fused_grad_accumulation"] = False
+    if rng.random() < 0.15:
+        so["grad_reduce_in_bf16"] = True
+    layers = rng.choice([4, 6, 8, 12])
+    mo = dict(CAP) if moe and rng.random() < 0.8 else {}
+    return (base, model, layers, mo, so)
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    rng = random.Random(seed)
+    system = os.environ.get("SYSTEM", "b200_bf16_ceperm")
+    stats = {"identical": 0, "both_reject": 0, "diff": 0}
+    diffs = []
+    for i in range(n):
+        case = sample(rng)
+        res = []
+        for impl in ("ref", "new"):
+            try:
+                res.append(run(impl, case, system))
+            except Exception as ex:
+                res.append({"error": f"{type(ex).__name__}: {str(ex)[:120]}"})
+        a, b = res
+        if "error" in a and "error" in b:
+            stats["both_reject"] += 1
+        elif a == b:
+            stats["identical"] += 1
+        else:
+            stats["diff"] += 1
+            diffs.append({"case": case, "ref": a, "new": b})
+            print("DIFF", i, json.dumps(case))
+            print("   ref:", json.dumps(a)[:600])
+            print("   new:", json.dumps(b)[:600])
+    print(json.dumps(stats))
+    return diffs
+
+
+if __name__ == "__main__":
+    sys.exit(1 if main() else 0)
