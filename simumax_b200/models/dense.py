@@ -142,7 +142,7 @@ def linear_col(st: StrategyConfig, in_features, out_features, in_shape, name, *,
             steps.append(comm_step(system, "all_reduce", size, st.tp_size, st.tp_net, "all_reduce", fwd=False))
         steps.append(_atom(n, "Linear"))
         if st.tp_size > 1 and st.enable_sequence_parallel:
-            steps.append(comm_step(system, "all_gather", size, st.tp_size, st.tp_net, "all_gather", fwd=False, exposed=x_regather))
+            steps.append(comm_step(system, "all_gather", size, st.tp_size, st.tp_net, "all_gather_bwd", fwd=False, exposed=x_regather))
         return steps
     node.sim_steps = sim
     return node, out_shape

@@ -57,24 +57,30 @@ def run(which, case):
     return {"end": round(end, 6), "mem": mem}
 
 
-bad = 0
-only = [int(x) for x in sys.argv[1:]]
-for i, case in enumerate(CASES):
-    if only and i not in only:
-        continue
-    res = {}
-    for which in ("ref", "new"):
-        try:
-            res[which] = run(which, case)
-        except Exception as ex:
-            import traceback
-            if which == "new":
-                traceback.print_exc()
-            res[which] = {"error": f"{type(ex).__name__}: {str(ex)[:150]}"}
-    ok = res["ref"] == res["new"] or ("error" in res["ref"] and "error" in res["new"])
-    bad += not ok
-    print("OK  " if ok else "DIFF", i, case[0], case[1], case[5], "merge" if case[6] else "world")
-    if not ok or "error" in res["ref"]:
-        print("   ref:", json.dumps(res["ref"])[:400])
-        print("   new:", json.dumps(res["new"])[:400])
-print("mismatches:", bad)
+def main():
+    bad = 0
+    only = [int(x) for x in sys.argv[1:]]
+    for i, case in enumerate(CASES):
+        if only and i not in only:
+            continue
+        res = {}
+        for which in ("ref", "new"):
+            try:
+                res[which] = run(which, case)
+            except Exception as ex:
+                import traceback
+                if which == "new":
+                    traceback.print_exc()
+                res[which] = {"error": f"{type(ex).__name__}: {str(ex)[:150]}"}
+        ok = res["ref"] == res["new"] or ("error" in res["ref"] and "error" in res["new"])
+        bad += not ok
+        print("OK  " if ok else "DIFF", i, case[0], case[1], case[5], "merge" if case[6] else "world")
+        if not ok or "error" in res["ref"]:
+            print("   ref:", json.dumps(res["ref"])[:400])
+            print("   new:", json.dumps(res["new"])[:400])
+    print("mismatches:", bad)
+    return bad
+
+
+if __name__ == "__main__":
+    sys.exit(1 if main() else 0)
