@@ -100,6 +100,59 @@ class Session:
         except (AssertionError, ValueError, KeyError, NotImplementedError) as e:
             return Evaluation(False, warnings=caught, error=f"{type(e).__name__}: {e}", log=buf.getvalue())
 
+    def model_summary(self) -> Dict[str, object]:
+        """Architecture facts shown in the "model details" panel (parameter counts, FLOPs per token, MoE / MLA flags)."""
+        m = ModelConfig.init_from_dict(dict(self.model_dict))
+        out = {"model_name": m.model_name, "layers": m.layer_num, "hidden": m.hidden_size, "heads": m.head_num,
+               "kv_heads": m.kv_head_num, "ffn": m.intermediate_size, "vocab": m.vocab_size, "experts": m.expert_num,
+               "attention": getattr(m, "attention_type", None) or "mha/gqa"}
+        for name in ("param_numel", "activated_param_numel", "flops_per_token"):
+            attr = getattr(m, name, None)
+            try:
+                out[name] = attr() if callable(attr) else attr
+            except Exception:                    # some counters need a strategy (sequence length); they are optional here
+                pass
+        return out
+
+    def suggestions(self, ev: Evaluation) -> List[str]:
+        """Plain-language hints derived from one evaluation (reference app: "提示/建议" panel)."""
+        from simumax_b200.core.utils import parse_bytes
+        tips: List[str] = []
+        if not ev.ok:
+            return [f"configuration rejected: {ev.error}"]
+        s = self.strategy_dict
+        budget = float(self.system_dict["accelerator"]["mem_gbs"]) * 2 ** 30
+        stages = ev.memory if "peak_mem" not in ev.memory else {"stage": ev.memory}
+        peaks = {k: parse_bytes(v["peak_mem"]) for k, v in stages.items() if isinstance(v, dict) and "peak_mem" in v}
+        worst = max(peaks.values()) if peaks else 0
+        if worst > budget:
+            over = (worst - budget) / 2 ** 30
+            tips.append(f"peak memory exceeds the {budget / 2 ** 30:.0f} GiB device by {over:.1f} GiB: raise tp / pp, enable "
+                        f"recompute (full_block on a few layers first) or shrink the micro-batch")
+        elif worst and worst < 0.5 * budget and s.get("enable_recompute"):
+            tips.append("less than half of the device memory is used with recompute on: recompute fewer layers or none")
+        elif worst and worst < 0.5 * budget:
+            tips.append("less than half of the device memory is used: a larger micro-batch or less model parallelism would raise MFU")
+        br = ev.cost.get("breakdown_result", {})
+        ms = lambda v: float(str(v).split()[0]) if v is not None else 0.0
+        total = ms(ev.cost.get("duration_time_per_iter"))
+        if total > 0:
+            if ms(br.get("intra_exposed_time")) > 0.15 * total:
+                tips.append("tensor / expert-parallel collectives take more than 15 % of the iteration: lower tp (or ep), or turn on "
+                            "sequence parallelism; on this repo's runtime set tp_overlap_model (fused AG->GEMM / GEMM->RS kernels)")
+            if ms(br.get("dp_exposed_time")) > 0.10 * total:
+                tips.append("data-parallel gradient / parameter collectives exceed 10 % of the iteration: more micro-batches per step "
+                            "amortise them (dp_overlap_model describes the overlapped runtime)")
+            stage_t = ev.cost.get("all_chunk_times", {})
+            bubbles = [ms(v.get("bubble_time")) for v in stage_t.values() if isinstance(v, dict)]
+            if bubbles and max(bubbles) > 0.15 * total:
+                tips.append("pipeline bubble above 15 %: increase micro_batch_num or use interleaved (virtual) stages")
+        if ev.misses:
+            n = sum(len(v) for v in ev.misses.values())
+            tips.append(f"{n} operator shapes are not in the efficiency table of this system config and fall back to defaults: "
+                        f"run `python -m simumax_b200.calib.calibrate ops --supplement <system.json>` on the target machine")
+        return tips
+
     def report_zip(self, ev: Evaluation) -> bytes:
         out = io.BytesIO()
         with zipfile.ZipFile(out, "w", zipfile.ZIP_DEFLATED) as z:
@@ -152,7 +205,20 @@ def main():  # pragma: no cover - needs streamlit
         upd["enable_sequence_parallel"] = st.checkbox("sequence parallel", value=bool(s.get("enable_sequence_parallel", True)))
         upd["fp8"] = st.checkbox("fp8 linears", value=bool(s.get("fp8", False)))
         layers = st.number_input("layer_num", min_value=1, value=int(sess.model_dict.get("layer_num", 32)))
+        with st.expander("uneven pipeline split (advanced)"):
+            first = st.number_input("num_layers_in_first_pipeline_stage (0 = even)", min_value=0, value=0)
+            last = st.number_input("num_layers_in_last_pipeline_stage (0 = even)", min_value=0, value=0)
+            upd["num_layers_in_first_pipeline_stage"] = int(first) or None
+            upd["num_layers_in_last_pipeline_stage"] = int(last) or None
+        with st.expander("model parameters"):
+            mupd = {}
+            for key in ("hidden_size", "head_num", "kv_head_num", "intermediate_size", "vocab_size", "expert_num", "topk"):
+                if key in sess.model_dict and isinstance(sess.model_dict[key], int):
+                    mupd[key] = int(st.number_input(key, min_value=1, value=int(sess.model_dict[key])))
+            sess.apply(model=mupd)
         sess.apply(strategy=upd, model={"layer_num": int(layers)})
+        with st.expander("model details", expanded=False):
+            st.json(sess.model_summary())
     with tab_hw:
         acc = sess.system_dict["accelerator"]
         c1, c2, c3 = st.columns(3)
@@ -176,6 +242,13 @@ def main():  # pragma: no cover - needs streamlit
             left, right = st.columns(2)
             left.subheader("Memory"); left.json(ev.memory, expanded=False)
             right.subheader("Time breakdown"); right.json(ev.cost.get("breakdown_result", ev.cost), expanded=False)
+            tips = sess.suggestions(ev)
+            if tips:
+                st.subheader("Suggestions")
+                for t in tips:
+                    st.info(t)
+            with st.expander("achieved collective bandwidths"):
+                st.json(json.loads(json.dumps(sess.perf.system.real_comm_bw, default=str)))
             st.subheader("Efficiency table")
             st.write({"hits": ev.hits, "misses": {k: len(v) for k, v in ev.misses.items()}})
             st.download_button("Download analysis (zip)", sess.report_zip(ev), file_name="simumax_b200_analysis.zip")

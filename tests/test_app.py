@@ -43,3 +43,20 @@ def test_session_reports_invalid_strategy():
     s.apply(strategy={"tp_size": 3})
     ev = s.evaluate()
     assert not ev.ok and "divisible" in ev.error
+
+
+def test_model_summary_and_suggestions():
+    app = _load()
+    s = app.Session("b200_nominal", "llama3-70b", "tp1_pp1_dp8_mbs1")
+    info = s.model_summary()
+    assert info["layers"] == 80 and info["hidden"] == 8192 and info["kv_heads"] == 8
+    ev = s.evaluate()                      # 70B on tp1 / pp1 cannot fit on one 180 GB device
+    tips = s.suggestions(ev)
+    assert ev.ok and any("exceeds" in t for t in tips), tips
+    s2 = app.Session("b200_nominal", "llama3-8b", "tp8_pp1_dp1_mbs1")
+    s2.apply(strategy={"micro_batch_num": 1})
+    tips2 = s2.suggestions(s2.evaluate())
+    assert any("collectives take more than 15" in t for t in tips2) and any("less than half" in t for t in tips2), tips2
+    bad = app.Session("b200_nominal", "llama3-8b", "tp1_pp1_dp8_mbs1")
+    bad.apply(strategy={"tp_size": 3})
+    assert bad.suggestions(bad.evaluate())[0].startswith("configuration rejected")
