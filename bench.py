@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--attention-bwd", default="auto")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--tp", type=int, default=1, help="tensor(+sequence)-parallel size; >1 runs TPLlamaTrainer on the fused "
-                    "all-gather->GEMM / GEMM->reduce-scatter kernels (must equal --gpus: dp = 1); default = data parallel")
+                    "all-gather->GEMM / GEMM->reduce-scatter kernels; --gpus / --tp replicas run data parallel (ZeRO-1); default 1 = data parallel")
     return ap.parse_args()
 
 
@@ -205,17 +205,22 @@ def main():
         dims.layers = a.layers
     B, S, MB = a.micro_batch, a.seq_len, a.micro_batches
     tp = a.tp
-    assert tp == 1 or tp == world, "--tp must equal --gpus (the tensor-parallel runtime runs with dp = 1)"
+    assert world % tp == 0, "--tp must divide --gpus"
     dp = world // tp
     if tp > 1:
         from simumax_b200.runtime.tp_trainer import TPLlamaTrainer
-        tr = TPLlamaTrainer(dims, B, S, seed=1234)
+        tp_group = dp_group = None
+        if dp > 1:                                   # rank layout as in the analytical model: tp fastest, then dp
+            tp_groups = [dist.new_group(list(range(i * tp, (i + 1) * tp))) for i in range(dp)]
+            dp_groups = [dist.new_group(list(range(j, world, tp))) for j in range(tp)]
+            tp_group, dp_group = tp_groups[rank // tp], dp_groups[rank % tp]
+        tr = TPLlamaTrainer(dims, B, S, tp_group=tp_group, dp_group=dp_group, seed=1234)
     else:
         tr = LlamaTrainer(dims, B, S, dp_group=dist.group.WORLD if world > 1 else None, attention_bwd=a.attention_bwd,
                           seed=1234)
     # distinct synthetic token batches per step and micro-batch, staged in pinned host memory (e2e) and on device
     n_sets = max(a.steps, 1)
-    gen = torch.Generator().manual_seed(1000 + (rank if tp == 1 else 0))       # TP ranks share the batch
+    gen = torch.Generator().manual_seed(1000 + rank // tp)       # the ranks of one TP group share their replica's batch
     host = [[(torch.randint(0, mc.vocab_size, (B, S), generator=gen).pin_memory(),
               torch.randint(0, mc.vocab_size, (B, S), generator=gen).pin_memory()) for _ in range(MB)] for _ in range(n_sets)]
     dev = [[(t.cuda().view(-1), y.cuda().view(-1)) for t, y in step] for step in host]
@@ -269,7 +274,7 @@ def main():
             "vs_baseline": value / (BASELINE_TOK_S_PER_GPU * world), "dtype": "bf16",
             "data": "synthetic random tokens, random-init weights",
             "config": {"model": a.model, "global_batch": B * MB * dp, "seq_len": S,
-                       "parallelism": f"dp{world}_zero1_tp1_pp1" if tp == 1 else f"dp1_tp{tp}_sp_pp1 (fused AG->GEMM / GEMM->RS kernels)",
+                       "parallelism": f"dp{world}_zero1_tp1_pp1" if tp == 1 else f"dp{dp}_zero1_tp{tp}_sp_pp1 (fused AG->GEMM / GEMM->RS kernels)",
                        "micro_batch": B, "micro_batches": MB,
                        "layers": dims.layers, "padded_vocab": dims.vocab, "params": dims.total_numel(),
                        "optimizer": "AdamW fp32 master/m/v, fp32 main grads, grad clip 1.0", "recompute": "none",

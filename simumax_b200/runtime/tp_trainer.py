@@ -44,9 +44,15 @@ def _up(n: int, m: int) -> int:
 class TPLlamaTrainer:
     def __init__(self, dims: LlamaDims, micro_batch: int, seq_len: int, tp_group: Optional[dist.ProcessGroup] = None,
                  lr: float = 1e-4, weight_decay: float = 0.1, betas=(0.9, 0.95), max_grad_norm: float = 1.0, seed: int = 1234,
-                 device=None):
+                 device=None, dp_group: Optional[dist.ProcessGroup] = None):
+        """``dp_group``: data-parallel replicas of this TP group (same TP rank in every replica).  With it the optimizer is
+        ZeRO-1 over the replicas the way Megatron's distributed optimizer runs in the reference's measurement contract (overlap
+        features off): one reduce-scatter of the fp32 main grads, AdamW on the local shard, one all-gather of the bf16 params."""
         assert dist.is_initialized(), "TPLlamaTrainer needs an initialised process group (one rank per GPU)"
         self.d = d = dims
+        self.dp_group = dp_group
+        self.dp = dist.get_world_size(dp_group) if dp_group is not None else 1
+        self.dp_rank = dist.get_rank(dp_group) if dp_group is not None else 0
         self.group = tp_group or dist.group.WORLD
         self.tp = W = dist.get_world_size(self.group)
         self.rank = r = dist.get_rank(self.group)
@@ -68,8 +74,11 @@ class TPLlamaTrainer:
         # ---- parameters: [tp-sharded matrices | replicated norm weights]; fp32 main grads share the layout
         n_shard = self.VW * H + L * (self.qkvW * H + H * self.oW + 2 * self.FW * H + H * self.FW) + self.VW * H
         n_rep = (2 * L + 1) * H
-        self.n_shard, self.n_rep = _up(n_shard, 1024), _up(n_rep, 1024)
+        self.n_shard, self.n_rep = _up(n_shard, 1024), _up(n_rep, 1024 * self.dp)
         self.P = self.n_shard + self.n_rep
+        if self.P % (1024 * self.dp):
+            self.n_shard += 1024 * self.dp - self.P % (1024 * self.dp)       # equal, 4 KB aligned ZeRO-1 shards
+            self.P = self.n_shard + self.n_rep
         # ---- symmetric workspace layout (bytes)
         act = T * H * 2
         off = 0
@@ -93,13 +102,16 @@ class TPLlamaTrainer:
         # the replicated (norm) gradients are all-reduced in place in the workspace, so they live there
         self.grads = _Flat(self.P, torch.float32, dev)
         self.w, self.g = self._carve(self.params), self._carve(self.grads)
-        gen = torch.Generator(device=dev).manual_seed(seed + 7919 * r)
+        gen = torch.Generator(device=dev).manual_seed(seed + 7919 * r)       # same weights in every data-parallel replica
         self.params.buf.normal_(0.0, 0.02, generator=gen)
         self._fill_norms()
         self.grads.buf.zero_()
-        self.master = self.params.buf.float()
-        self.m = torch.zeros(self.P, dtype=torch.float32, device=dev)
-        self.v = torch.zeros(self.P, dtype=torch.float32, device=dev)
+        self.zshard = self.P // self.dp                                       # ZeRO-1: this replica's slice of the flat buffers
+        self.zlo = self.dp_rank * self.zshard
+        self.master = self.params.buf[self.zlo:self.zlo + self.zshard].float()
+        self.m = torch.zeros(self.zshard, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(self.zshard, dtype=torch.float32, device=dev)
+        self.grad_shard = torch.empty(self.zshard, dtype=torch.float32, device=dev) if self.dp > 1 else None
         self.sqnorm = ws.view(self.off_sc, torch.float32, 4)
         self.sqnorm_out = ws.view(self.off_sc + 256, torch.float32, 4)
         # ---- activations
@@ -170,11 +182,11 @@ class TPLlamaTrainer:
             self.w["ln1"][i].copy_(full["ln1"][i])
             self.w["ln2"][i].copy_(full["ln2"][i])
         self.w["final_norm"].copy_(full["final_norm"])
-        self.master.copy_(self.params.buf)
+        self.master.copy_(self.params.buf[self.zlo:self.zlo + self.zshard])
 
     def memory_bytes(self) -> dict:
         act = sum(t.numel() * t.element_size() for t in self.act.values())
-        return {"params_bf16": self.P * 2, "main_grads_fp32": self.P * 4, "optimizer_fp32": self.P * 12, "activations": act,
+        return {"params_bf16": self.P * 2, "main_grads_fp32": self.P * 4, "optimizer_fp32": self.zshard * 12, "activations": act,
                 "symmetric_workspace": self.ws.in_bytes + self.ws.out_bytes, "logits": self.logits.numel() * 2,
                 "torch_max_allocated": torch.cuda.max_memory_allocated(self.device)}
 
@@ -283,12 +295,29 @@ class TPLlamaTrainer:
         rep = ws.view(self.off_ln_out, torch.float32, n_rep)
         self.grads.buf[self.n_shard:].copy_(rep)
         self.sqnorm.zero_()
-        E.sqnorm(self.grads.buf[:self.n_shard], out=self.sqnorm[:1])
-        if self.rank == 0:
-            E.sqnorm(self.grads.buf[self.n_shard:], out=self.sqnorm[:1])
+        if self.dp == 1:
+            E.sqnorm(self.grads.buf[:self.n_shard], out=self.sqnorm[:1])
+            if self.rank == 0:
+                E.sqnorm(self.grads.buf[self.n_shard:], out=self.sqnorm[:1])
+            ws.all_reduce(16, in_off=self.off_sc, out_off=self.off_sc + 256, dtype=torch.float32, ctas=1)
+            E.adamw_(self.master, self.m, self.v, self.grads.buf, self.params.buf, self.lr, b1, b2, 1e-8, self.wd, self.step_count,
+                     sqnorm_t=self.sqnorm_out[:1], max_norm=self.max_norm, zero_grad=True)
+            return
+        # ---- ZeRO-1 over the data-parallel replicas (NCCL, exposed -- the reference's measurement contract)
+        lo, hi = self.zlo, self.zlo + self.zshard
+        dist.reduce_scatter_tensor(self.grad_shard, self.grads.buf, op=dist.ReduceOp.SUM, group=self.dp_group)
+        cut = min(max(self.n_shard - lo, 0), self.zshard)          # [0, cut) of my shard = TP-sharded matrices, rest = replicated norms
+        if cut > 0:
+            E.sqnorm(self.grad_shard[:cut], out=self.sqnorm[:1])
+        if cut < self.zshard and self.rank == 0:
+            E.sqnorm(self.grad_shard[cut:], out=self.sqnorm[:1])
         ws.all_reduce(16, in_off=self.off_sc, out_off=self.off_sc + 256, dtype=torch.float32, ctas=1)
-        E.adamw_(self.master, self.m, self.v, self.grads.buf, self.params.buf, self.lr, b1, b2, 1e-8, self.wd, self.step_count,
-                 sqnorm_t=self.sqnorm_out[:1], max_norm=self.max_norm, zero_grad=True)
+        dist.all_reduce(self.sqnorm_out, group=self.dp_group)
+        # grads hold the SUM over replicas of per-replica means -> prescale by 1/dp inside the fused optimizer kernel
+        E.adamw_(self.master, self.m, self.v, self.grad_shard, self.params.buf[lo:hi], self.lr, b1, b2, 1e-8, self.wd,
+                 self.step_count, sqnorm_t=self.sqnorm_out[:1], max_norm=self.max_norm, grad_prescale=1.0 / self.dp, zero_grad=False)
+        self.grads.buf.zero_()
+        dist.all_gather_into_tensor(self.params.buf, self.params.buf[lo:hi].clone(), group=self.dp_group)
 
     def synchronize(self) -> None:
         torch.cuda.synchronize(self.device)

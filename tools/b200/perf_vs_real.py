@@ -80,7 +80,13 @@ def measure(model, layers, seq, mbs, mbc, steps, warmup, tp=1):
     torch.cuda.reset_peak_memory_stats()
     if tp > 1:
         from simumax_b200.runtime.tp_trainer import TPLlamaTrainer
-        tr = TPLlamaTrainer(dims, mbs, seq)
+        tp_group = dp_group = None
+        if world > tp:
+            rank, dp = dist.get_rank(), world // tp
+            tp_groups = [dist.new_group(list(range(i * tp, (i + 1) * tp))) for i in range(dp)]
+            dp_groups = [dist.new_group(list(range(j, world, tp))) for j in range(tp)]
+            tp_group, dp_group = tp_groups[rank // tp], dp_groups[rank % tp]
+        tr = TPLlamaTrainer(dims, mbs, seq, tp_group=tp_group, dp_group=dp_group)
     else:
         tr = LlamaTrainer(dims, mbs, seq, dp_group=dist.group.WORLD if world > 1 else None)
     g = torch.Generator(device="cuda").manual_seed(5)
@@ -116,7 +122,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--cases", nargs="*", default=None)
-    ap.add_argument("--tp", action="store_true", help="tensor-parallel cases (tp = world size, sequence parallel, fused kernels)")
+    ap.add_argument("--tp", action="store_true", help="tensor-parallel cases (sequence parallel, fused kernels)")
+    ap.add_argument("--tp-size", type=int, default=0, help="with --tp: tensor-parallel size (default = world size); the remaining "
+                    "factor runs data parallel with ZeRO-1, e.g. 8 GPUs --tp-size 2 = the reference's tp2_dp4 rows")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -127,7 +135,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank = dist.get_rank() if world > 1 else 0
     rows = []
-    tp = world if a.tp else 1
+    tp = (a.tp_size or world) if a.tp else 1
+    assert world % tp == 0
     for name, model, layers, seq, mbs, mbc in (TP_CASES if a.tp else CASES):
         if a.cases and name not in a.cases:
             continue
