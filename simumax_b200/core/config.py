@@ -243,6 +243,9 @@ class StrategyConfig(Config):
     #   re-gather disappears because the gathered activation is what gets saved (so LinearCol caches the full sequence)
     # * fused_optimizer_model: one l2-norm pass + one fused AdamW pass (read grad/master/m/v, write master/m/v/bf16 param,
     #   zero the grad) instead of Megatron's seven-kernel chain
+    # * vpp_async_perf_via_simulation: perf() of asynchronous interleaved pipelining takes its schedule time from the
+    #   discrete-event engine (the reference raises there and offers simulate() only)
+    vpp_async_perf_via_simulation: bool = False
     tp_overlap_model: bool = False
     tp_overlap_exposed_ag: float = 0.6
     tp_overlap_exposed_rs: float = 0.4

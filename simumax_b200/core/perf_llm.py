@@ -530,6 +530,9 @@ class PerfLLM(PerfBase):
     def _compute_pp_total_time(self, return_schedules=False):
         if self._vp_size() > 1 and self.vpp_stage_chunk_names.get(FIRST_CHUNK):
             if self.strategy.pp_comm_async:
+                if getattr(self.strategy, "vpp_async_perf_via_simulation", False):
+                    from ..sim.runner import simulate_schedule       # extension: time the schedule with the event engine
+                    return simulate_schedule(self, return_schedules=return_schedules)
                 raise RuntimeError("analysis_cost() does not support async VPP perf timing yet; "
                                    "use pp_comm_async=False for perf timing or simulate() for async VPP traces")
             from .schedule_vpp import compute_interleaved_sync_schedule

@@ -27,11 +27,8 @@ def should_enable_memory_timeline(strategy) -> bool:
     return strategy.pp_size == 1 or (not getattr(strategy, "pp_comm_async", True))
 
 
-def run_simulation(perf, save_path, merge_lanes: bool = True, quiet: bool = False) -> dict:
+def _build_engine(perf, merge_lanes: bool, tracker, with_optimizer: bool) -> Engine:
     st = perf.strategy
-    t0 = time.time()
-    os.makedirs(save_path, exist_ok=True)
-    tracker = SimuMemoryTracker() if should_enable_memory_timeline(st) else None
     engine = Engine(merge_lanes=merge_lanes, memory_tracker=tracker)
     n_ranks = st.pp_size if merge_lanes else st.world_size
     vp = perf._vp_size()
@@ -51,8 +48,42 @@ def run_simulation(perf, save_path, merge_lanes: bool = True, quiet: bool = Fals
             jobs = build_interleaved_program(perf, chunks, args, with_mem)
         else:
             jobs = build_1f1b_program(perf, chunks[0], args, with_mem)
-        jobs.append(build_optimizer_tail(perf, key, args))
+        if with_optimizer:
+            jobs.append(build_optimizer_tail(perf, key, args))
         engine.add_rank(rank, jobs)
+    return engine
+
+
+def simulate_schedule(perf, return_schedules: bool = False):
+    """Pipeline-schedule time (ms, no optimizer / data-parallel tail) from the discrete-event engine, one lane per stage.
+
+    Used by ``PerfLLM`` for schedules the closed-form evaluators do not cover (asynchronous interleaved pipelining: the
+    reference raises in ``perf()`` and offers ``simulate()`` only, perf_llm.py:2697-2701).  With ``return_schedules`` the compute
+    and p2p events come back as per-stage records in the format ``core/trace_export.py`` draws."""
+    engine = _build_engine(perf, merge_lanes=True, tracker=None, with_optimizer=False)
+    total = engine.run()
+    if not return_schedules:
+        return total
+    order = {r: i for i, r in enumerate(sorted(engine.ranks))}
+    records = [[] for _ in order]
+    for e in engine.events:
+        if e.kind == "compute":
+            kind = "B" if e.phase == "bwd" else "F"
+        elif e.kind == "p2p":
+            kind = "send" if "send" in e.name else "recv"
+        else:
+            continue
+        records[order[e.rank]].append({"kind": kind, "label": e.name.split("-")[-1], "start": e.start, "end": e.end,
+                                       "duration": e.end - e.start, "mb": None, "gid": e.gid})
+    return total, records
+
+
+def run_simulation(perf, save_path, merge_lanes: bool = True, quiet: bool = False) -> dict:
+    st = perf.strategy
+    t0 = time.time()
+    os.makedirs(save_path, exist_ok=True)
+    tracker = SimuMemoryTracker() if should_enable_memory_timeline(st) else None
+    engine = _build_engine(perf, merge_lanes, tracker, with_optimizer=True)
     end_t = engine.run()
     if not quiet:
         print(f"end in {end_t}")
