@@ -246,6 +246,9 @@ class StrategyConfig(Config):
     # * vpp_async_perf_via_simulation: perf() of asynchronous interleaved pipelining takes its schedule time from the
     #   discrete-event engine (the reference raises there and offers simulate() only)
     vpp_async_perf_via_simulation: bool = False
+    # * cp_comm_type "all_gather" (completed: the reference stops at the flops) and "p2p" (ring attention) are extensions;
+    #   cp_p2p_exposed is the fraction of the ring's neighbour transfers that is not hidden behind the previous block's attention
+    cp_p2p_exposed: float = 1.0
     tp_overlap_model: bool = False
     tp_overlap_exposed_ag: float = 0.6
     tp_overlap_exposed_rs: float = 0.4

@@ -343,6 +343,11 @@ def core_attention(st: StrategyConfig, system: SystemConfig, head_size, head_num
             kv_mem = (k_n + v_n) * e
             node.act.fwd_peak_mem_no_cache += kv_mem * (st.cp_size - 1)
             node.act.bwd_peak_mem_no_cache += 2 * kv_mem * (st.cp_size - 1)
+        elif st.cp_size > 1 and st.cp_comm_type == "p2p" and not mla:
+            # ring attention (extension): the K/V block being used plus the one in flight; backward also circulates dK/dV
+            kv_mem = (k_n + v_n) * e
+            node.act.fwd_peak_mem_no_cache += kv_mem
+            node.act.bwd_peak_mem_no_cache += 3 * kv_mem
     else:
         sm_n = B * head_num * S * S
         cache = (q_n + k_n + v_n + sm_n) * e
@@ -359,17 +364,23 @@ def core_attention(st: StrategyConfig, system: SystemConfig, head_size, head_num
 
     # ---- flops: after the all-to-all every rank sees the full sequence with heads/cp
     seq, heads = S, head_num
+    seq_kv = None
     if st.cp_size > 1:
         if st.cp_comm_type == "a2a" or mla:
             assert head_num % st.cp_size == 0, f"head_num {head_num} must be divisible by cp_size {st.cp_size}"
             seq = S * st.cp_size
             heads = head_num // st.cp_size
+        elif st.cp_comm_type in ("all_gather", "p2p"):
+            # extension (the reference raises here, dense_module.py:1521-1522): all heads, local queries against the whole
+            # sequence of keys -- S x (S * cp) scores per head, the same work per rank as the all-to-all flavour
+            seq_kv = S * st.cp_size
         else:
             raise NotImplementedError(f"cp_comm_type {st.cp_comm_type} not implemented yet.")
+    sq_skv = seq * (seq if seq_kv is None else seq_kv)
     if mla:
-        base = B * heads * head_size * seq * seq + B * heads * vd * seq * seq
+        base = B * heads * head_size * sq_skv + B * heads * vd * sq_skv
     else:
-        base = 2 * B * heads * head_size * seq * seq
+        base = 2 * B * heads * head_size * sq_skv
     base *= 1 - st.attention_sparse_ratio
     node.compute.fwd_flops = 2 * base
     node.compute.bwd_grad_act_flops = 4 * base + (base if st.use_flash_sdp else 0)
@@ -410,10 +421,21 @@ def core_attention(st: StrategyConfig, system: SystemConfig, head_size, head_num
                     node.comms.append(CollectiveSpec("all2all", size, st.cp_size, st.cp_net, stage_name, phase, group="cp"))
         elif st.cp_comm_type == "all_gather":
             kv_mem = (k_c + v_c) * e
-            size = kv_mem * st.cp_size * e
+            # bytes of the gathered K + V (the reference multiplies by the element size once more, dense_module.py:1375-1378;
+            # its all_gather flavour never runs to the end, so there is no number to stay compatible with)
+            size = kv_mem * st.cp_size
             node.comms.append(CollectiveSpec("all_gather", size, st.cp_size, st.cp_net, "Attention_FWD_CP", "fwd", group="cp"))
             node.comms.append(CollectiveSpec("all_gather", size, st.cp_size, st.cp_net, "Attention_BWD_CP1", "bwd_grad_act", group="cp"))
             node.comms.append(CollectiveSpec("reduce_scatter", size, st.cp_size, st.cp_net, "Attention_BWD_CP2", "bwd_grad_act", group="cp"))
+        elif st.cp_comm_type == "p2p":
+            # ring attention (extension): cp - 1 hops of the local K/V block forward, K/V and dK/dV backward; each hop is a
+            # neighbour send/recv that Megatron / TE overlap with the attention of the previous block
+            kv_block = (k_c + v_c) * e
+            hide = float(getattr(st, "cp_p2p_exposed", 1.0))
+            node.comms.append(CollectiveSpec("p2p", kv_block * (st.cp_size - 1), 2, st.cp_net, "Attention_FWD_CP_RING", "fwd",
+                                             group="cp", exposed=hide))
+            node.comms.append(CollectiveSpec("p2p", 2 * kv_block * (st.cp_size - 1), 2, st.cp_net, "Attention_BWD_CP_RING",
+                                             "bwd_grad_act", group="cp", exposed=hide))
         else:
             raise NotImplementedError(f"cp_comm_type {st.cp_comm_type} not implemented yet.")
     node.cp_specs = specs

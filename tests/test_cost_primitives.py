@@ -90,3 +90,21 @@ def test_runtime_semantics_knobs_are_off_by_default_and_monotone():
     from simumax_b200.core.utils import parse_bytes
     peak = lambda d: max(parse_bytes(v["peak_mem"]) for v in d.values()) if "peak_mem" not in d else parse_bytes(d["peak_mem"])
     assert peak(tp[3]) > peak(base[3])
+
+
+def test_context_parallel_flavours_extension():
+    """cp_comm_type: "a2a" is the reference's formal path; "all_gather" (finished here) and "p2p" (ring) are extensions: same
+    attention work per rank, different collectives."""
+    from helpers import build
+
+    def run(**over):
+        p = build("tp2_pp1_dp4_mbs1", "llama3-70b", "b200_nominal", 8, seq_len=32768, cp_size=4, world_size=32, **over)
+        c = p.analysis_cost().data
+        ms = lambda v: float(str(v).split()[0]) * (1e3 if str(v).split()[1] == "s" else 1.0)
+        return ms(c["duration_time_per_iter"]), ms(c["breakdown_result"]["intra_exposed_time"]), c["flops_info"]["model_flops"]
+
+    a2a, ag, ring = run(cp_comm_type="a2a"), run(cp_comm_type="all_gather"), run(cp_comm_type="p2p")
+    hidden = run(cp_comm_type="p2p", cp_p2p_exposed=0.0)
+    assert a2a[2] == ag[2] == ring[2]                     # identical model FLOPs
+    assert ring[1] < a2a[1] and hidden[1] < ring[1]       # neighbour transfers are cheaper than the all-to-alls; hiding them helps
+    assert all(0.8 * a2a[0] < x[0] < 1.2 * a2a[0] for x in (ag, ring, hidden))
