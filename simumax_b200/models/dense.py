@@ -450,6 +450,13 @@ def core_attention(st: StrategyConfig, system: SystemConfig, head_size, head_num
             steps += [a2a(nm, sz, False) for nm, sz in reversed(specs["bwd_post"])]
             steps += [a2a(nm, sz, True) for nm, sz in specs["fwd_post"]]
             steps += [a2a(nm, sz, False) for nm, sz in reversed(specs["bwd_pre"])]
+        elif st.cp_size > 1:
+            # gathered-K/V and ring flavours (extensions): replay the evaluated collectives over the cp group
+            for spec in n.comms:
+                fwd = spec.phase == "fwd"
+                label = "ring_p2p" if spec.op == "p2p" else spec.op
+                steps.append(SimStep(kind="comm", name=label, fwd_cost=spec.time if fwd else 0.0, bwd_cost=0.0 if fwd else spec.time,
+                                     comm_op=label, group="cp", comm_num=st.cp_size, stage=spec.stage))
         steps.append(_atom(n, "AttentionScore"))
         return steps
     node.sim_steps = sim
