@@ -32,6 +32,7 @@ DEFAULT_WORKLOADS: List[Tuple[str, str, dict, dict]] = [
     ("llama3-70b", "tp8_pp1_dp1_mbs1", {"layer_num": 12}, {}),
     ("llama3-70b", "tp2_pp1_dp4_mbs1", {"layer_num": 12}, {"seq_len": 8192}),
     ("llama3-70b", "tp4_pp1_dp2_mbs1", {"layer_num": 12}, {"seq_len": 8192}),
+    ("llama3-405b_padding_128", "tp8_pp1_dp1_mbs1", {"layer_num": 4}, {}),
     # fp8 linears (the reference ships no fp8 numbers for B200 at all)
     ("llama3-8b", "tp1_pp1_dp8_mbs1", {}, {"fp8": True}),
     ("llama3-70b", "tp2_pp1_dp4_mbs1", {"layer_num": 12}, {"fp8": True}),

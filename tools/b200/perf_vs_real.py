@@ -37,7 +37,23 @@ TP_CASES = [      # measured with TPLlamaTrainer: tp = world, sequence parallel,
     ("llama3_8b_full_s4096_tp",    "llama3-8b",  None,   4096,  1,   4),
     ("llama3_70b_l12_s4096_tp",    "llama3-70b", 12,     4096,  1,   4),
     ("llama3_70b_l12_s8192_tp",    "llama3-70b", 12,     8192,  1,   2),
+    # the remaining tp8_dp1 rows of the reference's published B200 table (same model / layers / seq / micro-batches)
+    ("llama3_70b_l12_s4096_mbc8_tp",  "llama3-70b", 12,   4096,  1,   8),
+    ("llama3_70b_l12_s4096_mbc32_tp", "llama3-70b", 12,   4096,  1,   32),
+    ("llama3_405b_l4_s4096_tp",       "llama3-405b_padding_128", 4, 4096, 1, 4),
+    ("llama3_405b_l4_s4096_mbc8_tp",  "llama3-405b_padding_128", 4, 4096, 1, 8),
 ]
+
+# (model, layers, seq, mbs, mbc, tp, dp) -> (Megatron-LM + TE measured ms, peak GiB, reference-predicted ms) as published by the
+# reference authors for 8 x B200 (docs/b200/b200_release_v1.2_summary.md).  Quoted, not re-measured here.
+PUBLISHED = {
+    ("llama3-70b", 12, 4096, 1, 4, 8, 1): (280.9, 28.29, 255.71), ("llama3-70b", 12, 4096, 1, 8, 8, 1): (556.7, 28.29, 493.39),
+    ("llama3-70b", 12, 4096, 1, 32, 8, 1): (2073.7, 28.29, 1919.4), ("llama3-70b", 12, 4096, 1, 4, 2, 4): (725.5, 60.68, 698.81),
+    ("llama3-70b", 12, 4096, 1, 4, 4, 2): (409.8, 39.07, 395.23), ("llama3-70b", 12, 4096, 1, 8, 2, 4): (1387.0, 60.68, 1309.8),
+    ("llama3-70b", 12, 4096, 1, 8, 4, 2): (765.6, 39.07, 747.66),
+    ("llama3-405b_padding_128", 4, 4096, 1, 4, 8, 1): (258.8, 38.57, 255.83), ("llama3-405b_padding_128", 4, 4096, 1, 8, 8, 1): (488.1, 38.57, 486.81),
+    ("llama3-405b_padding_128", 4, 4096, 1, 4, 2, 4): (907.3, 81.59, 860.73), ("llama3-405b_padding_128", 4, 4096, 1, 4, 4, 2): (476.0, 52.89, 452.92),
+}
 
 
 def predict(model, layers, seq, mbs, mbc, world, system, tp=1, runtime_semantics=False):
@@ -151,10 +167,15 @@ def main():
                    "mem_err_pct": 100 * (pred["peak_gib"] - real["peak_gib"]) / real["peak_gib"] if pred["peak_gib"] else None,
                    "pred_runtime_semantics_ms": pred_rt["iter_ms"],
                    "time_err_runtime_semantics_pct": 100 * (pred_rt["iter_ms"] - real["iter_ms"]) / real["iter_ms"],
-                   "pred_mfu": pred["mfu"], "real_tokens_per_s": real["tokens_per_s"], "efficiency_misses": pred["miss"]}
+                   "pred_mfu": pred["mfu"],
+                   "published_megatron": (lambda v: None if v is None else {"real_ms": v[0], "real_gib": v[1], "reference_pred_ms": v[2],
+                                                                           "speedup_vs_megatron": v[0] / real["iter_ms"]})(
+                       PUBLISHED.get((model, layers, seq, mbs, mbc, tp, world // tp))), "real_tokens_per_s": real["tokens_per_s"], "efficiency_misses": pred["miss"]}
             rows.append(row)
             print(f"{name:28s} n={world} time pred {row['pred_ms']:9.2f} ms real {row['real_ms']:9.2f} ms ({row['time_err_pct']:+6.2f} %, runtime semantics {row['time_err_runtime_semantics_pct']:+6.2f} %)   "
-                  f"mem pred {row['pred_gib']:.2f} GiB real {row['real_gib']:.2f} GiB ({row['mem_err_pct']:+6.2f} %)", flush=True)
+                  f"mem pred {row['pred_gib']:.2f} GiB real {row['real_gib']:.2f} GiB ({row['mem_err_pct']:+6.2f} %)"
+                  + (f"   published Megatron {row['published_megatron']['real_ms']:.1f} ms -> {row['published_megatron']['speedup_vs_megatron']:.2f}x"
+                     if row["published_megatron"] else ""), flush=True)
     if rank == 0:
         os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
         json.dump({"system": a.system, "world": world, "rows": rows}, open(a.out, "w"), indent=1)

@@ -18,6 +18,9 @@ if [ "$MAXG" -ge 8 ]; then
         --out "$OUT/perf_vs_real_tp${tp}_dp$((8 / tp)).json" | tail -2
   done
 fi
+echo "== 2b. the other tp8_dp1 rows of the reference's published table (70B-l12 mbc8 / mbc32, 405B-l4): measured vs Megatron's published ms"
+[ "$MAXG" -ge 8 ] && run 400 8 29820 tools/b200/perf_vs_real.py --tp --out "$OUT/perf_vs_real_tp8_published.json" \
+    --cases llama3_70b_l12_s4096_tp llama3_70b_l12_s4096_mbc8_tp llama3_405b_l4_s4096_tp llama3_405b_l4_s4096_mbc8_tp | tail -5
 echo "== 3. sustained-clock calibration of the bench shapes (1 GPU), then predicted vs measured with it"
 timeout 600 python -m simumax_b200.calib.calibrate ops --sustained-ms 300 --limit-per-op 40 --out "$OUT/calib_ops_sustained.json" | tail -5
 python -m simumax_b200.calib.calibrate merge --ops "$OUT/calib_ops_sustained.json" --base simumax_b200/configs/system/b200_sm100a_calibrated.json \
