@@ -65,3 +65,21 @@ def test_system_loads_and_serialises(name):
     assert again.to_config_dict() == s.to_config_dict()
     assert s.compute_mem_access_time("default", 0) == 0
     assert s.compute_mem_access_time("default", 1 << 30) > 0
+
+
+def test_command_line_front_end(tmp_path, capsys):
+    """python -m simumax_b200 perf / simulate / trace / list (the reference ships example scripts only)."""
+    import json
+    from simumax_b200.__main__ import main
+    assert main(["perf", "-m", "llama3-8b", "-s", "tp2_pp1_dp4_mbs1", "--system", "b200_nominal", "--layers", "4",
+                 "--set", "micro_batch_num=4", "--set", "model.vocab_size=32000"]) == 0
+    head = json.loads(capsys.readouterr().out)
+    assert head["mfu"] > 0 and "mbc4" in head["parallelism"] and head["tokens_per_s_per_gpu"] > 0
+    out = tmp_path / "sim"
+    assert main(["simulate", "-m", "llama3-8b", "-s", "tp1_pp2_dp4_mbs1", "--system", "b200_nominal", "--layers", "4", "--out", str(out)]) == 0
+    sim = json.loads(capsys.readouterr().out)
+    assert sim["lanes"] == 2 and sim["simulated_end_ms"] > 0 and (out / "tracing_logs.json").exists()
+    assert main(["trace", str(out / "log.log"), str(out / "again.json")]) == 0 and (out / "again.json").exists()
+    capsys.readouterr()
+    assert main(["list"]) == 0
+    assert "llama3-8b" in json.loads(capsys.readouterr().out)["models"]
