@@ -16,7 +16,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 

@@ -13,7 +13,7 @@ TransformerEngine / cuDNN; here the timed kernels are csrc/gemm_tcgen05.cu, csrc
 from __future__ import annotations
 
 import math
-from typing import Callable, Dict, List, Optional
+from typing import Callable, Dict, Optional
 
 import torch
 

@@ -5,8 +5,6 @@ so every entry point that takes a config *path* keeps working, and users can sti
 """
 from __future__ import annotations
 
-import json
-import os
 from typing import Dict
 
 # name -> ModelConfig fields

@@ -8,7 +8,6 @@ execution pass as in reference core/graph.py).
 from __future__ import annotations
 
 import json
-import os
 from typing import Dict, List
 
 

@@ -15,17 +15,14 @@ port unchanged; internally everything runs on the flat op IR (core/ir.py, models
 from __future__ import annotations
 
 import json
-import math
 import os
-from copy import deepcopy
-from typing import Dict, List, Optional, Union
+from typing import Dict, List, Union
 
 from .config import (ENABLE_SIMU_GRAPH, SIMU_CHECK, TMP_PATH, ModelConfig, StrategyConfig, SystemConfig,
                      set_capture_graph_only)
 from .records import PeakPoint, Result
 from .schedule import (effective_straggler_samples, one_f_one_b, straggler_increase_ratio)
-from .utils import (HumanReadableSize, convert_final_result_to_human_format, get_pp_p2p_comm_size,
-                    human_readable_bytes)
+from .utils import HumanReadableSize, convert_final_result_to_human_format, get_pp_p2p_comm_size
 from ..models.llm import StageChunk
 
 FIRST_CHUNK = "first_stage_chunk"

@@ -7,7 +7,7 @@ Everything is kept as raw numbers; human formatting happens only at the JSON edg
 from __future__ import annotations
 
 from dataclasses import asdict, dataclass, field, fields
-from typing import List, Optional, Set, Tuple
+from typing import Optional, Set, Tuple
 
 
 class RecomputeStatus:

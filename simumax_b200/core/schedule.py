@@ -11,7 +11,7 @@ discrete-event simulator so both paths agree by construction.
 from __future__ import annotations
 
 from collections import deque
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Sequence, Tuple
 
 
 class _Op:

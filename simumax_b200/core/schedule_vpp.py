@@ -12,7 +12,7 @@ peak = static + max over the walk of (live cache + phase peak inside the chunk).
 from __future__ import annotations
 
 import heapq
-from typing import Dict, List
+from typing import List
 
 from .utils import convert_final_result_to_human_format
 

@@ -13,7 +13,6 @@ import os
 from copy import deepcopy
 from typing import List
 
-from .utils import HumanReadableSize
 
 
 def merge_dict(cur: dict, merged: dict) -> dict:

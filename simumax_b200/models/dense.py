@@ -7,9 +7,9 @@ docstring cites the lines it mirrors.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import List, Tuple
 
-from ..core.config import ModelConfig, StrategyConfig, SystemConfig
+from ..core.config import StrategyConfig, SystemConfig
 from ..core.ir import (DT, CollectiveSpec, OpNode, SimStep, comm_step, dense_param_memory, ishape, linear_gemm_table,
                        linear_shape_key, numel, record_te_dummy_wgrad)
 

@@ -15,7 +15,6 @@ from typing import List, Tuple
 from ..core.config import MLPRecomputeConfig, StrategyConfig, SystemConfig
 from ..core.ir import (DT, PHASES, CollectiveSpec, OpNode, SimStep, comm_step, dense_param_memory, ishape, linear_gemm_table,
                        linear_shape_key, moe_param_memory, numel, record_te_dummy_wgrad)
-from ..core.records import CostInfo
 from . import dense as D
 
 

@@ -19,7 +19,6 @@ from typing import List, Optional, Tuple
 import torch
 import torch.distributed as dist
 
-from ..ops import _lib
 from ..ops import elementwise as E
 from ..ops.attention import fmha_fwd
 from ..ops.gemm import gemm

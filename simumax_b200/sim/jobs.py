@@ -6,10 +6,9 @@ the model (every scope costs 2 us when it closes), recomputed layers use the fla
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import List, Optional, Tuple
 
 from ..core.ir import OpNode, SimStep
-from ..core.records import RecomputeStatus
 from ..core.utils import get_rank_group
 from .engine import Atom, Coll, RecomputeBlock, Scope
 from .memory import OpMemoryProfile

@@ -13,7 +13,7 @@ import os
 import pickle
 import time
 
-from ..core.utils import get_pp_stage_representative_rank, get_rank_group
+from ..core.utils import get_pp_stage_representative_rank
 from .engine import Engine
 from .jobs import RankArgs
 from .memory import SimuMemoryTracker

@@ -10,7 +10,7 @@ share one source of truth.
 """
 from __future__ import annotations
 
-from typing import Callable, List, Tuple
+from typing import List, Tuple
 
 from ..core.utils import get_pp_p2p_comm_size
 from .engine import AsyncPost, AsyncWait, Atom, BlockingP2P, Coll, Scope
