@@ -791,10 +791,14 @@ class PerfLLM(PerfBase):
         self.run_estimate()
         return self.analysis(save_path=save_path, console_log=console_log)
 
-    def simulate(self, save_path, merge_lanes=True):
-        """Discrete-event replay of the iteration: Chrome trace + memory timeline artifacts."""
+    def simulate(self, save_path, merge_lanes=True, memory_timeline="auto"):
+        """Discrete-event replay of the iteration: Chrome trace + memory timeline artifacts.
+
+        ``memory_timeline``: "auto" follows the reference (memory artifacts only without pipeline parallelism or with blocking
+        p2p, core/simu_artifacts.py:9-10); ``True`` also tracks memory under asynchronous pipeline communication (extension:
+        this engine's tracker hangs off the scope events, which do not depend on the p2p mode), ``False`` switches it off."""
         from ..sim.runner import run_simulation
-        return run_simulation(self, save_path, merge_lanes=merge_lanes)
+        return run_simulation(self, save_path, merge_lanes=merge_lanes, memory_timeline=memory_timeline)
 
     # search API lives in core/search.py and is mixed in below
 from .search import SearchMixin  # noqa: E402

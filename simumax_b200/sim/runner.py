@@ -78,11 +78,12 @@ def simulate_schedule(perf, return_schedules: bool = False):
     return total, records
 
 
-def run_simulation(perf, save_path, merge_lanes: bool = True, quiet: bool = False) -> dict:
+def run_simulation(perf, save_path, merge_lanes: bool = True, quiet: bool = False, memory_timeline="auto") -> dict:
     st = perf.strategy
     t0 = time.time()
     os.makedirs(save_path, exist_ok=True)
-    tracker = SimuMemoryTracker() if should_enable_memory_timeline(st) else None
+    want_mem = should_enable_memory_timeline(st) if memory_timeline == "auto" else bool(memory_timeline)
+    tracker = SimuMemoryTracker() if want_mem else None
     engine = _build_engine(perf, merge_lanes, tracker, with_optimizer=True)
     end_t = engine.run()
     if not quiet:

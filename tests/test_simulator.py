@@ -132,3 +132,24 @@ def test_async_vpp_perf_via_simulation_extension():
     assert 0 <= end - t_async < 5.0          # the full replay adds the optimizer-side world barrier, nothing else
     total, records = ext._compute_pp_total_time(return_schedules=True)
     assert len(records) == 4 and all(any(r["kind"] == "F" for r in rows) and any(r["kind"] == "B" for r in rows) for rows in records)
+
+
+def test_memory_timeline_under_async_pipeline_extension(tmp_path):
+    """The reference writes no memory artifacts when pipeline p2p is asynchronous; opt-in here, and the simulated per-stage peaks
+    equal the analytic ones."""
+    import contextlib
+    import io
+
+    from helpers import build
+    from simumax_b200.core.utils import parse_bytes
+    p = build("tp1_pp2_dp4_mbs1", "llama3-8b", "b200_nominal", 8, pp_size=4, micro_batch_num=8, pp_comm_async=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        plain = p.simulate(str(tmp_path / "a"))
+        ext = p.simulate(str(tmp_path / "b"), memory_timeline=True)
+    assert "memory" not in plain and not (tmp_path / "a" / "simu_memory_result.json").exists()
+    assert (tmp_path / "b" / "simu_memory_viz_snapshot.pickle").exists()
+    sim = sorted(ext["memory"]["peak_allocated_bytes_by_rank"].values())
+    mem = p.analysis_mem().data
+    ana = {k: parse_bytes(v["peak_mem"]) for k, v in mem.items() if isinstance(v, dict) and "peak_mem" in v}
+    assert abs(max(sim) - max(ana.values())) < 1e-3 * max(sim)
+    assert abs(plain["end_time_ms"] - ext["end_time_ms"]) < 1e-9
