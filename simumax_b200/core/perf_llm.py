@@ -791,6 +791,39 @@ class PerfLLM(PerfBase):
         self.run_estimate()
         return self.analysis(save_path=save_path, console_log=console_log)
 
+    def estimate_dualpipe(self, model_name=None) -> dict:
+        """DualPipe / ZB1P what-if for the configured job (extension: the reference ships the closed forms in pp_simu/utils.py
+        but does not connect them to the model).  Takes one stage chunk's evaluated ops: F = forward compute + collectives,
+        B = full backward, W = its weight-gradient part, and the mutually overlapped F&B pair layer by layer (compute of one
+        direction hides the expert / tensor-parallel collectives of the other); returns bubbles, durations and MFUs of 1F1B,
+        ZB1P and DualPipe for the strategy's ``pp_size`` and ``micro_batch_num`` (schedule time only, no optimizer)."""
+        from ..pp_simu.utils import cal_FandB_multi_layers, perf_dualpp
+        if model_name is None:       # the slowest stage paces a pipeline; the closed forms assume identical stages
+            model_name = max(self.model_chunk_dict, key=lambda k: self._compute_single_batch_fwd_bwd_time(k, chunk=True))
+        chunk = self.model_chunk_dict[model_name]
+        s = self.strategy
+        per_layer = {}
+        f = b = w = 0.0
+        for n in chunk.nodes:
+            c = n.cost
+            nf = c.fwd_compute_time
+            nb = c.bwd_grad_act_time + c.bwd_grad_w_time + c.recompute_compute_time
+            cf, cb = c.fwd_net_time, c.bwd_grad_act_net_time + c.bwd_grad_w_net_time + c.recompute_net_time
+            f += nf + cf
+            b += nb + cb
+            w += c.bwd_grad_w_time
+            acc = per_layer.setdefault(n.layer_idx if isinstance(n.layer_idx, int) and n.layer_idx >= 0 else -1, [0.0, 0.0, 0.0, 0.0])
+            acc[0] += nf; acc[1] += nb; acc[2] += cf; acc[3] += cb
+        layers = [v for _, v in sorted(per_layer.items())]
+        fb = cal_FandB_multi_layers([v[0] for v in layers], [v[1] for v in layers], [v[2] for v in layers], [v[3] for v in layers])
+        flops = chunk.get_compute_info().fwd_flops + chunk.get_compute_info().bwd_flops
+        peak = self.system.accelerator.op["matmul"].tflops
+        pp = s.pp_size if s.pp_size % 2 == 0 else s.pp_size + 1
+        out = perf_dualpp(max(pp, 2), s.micro_batch_num, f, b, w, f_and_b=fb["overlapped"], flops_per_microbatch=flops, peak_tflops=peak)
+        out.update({"chunk": model_name, "pp_size_used": max(pp, 2), "f_ms": f, "b_ms": b, "w_ms": w, "f_and_b_overlapped_ms": fb["overlapped"],
+                    "f_and_b_serial_ms": fb["serial"]})
+        return out
+
     def simulate(self, save_path, merge_lanes=True, memory_timeline="auto"):
         """Discrete-event replay of the iteration: Chrome trace + memory timeline artifacts.
 

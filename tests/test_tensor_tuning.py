@@ -34,3 +34,19 @@ def test_grid_searcher_finds_fitting_strategies():
     assert len(top) == 3 and top[0].mfu >= top[1].mfu >= top[2].mfu
     budget = s.system_config.accelerator.mem_gbs * 1024 ** 3
     assert all(h.peak_mem_bytes <= budget and h.strategy.micro_batch_size >= 1 for h in top)
+
+
+def test_dualpipe_what_if_is_wired_to_the_model():
+    """PerfLLM.estimate_dualpipe(): the DualPipe / ZB1P closed forms (pp_simu/utils.py) fed with the evaluated stage chunk."""
+    from helpers import MOE, build
+    p = build("ep4_pp2_dp4_mbs1", "deepseekv2", "b200_nominal", 8, model_over=MOE, pp_size=4, world_size=32, micro_batch_num=16)
+    d = p.estimate_dualpipe()
+    assert d["pp_size_used"] == 4 and d["f_ms"] > 0 and d["b_ms"] > d["f_ms"] > d["w_ms"] > 0
+    assert d["f_and_b_overlapped_ms"] <= d["f_and_b_serial_ms"]
+    assert d["bubble_dualpipe"] < d["bubble_zb1p"] < d["bubble_1f1b"]
+    assert d["mfu_dualpipe"] > d["mfu_zb1p"] > d["mfu_1f1b"] > 0
+    # default = the slowest stage: its 1F1B closed form agrees with the schedule evaluator up to p2p and stage imbalance
+    c = p.analysis_cost().data
+    sched = c["raw"]["schedule_time_ms"]
+    assert d["chunk"] == "last_stage_chunk" and abs(d["duration_1f1b"] - sched) / sched < 0.05
+    assert p.estimate_dualpipe("first_stage_chunk")["duration_1f1b"] < d["duration_1f1b"]
