@@ -114,6 +114,40 @@ class PerfBase:
         if capture_graph:
             self.graph = self.capture(save_path)
         self._run()
+        self._write_debug_points()
+
+    def _write_debug_points(self) -> None:
+        """``debug_points`` (first stage) / ``debug_points_last_stage``: ops whose scope path (``"GPTModel -> ... -> LinearCol"``)
+        or dotted name is listed get their F / B / W / recompute / collective times appended to ``<TMP_PATH>/cost_log.json``
+        (reference base_struct.py:771-800)."""
+        wanted = [(FIRST_CHUNK, self.debug_points or []), (LAST_CHUNK, self.debug_points_last_stage or [])]
+        if not any(points for _, points in wanted):
+            return
+        found = {}
+        for key, points in wanted:
+            chunks = getattr(self, "model_chunk_dict", {})
+            chunk = chunks.get(key) or (chunks.get(FIRST_CHUNK) if key == LAST_CHUNK else None)      # pp = 1: one chunk is both
+            if chunk is None or not points:
+                continue
+            for n in chunk.nodes:
+                hit = next((pt for pt in points if pt in (n.path, n.name) or n.path.endswith(pt) or n.name.endswith(pt)), None)
+                if hit is None:
+                    continue
+                c = n.cost
+                found[f"{key}: {n.path} ({n.name})"] = {"cost_F": c.fwd_compute_time, "cost_B": c.bwd_grad_act_time,
+                                                          "cost_W": c.bwd_grad_w_time, "recompute_F": c.recompute_compute_time,
+                                                          "net_F": c.fwd_net_time, "net_B": c.bwd_grad_act_net_time + c.bwd_grad_w_net_time}
+        if not found:
+            return
+        os.makedirs(TMP_PATH, exist_ok=True)
+        path = os.path.join(TMP_PATH, "cost_log.json")
+        try:
+            existing = json.load(open(path, encoding="utf-8")) if os.path.exists(path) else {}
+        except json.JSONDecodeError:
+            existing = {}
+        existing.update(found)
+        with open(path, "w", encoding="utf-8") as fh:
+            json.dump(existing, fh, indent=4, ensure_ascii=False)
 
 
 class PerfLLM(PerfBase):

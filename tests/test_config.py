@@ -83,3 +83,18 @@ def test_command_line_front_end(tmp_path, capsys):
     capsys.readouterr()
     assert main(["list"]) == 0
     assert "llama3-8b" in json.loads(capsys.readouterr().out)["models"]
+
+
+def test_debug_points_write_cost_log(tmp_path, monkeypatch):
+    """configure(debug_points=[...]) -> <TMP_PATH>/cost_log.json with the F / B / W / collective times of the matching ops."""
+    import json
+    import simumax_b200.core.perf_llm as pl
+    from helpers import build
+    monkeypatch.setattr(pl, "TMP_PATH", str(tmp_path))
+    p = build("tp2_pp1_dp4_mbs1", "llama3-8b", "b200_nominal", 2, run=False)
+    p.debug_points = ["self.layer_1.mlp.linear_fc1"]
+    p.debug_points_last_stage = ["parallel_ce"]
+    p.run_estimate()
+    log = json.load(open(tmp_path / "cost_log.json"))
+    (key, rec), = [(k, v) for k, v in log.items() if "linear_fc1" in k]
+    assert "first_stage_chunk" in key and rec["cost_F"] > 0 and rec["cost_W"] > 0 and rec["net_F"] > 0

@@ -29,5 +29,8 @@ timeout 300 python tools/b200/perf_vs_real.py --system b200_sm100a_sustained --c
 echo "== 4. ncu capture of the fused GEMM -> reduce-scatter epilogue + consumer (1 GPU, world = 1)"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:'gemm_2cta|rs_consume' -c 6 -f -o "$OUT/prof_fused" \
     python tools/ncu_fused.py > "$OUT/ncu_fused.log" 2>&1 && python tools/ncu_summary.py "$OUT/prof_fused.ncu-rep" profiles/gemm_rs_fused_ncu_summary.json
+echo "== 4b. compute-sanitizer memcheck over the elementwise kernels (the GEMM / attention passes take ~10 min each: tools/sanitize_kernels.sh)"
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 66 --print-limit 5 python -m pytest tests/test_elementwise_gpu.py -q -m gpu -x \
+    > "$OUT/sanitize_memcheck_elementwise.log" 2>&1; echo "   rc=$? $(grep -c 'ERROR SUMMARY: 0 errors' "$OUT/sanitize_memcheck_elementwise.log") clean"
 echo "== 5. opt-in GPU test"
 SMX_TEST_PP=1 timeout 300 python -m pytest tests/test_collectives_gpu.py -q -m gpu -k pipeline 2>&1 | tail -2
