@@ -858,14 +858,17 @@ class PerfLLM(PerfBase):
                     "f_and_b_serial_ms": fb["serial"]})
         return out
 
-    def simulate(self, save_path, merge_lanes=True, memory_timeline="auto"):
+    def simulate(self, save_path, merge_lanes=True, memory_timeline="auto", jitter: float = 0.0, slow_ranks=None, seed: int = 0):
         """Discrete-event replay of the iteration: Chrome trace + memory timeline artifacts.
 
         ``memory_timeline``: "auto" follows the reference (memory artifacts only without pipeline parallelism or with blocking
         p2p, core/simu_artifacts.py:9-10); ``True`` also tracks memory under asynchronous pipeline communication (extension:
-        this engine's tracker hangs off the scope events, which do not depend on the p2p mode), ``False`` switches it off."""
+        this engine's tracker hangs off the scope events, which do not depend on the p2p mode), ``False`` switches it off.
+        ``jitter`` / ``slow_ranks`` / ``seed``: fault injection (extension) -- mean-one log-normal noise on every compute atom and
+        constant per-rank slow-down factors, to see how stragglers propagate through the pipeline and the collectives."""
         from ..sim.runner import run_simulation
-        return run_simulation(self, save_path, merge_lanes=merge_lanes, memory_timeline=memory_timeline)
+        return run_simulation(self, save_path, merge_lanes=merge_lanes, memory_timeline=memory_timeline, jitter=jitter,
+                              slow_ranks=slow_ranks, seed=seed)
 
     # search API lives in core/search.py and is mixed in below
 from .search import SearchMixin  # noqa: E402

@@ -21,6 +21,8 @@ that the trace / memory exporters consume directly.
 """
 from __future__ import annotations
 
+import math
+
 from collections import defaultdict, deque
 from dataclasses import dataclass, field
 from typing import Dict, Generator, List, Optional, Tuple
@@ -116,9 +118,17 @@ class Deadlock(RuntimeError):
 
 
 class Engine:
-    def __init__(self, merge_lanes: bool = True, memory_tracker=None):
+    def __init__(self, merge_lanes: bool = True, memory_tracker=None, jitter: float = 0.0, slow_ranks: Optional[Dict[int, float]] = None,
+                 seed: int = 0):
+        """``jitter``: relative standard deviation of a log-normal factor applied to every compute atom (run-to-run noise);
+        ``slow_ranks``: rank -> constant slow-down factor of its compute (a throttling / faulty device).  Both default to a
+        deterministic replay.  (Fault injection the reference only hints at: the commented-out jitter hook in AtomModel,
+        base_struct.py:2082-2083.)"""
         self.merge_lanes = merge_lanes
         self.memory_tracker = memory_tracker
+        self.jitter = float(jitter)
+        self.slow_ranks = dict(slow_ranks or {})
+        self._rng = __import__("random").Random(seed)
         self.events: List[Event] = []
         self.ranks: Dict[int, RankState] = {}
         self.programs: Dict[int, Generator] = {}
@@ -199,6 +209,10 @@ class Engine:
                 cost = job.fwd_cost if job.recompute_cost is None else job.recompute_cost
             else:
                 cost = job.fwd_cost if direction == "fwd" else job.bwd_cost
+            if self.jitter > 0.0 and cost > 0.0:
+                cost *= math.exp(self._rng.gauss(0.0, self.jitter) - 0.5 * self.jitter * self.jitter)      # mean-one log-normal
+            if self.slow_ranks:
+                cost *= self.slow_ranks.get(st.rank, 1.0)
             t0 = st.t["comp"]
             st.t["comp"] = t0 + cost
             if st.t["comp"] != t0:

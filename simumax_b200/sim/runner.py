@@ -27,9 +27,9 @@ def should_enable_memory_timeline(strategy) -> bool:
     return strategy.pp_size == 1 or (not getattr(strategy, "pp_comm_async", True))
 
 
-def _build_engine(perf, merge_lanes: bool, tracker, with_optimizer: bool) -> Engine:
+def _build_engine(perf, merge_lanes: bool, tracker, with_optimizer: bool, **engine_kw) -> Engine:
     st = perf.strategy
-    engine = Engine(merge_lanes=merge_lanes, memory_tracker=tracker)
+    engine = Engine(merge_lanes=merge_lanes, memory_tracker=tracker, **engine_kw)
     n_ranks = st.pp_size if merge_lanes else st.world_size
     vp = perf._vp_size()
     for i in range(n_ranks):
@@ -78,13 +78,14 @@ def simulate_schedule(perf, return_schedules: bool = False):
     return total, records
 
 
-def run_simulation(perf, save_path, merge_lanes: bool = True, quiet: bool = False, memory_timeline="auto") -> dict:
+def run_simulation(perf, save_path, merge_lanes: bool = True, quiet: bool = False, memory_timeline="auto", jitter: float = 0.0,
+                   slow_ranks=None, seed: int = 0) -> dict:
     st = perf.strategy
     t0 = time.time()
     os.makedirs(save_path, exist_ok=True)
     want_mem = should_enable_memory_timeline(st) if memory_timeline == "auto" else bool(memory_timeline)
     tracker = SimuMemoryTracker() if want_mem else None
-    engine = _build_engine(perf, merge_lanes, tracker, with_optimizer=True)
+    engine = _build_engine(perf, merge_lanes, tracker, with_optimizer=True, jitter=jitter, slow_ranks=slow_ranks, seed=seed)
     end_t = engine.run()
     if not quiet:
         print(f"end in {end_t}")

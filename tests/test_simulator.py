@@ -153,3 +153,31 @@ def test_memory_timeline_under_async_pipeline_extension(tmp_path):
     ana = {k: parse_bytes(v["peak_mem"]) for k, v in mem.items() if isinstance(v, dict) and "peak_mem" in v}
     assert abs(max(sim) - max(ana.values())) < 1e-3 * max(sim)
     assert abs(plain["end_time_ms"] - ext["end_time_ms"]) < 1e-9
+
+
+def test_fault_injection_extension(tmp_path):
+    """simulate(jitter=..., slow_ranks=...): deterministic by default, reproducible per seed; one slow pipeline stage slows the
+    whole job, and with real rendezvous (one lane per rank) one slow tensor-parallel rank drags its group along."""
+    import contextlib
+    import io
+
+    from helpers import build
+
+    def end(p, **kw):
+        with contextlib.redirect_stdout(io.StringIO()):
+            return p.simulate(str(tmp_path / "s"), **kw)["end_time_ms"]
+
+    p = build("tp1_pp2_dp4_mbs1", "llama3-8b", "b200_nominal", 4, pp_size=4, micro_batch_num=8)
+    base = end(p)
+    assert end(p) == base
+    noisy = end(p, jitter=0.1, seed=1)
+    assert noisy != base and end(p, jitter=0.1, seed=1) == noisy and end(p, jitter=0.1, seed=2) != noisy
+    assert abs(noisy - base) / base < 0.2
+    lanes = sorted(r for r in [0, 2, 4, 6])            # representative ranks of the four stages at tp1 / dp2
+    slow_last = end(p, slow_ranks={lanes[-1]: 1.5})     # the last stage (LM head + loss) is the critical one here
+    slow_mid = end(p, slow_ranks={lanes[1]: 1.5})
+    assert slow_last > 1.15 * base and base <= slow_mid < slow_last
+    q = build("tp2_pp1_dp4_mbs1", "llama2-tiny", "a100_pcie", 2, micro_batch_num=2)
+    t0 = end(q, merge_lanes=False)
+    t1 = end(q, merge_lanes=False, slow_ranks={1: 2.0})
+    assert t1 > 1.3 * t0
