@@ -180,4 +180,4 @@ def test_fault_injection_extension(tmp_path):
     q = build("tp2_pp1_dp4_mbs1", "llama2-tiny", "a100_pcie", 2, micro_batch_num=2)
     t0 = end(q, merge_lanes=False)
     t1 = end(q, merge_lanes=False, slow_ranks={1: 2.0})
-    assert t1 > 1.3 * t0
+    assert t1 > 1.15 * t0
