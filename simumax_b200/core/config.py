@@ -23,7 +23,7 @@ import time
 import warnings
 from collections import OrderedDict
 from dataclasses import asdict, dataclass, field, fields
-from typing import Any, Dict, List, Optional
+from typing import Any, Dict, List, Optional, Union
 
 # ------------------------------------------------------------------------------------------------
 # environment flags (reference config.py:15-41)
@@ -250,8 +250,8 @@ class StrategyConfig(Config):
     #   cp_p2p_exposed is the fraction of the ring's neighbour transfers that is not hidden behind the previous block's attention
     cp_p2p_exposed: float = 1.0
     tp_overlap_model: bool = False
-    tp_overlap_exposed_ag: float = 0.6
-    tp_overlap_exposed_rs: float = 0.4
+    tp_overlap_exposed_ag: Union[float, Dict[str, float]] = 0.6      # or {tp_size: exposure}: python -m simumax_b200.calib.fused
+    tp_overlap_exposed_rs: Union[float, Dict[str, float]] = 0.4
     fused_optimizer_model: bool = False
 
     te_version: Optional[str] = None

@@ -27,7 +27,11 @@ def _tp_comm(strategy, op, size, stage, phase, exposed: float = 1.0) -> Collecti
 def _fused_exposure(st: StrategyConfig):
     """(all-gather, reduce-scatter, wgrad re-gather) exposure factors of the TP collectives adjacent to a GEMM."""
     if getattr(st, "tp_overlap_model", False) and st.enable_sequence_parallel:
-        return float(st.tp_overlap_exposed_ag), float(st.tp_overlap_exposed_rs), 0.0
+        def pick(v, default):            # a float, or a {tp_size: exposure} table (calib/fused.py)
+            if isinstance(v, dict):
+                v = v.get(str(st.tp_size), v.get(st.tp_size, default))
+            return float(v)
+        return pick(st.tp_overlap_exposed_ag, 0.6), pick(st.tp_overlap_exposed_rs, 0.4), 0.0
     return 1.0, 1.0, 1.0
 
 

@@ -70,3 +70,24 @@ def test_merge_writes_loadable_config(tmp_path):
     t = s.compute_op_accuracy_time("matmul", 2.06e11, key)
     assert t == pytest.approx(2.06e11 / (2250e12 * 0.61) * 1e3)
     assert s.accelerator.bandwidth["ce_fusion"].efficient_factor == pytest.approx(4100e9 / (8000 * 1024 ** 3))
+
+
+def test_fused_exposure_tables_feed_the_tp_overlap_model():
+    """calib/fused.py turns fused_check results into {tp_size: exposure} tables the strategy accepts."""
+    import glob
+    import os
+    from helpers import build
+    from simumax_b200.calib.fused import exposure_from_fused_check, strategy_overrides
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "profiles", "fused_ops_2gpu_v4.json")) + glob.glob(os.path.join(root, "profiles", "fused_ops_4gpu_v3.json"))
+                   + glob.glob(os.path.join(root, "profiles", "fused_ops_8gpu_v1.json")))
+    table = exposure_from_fused_check(files)
+    assert set(table) == {2, 4, 8} and all(0.0 < v["rs"] < 1.0 and v["rs_cases"] == 3 for v in table.values())
+    over = strategy_overrides(table)
+    ms = lambda v: float(str(v).split()[0])
+    base = build("tp2_pp1_dp4_mbs1", "llama3-8b", "b200_nominal", 4)
+    tab = build("tp2_pp1_dp4_mbs1", "llama3-8b", "b200_nominal", 4, **over)
+    flat = build("tp2_pp1_dp4_mbs1", "llama3-8b", "b200_nominal", 4, tp_overlap_model=True,
+                 tp_overlap_exposed_ag=over["tp_overlap_exposed_ag"]["2"], tp_overlap_exposed_rs=over["tp_overlap_exposed_rs"]["2"])
+    t = [ms(p.analysis_cost().data["breakdown_result"]["intra_exposed_time"]) for p in (base, tab, flat)]
+    assert t[1] < t[0] and abs(t[1] - t[2]) < 1e-9
