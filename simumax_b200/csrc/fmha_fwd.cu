@@ -52,7 +52,10 @@ struct FmhaParams {
   long long lse_stride_b, lse_stride_h;           // elements (lse is [B, H, S_q] fp32)
 };
 
-template <int D_QK, int D_V>
+// P_TMEM (experimental, SMX_FMHA_P_TMEM=1): the probabilities never touch shared memory -- the softmax threads write them as
+// packed bf16 into 32 TMEM columns with tcgen05.st and the P V product takes its A operand from TMEM (tcgen05.mma [d], [a], b-desc).
+// Saves the 16 KB smem store and 16 KB of operand reads per key tile of a kernel that is shared-memory-bandwidth bound.
+template <int D_QK, int D_V, bool P_TMEM = false>
 __global__ void __launch_bounds__(kFmhaThreads, (D_QK <= 128 ? 2 : 1))
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ o_ptr,
@@ -112,6 +115,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t tmem_base = *tmem_base_ptr;
   const uint32_t tmem_s = tmem_base;          // columns [0, 64)
   const uint32_t tmem_o = tmem_base + 64;     // columns [64, 64 + D_V)
+  const uint32_t tmem_p = tmem_base + 64 + D_V;   // P_TMEM only: 32 columns of packed bf16 pairs (64 keys)
+  static_assert(!P_TMEM || 64 + D_V + 32 <= Cfg::kTmemCols, "no TMEM columns left for P");
 
   if (warp_idx == 0) {
     // ============================ TMA producer ============================
@@ -180,8 +185,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (elect_one()) {
         const uint64_t b0 = kV_mn + stage * kStageStep;
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)
-          umma_f16<1>(tmem_o, kP_km + k * 2, b0 + k * ((16 * 128) >> 4), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < BKV / 16; ++k) {
+          if constexpr (P_TMEM)      // 16 keys = 8 packed columns per K step
+            umma_f16_ts(tmem_o, tmem_p + k * 8, b0 + k * ((16 * 128) >> 4), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          else
+            umma_f16<1>(tmem_o, kP_km + k * 2, b0 + k * ((16 * 128) >> 4), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        }
         umma_commit<1>(pv_done);
         umma_commit<1>(&kv_empty[stage]);
       }
@@ -256,6 +265,23 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       m_used = m_new;
       const float mc = (m_used == -INFINITY) ? 0.f : m_used * c_log2;
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      if constexpr (P_TMEM) {
+        // P row -> packed bf16 pairs -> 32 TMEM columns of this thread's lane (keys 2c, 2c+1 in column c)
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float e0 = exp2f(__uint_as_float(r[2 * c]) * c_log2 - mc);
+          const float e1 = exp2f(__uint_as_float(r[2 * c + 1]) * c_log2 - mc);
+          sum4[c & 3] += e0 + e1;
+          pk[c] = pack_bf16x2(e0, e1);
+        }
+        l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+        tmem_st_32x32b_x16(tmem_p + lane_addr, *reinterpret_cast<uint32_t(*)[16]>(&pk[0]));
+        tmem_st_32x32b_x16(tmem_p + lane_addr + 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+      } else {
       // P row -> bf16 -> 128B-swizzled K-major smem tile [128 rows][64 kv]
       uint8_t* prow = sP + row_in_tile * 128;
 #pragma unroll
@@ -277,6 +303,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       fence_proxy_async_smem();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tcgen05_fence_before();
       __syncwarp();
+      }
       if (lane == 0) mbar_arrive(p_full);
     }
     // ---- epilogue
@@ -341,11 +368,11 @@ inline int make_tmap_4d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t
   return 0;
 }
 
-template <int D_QK, int D_V>
+template <int D_QK, int D_V, bool P_TMEM = false>
 int launch_fmha_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, void* o, float* lse,
                     const FmhaParams& p, cudaStream_t stream) {
   using Cfg = FmhaCfg<D_QK, D_V>;
-  auto kern = fmha_fwd_kernel<D_QK, D_V>;
+  auto kern = fmha_fwd_kernel<D_QK, D_V, P_TMEM>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -381,6 +408,8 @@ int smx_fmha_fwd(const void* q, const void* k, const void* v, void* o, float* ls
   p.B = B; p.S_q = S_q; p.S_kv = S_kv; p.H = H; p.H_kv = H_kv; p.scale = scale; p.causal = causal;
   p.o_stride_b = o_sb; p.o_stride_s = o_ss; p.o_stride_h = o_sh;
   p.lse_stride_b = (long long)H * S_q; p.lse_stride_h = S_q;
+  static const bool p_tmem = [] { const char* e = getenv("SMX_FMHA_P_TMEM"); return e && e[0] == '1'; }();
+  if (d_qk == 128 && d_v == 128 && p_tmem) return smx::launch_fmha_fwd<128, 128, true>(tq, tk, tv, o, lse, p, stream);
   if (d_qk == 128 && d_v == 128) return smx::launch_fmha_fwd<128, 128>(tq, tk, tv, o, lse, p, stream);
   if (d_qk == 64 && d_v == 64) return smx::launch_fmha_fwd<64, 64>(tq, tk, tv, o, lse, p, stream);
   if (d_qk == 192 && d_v == 128) return smx::launch_fmha_fwd<192, 128>(tq, tk, tv, o, lse, p, stream);

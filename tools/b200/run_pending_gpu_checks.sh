@@ -32,5 +32,9 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:'gem
 echo "== 4b. compute-sanitizer memcheck over the elementwise kernels (the GEMM / attention passes take ~10 min each: tools/sanitize_kernels.sh)"
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 66 --print-limit 5 python -m pytest tests/test_elementwise_gpu.py -q -m gpu -x \
     > "$OUT/sanitize_memcheck_elementwise.log" 2>&1; echo "   rc=$? $(grep -c 'ERROR SUMMARY: 0 errors' "$OUT/sanitize_memcheck_elementwise.log") clean"
+echo "== 4c. experimental attention forward with P in TMEM (tcgen05.st + TMEM-A MMA): correctness, then A/B timing"
+SMX_FMHA_P_TMEM=1 timeout 300 python -m pytest tests/test_attention_gpu.py -q -m gpu -x 2>&1 | tail -2
+timeout 200 python tools/fmha_bench.py > "$OUT/fmha_fwd_smem_p.log" 2>&1; SMX_FMHA_P_TMEM=1 timeout 200 python tools/fmha_bench.py > "$OUT/fmha_fwd_tmem_p.log" 2>&1
+tail -3 "$OUT/fmha_fwd_smem_p.log" "$OUT/fmha_fwd_tmem_p.log"
 echo "== 5. opt-in GPU test"
 SMX_TEST_PP=1 timeout 300 python -m pytest tests/test_collectives_gpu.py -q -m gpu -k pipeline 2>&1 | tail -2
