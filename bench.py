@@ -286,6 +286,19 @@ def main():
         }
         if pred and "tokens_per_s" in pred:
             out["prediction_error_pct"] = 100.0 * (pred["tokens_per_s"] - value) / value
+        try:     # achieved model FLOP rate against the driver-measured cuBLAS bf16 throughput (MEASURED_PEAKS.json)
+            peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {"bf16_tflops": 1671.6, "bf16_tflops_sustained": 1391.5,
+                                                                                    "note": "fallback: profiling recipe values"}
+            mc.layer_num = dims.layers
+            tf = value * mc.flops_per_token(S / 2) / 1e12 / world          # causal attention: half the S x S scores are computed
+            out["roofline"] = {"model_tflops_per_gpu": tf, "model_tflops_per_gpu_full_attention_convention": value * mc.flops_per_token(S) / 1e12 / world,
+                               "cublas_bf16_tflops_burst": peaks.get("bf16_tflops"),
+                               "cublas_bf16_tflops_sustained": peaks.get("bf16_tflops_sustained"),
+                               "fraction_of_sustained_cublas": tf / peaks["bf16_tflops_sustained"] if peaks.get("bf16_tflops_sustained") else None,
+                               "fraction_of_nominal_2250": tf / 2250.0}
+        except Exception as e:
+            out["roofline"] = {"error": f"{type(e).__name__}: {e}"}
         if a.layers:
             out["invalid"] = "debug run with --layers override"
         print(json.dumps(out))
