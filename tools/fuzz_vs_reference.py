@@ -60,6 +60,22 @@ def sample(rng: random.Random):
         so["use_fused_grad_accumulation"] = False
     if rng.random() < 0.15:
         so["grad_reduce_in_bf16"] = True
+    r = rng.random()
+    if r < 0.2:            # explicit recompute flavour
+        so["enable_recompute"] = True
+        so["recompute_granularity"] = rng.choice(["full_block", "attn_only", "mlp_only", "sdp_only", "selective_recompute"])
+        so["recompute_layer_num"] = rng.choice([1, 2, 4])
+        if so["recompute_granularity"] == "selective_recompute":
+            for flag in ("attn_recompute", "mla_rms_recompute", "mlp_recompute", "mlp_rms_recompute"):
+                so[flag] = rng.random() < 0.5
+    elif r < 0.32:         # Megatron-0.14 style module list
+        mods = ["layernorm", "core_attn", "mlp"] + (["moe", "moe_act", "mla_up_proj", "shared_experts"] if moe else [])
+        so.update(enable_recompute=True, recompute_granularity="selective_recompute", recompute_layer_num=rng.choice([2, 4]),
+                  megatron_recompute=True, megatron_recompute_modules=rng.sample(mods, rng.randint(1, min(3, len(mods)))))
+    if pp > 1 and rng.random() < 0.2:      # interleaved (virtual) stages, blocking p2p: the only VPP flavour perf() supports
+        so.update(interleaving_size=2, pp_comm_async=False, micro_batch_num=rng.choice([2 * pp, 4 * pp]))
+    if rng.random() < 0.1:
+        so["recompute_variance"] = True
     layers = rng.choice([4, 6, 8, 12])
     mo = dict(CAP) if moe and rng.random() < 0.8 else {}
     return (base, model, layers, mo, so)
