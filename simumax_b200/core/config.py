@@ -560,6 +560,10 @@ class AcceleratorConfig:
     bandwidth: Dict[str, BandwidthConfig]
     op: Dict[str, CompOpConfig]
     mode: str
+    # extension over the reference schema (absent / 0 = reference behaviour): a constant added to every op phase that
+    # launches a kernel -- launch gap + prologue / tail the roofline does not see (the reference always
+    # under-predicts time; a per-op launch term calibrated on the box is the most direct correction)
+    kernel_launch_overhead_us: float = 0.0
 
 
 @dataclass
@@ -614,6 +618,7 @@ class SystemConfig(Config):
         intra_with_pcie = nets.pop("intra_with_pcie") if "intra_with_pcie" in nets else False
         accelerator = AcceleratorConfig(
             backend=acc["backend"], mem_gbs=acc["mem_gbs"], mode=acc["mode"],
+            kernel_launch_overhead_us=float(acc.get("kernel_launch_overhead_us", 0.0)),
             bandwidth={k: BandwidthConfig(**v) for k, v in acc["bandwidth"].items()},
             op={k: CompOpConfig(**v) for k, v in acc["op"].items()})
         networks = {
@@ -642,6 +647,8 @@ class SystemConfig(Config):
             "op": {k: drop_none(asdict(v)) for k, v in acc.op.items()},
             "bandwidth": {k: drop_none(asdict(v)) for k, v in acc.bandwidth.items()},
             "mode": acc.mode}
+        if acc.kernel_launch_overhead_us:
+            out["accelerator"]["kernel_launch_overhead_us"] = acc.kernel_launch_overhead_us
         out["networks"] = nets
         return out
 

@@ -142,12 +142,17 @@ def evaluate(node: OpNode, system: SystemConfig) -> OpNode:
         cost.recompute_net_time = 0
         cost.recompute_net_exposed_time = 0
 
+    launch_ms = getattr(system.accelerator, "kernel_launch_overhead_us", 0.0) / 1e3
+
     def phase_time(phase, flops, nbytes):
         op_name = node.ops[phase]
         cd = system.compute_op_accuracy_time(op_name, flops, shape_desc=node.shape_key(phase), reture_detail=True)
         io = system.compute_mem_access_time(op_name, nbytes, reture_detail=True)
         node.details[phase] = {"compute_details": cd, "io_details": io}
-        return system.compute_end2end_time(compute_time=cd["compute_only_time"], mem_time=io["io_time"])
+        t = system.compute_end2end_time(compute_time=cd["compute_only_time"], mem_time=io["io_time"])
+        if launch_ms and (flops or nbytes):
+            t += launch_ms                    # extension: per-kernel launch gap (0 unless the system config sets it)
+        return t
 
     cost.fwd_compute_time = phase_time("fwd", c.fwd_flops, c.fwd_accessed_mem)
     cost.bwd_grad_act_time = phase_time("bwd_grad_act", c.bwd_grad_act_flops, c.bwd_grad_act_accessed_mem)

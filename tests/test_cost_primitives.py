@@ -108,3 +108,27 @@ def test_context_parallel_flavours_extension():
     assert a2a[2] == ag[2] == ring[2]                     # identical model FLOPs
     assert ring[1] < a2a[1] and hidden[1] < ring[1]       # neighbour transfers are cheaper than the all-to-alls; hiding them helps
     assert all(0.8 * a2a[0] < x[0] < 1.2 * a2a[0] for x in (ag, ring, hidden))
+
+
+def test_kernel_launch_overhead_extension(tmp_path):
+    """accelerator.kernel_launch_overhead_us (default 0 = reference): a constant per kernel-launching op phase; survives the
+    config round trip and scales with the op count, not with the problem size."""
+    import json
+    from helpers import build
+    from simumax_b200.configs import get_simu_system_config
+    from simumax_b200.core.config import SystemConfig
+    base = json.load(open(get_simu_system_config("b200_nominal")))
+    assert "kernel_launch_overhead_us" not in base["accelerator"]
+    base["accelerator"]["kernel_launch_overhead_us"] = 5.0
+    base["sys_name"] = "b200_launch5"
+    path = tmp_path / "sys.json"
+    path.write_text(json.dumps(base))
+    assert SystemConfig.init_from_config_file(str(path)).to_config_dict()["accelerator"]["kernel_launch_overhead_us"] == 5.0
+    ms = lambda p: float(str(p.analysis_cost().data["duration_time_per_iter"]).split()[0])
+    plain = build("tp8_pp1_dp1_mbs1", "llama3-8b", "b200_nominal", 8, micro_batch_num=4)
+    slow = build("tp8_pp1_dp1_mbs1", "llama3-8b", str(path), 8, micro_batch_num=4)
+    ops = sum(1 for n in plain.model_chunk_dict["first_stage_chunk"].nodes for ph in ("fwd", "bwd_grad_act", "bwd_grad_w")
+              if getattr(n.compute, {"fwd": "fwd_flops", "bwd_grad_act": "bwd_grad_act_flops", "bwd_grad_w": "bwd_grad_w_flops"}[ph])
+              or getattr(n.compute, {"fwd": "fwd_accessed_mem", "bwd_grad_act": "bwd_grad_act_accessed_mem", "bwd_grad_w": "bwd_grad_w_accessed_mem"}[ph]))
+    extra = ms(slow) - ms(plain)
+    assert abs(extra - 4 * ops * 5e-3) < 0.02 * extra and extra > 1.0
