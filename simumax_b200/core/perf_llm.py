@@ -492,11 +492,11 @@ class PerfLLM(PerfBase):
         return MIDDLE_CHUNK
 
     def _vpp_stage_result_key(self, pp_rank: int):
-        if pp_rank == 0:
+        if self.strategy.pp_size <= 1 or pp_rank == 0:
             return "first_stage"
         if pp_rank == self.strategy.pp_size - 1:
             return "last_stage"
-        return f"middle_stage_{pp_rank}"
+        return f"pp_stage_{pp_rank}"            # reference perf_llm.py:1688-1693
 
     def get_pp_stage_peak_mem(self, mem_result, peak_mem_key, toG: bool = False):
         assert peak_mem_key in ("peak_mem_with_reserved", "peak_mem"), \

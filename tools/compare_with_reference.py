@@ -45,6 +45,10 @@ CASES = [
      {"recompute_granularity": "selective_recompute", "recompute_layer_num": 4, "megatron_recompute": True,
       "megatron_recompute_modules": ["moe"]}),
     ("ep4_pp2_dp4_mbs1", "deepseekv2", 4, {"moe_pad_expert_input_to_capacity": True, "capacity": 1}, {"etp_size": 2, "ep_size": 2, "fp8": True}),
+    # found by tools/fuzz_vs_reference.py: interleaved stages with pp > 2 (memory result keys of the middle ranks)
+    ("ep4_pp2_dp4_mbs1", "mixtral-8x7b", 8, {"moe_pad_expert_input_to_capacity": True, "capacity": 1},
+     {"world_size": 8, "pp_size": 4, "ep_size": 1, "tp_size": 1, "etp_size": 1, "enable_sequence_parallel": False, "seq_len": 16384,
+      "micro_batch_size": 1, "micro_batch_num": 16, "te_version": "2.11.0", "interleaving_size": 2, "pp_comm_async": False}),
 ]
 
 
