@@ -40,6 +40,24 @@ def sample(rng):
         so["recompute_layer_num"] = rng.choice([1, 2])
     if rng.random() < 0.2:
         so["seq_len"] = rng.choice([2048, 8192])
+    r = rng.random()
+    if r < 0.25 and "vp2" not in base:
+        so["enable_recompute"] = True
+        so["recompute_granularity"] = rng.choice(["full_block", "attn_only", "mlp_only", "sdp_only", "selective_recompute"])
+        so["recompute_layer_num"] = rng.choice([1, 2])
+        if so["recompute_granularity"] == "selective_recompute":
+            for flag in ("attn_recompute", "mlp_recompute", "mlp_rms_recompute"):
+                so[flag] = rng.random() < 0.5
+    elif r < 0.35 and "vp2" not in base:
+        so["enable_recompute"] = False
+    if not moe and so.get("tp_size", 1) > 1 and rng.random() < 0.3:
+        so["enable_sequence_parallel"] = False
+    if not moe and "vp2" not in base and rng.random() < 0.15:
+        so.update(cp_size=2, seq_len=8192, cp_a2a_mode=rng.choice(["sync_cp", "async_cp"]))
+    if moe and rng.random() < 0.5:
+        so["dispatch_probs"] = True
+    if rng.random() < 0.2:
+        so["micro_batch_size"] = 2
     layers = rng.choice([4, 8]) if "vp2" not in base else 8
     return (base, model, system, layers, dict(MOE) if moe else {}, so, True)
 

@@ -76,8 +76,26 @@ def sample(rng: random.Random):
         so.update(interleaving_size=2, pp_comm_async=False, micro_batch_num=rng.choice([2 * pp, 4 * pp]))
     if rng.random() < 0.1:
         so["recompute_variance"] = True
+    # rarely used switches
+    for key, prob, values in (("use_flash_sdp", 0.08, [False]), ("use_math_sdp", 0.05, [True]), ("enable_dropout", 0.05, [True]),
+                              ("use_fused_norm", 0.05, [False]), ("use_fused_swiglu", 0.05, [False]), ("use_accm_weight", 0.05, [False]),
+                              ("use_fp32_accum_grad", 0.05, [False]), ("attention_sparse_ratio", 0.05, [0.25, 0.5]),
+                              ("account_for_embedding_in_pipeline_split", 0.08, [True]), ("account_for_loss_in_pipeline_split", 0.08, [True]),
+                              ("cache_groupgemm_col_fp8_inputs", 0.05, [True]), ("offload_groupgemm_col_inputs", 0.05, [True]),
+                              ("enable_straggler_model", 0.2, [False]), ("overlap_grad_reduce", 0.1, [False]), ("zero_state", 0.05, [2, 3])):
+        if rng.random() < prob:
+            so[key] = rng.choice(values)
+    if pp > 1 and rng.random() < 0.15:
+        so["num_layers_in_last_pipeline_stage"] = rng.choice([1, 2])
+    if pp > 1 and rng.random() < 0.1:
+        so["num_layers_in_first_pipeline_stage"] = rng.choice([1, 2])
+    if moe and rng.random() < 0.1:
+        mo_extra = {"group_linear_mode": "sequential"}
+    else:
+        mo_extra = {}
     layers = rng.choice([4, 6, 8, 12])
     mo = dict(CAP) if moe and rng.random() < 0.8 else {}
+    mo.update(mo_extra)
     return (base, model, layers, mo, so)
 
 
@@ -85,11 +103,12 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 60
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     rng = random.Random(seed)
-    system = os.environ.get("SYSTEM", "b200_bf16_ceperm")
+    systems = [os.environ["SYSTEM"]] if os.environ.get("SYSTEM") else ["b200_bf16_ceperm", "b200_bf16_ceperm", "a100_pcie"]
     stats = {"identical": 0, "both_reject": 0, "diff": 0}
     diffs = []
     for i in range(n):
         case = sample(rng)
+        system = rng.choice(systems)
         res = []
         for impl in ("ref", "new"):
             try:
@@ -104,7 +123,7 @@ def main():
         else:
             stats["diff"] += 1
             diffs.append({"case": case, "ref": a, "new": b})
-            print("DIFF", i, json.dumps(case))
+            print("DIFF", i, system, json.dumps(case))
             print("   ref:", json.dumps(a)[:600])
             print("   new:", json.dumps(b)[:600])
     print(json.dumps(stats))
