@@ -96,7 +96,7 @@ def linear_col(st: StrategyConfig, in_features, out_features, in_shape, name, *,
     out_shape = ishape([B, s_full, out_local])
     out_numel = B * out_shape[1] * out_local
     node = OpNode(name=name, kind="LinearCol", display=display, layer_idx=layer_idx,
-                  in_shapes=[ishape(in_shape)], out_shapes=[out_shape], in_bytes=numel(in_shape) * DT["bf16"],
+                  in_shapes=[ishape(in_shape)], out_shapes=[out_shape], in_bytes=numel(in_shape) * (1 if fp8 else DT["bf16"]),
                   weight_shape=[int(out_local), int(in_features)], enable_recompute=enable_recompute)
     use_var = bool(st.recompute_variance) or use_variance_tail_model
     if is_last_recompute and enable_recompute and use_var:
@@ -166,7 +166,7 @@ def linear_row(st: StrategyConfig, in_features, out_features, in_shape, name, *,
     tokens_x_in = B * S * Hin
     out_numel_full = B * out_shape[1] * out_features * (st.tp_size if st.enable_sequence_parallel else 1)
     node = OpNode(name=name, kind="LinearRow", display=display, layer_idx=layer_idx,
-                  in_shapes=[ishape(in_shape)], out_shapes=[out_shape], in_bytes=numel(in_shape) * DT["bf16"],
+                  in_shapes=[ishape(in_shape)], out_shapes=[out_shape], in_bytes=numel(in_shape) * (1 if st.fp8 else DT["bf16"]),
                   weight_shape=[int(out_features), int(in_local)], enable_recompute=enable_recompute)
     use_var = bool(st.recompute_variance) or use_variance_tail_model
     if is_last_recompute and enable_recompute and use_var:

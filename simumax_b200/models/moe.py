@@ -214,7 +214,9 @@ def group_linear(st: StrategyConfig, kind: str, in_features, out_features, local
     assert in_f == Hin, f"input_size {in_f} != hidden_size {Hin}"
     out_shape = ishape([tokens, out_f])
     cls = "GroupLinearCol" if kind == "col" else "GroupLinearRow"
-    in_bytes = numel(in_shape) * DT["bf16"] + sum(numel(s) * b for s, b in extra_inputs)
+    # the input is the quantizer's Float8Tensor under fp8 (1 byte / element): matters when this op opens a recompute segment,
+    # i.e. when the quantizer in front of it is not recomputed (cache_groupgemm_col_fp8_inputs)
+    in_bytes = numel(in_shape) * (1 if st.fp8 else DT["bf16"]) + sum(numel(s) * b for s, b in extra_inputs)
     node = OpNode(name=name, kind=cls, display=cls, layer_idx=layer_idx,
                   in_shapes=[ishape(in_shape)] + [ishape(s) for s, _ in extra_inputs], out_shapes=[out_shape],
                   in_bytes=in_bytes, weight_shape=[int(out_f), int(in_f)], enable_recompute=enable_recompute,
@@ -255,6 +257,12 @@ def group_linear(st: StrategyConfig, kind: str, in_features, out_features, local
 def emit_expert_mlp(em, layer_idx: int, shape, rc: MLPRecomputeConfig):
     from .llm import emit_mlp
     cfg, st, system = em.model, em.st, em.system
+    assert cfg.group_linear_mode in ("parallel", "serial"), cfg.group_linear_mode      # reference moe_module.py:854,1078
+    if cfg.group_linear_mode == "serial":
+        # The reference's legacy serial mode instantiates LinearCol children for the column AND the row expert linears and
+        # accounts expert states like dense (dp-sharded) parameters (moe_module.py:878-900,1101-1134; SURVEY 7.5 lists it as a
+        # quirk).  Its numbers are not meaningful, so it is not reproduced.
+        raise NotImplementedError("group_linear_mode='serial' (one GEMM per expert) is not modelled; use 'parallel' (grouped GEMM)")
     local_experts = cfg.expert_num // st.ep_size
     ffn = cfg.moe_ffn_hidden_size if cfg.moe_ffn_hidden_size is not None else cfg.intermediate_size
     fc1_out = 2 * ffn if cfg.use_swiglu else ffn

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 from typing import List, Optional, Tuple
 
+from ..core.records import RecomputeStatus
 from ..core.ir import OpNode, SimStep
 from ..core.utils import get_rank_group
 from .engine import Atom, Coll, RecomputeBlock, Scope
@@ -86,12 +87,10 @@ def build_chunk_jobs(chunk, args: RankArgs, system, chunk_prefix: str = "", with
     leaf_bwd: List[Scope] = []
     leaf_rc: List[Optional[Scope]] = []
     labels: List[str] = []
-    # the replay re-derives checkpoint segments per layer as maximal runs of recompute-enabled ops
-    seg_first = [False] * len(chunk.nodes)
-    for k, node in enumerate(chunk.nodes):
-        if node.enable_recompute:
-            same_layer_prev = k > 0 and chunk.nodes[k - 1].scope[:1] == node.scope[:1] and bool(node.scope)
-            seg_first[k] = not (same_layer_prev and chunk.nodes[k - 1].enable_recompute)
+    # which op keeps its *inputs* through the real forward: the one the activation walker marked FIRST (after breakpoints).
+    # A one-op segment (sdp_only) ends up LAST, not FIRST, in the reference (language_model.py:289-315) and therefore caches
+    # nothing in the forward pass and everything in the replay -- same here.
+    seg_first = [node.enable_recompute and node.recompute_status == RecomputeStatus.FIRST for node in chunk.nodes]
     for k, node in enumerate(chunk.nodes):
         label = "-".join([root_label] + list(node.scope) + [node.display or node.kind])
         labels.append(label)

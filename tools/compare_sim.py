@@ -21,6 +21,9 @@ CASES = [
     ("tp1_pp4_vp2_sync_mbs1_mbc8_no_ckpt", "llama3-70b", "b200_bf16_ceperm", 8, {}, {"pp_comm_async": True}, True),
     ("tp2_pp1_dp4_mbs1", "llama2-tiny", "a100_pcie", 2, {}, {}, False),
     ("tp1_pp2_dp4_mbs1", "llama2-tiny", "a100_pcie", 2, {}, {"tp_size": 2, "micro_batch_num": 4}, False),
+    # found by tools/fuzz_sim_vs_reference.py: a one-op recompute segment (sdp_only) is LAST, not FIRST -> caches in the replay
+    ("tp2_pp1_dp4_mbs1", "llama3-8b", "b200_bf16_ceperm", 4, {}, {"enable_recompute": True, "recompute_granularity": "sdp_only",
+                                                                   "recompute_layer_num": 1, "micro_batch_num": 2}, True),
 ]
 
 

@@ -49,6 +49,10 @@ CASES = [
     ("ep4_pp2_dp4_mbs1", "mixtral-8x7b", 8, {"moe_pad_expert_input_to_capacity": True, "capacity": 1},
      {"world_size": 8, "pp_size": 4, "ep_size": 1, "tp_size": 1, "etp_size": 1, "enable_sequence_parallel": False, "seq_len": 16384,
       "micro_batch_size": 1, "micro_batch_num": 16, "te_version": "2.11.0", "interleaving_size": 2, "pp_comm_async": False}),
+    # found by the fuzzer: fp8 grouped linear opening a recompute segment keeps its 1-byte input (cache_groupgemm_col_fp8_inputs)
+    ("ep4_pp2_dp4_mbs1_full_recompute", "deepseekv3", 4, {},
+     {"world_size": 16, "pp_size": 4, "ep_size": 2, "tp_size": 1, "etp_size": 1, "enable_sequence_parallel": False, "seq_len": 2048,
+      "micro_batch_size": 2, "micro_batch_num": 4, "fp8": True, "cache_groupgemm_col_fp8_inputs": True}),
 ]
 
 

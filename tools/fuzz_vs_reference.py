@@ -89,10 +89,8 @@ def sample(rng: random.Random):
         so["num_layers_in_last_pipeline_stage"] = rng.choice([1, 2])
     if pp > 1 and rng.random() < 0.1:
         so["num_layers_in_first_pipeline_stage"] = rng.choice([1, 2])
-    if moe and rng.random() < 0.1:
-        mo_extra = {"group_linear_mode": "sequential"}
-    else:
-        mo_extra = {}
+    # (group_linear_mode="serial" is deliberately not sampled: legacy path of the reference, not reproduced -- models/moe.py)
+    mo_extra = {"group_linear_mode": "bogus"} if moe and rng.random() < 0.03 else {}
     layers = rng.choice([4, 6, 8, 12])
     mo = dict(CAP) if moe and rng.random() < 0.8 else {}
     mo.update(mo_extra)
