@@ -52,12 +52,12 @@ CASES = [
     # found by the fuzzer: fp8 grouped linear opening a recompute segment keeps its 1-byte input (cache_groupgemm_col_fp8_inputs)
     ("ep4_pp2_dp4_mbs1_full_recompute", "deepseekv3", 4, {},
      {"world_size": 16, "pp_size": 4, "ep_size": 2, "tp_size": 1, "etp_size": 1, "enable_sequence_parallel": False, "seq_len": 2048,
-      "micro_batch_size": 2, "micro_batch_num": 4, "fp8": True, "cache_groupgemm_col_fp8_inputs": True}),
+      "micro_batch_size": 2, "micro_batch_num": 4, "fp8": True, "cache_groupgemm_col_fp8_inputs": True}, "a100_pcie"),
 ]
 
 
 def run(mod_prefix, case, system):
-    strategy, model, layers, mover, sover = case
+    strategy, model, layers, mover, sover = case[:5]
     if mod_prefix == "ref":
         sys.path.insert(0, REF)
         from simumax.core.config import ModelConfig, StrategyConfig, SystemConfig
@@ -97,12 +97,13 @@ def main():
     for i, case in enumerate(CASES):
         if only and i not in only:
             continue
+        sysname = case[5] if len(case) > 5 else system          # optional per-case system config
         try:
-            a = run("ref", case, system)
+            a = run("ref", case, sysname)
         except Exception as ex:
             a = {"error": f"{type(ex).__name__}: {ex}"}
         try:
-            b = run("new", case, system)
+            b = run("new", case, sysname)
         except Exception as ex:
             import traceback
             traceback.print_exc()
