@@ -55,6 +55,7 @@ class OpNode:
     name: str                        # dotted full name, e.g. self.layer_0.attention.linear_qkv
     kind: str                        # reference class name (Embedding, LinearCol, ...)
     scope: Tuple[str, ...] = ()      # enclosing composite names, outermost first
+    ref_path: str = ""               # "(0)LLMModel -> (4)LLMBlock -> (3)MLP -> (1)Swiglu": the reference's module-tree path
     display: str = ""                # trace/call-stack label of the op
     layer_idx: Optional[int] = None
     in_shapes: List[List[int]] = field(default_factory=list)
@@ -92,7 +93,9 @@ class OpNode:
 
     @property
     def path(self) -> str:
-        return " -> ".join(self.scope + (self.kind,))
+        """The reference's ``current_full_module_path`` (child index + class name per level, base_struct.py:947-958) when the
+        emitter recorded it, else the scope display names."""
+        return self.ref_path or " -> ".join(self.scope + (self.kind,))
 
     def get_act_info(self) -> ActivationInfo:
         return self.act

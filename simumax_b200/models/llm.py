@@ -31,6 +31,9 @@ class Emitter:
         self._names: List[str] = ["self"]
         self._scopes: List[str] = []
         self.scope_tree: List[tuple] = []      # (depth, scope display name, first op index, last op index)
+        # reference module-tree path bookkeeping: every composite / leaf takes the next child index of its parent, in call order
+        self._child_counts: List[int] = [0]
+        self._ref_path: List[str] = ["(0)LLMModel"]
 
     # naming -------------------------------------------------------------------------------------
     def name(self, leaf: str) -> str:
@@ -41,6 +44,11 @@ class Emitter:
             self.em, self.attr, self.display = em, attr, display
 
         def __enter__(self):
+            em = self.em
+            idx = em._child_counts[-1]
+            em._child_counts[-1] += 1
+            em._child_counts.append(0)
+            em._ref_path.append(f"({idx}){em.ref_class(self.display)}")
             self.em._names.append(self.attr)
             self.em._scopes.append(self.display)
             self.start = len(self.em.nodes)
@@ -51,11 +59,26 @@ class Emitter:
             self.em.scope_tree.append((self.depth, self.display, self.start, len(self.em.nodes), tuple(self.em._scopes)))
             self.em._names.pop()
             self.em._scopes.pop()
+            self.em._child_counts.pop()
+            self.em._ref_path.pop()
 
     def scope(self, attr: str, display: str):
         return Emitter._Scope(self, attr, display)
 
+    def ref_class(self, display: str) -> str:
+        """Reference class name of a composite scope (display names follow Megatron's module names instead)."""
+        if display.startswith("TransformerLayer"):
+            return "LLMBlock"
+        if display == "SelfAttention":
+            return "MLAAttention" if getattr(self.model, "attention_type", None) == "mla" else "Attention"
+        if display == "MoELayer":
+            return "ExpertMLP"
+        return display
+
     def add(self, node: OpNode) -> OpNode:
+        idx = self._child_counts[-1]
+        self._child_counts[-1] += 1
+        node.ref_path = " -> ".join(self._ref_path + [f"({idx}){node.kind}"])
         node.scope = tuple(self._scopes)
         self.nodes.append(node)
         return node
@@ -215,12 +238,18 @@ def _retarget(text: str, src: int, dst: int, prefix: str) -> str:
     return text.replace(f"{prefix}{src}", f"{prefix}{dst}", 1) if src != dst else text
 
 
-def _clone_block(nodes: List[OpNode], tree: List[tuple], src: int, dst: int, base: int):
-    """Copies of a cached block's nodes / scope records renamed from layer ``src`` to ``dst``, node indices rebased to ``base``."""
+def _clone_block(nodes: List[OpNode], tree: List[tuple], src: int, dst: int, base: int, block_idx: Optional[int] = None):
+    """Copies of a cached block's nodes / scope records renamed from layer ``src`` to ``dst``, node indices rebased to ``base``;
+    ``block_idx`` = child index of the block under the root (second component of the reference-style module path)."""
     from copy import copy
     out = []
     for n in nodes:
         m = copy(n)
+        if block_idx is not None and n.ref_path:
+            parts = n.ref_path.split(" -> ")
+            if len(parts) > 1:
+                parts[1] = f"({block_idx})" + parts[1].split(")", 1)[1]
+                m.ref_path = " -> ".join(parts)
         m.name = _retarget(n.name, src, dst, "layer_")
         m.scope = tuple(_retarget(sn, src, dst, "TransformerLayer") for sn in n.scope)
         if isinstance(n.layer_idx, int) and n.layer_idx == src:
@@ -311,7 +340,9 @@ class StageChunk:
                 tpl, tree, src, first_rel, shape, delta = hit
                 _merge_books(self.system, delta)
                 base = len(em.nodes)
-                nodes, scopes = _clone_block(tpl, tree, src, i, base)
+                block_idx = em._child_counts[-1]          # the block takes the next child slot of the root, as emit_block would
+                em._child_counts[-1] += 1
+                nodes, scopes = _clone_block(tpl, tree, src, i, base, block_idx)
                 em.nodes.extend(nodes)
                 em.scope_tree.extend(scopes)
                 first_idx = base + first_rel
