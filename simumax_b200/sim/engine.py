@@ -384,7 +384,7 @@ class Engine:
                     a["ready_t"] = end
                     for x in (s, r):
                         self.events.append(Event(x["rank"], x["name"], "p2p", "fwd", x["launch_t"], x["end_t"],
-                                                 lane=x["stream"], gid=str(x["gid"][1]), post=x["issue_t"],
+                                                 lane=x["stream"], gid=f"{x['gid'][0]}:{x['gid'][1]}", post=x["issue_t"],
                                                  order=x["order"]))
 
     def _exec_async_wait(self, st, job: AsyncWait):
@@ -403,4 +403,4 @@ class Engine:
         st.t["comp"] = max(st.t["comp"], a["ready_t"])
         recv_end = a["recv"]["end_t"]
         if st.t["comp"] > t0 and a["ready_t"] > t0:
-            self._emit(st, job.name, "wait", "fwd", t0, st.t["comp"], lane="wait", gid=job.gid)
+            self._emit(st, job.name, "wait", "fwd", t0, st.t["comp"], lane="wait", gid=f"fwd:{job.gid}")

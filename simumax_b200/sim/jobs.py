@@ -71,7 +71,7 @@ def _steps_to_jobs(node: OpNode, steps: List[SimStep], label: str, args: RankArg
             gid = (f"{s.comm_op}{args.comm_order}-{_mb_tag(args)}{layer}-name:{node.kind}-{gname}:"
                    f"{args.info[gid_key]}" + (f"-stage:{s.stage}" if s.group == "cp" else ""))
             args.comm_order += 1
-            jobs.append(Coll(name=f"{label}-{s.comm_op}", gid=gid, group_size=s.comm_num, fwd_cost=s.fwd_cost,
+            jobs.append(Coll(name=f"{label}-{s.name or s.comm_op}", gid=gid, group_size=s.comm_num, fwd_cost=s.fwd_cost,
                              bwd_cost=s.bwd_cost))
     return jobs
 

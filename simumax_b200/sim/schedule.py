@@ -292,18 +292,14 @@ def build_interleaved_program(perf, stage_chunks: list, args: RankArgs, with_mem
     p2p = _P2P(args.rank, rank, pp, args.info["pp_group_id"], _p2p_cost(st, system, perf.model_config.hidden_size), use_async)
     total, last_stage = plan.total, plan.total_stages - 1
     jobs: list = []
-    bwd_trees = {}
 
     def model(chunk_idx, real_mb, direction):
-        key = (chunk_idx, real_mb)
-        if direction == "fwd":
-            args.microbatch, args.chunk_idx = real_mb, chunk_idx
-            f, b = build_chunk_jobs(stage_chunks[chunk_idx], args, system, chunk_prefix=f"-chunk{chunk_idx}-",
-                                    with_memory=with_memory)
-            bwd_trees[key] = b
-            jobs.append(("fwd", f))
-        else:
-            jobs.append(("bwd", bwd_trees.pop(key)))
+        # the backward tree is built when the schedule reaches it (the reference instantiates the chunk a second time there,
+        # pipeline_schedule.py:303-304), so its collectives draw fresh comm_order numbers -> identical gids in the log / trace
+        args.microbatch, args.chunk_idx = real_mb, chunk_idx
+        f, b = build_chunk_jobs(stage_chunks[chunk_idx], args, system, chunk_prefix=f"-chunk{chunk_idx}-",
+                                with_memory=with_memory)
+        jobs.append(("fwd", f) if direction == "fwd" else ("bwd", b))
 
     ftag = lambda v, mb: f"forward-v{v}-mb{mb}"
     btag = lambda v, mb: f"backward-v{v}-mb{mb}"

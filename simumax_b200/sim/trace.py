@@ -1,74 +1,187 @@
 """Structured simulator events -> Chrome trace (``tracing_logs.json``), no text-log round trip.
 
-Lane vocabulary matches the reference viewer layout (generate_tracing.py:65-80): per rank (pid ``rankN``) the
-threads ``fwd_scope, bwd_scope, fwd_compute, bwd_compute, pp_fwd, pp_bwd, pp_batch_scope, comm, wait``;
-times are microseconds; matching async send/recv pairs are linked with flow arrows.
+Same records as the reference viewer layout (generate_tracing.py:65-104, :152-480): per rank (pid ``rankN``) the threads
+``00_fwd_scope, 01_bwd_scope, 02_fwd_compute, 03_bwd_compute, 04_pp_fwd, 05_pp_bwd, 06_pp_batch_scope, 07_pp_detail_k,
+08_comm, 09_wait``; times are microseconds; matching send/recv pairs carry a ``[gN]`` tag and one flow arrow.
 """
 from __future__ import annotations
 
+import heapq
 import json
 import re
 from typing import Dict, List
 
 from .engine import Event
 
-LANES = ["fwd_scope", "bwd_scope", "fwd_compute", "bwd_compute", "pp_fwd", "pp_bwd", "pp_batch_scope", "comm", "wait"]
-_SORT = {name: i for i, name in enumerate(LANES)}
+# lane -> (ordered thread id, sort index); the numeric prefix keeps the viewer's lane order stable (generate_tracing.py:65-104)
+_LANE_ORDER = {"fwd_scope": ("00_fwd_scope", 0), "bwd_scope": ("01_bwd_scope", 1), "fwd_compute": ("02_fwd_compute", 2),
+               "bwd_compute": ("03_bwd_compute", 3), "pp_fwd": ("04_pp_fwd", 4), "pp_bwd": ("05_pp_bwd", 5),
+               "pp_batch_scope": ("06_pp_batch_scope", 6), "comm": ("08_comm", 80), "wait": ("09_wait", 90)}
+LANES = list(_LANE_ORDER)
+_SEND = ("send_", "async_send", "sync_send")
+_RECV = ("recv_", "async_recv", "sync_recv")
+_FWD_DIR = ("async_send_next", "async_recv_prev", "async_wait_recv_prev")
+_BWD_DIR = ("async_send_prev", "async_recv_next", "async_wait_recv_next")
 
 
-def _lane(ev: Event) -> str:
-    if ev.kind == "scope":
-        if "batch_pp_comm" in ev.name:
-            return "pp_batch_scope"
-        return "bwd_scope" if ev.phase == "bwd" else "fwd_scope"
-    if ev.kind == "compute":
-        return "bwd_compute" if ev.phase == "bwd" else "fwd_compute"
-    if ev.kind == "p2p":
-        if ev.lane in ("pp_fwd", "pp_bwd"):
-            return ev.lane
-        return "pp_bwd" if "backward" in (ev.gid or "") else "pp_fwd"
-    if ev.kind == "wait":
-        return "wait"
-    return "comm"
+def _tid_for(lane: str):
+    """(thread id, sort index) of a lane; blocking p2p detail sub-lanes sort after the batch scope."""
+    if lane.startswith("pp_detail"):
+        suffix = lane[len("pp_detail_"):]
+        return f"07_{lane}", 60 + (int(suffix) if suffix.isdigit() else 0)
+    return _LANE_ORDER.get(lane, (f"99_{lane}", 100))
+
+
+def _classify(e: Event, base: str):
+    """-> (stream type, lane) of one finished job."""
+    if e.kind == "wait" or base.startswith(("async_wait_send", "async_wait_recv")):
+        return "wait", "wait"
+    if e.kind == "scope" and base.startswith("batch_pp"):
+        return "scope", "scope"
+    if e.kind in ("p2p", "comm"):
+        if base.startswith(("send_", "recv_")):
+            return "comm", "pp_detail"                  # blocking p2p: packed into sub-lanes below
+        if base.startswith(_FWD_DIR):
+            return "comm", "pp_fwd"
+        if base.startswith(_BWD_DIR):
+            return "comm", "pp_bwd"
+        return "comm", "comm"
+    return "compute", "compute"
 
 
 def build_trace(events: List[Event]) -> List[dict]:
-    out: List[dict] = []
-    ranks = sorted({e.rank for e in events})
-    for i, r in enumerate(ranks):
-        out.append({"name": "process_name", "ph": "M", "pid": f"rank{r}", "args": {"name": f"rank{r}"}})
-        out.append({"name": "process_sort_index", "ph": "M", "pid": f"rank{r}", "args": {"sort_index": i}})
-        for lane in LANES:
-            out.append({"name": "thread_name", "ph": "M", "pid": f"rank{r}", "tid": lane, "args": {"name": lane}})
-            out.append({"name": "thread_sort_index", "ph": "M", "pid": f"rank{r}", "tid": lane,
-                        "args": {"sort_index": _SORT[lane]}})
-    flows: Dict[str, list] = {}
+    """Chrome-trace records with the reference viewer layout (generate_tracing.py:152-480): ordered lanes per rank, module
+    envelopes on the scope lanes and leaf kernels on the compute lanes, blocking p2p packed into non-overlapping
+    ``pp_detail_k`` lanes, async p2p drawn from its post time when the lane was idle, ``[gN]`` tags + one flow arrow per
+    matched send/recv pair."""
+    recs: List[dict] = []
+    ends: Dict[str, list] = {}
     for e in events:
-        lane = _lane(e)
-        short = e.name.split("-")[-1] if e.kind != "scope" else e.name
-        rec = {"name": short, "cat": e.kind, "ph": "X", "ts": e.start * 1e3, "dur": max(0.0, (e.end - e.start) * 1e3),
-               "pid": f"rank{e.rank}", "tid": lane,
-               "args": {"call_stack": e.name, "phase": e.phase, "cost_ms": e.end - e.start}}
-        if e.gid is not None:
-            rec["args"]["gid"] = e.gid
-        if e.post is not None:
-            rec["args"]["post_ts"] = e.post * 1e3
-            rec["args"]["order"] = e.order
-        out.append(rec)
-        if e.kind == "p2p" and e.gid:
-            flows.setdefault(e.gid, []).append((e, lane))
-    fid = 0
-    for gid, pair in flows.items():
-        if len(pair) != 2:
+        if e.gid:
+            base = e.name.split("-")[-1]
+            ends.setdefault(e.gid, [False, False])
+            ends[e.gid][0] |= base.startswith(_SEND)
+            ends[e.gid][1] |= base.startswith(_RECV)
+    corr: Dict[str, int] = {}
+    for i, e in enumerate(events):
+        stack = e.name.split("-")[1:] or [e.name]
+        base = stack[-1]
+        stream, lane = _classify(e, base)
+        if stream == "compute":
+            tid = "bwd_compute" if e.phase == "recompute_fwd" else f"{e.phase}_compute"
+        else:
+            tid = "pp_batch_scope" if stream == "scope" else lane
+        cid = None
+        if stream == "comm" and e.gid and all(ends.get(e.gid, (False, False))):
+            cid = corr.setdefault(e.gid, len(corr))
+        recs.append({"name": base if cid is None else f"{base}[g{cid}]", "cat": stream, "ph": "X", "ts": e.start * 1e3,
+                     "dur": max(0.0, (e.end - e.start) * 1e3), "pid": f"rank{e.rank}", "tid": tid, "id": i,
+                     "args": {"call_stack": stack, "stream_type": stream, "lane": lane, "lane_base": lane, "direction": e.phase,
+                              "gid": e.gid, "correlation_id": cid, "base_name": base,
+                              "post_ts": None if e.post is None else e.post * 1e3, "post_order": e.order}})
+
+    # blocking send/recv of one rank may overlap in time: greedy interval colouring into pp_detail_0, _1, ...
+    detail: Dict[str, list] = {}
+    for r in recs:
+        if r["cat"] == "comm" and r["args"]["lane"] == "pp_detail":
+            detail.setdefault(r["pid"], []).append(r)
+    for rs in detail.values():
+        rs.sort(key=lambda r: (r["ts"], r["dur"], r["id"]))
+        busy, free, used = [], [], 0
+        for r in rs:
+            while busy and busy[0][0] <= r["ts"] + 1e-9:
+                heapq.heappush(free, heapq.heappop(busy)[1])
+            if free:
+                k = heapq.heappop(free)
+            else:
+                k, used = used, used + 1
+            r["tid"] = r["args"]["lane"] = f"pp_detail_{k}"
+            r["args"]["detail_lane_idx"] = k
+            heapq.heappush(busy, (r["ts"] + r["dur"], k))
+
+    # async p2p: show the slice from its local post time if the lane had nothing else to do (no false bubble)
+    per_lane: Dict[tuple, list] = {}
+    for r in recs:
+        if r["cat"] == "comm":
+            per_lane.setdefault((r["pid"], r["tid"]), []).append(r)
+    for rs in per_lane.values():
+        rs.sort(key=lambda r: (r["ts"], r["id"]))
+        tail = None
+        for r in rs:
+            post = r["args"]["post_ts"]
+            if post is not None:
+                begin = post if tail is None else max(post, tail)
+                if begin < r["ts"]:
+                    r["dur"] = max(0.0, r["ts"] + r["dur"] - begin)
+                    r["ts"] = begin
+            tail = r["ts"] + r["dur"]
+    # back-to-back pipeline transfers would be swallowed by the viewer: trim 10 % (<= 0.5 ns) off both ends
+    for r in recs:
+        if r["cat"] == "comm" and r["args"]["gid"] and "send_recv-" in r["args"]["gid"] and r["dur"] > 0.0:
+            pad = min(5e-4, r["dur"] * 0.1)
+            if r["dur"] > 2.0 * pad:
+                r["ts"] += pad
+                r["dur"] -= 2.0 * pad
+
+    # a compute-stream job that encloses another one of its own subtree is a module envelope -> scope lane
+    inside: Dict[tuple, list] = {}
+    for r in recs:
+        if r["cat"] == "compute":
+            st = tuple(r["args"]["call_stack"])
+            for k in range(1, len(st)):
+                inside.setdefault((r["pid"], st[:k]), []).append((r["ts"], r["ts"] + r["dur"]))
+    for r in recs:
+        if r["cat"] != "compute":
             continue
-        (a, la), (b, lb) = pair
-        src, dst = ((a, la), (b, lb)) if "send" in a.name else ((b, lb), (a, la))
-        fid += 1
-        out.append({"name": "p2p", "cat": "flow", "ph": "s", "id": fid, "ts": src[0].start * 1e3,
-                    "pid": f"rank{src[0].rank}", "tid": src[1]})
-        out.append({"name": "p2p", "cat": "flow", "ph": "f", "bp": "e", "id": fid, "ts": dst[0].end * 1e3,
-                    "pid": f"rank{dst[0].rank}", "tid": dst[1]})
-    return out
+        base, lo, hi = r["args"]["base_name"], r["ts"], r["ts"] + r["dur"] + 1e-9
+        if base in ("recompute_block", "checkpoint_bwd") or any(
+                a >= lo and b <= hi for a, b in inside.get((r["pid"], tuple(r["args"]["call_stack"])), ())):
+            r["cat"] = "scope"
+            if r["args"]["direction"] == "recompute_fwd":
+                r["tid"] = "bwd_scope"
+                if base == "recompute_block":
+                    r["name"] = "recompute_fwd"
+            else:
+                r["tid"] = f"{r['args']['direction']}_scope"
+
+    # one arrow per matched pipeline transfer, anchored just inside the two slices
+    pairs: Dict[str, list] = {}
+    for r in recs:
+        gid = r["args"]["gid"]
+        if r["cat"] == "comm" and gid and "send_recv-" in gid:
+            pairs.setdefault(gid, []).append(r)
+    flows = []
+    for gid, rs in pairs.items():
+        snd = [r for r in rs if r["args"]["base_name"].startswith(_SEND)]
+        rcv = [r for r in rs if r["args"]["base_name"].startswith(_RECV)]
+        if len(snd) != 1 or len(rcv) != 1:
+            continue
+        for ph, r, at_end in (("s", snd[0], False), ("f", rcv[0], True)):
+            pad = min(1e-3, r["dur"] * 0.25) if r["dur"] > 0.0 else 0.0
+            rec = {"name": f"pair:{gid}", "cat": "comm_pair", "ph": ph, "pid": r["pid"], "tid": r["tid"], "id": len(flows) // 2,
+                   "ts": r["ts"] + (max(0.0, r["dur"] - pad) if at_end else pad), "args": {"gid": gid}}
+            if ph == "f":
+                rec["bp"] = "e"
+            flows.append(rec)
+    recs.extend(flows)
+
+    order: Dict[str, tuple] = {}
+    for r in recs:
+        ordered = _tid_for(r["tid"])
+        order[ordered[0]] = ordered
+        r["tid"] = ordered[0]
+    meta: List[dict] = []
+    pids = sorted({r["pid"] for r in recs}, key=lambda p: int(re.sub(r"\D", "", p) or 0))
+    for i, pid in enumerate(pids):
+        meta.append({"name": "process_name", "ph": "M", "pid": pid, "args": {"name": pid}})
+        meta.append({"name": "process_sort_index", "ph": "M", "pid": pid, "args": {"sort_index": i}})
+        meta.append({"name": "sort_index", "ph": "M", "pid": pid, "args": {"sort_index": i}})
+        for tid in sorted({r["tid"] for r in recs if r["pid"] == pid}):
+            idx = order[tid][1]
+            meta.append({"name": "thread_name", "ph": "M", "pid": pid, "tid": tid, "args": {"name": tid.split("_", 1)[1]}})
+            meta.append({"name": "thread_sort_index", "ph": "M", "pid": pid, "tid": tid, "args": {"sort_index": idx}})
+            meta.append({"name": "sort_index", "ph": "M", "pid": pid, "tid": tid, "args": {"sort_index": idx}})
+    return meta + recs
 
 
 def write_trace(events: List[Event], path: str, memory_events: List[dict] = None) -> int:

@@ -53,3 +53,52 @@ def test_random_simulations_identical():
         case = fs.sample(rng)
         a, b = _both(cs.run, case)
         assert a == b or ("error" in a and "error" in b), (case, a, b)
+
+
+@pytest.mark.timeout(900)
+def test_trace_records_identical(tmp_path):
+    """Every Chrome-trace record (lanes, envelopes, [gN] tags, flow arrows, counters, metadata) of three schedules: tp2,
+    async 1F1B and blocking 1F1B -- only the documented wait-lane extras may differ (tools/deep_compare_trace.py)."""
+    import compare_sim as cs
+    import deep_compare_trace as dt
+    for i in (0, 1, 2):
+        c, examples = dt.compare(dt.run("ref", cs.CASES[i]), dt.run("new", cs.CASES[i]))
+        assert c["diff"] == 0 and c["time"] == 0 and c["dropped"] == 0, (i, dict(c), examples[:4])
+        assert c["same"] > 900
+
+
+@pytest.mark.timeout(900)
+def test_reference_log_converts_to_reference_trace(tmp_path):
+    """``process_log_file`` on a log written by the reference reproduces the reference's own tracing_logs.json field by field
+    (blocking interleaved schedule: batch scopes, pp_detail sub-lanes, pair arrows)."""
+    import io
+    import json
+    from contextlib import redirect_stdout
+
+    import compare_sim as cs
+    from simumax_b200.sim.trace import process_log_file
+    sys.path.insert(0, REF)
+    from simumax.core.config import ModelConfig, StrategyConfig, SystemConfig
+    from simumax.core.perf_llm import PerfLLM
+    p = PerfLLM()
+    with redirect_stdout(io.StringIO()):
+        p.configure(strategy_config=StrategyConfig.init_from_config_file(f"{cs.CFG}/strategy/tp1_pp4_vp2_sync_mbs1_mbc8_no_ckpt.json"),
+                    model_config=ModelConfig.init_from_config_file(f"{cs.CFG}/models/llama3-8b.json"),
+                    system_config=SystemConfig.init_from_config_file(f"{cs.CFG}/system/b200_bf16_ceperm.json"))
+        p.model_config.layer_num = 8
+        p.run_estimate()
+        p.simulate(str(tmp_path), merge_lanes=True)
+    process_log_file(str(tmp_path / "log.log"), str(tmp_path / "ours.json"))
+    ref = [r for r in json.load(open(tmp_path / "tracing_logs.json")) if r.get("ph") != "C"]
+    ours = json.load(open(tmp_path / "ours.json"))
+    assert len(ref) == len(ours)
+
+    def split(r):
+        r = json.loads(json.dumps(r))
+        times = (r.pop("ts", 0.0), r.pop("dur", 0.0), (r.get("args") or {}).pop("post_ts", None) or 0.0)
+        r.pop("id", None)                         # record ids number the records / arrows in file order
+        return json.dumps(r, sort_keys=True), times
+    a, b = sorted(map(split, ref)), sorted(map(split, ours))
+    for (ka, ta), (kb, tb) in zip(a, b):
+        assert ka == kb
+        assert ta == pytest.approx(tb, abs=5e-3)      # microseconds; the reference goes through a 6-digit text log

@@ -1,4 +1,5 @@
 import json
+import re
 import pickle
 
 import pytest
@@ -18,7 +19,15 @@ def test_tiny_llama_trace_golden(tmp_path):
     assert r["memory"]["peak_op_by_rank"]["rank0"] == {"op_name": "self.parallel_ce", "phase": "fwd"}
     assert r["cache_tokens"] == 152
     trace = json.load(open(tmp_path / "tracing_logs.json"))
-    assert any(e.get("ph") == "C" for e in trace) and any(e.get("tid") == "comm" for e in trace)
+    assert any(e.get("ph") == "C" for e in trace)
+    # viewer layout of the reference (generate_tracing.py:65-104): ordered lanes, envelopes on the scope lanes
+    x = [e for e in trace if e.get("ph") == "X"]
+    assert {e["tid"] for e in x} == {"00_fwd_scope", "01_bwd_scope", "02_fwd_compute", "03_bwd_compute", "08_comm"}
+    assert all(e["cat"] == "scope" for e in x if e["tid"].endswith("_scope"))
+    emb = next(e for e in x if e["name"] == "LanguageModelEmbedding_0")
+    assert emb["args"]["call_stack"] == ["microbatch0", "GPTModel_first_pp_stage", "LanguageModelEmbedding_0"]
+    names = {(m["name"], m.get("tid")) for m in trace if m.get("ph") == "M"}
+    assert ("thread_sort_index", "08_comm") in names and ("process_sort_index", None) in names
     snap = json.load(open(tmp_path / "simu_memory_snapshot.json"))
     assert snap["schema"] == "simumax_memory_snapshot_v1"
     allocs = [e for e in snap["cache_tokens"] if e["action"] == "alloc"]
@@ -26,6 +35,39 @@ def test_tiny_llama_trace_golden(tmp_path):
     assert len(allocs) == len(frees) == 152
     viz = pickle.load(open(tmp_path / "simu_memory_viz_snapshot.pickle", "rb"))
     assert "device_traces" in viz and "segments" in viz and viz["segments"][0]["total_size"] >= 3967209472
+
+
+def test_trace_layout_pipeline_lanes(tmp_path):
+    """Async p2p lands on pp_fwd / pp_bwd with a [gN] tag + one flow arrow per pair; blocking p2p is packed into
+    non-overlapping pp_detail_k lanes under a pp_batch_scope envelope (generate_tracing.py:232-262, :370-420)."""
+    p = build("tp1_pp2_dp4_mbs1", "llama3-8b", "b200_nominal", 4)
+    p.simulate(str(tmp_path / "a"), merge_lanes=True)
+    tr = json.load(open(tmp_path / "a" / "tracing_logs.json"))
+    x = [e for e in tr if e.get("ph") == "X"]
+    p2p = [e for e in x if e["tid"] in ("04_pp_fwd", "05_pp_bwd")]
+    assert p2p and all(re.search(r"\[g\d+\]$", e["name"]) for e in p2p)
+    assert all(e["args"]["gid"].startswith("fwd:send_recv-") and e["args"]["post_ts"] is not None for e in p2p)
+    flows = [e for e in tr if e.get("cat") == "comm_pair"]
+    assert len(flows) == len(p2p) and {e["ph"] for e in flows} == {"s", "f"}
+    by_id = {}
+    for f in flows:
+        by_id.setdefault(f["id"], []).append(f)
+    assert all(len(v) == 2 and v[0]["pid"] != v[1]["pid"] and v[0]["name"] == v[1]["name"] for v in by_id.values())
+    assert any(e["tid"] == "09_wait" for e in x)
+
+    q = build("tp1_pp4_vp2_sync_mbs1_mbc8_no_ckpt", "llama3-70b", "b200_nominal", 8)
+    q.simulate(str(tmp_path / "b"), merge_lanes=True)
+    tr = json.load(open(tmp_path / "b" / "tracing_logs.json"))
+    x = [e for e in tr if e.get("ph") == "X"]
+    assert any(e["tid"] == "06_pp_batch_scope" and e["cat"] == "scope" for e in x)
+    detail = [e for e in x if e["tid"].startswith("07_pp_detail_")]
+    assert detail and len({e["tid"] for e in detail}) >= 2
+    lanes = {}
+    for e in detail:
+        lanes.setdefault((e["pid"], e["tid"]), []).append((e["ts"], e["ts"] + e["dur"]))
+    for spans in lanes.values():                      # no two slices of one sub-lane overlap
+        spans.sort()
+        assert all(b[0] >= a[1] - 1e-6 for a, b in zip(spans, spans[1:]))
 
 
 CASES = [("tp1_pp2_dp4_mbs1", "llama3-8b", 4, {}, {}),
