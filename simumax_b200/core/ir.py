@@ -57,6 +57,7 @@ class OpNode:
     scope: Tuple[str, ...] = ()      # enclosing composite names, outermost first
     ref_path: str = ""               # "(0)LLMModel -> (4)LLMBlock -> (3)MLP -> (1)Swiglu": the reference's module-tree path
     display: str = ""                # trace/call-stack label of the op
+    repr_args: str = ""              # the reference's extra_repr() of this module class (model_arch tree view)
     layer_idx: Optional[int] = None
     in_shapes: List[List[int]] = field(default_factory=list)
     out_shapes: List[List[int]] = field(default_factory=list)
@@ -120,8 +121,8 @@ def evaluate(node: OpNode, system: SystemConfig) -> OpNode:
     (reference base_struct.py:821-858, config.py:815-893,1019-1035).
     """
     c = node.compute
-    if node.enable_recompute:
-        c.recompute_flops = c.fwd_flops
+    if node.enable_recompute and node.kind != "Float8Quantizer":     # the cast's replay is timed but not counted in the traffic
+        c.recompute_flops = c.fwd_flops                               # statistic (reference dense_module.py:2384-2388)
         c.recompute_accessed_mem = c.fwd_accessed_mem
     else:
         c.recompute_flops = 0

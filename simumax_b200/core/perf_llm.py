@@ -753,7 +753,7 @@ class PerfLLM(PerfBase):
     # ---------------------------------------------------------------- results
     def _write_results(self, save_path, mem_result: Result, compute_result: Result, with_strategy=True):
         os.makedirs(save_path, exist_ok=True)
-        arch = "\n\n".join(f"{k}:\n{v!r}" for k, v in self.model_chunk_dict.items())
+        arch = str(dict(self.model_chunk_dict))            # {'first_stage_chunk': LLMModel(...), ...} like the reference
         base_info = {"arch": arch, "all_param": self.model_config.param_numel,
                      "act_param": self.model_config.activated_param_numel}
         dump = lambda o: json.dumps(o, indent=2, sort_keys=False, ensure_ascii=False, default=str)

@@ -51,7 +51,7 @@ def embedding(st: StrategyConfig, hidden, vocab, in_shape, name, display="Langua
     w_bytes = v_local * hidden * e
     y_bytes = B * S * hidden * e
     node = OpNode(name=name, kind="Embedding", display=display, in_shapes=[ishape(in_shape)], out_shapes=[out_shape],
-                  in_bytes=numel(in_shape) * DT["bf16"])
+                  in_bytes=numel(in_shape) * DT["bf16"], repr_args=f"hidden_size={hidden},vocab_size={v_local}")
     node.mem = dense_param_memory(st, v_local * hidden, e, v_local * hidden * st.tp_size)
     node.act.fwd_peak_mem_no_cache = ids_bytes + y_bytes + (0 if st.use_accm_weight else w_bytes)
     node.act.bwd_peak_mem_no_cache = w_bytes
@@ -97,7 +97,9 @@ def linear_col(st: StrategyConfig, in_features, out_features, in_shape, name, *,
     out_numel = B * out_shape[1] * out_local
     node = OpNode(name=name, kind="LinearCol", display=display, layer_idx=layer_idx,
                   in_shapes=[ishape(in_shape)], out_shapes=[out_shape], in_bytes=numel(in_shape) * (1 if fp8 else DT["bf16"]),
-                  weight_shape=[int(out_local), int(in_features)], enable_recompute=enable_recompute)
+                  weight_shape=[int(out_local), int(in_features)], enable_recompute=enable_recompute,
+                  repr_args=f"input_size={in_features},output_size={out_local},use_bias=False,enable_recompute={enable_recompute}, "
+                            f"TP={st.tp_size}")
     use_var = bool(st.recompute_variance) or use_variance_tail_model
     if is_last_recompute and enable_recompute and use_var:
         node.is_variance_node = True
@@ -167,7 +169,9 @@ def linear_row(st: StrategyConfig, in_features, out_features, in_shape, name, *,
     out_numel_full = B * out_shape[1] * out_features * (st.tp_size if st.enable_sequence_parallel else 1)
     node = OpNode(name=name, kind="LinearRow", display=display, layer_idx=layer_idx,
                   in_shapes=[ishape(in_shape)], out_shapes=[out_shape], in_bytes=numel(in_shape) * (1 if st.fp8 else DT["bf16"]),
-                  weight_shape=[int(out_features), int(in_local)], enable_recompute=enable_recompute)
+                  weight_shape=[int(out_features), int(in_local)], enable_recompute=enable_recompute,
+                  repr_args=f"input_size={in_local},output_size={out_features},use_bias=False,enable_recompute={enable_recompute}, "
+                            f"TP={st.tp_size}")
     use_var = bool(st.recompute_variance) or use_variance_tail_model
     if is_last_recompute and enable_recompute and use_var:
         node.is_variance_node = True
@@ -225,7 +229,9 @@ def layernorm(st: StrategyConfig, norm_size, in_shape, name, *, has_cached_input
     n = B * S * Hn
     out_shape = ishape(in_shape)
     node = OpNode(name=name, kind="LayerNorm", display=display, in_shapes=[ishape(in_shape)], out_shapes=[out_shape],
-                  in_bytes=numel(in_shape) * DT["bf16"], weight_shape=[int(norm_size)], enable_recompute=enable_recompute)
+                  in_bytes=numel(in_shape) * DT["bf16"], weight_shape=[int(norm_size)], enable_recompute=enable_recompute,
+                  repr_args=f"norm_size={norm_size},norm_type=rms_norm,use_fused_norm={st.use_fused_norm},"
+                            f"enable_recompute={enable_recompute}")
     x_bytes = y_bytes = n * e
     g_bytes = norm_size * e
     rstd = n / norm_size * e
@@ -311,7 +317,9 @@ def core_attention(st: StrategyConfig, system: SystemConfig, head_size, head_num
     out_shape = ishape([B, S, head_num * vd])
     node = OpNode(name=name, kind="MLACoreAttention" if mla else "CoreAttention", display=display,
                   in_shapes=[ishape(in_shape)], out_shapes=[out_shape], in_bytes=numel(in_shape) * DT["bf16"],
-                  enable_recompute=enable_recompute)
+                  enable_recompute=enable_recompute,
+                  repr_args=f"head_size={head_size},head_num={head_num},kv_head_num={kv_head_num},use_math_sdp={st.use_math_sdp},"
+                            f"use_flash_sdp={st.use_flash_sdp},enable_recompute={enable_recompute}")
     use_var = bool(st.recompute_variance) or use_variance_tail_model
     if is_last_recompute and enable_recompute and use_var:
         node.is_variance_node = True
@@ -470,10 +478,12 @@ def core_attention(st: StrategyConfig, system: SystemConfig, head_size, head_num
 # ------------------------------------------------------------------------------------------------
 # zero-cost layout ops (RotaryEmbedding, Cat / Concat / Split / Add)
 # ------------------------------------------------------------------------------------------------
-def passthrough(kind, in_shapes, out_shapes, name, *, enable_recompute=False, display=None) -> OpNode:
+def passthrough(kind, in_shapes, out_shapes, name, *, enable_recompute=False, display=None, dim=-1) -> OpNode:
+    args = {"SplitModule": f"split_dim={dim}, ", "ConcatModule": f"concat_dim={dim}, "}.get(kind, "")
     node = OpNode(name=name, kind=kind, display=display or kind, in_shapes=[ishape(s) for s in in_shapes],
                   out_shapes=[ishape(s) for s in out_shapes],
-                  in_bytes=sum(numel(s) for s in in_shapes) * DT["bf16"], enable_recompute=enable_recompute)
+                  in_bytes=sum(numel(s) for s in in_shapes) * DT["bf16"], enable_recompute=enable_recompute,
+                  repr_args=f"{args}enable_recompute={enable_recompute}")
     node.sim_steps = lambda nd, system=None: []
     return node
 
@@ -492,7 +502,8 @@ def swiglu(st: StrategyConfig, in_shape, name, *, is_fused=None, has_cached_inpu
     in_shapes = [ishape(in_shape)]
     in_bytes = numel(in_shape) * DT["bf16"]
     node = OpNode(name=name, kind="Swiglu", display=display, in_shapes=in_shapes, out_shapes=[out_shape],
-                  in_bytes=in_bytes, enable_recompute=enable_recompute)
+                  in_bytes=in_bytes, enable_recompute=enable_recompute,
+                  repr_args=f"is_fused={fused},enable_recompute={enable_recompute}")
     cache = (2 * y if fused else 3 * y)
     if has_cached_inputs:
         cache -= 2 * y
@@ -520,7 +531,8 @@ def gelu(st: StrategyConfig, in_shape, name, *, has_cached_inputs=False, enable_
     x = numel(in_shape) * e
     out_shape = ishape(in_shape)
     node = OpNode(name=name, kind="Gelu", display=display, in_shapes=[ishape(in_shape)], out_shapes=[out_shape],
-                  in_bytes=numel(in_shape) * DT["bf16"], enable_recompute=enable_recompute)
+                  in_bytes=numel(in_shape) * DT["bf16"], enable_recompute=enable_recompute,
+                  repr_args=f"enable_recompute={enable_recompute}")
     node.act.activation_mem_cache = 3 * x - (x if has_cached_inputs else 0)
     node.act.fwd_peak_mem_no_cache = 2 * x
     node.act.bwd_peak_mem_no_cache = 2 * x
@@ -593,7 +605,8 @@ def fp8_quantizer(st: StrategyConfig, in_shape, name, *, enable_recompute=False,
     x = numel(in_shape) * DT["bf16"]
     y = numel(in_shape) * DT["fp8"]
     node = OpNode(name=name, kind="Float8Quantizer", display=display, in_shapes=[ishape(in_shape)],
-                  out_shapes=[ishape(in_shape)], in_bytes=x, enable_recompute=enable_recompute)
+                  out_shapes=[ishape(in_shape)], in_bytes=x, enable_recompute=enable_recompute,
+                  repr_args=f"enable_recompute={enable_recompute}")
     node.act.fwd_peak_mem_no_cache = x + y
     node.compute.fwd_accessed_mem = x + y
     node.sim_steps = lambda nd, system=None: []      # the cast is not replayed as a separate op

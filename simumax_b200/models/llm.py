@@ -40,15 +40,15 @@ class Emitter:
         return ".".join(self._names + [leaf])
 
     class _Scope:
-        def __init__(self, em, attr, display):
-            self.em, self.attr, self.display = em, attr, display
+        def __init__(self, em, attr, display, ref_cls=None):
+            self.em, self.attr, self.display, self.ref_cls = em, attr, display, ref_cls
 
         def __enter__(self):
             em = self.em
             idx = em._child_counts[-1]
             em._child_counts[-1] += 1
             em._child_counts.append(0)
-            em._ref_path.append(f"({idx}){em.ref_class(self.display)}")
+            em._ref_path.append(f"({idx}){self.ref_cls or em.ref_class(self.display)}")
             self.em._names.append(self.attr)
             self.em._scopes.append(self.display)
             self.start = len(self.em.nodes)
@@ -62,8 +62,8 @@ class Emitter:
             self.em._child_counts.pop()
             self.em._ref_path.pop()
 
-    def scope(self, attr: str, display: str):
-        return Emitter._Scope(self, attr, display)
+    def scope(self, attr: str, display: str, ref_cls: str = None):
+        return Emitter._Scope(self, attr, display, ref_cls)
 
     def ref_class(self, display: str) -> str:
         """Reference class name of a composite scope (display names follow Megatron's module names instead)."""
@@ -99,7 +99,9 @@ def _linear(em: Emitter, attr: str, kind: str, in_f, out_f, shape, display, **kw
     """Emit a (possibly fp8-wrapped) linear under attribute ``attr``; returns (linear node, out shape)."""
     ctor = D.linear_col if kind == "col" else D.linear_row
     if em.st.fp8 and kw.pop("wrap_fp8", True):
-        with em.scope(attr, "QuantizedColLinear"):
+        # both wrappers are *displayed* as QuantizedColLinear in call stacks (the row variant keeps the column one's
+        # specific_name, dense_module.py:2438), the module tree shows the real class
+        with em.scope(attr, "QuantizedColLinear", ref_cls="QuantizedColLinear" if kind == "col" else "QuantizedRowLinear"):
             _maybe_quantize(em, attr, shape, kw.get("enable_recompute", False))
             node, out = ctor(em.st, in_f, out_f, shape, em.name("linear"), display=display, **kw)
             em.add(node)
@@ -360,14 +362,11 @@ class StageChunk:
         self.scope_tree = em.scope_tree
         self.layer_first_nodes = [self.nodes[i] for i in firsts if i < len(self.nodes)]
         assign_recompute_status(self.nodes)
-        mem, comp, cost = MemoryInfo(), ComputeInfo(), CostInfo()
         for n in self.nodes:
             if id(n) not in cached_nodes:
                 evaluate(n, self.system)
-            mem = mem + n.mem
-            comp = comp + n.compute
-            cost = cost + n.cost
-        self._model_info, self._compute_info, self._cost_info = mem, comp, cost
+        from ..core.arch_repr import hierarchical_totals
+        self._model_info, self._compute_info, self._cost_info = hierarchical_totals(self.nodes)
         self._info_ready = True
         return shape
 
@@ -454,6 +453,11 @@ class StageChunk:
         return out
 
     def __repr__(self) -> str:
+        """The reference's nested module view with per-module totals (base_struct.py:1004-1068); ``summary()`` is the flat table."""
+        from ..core.arch_repr import chunk_repr
+        return chunk_repr(self)
+
+    def summary(self) -> str:
         lines = [f"{self.specific_name}(layers={self.layer_num}, pre={self.preprocess}, post={self.postprocess})"]
         for n in self.nodes:
             c = n.cost

@@ -220,7 +220,8 @@ def group_linear(st: StrategyConfig, kind: str, in_features, out_features, local
     node = OpNode(name=name, kind=cls, display=cls, layer_idx=layer_idx,
                   in_shapes=[ishape(in_shape)] + [ishape(s) for s, _ in extra_inputs], out_shapes=[out_shape],
                   in_bytes=in_bytes, weight_shape=[int(out_f), int(in_f)], enable_recompute=enable_recompute,
-                  offload_inputs=offload_inputs)
+                  offload_inputs=offload_inputs,
+                  repr_args=f"input_size={in_f},output_size={out_f},local_expert_num={local_experts},use_bias=False")
     use_var = bool(st.recompute_variance) or use_variance_tail_model
     if is_last_recompute and enable_recompute and use_var:
         node.is_variance_node = True

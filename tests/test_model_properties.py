@@ -63,3 +63,24 @@ def test_result_files(tmp_path):
     assert tr["displayTimeUnit"] == "ms" and any(e.get("ph") == "X" for e in tr["traceEvents"])
     g = p.capture(str(tmp_path))
     assert len(g.nodes) > 10 and (tmp_path / "model_graph.json").exists()
+
+
+def test_model_arch_is_the_nested_module_view(tmp_path):
+    """``model_arch``: torch-style nested blocks, identical layers folded into ``(a->b)``, and under every module its time /
+    FLOP / static-memory totals (reference MetaModule.__repr__, base_struct.py:1004-1068)."""
+    import json
+    import re
+    p = build("tp2_pp1_dp4_mbs1", "llama3-8b", "b200_nominal", 4)
+    p.analysis(save_path=str(tmp_path), console_log=False)
+    text = (tmp_path / "model_arch").read_text()
+    assert text.startswith("{'first_stage_chunk': LLMModel(\n  (0): Embedding(hidden_size=4096,vocab_size=")
+    assert "  (1->4): LLMBlock(\n" in text                       # four identical layers, one entry
+    assert "      (0): LinearCol(input_size=4096,output_size=3072,use_bias=False,enable_recompute=False, TP=2)\n" in text
+    assert "(1): CoreAttention(head_size=128,head_num=16.0,kv_head_num=4.0,use_math_sdp=False,use_flash_sdp=True," in text
+    assert text.count("\t1. cost: (total_time=") == text.count("\t2. memory: (d_w=") == 16   # 12 leaves + 3 composites + root
+    assert json.loads((tmp_path / "base_info.json").read_text())["arch"] == text
+    # a composite's totals are the sums of its children's
+    chunk = p.model_chunk_dict["first_stage_chunk"]
+    root_total = float(re.findall(r"total_time=([0-9.]+) ms", text)[-1])
+    assert root_total == pytest.approx(chunk.get_cost_info().all_time, abs=0.005)
+    assert "self.layer_0.mlp.linear_fc1" in chunk.summary()      # the flat per-op table is still available

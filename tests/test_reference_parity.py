@@ -102,3 +102,17 @@ def test_reference_log_converts_to_reference_trace(tmp_path):
     for (ka, ta), (kb, tb) in zip(a, b):
         assert ka == kb
         assert ta == pytest.approx(tb, abs=5e-3)      # microseconds; the reference goes through a 6-digit text log
+
+
+@pytest.mark.timeout(600)
+def test_model_arch_text_identical():
+    """model_arch / base_info["arch"]: the nested module view with per-module time, FLOP and static-memory totals, byte for
+    byte -- dense tp2, MLA + MoE with pipeline stages, fp8 wrappers with full recompute."""
+    import compare_with_reference as cw
+    import deep_compare_with_reference_lib as dl
+    for i in (0, 4, 20):
+        case = cw.CASES[i]
+        system = case[5] if len(case) > 5 else "b200_bf16_ceperm"
+        a, b = dl.run("ref", case, system), dl.run("new", case, system)
+        assert a["arch"] == b["arch"], i
+        assert [d for d in dl.diff(a, b) if not d[0].endswith("/raw")] == []

@@ -1,55 +1,25 @@
 """Deep differential check: the COMPLETE analysis_mem() / analysis_cost() result dictionaries of the reference and of this
-repository (every key, every formatted value, the peak-path strings) for hand-picked and random configurations.
-    python tools/deep_compare_with_reference.py
+repository (every key, every formatted value, the peak-path strings) and the model_arch text (nested module view with
+per-module time / FLOP / memory totals) for hand-picked and random configurations.
+    python tools/deep_compare_with_reference.py [--cases 0,2,20] [--seed N] [--random K] [--fp8]
 """
-import sys, json, io, os, random, warnings
-from contextlib import redirect_stdout
-warnings.filterwarnings("ignore")
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import compare_with_reference as cw, fuzz_vs_reference as fz
-CFG=cw.CFG; REF=cw.REF
-def run(mod_prefix, case, system):
-    strategy, model, layers, mover, sover = case[:5]
-    if mod_prefix == "ref":
-        sys.path.insert(0, REF)
-        from simumax.core.config import ModelConfig, StrategyConfig, SystemConfig
-        from simumax.core.perf_llm import PerfLLM
-    else:
-        from simumax_b200.core.config import ModelConfig, StrategyConfig, SystemConfig
-        from simumax_b200.core.perf_llm import PerfLLM
-    st = StrategyConfig.init_from_config_file(f"{CFG}/strategy/{strategy}.json")
-    for k, v in sover.items(): setattr(st, k, v)
-    p = PerfLLM(); p._search_verbose = False
-    with redirect_stdout(io.StringIO()):
-        p.configure(strategy_config=st, model_config=ModelConfig.init_from_config_file(f"{CFG}/models/{model}.json"),
-                    system_config=SystemConfig.init_from_config_file(f"{CFG}/system/{system}.json"))
-        if layers: p.model_config.layer_num = layers
-        for k, v in mover.items(): setattr(p.model_config, k, v)
-        p.model_config.padded_vocab_size = True; p.model_config.make_vocab_size_divisible_by = 128
-        p.run_estimate()
-        mem = p.analysis_mem().data; cost = p.analysis_cost().data
-    return json.loads(json.dumps({"mem": mem, "cost": cost}, default=str))
-def diff(a,b,path="",out=None):
-    out = [] if out is None else out
-    if isinstance(a,dict) and isinstance(b,dict):
-        for k in sorted(set(a)|set(b)):
-            if k not in a: out.append((path+"/"+k,"<missing in ref>",str(b[k])[:60]))
-            elif k not in b: out.append((path+"/"+k,str(a[k])[:60],"<missing in new>"))
-            else: diff(a[k],b[k],path+"/"+k,out)
-    elif isinstance(a,list) and isinstance(b,list) and len(a)==len(b):
-        for i,(x,y) in enumerate(zip(a,b)): diff(x,y,f"{path}[{i}]",out)
-    else:
-        if a!=b:
-            try:
-                fa,fb=float(str(a).split()[0]),float(str(b).split()[0])
-                if abs(fa-fb)<=1e-9*max(abs(fa),abs(fb),1e-300): return out
-            except Exception: pass
-            out.append((path,str(a)[:60],str(b)[:60]))
-    return out
-cases=[cw.CASES[i] for i in (0,2,4,8,12,15,19)]
-rng=random.Random(5)
-while len(cases)<19:
-    c=fz.sample(rng); cases.append(c)
+import json, os, random, sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from deep_compare_with_reference_lib import SOFT, cw, diff, fz, run   # noqa: E402
+import argparse
+ap=argparse.ArgumentParser()
+ap.add_argument("--cases", default="0,2,4,8,12,15,19", help="indices into compare_with_reference.CASES")
+ap.add_argument("--seed", type=int, default=5)
+ap.add_argument("--random", type=int, default=12, help="number of random configurations from the fuzzer's sampler")
+ap.add_argument("--fp8", action="store_true", help="force fp8 on the random configurations")
+args=ap.parse_args()
+cases=[cw.CASES[int(i)] for i in args.cases.split(",") if i!=""]
+rng=random.Random(args.seed)
+for _ in range(args.random):
+    c=fz.sample(rng)
+    if args.fp8:
+        c=list(c[:5])+['a100_pcie']; c[4]=dict(c[4], fp8=True); c=tuple(c)      # a system with fp8 tables
+    cases.append(c)
 tot=0
 for c in cases:
     res=[]
@@ -59,6 +29,6 @@ for c in cases:
     if "error" in res[0] or "error" in res[1]:
         continue
     d=[x for x in diff(res[0],res[1]) if not x[0].endswith('/raw')]; tot+=1      # 'raw' (unformatted numbers) is an addition of this repo
-    print("OK " if not d else f"DIFF({len(d)})", c[0], c[1], json.dumps(c[4])[:80])
+    print("OK " if not d else f"DIFF({len(d)})", c[0], c[1], json.dumps(c[4])[:80], f"| arch lines {len(res[0]['arch'])}")
     for x in d[:6]: print("    ",x)
-print("compared",tot)
+print("compared",tot,"| values equal as numbers but not as text:",len(SOFT),SOFT[:3])
