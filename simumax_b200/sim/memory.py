@@ -155,65 +155,128 @@ class SimuMemoryTracker:
                 "events": self.snapshots, "cache_tokens": self.cache_token_events}
 
     def memory_viz_snapshot(self):
-        """Minimal ``torch.cuda.memory._snapshot()``-shaped dict: one segment per rank, alloc/free trace entries for
-        the static block, every cache token and every op-local temporary (loadable by pytorch.org/memory_viz)."""
+        """``torch.cuda.memory._snapshot()``-shaped dict (loadable by pytorch.org/memory_viz), same layout as the reference's
+        exporter (simu_memory.py:212-555): one segment per rank sized for a bump allocator (static block first, then every
+        cache token and op-local temporary at ever-increasing addresses), an alloc / free_requested / free_completed trace
+        whose frames read ``component:phase:kind:op[mbN,chunkK]``, a ``snapshot`` marker after the static block, and the final
+        block list (inactive + still-active blocks, gaps filled)."""
         def dev(rank_name):
             return int(rank_name[4:]) if isinstance(rank_name, str) else int(rank_name)
 
+        def frame(op, phase, kind, component, ev):
+            tags = [f"{k}{ev[f]}" for k, f in (("mb", "microbatch"), ("chunk", "chunk")) if ev.get(f) is not None]
+            return [{"filename": "simumax", "line": 0, "name": f"{component}:{phase}:{kind}:{op}" + (f"[{','.join(tags)}]" if tags else "")}]
+
+        kind_rank = {"init": 0, "start": 1, "peak": 2, "end": 3}
         ranks = sorted({s["rank"] for s in self.snapshots}, key=dev)
-        ndev = (max(dev(r) for r in ranks) + 1) if ranks else 0
-        out = {"device_traces": [[] for _ in range(ndev)], "segments": []}
+        out = {"device_traces": [[] for _ in range((max(map(dev, ranks)) + 1) if ranks else 0)], "segments": []}
         for rname in ranks:
             d = dev(rname)
-            base = (d + 1) << 40
-            static = int(self.static_bytes[d])
-            peak = int(self.peak_bytes[d])
             trace = out["device_traces"][d]
-            trace.append({"action": "segment_alloc", "addr": base, "size": max(peak, static), "stream": 0, "frames": []})
-            if static:
-                trace.append({"action": "alloc", "addr": base, "size": static, "stream": 0,
-                              "frames": [{"filename": "simumax", "line": 0, "name": "static:init:init:static"}]})
-            cursor = base + static
-            addr_of = {}
-            # cache tokens get bump-allocated addresses; temporaries live above the currently cached bytes
-            timeline = []
-            for ev in self.cache_token_events:
-                if ev["rank"] != rname:
-                    continue
-                ts = ev["alloc_ts_us"] if ev["action"] == "alloc" else ev["free_ts_us"]
-                timeline.append((ts, 0 if ev["action"] == "alloc" else 1, ev))
-            temps = [s for s in self.snapshots if s["rank"] == rname and s["kind"] == "peak" and s["temp_bytes"] > 0]
-            for s in temps:
-                timeline.append((s["ts_us"], 2, s))
-            timeline.sort(key=lambda x: (x[0], x[1]))
-            live_blocks = []
-            for ts, kind, ev in timeline:
-                if kind == 0:
-                    addr_of[ev["token_id"]] = cursor
-                    tag = f"[mb{ev['microbatch']}]" if ev["microbatch"] is not None else ""
-                    frames = [{"filename": "simumax", "line": 0, "name": f"cached:{ev['alloc_phase']}:alloc:{ev['op_name']}{tag}"}]
-                    trace.append({"action": "alloc", "addr": cursor, "size": ev["size_bytes"], "stream": 0, "frames": frames})
-                    live_blocks.append((cursor, ev["size_bytes"], frames, ev["token_id"]))
-                    cursor += ev["size_bytes"]
-                elif kind == 1:
-                    a = addr_of.pop(ev["token_id"], None)
-                    if a is not None:
-                        trace.append({"action": "free_requested", "addr": a, "size": ev["size_bytes"], "stream": 0, "frames": []})
-                        trace.append({"action": "free_completed", "addr": a, "size": ev["size_bytes"], "stream": 0, "frames": []})
-                        live_blocks = [b for b in live_blocks if b[3] != ev["token_id"]]
-                else:
-                    frames = [{"filename": "simumax", "line": 0, "name": f"temp:{ev['phase']}:peak:{ev['op_name']}"}]
-                    trace.append({"action": "alloc", "addr": cursor, "size": ev["temp_bytes"], "stream": 0, "frames": frames})
-                    trace.append({"action": "free_requested", "addr": cursor, "size": ev["temp_bytes"], "stream": 0, "frames": []})
-                    trace.append({"action": "free_completed", "addr": cursor, "size": ev["temp_bytes"], "stream": 0, "frames": []})
-            blocks = []
-            if static:
-                blocks.append({"address": base, "size": static, "requested_size": static, "state": "active_allocated",
-                               "frames": [{"filename": "simumax", "line": 0, "name": "static:init:init:static"}]})
-            for a, sz, frames, _ in live_blocks:
-                blocks.append({"address": a, "size": sz, "requested_size": sz, "state": "active_allocated", "frames": frames})
-            out["segments"].append({"device": d, "address": base, "total_size": max(peak, static), "allocated_size": static,
-                                    "active_size": static, "requested_size": static, "stream": 0,
-                                    "segment_type": "large", "segment_pool_id": (0, 0), "is_expandable": False,
-                                    "frames": [], "blocks": blocks})
+            events = sorted((e for e in self.snapshots if e["rank"] == rname),
+                            key=lambda e: (not (e["phase"] == "init" and e["kind"] == "init"), e["ts_us"], kind_rank.get(e["kind"], 9)))
+            tokens = sorted((e for e in self.cache_token_events if e["rank"] == rname),
+                            key=lambda e: (e["alloc_ts_us"] if e["action"] == "alloc" else e["free_ts_us"], e["action"] != "alloc",
+                                           e["token_id"]))
+            # a bump allocator never reuses an address: the segment must hold everything that is ever allocated
+            grown, seen = 0, {"cached_bytes": 0, "temp_bytes": 0}
+            for e in events:
+                for comp in seen:
+                    grown += max(0, int(e[comp]) - seen[comp])
+                    seen[comp] = int(e[comp])
+            grown = max(grown, sum(int(t["size_bytes"]) for t in tokens if t["action"] == "alloc"))
+            static = int(self.static_bytes[d])
+            base = (d + 1) << 40
+            seg_size = int(max(self.peak_bytes[d], grown + static))
+            if seg_size > 0:
+                trace.append({"action": "segment_alloc", "addr": base, "size": seg_size, "stream": 0, "frames": []})
+            bump = base + static
+            live = {"static_bytes": [], "temp_bytes": []}           # stacks of {"addr", "size", "frames"}
+            live_tokens, retired = {}, []
+            level = {"static_bytes": 0, "temp_bytes": 0}
+            marker_done = False
+            ti = 0
+
+            def log(action, blk):
+                trace.append({"action": action, "addr": blk["addr"], "size": blk["size"], "stream": 0, "frames": blk["frames"]})
+
+            def retire(blk):
+                retired.append({"address": blk["addr"], "size": blk["size"], "requested_size": blk["size"], "state": "inactive",
+                                "frames": blk["frames"]})
+
+            def drain(ts, inclusive):
+                nonlocal ti, bump
+                while ti < len(tokens):
+                    t = tokens[ti]
+                    tts = t["alloc_ts_us"] if t["action"] == "alloc" else t["free_ts_us"]
+                    if tts > ts or (tts == ts and not inclusive):
+                        return
+                    if t["action"] == "alloc":
+                        blk = {"addr": bump, "size": int(t["size_bytes"]),
+                               "frames": frame(t["op_name"], t["alloc_phase"], "alloc", "cached", t)}
+                        bump += blk["size"]
+                        live_tokens[t["token_id"]] = blk
+                        log("alloc", blk)
+                    else:
+                        blk = live_tokens.pop(t["token_id"])
+                        log("free_requested", blk)
+                        log("free_completed", blk)
+                        retire(blk)
+                    ti += 1
+
+            for e in events:
+                drain(e["ts_us"], False)
+                if not marker_done and not (e["phase"] == "init" and e["kind"] == "init"):
+                    trace.append({"action": "snapshot", "stream": 0, "frames": frame("static", "init", "snapshot", "static", {})})
+                    marker_done = True
+                for comp in ("static_bytes", "temp_bytes"):          # cached bytes are the tokens above
+                    delta = int(e[comp]) - level[comp]
+                    name = comp.split("_")[0]
+                    if delta > 0:
+                        if comp == "static_bytes":
+                            addr = base + level[comp]
+                        else:
+                            addr, bump = bump, bump + delta
+                        blk = {"addr": addr, "size": delta, "frames": frame(e["op_name"], e["phase"], e["kind"], name, e)}
+                        live[comp].append(dict(blk))
+                        log("alloc", blk)
+                    elif delta < 0:
+                        need = -delta
+                        while need > 0:
+                            if not live[comp]:
+                                raise RuntimeError(f"free underflow in memory_viz export for {name}: {need}")
+                            top = live[comp][-1]
+                            if top["size"] <= need:
+                                freed, rest = live[comp].pop(), None
+                            else:                                   # partial free: the tail of the block stays allocated
+                                freed = {"addr": top["addr"], "size": need, "frames": top["frames"]}
+                                rest = {"addr": top["addr"] + need, "size": top["size"] - need, "frames": top["frames"]}
+                                live[comp][-1] = rest
+                            need -= freed["size"]
+                            if comp != "static_bytes":
+                                log("free_requested", freed)
+                                log("free_completed", freed)
+                                if rest is not None:
+                                    log("alloc", rest)
+                            retire(freed)
+                    level[comp] = int(e[comp])
+                drain(e["ts_us"], True)
+            if not marker_done:
+                trace.append({"action": "snapshot", "stream": 0, "frames": frame("static", "init", "snapshot", "static", {})})
+
+            active = [{"address": b["addr"], "size": b["size"], "requested_size": b["size"], "state": "active_allocated",
+                       "frames": b["frames"]}
+                      for b in live["static_bytes"] + list(live_tokens.values()) + live["temp_bytes"]]
+            blocks, cursor = [], base
+            for b in sorted(retired + active, key=lambda b: b["address"]):
+                if cursor < b["address"]:
+                    blocks.append({"size": b["address"] - cursor, "state": "inactive"})
+                blocks.append({"size": b["size"], "requested_size": b["requested_size"], "frames": b["frames"], "state": b["state"]})
+                cursor = b["address"] + b["size"]
+            if cursor < base + seg_size:
+                blocks.append({"size": base + seg_size - cursor, "state": "inactive"})
+            in_use = int(self.static_bytes[d] + self.cached_bytes[d])
+            out["segments"].append({"device": d, "address": base, "total_size": seg_size, "stream": 0, "segment_type": "large",
+                                    "allocated_size": in_use, "active_size": in_use,
+                                    "blocks": blocks or [{"size": max(seg_size, 1), "state": "inactive"}]})
         return out

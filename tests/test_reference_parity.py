@@ -116,3 +116,15 @@ def test_model_arch_text_identical():
         a, b = dl.run("ref", case, system), dl.run("new", case, system)
         assert a["arch"] == b["arch"], i
         assert [d for d in dl.diff(a, b) if not d[0].endswith("/raw")] == []
+
+
+@pytest.mark.timeout(600)
+def test_memory_files_identical():
+    """simu_memory_snapshot.json, simu_memory_result.json and the torch memory_viz pickle (segment size, every alloc / free
+    trace entry with its frames, the final block list) of a recompute run and a pipeline run."""
+    import compare_sim as cs
+    import deep_compare_trace as dt
+    for i in (5, 2):
+        dt.run("ref", cs.CASES[i])
+        dt.run("new", cs.CASES[i])
+        assert dt.memory_files_differ() == [], i

@@ -1,6 +1,7 @@
 """Dev tool: record-by-record comparison of ``simulate()``'s ``log.log`` and ``tracing_logs.json`` with the reference (CPU only).
 
-``compare_sim.py`` checks the iteration end time and the memory peaks; this one checks every finished job and every Chrome-trace
+``compare_sim.py`` checks the iteration end time and the memory peaks; this one checks the memory snapshot / result / memory_viz
+pickle files and every finished job and every Chrome-trace
 record (lane, name, category, call stack, gid, [gN] correlation tag, post order, flow arrows, metadata; timestamps within the
 1 ns rounding of the reference's text-log round trip).  Documented, deliberate differences are counted separately:
 
@@ -50,7 +51,54 @@ def run(which, case):
         p.run_estimate()
         p.simulate(d, merge_lanes=merge)
     t = json.load(open(os.path.join(d, "tracing_logs.json")))
+    LAST_DIR[which] = d
     return t["traceEvents"] if isinstance(t, dict) else t
+
+
+LAST_DIR = {}
+
+
+def memory_files_differ():
+    """simu_memory_snapshot.json, simu_memory_result.json (minus this repo's extra ``peak_op_by_rank``) and the memory_viz
+    pickle of the two most recent runs; returns the list of differing files (op names of the helper modules the reference
+    leaves unnamed are normalised like in the trace)."""
+    import pickle
+    bad = []
+    a, b = LAST_DIR.get("ref"), LAST_DIR.get("new")
+    if not a or not b or not os.path.exists(os.path.join(a, "simu_memory_snapshot.json")):
+        return bad
+    pat = re.compile(r"self(\.[A-Za-z0-9_]+)*\.(" + "|".join(_UNNAMED_IN_REF) + r")")
+
+    def norm(obj):
+        return json.loads(pat.sub("self", json.dumps(obj, default=str, sort_keys=True)))
+
+    def per_rank(records):
+        """Records are appended in the order the host loop visits the ranks (not a property of the schedule): compare each
+        rank's own sequence; token ids are renumbered per rank for the same reason."""
+        out, ids = {}, {}
+        for r in records:
+            r = dict(r)
+            if str(r.get("op_name", "")).split(".")[-1] in _UNNAMED_IN_REF or r.get("op_name") == "self":
+                r.update(op_name="self", scope="", microbatch=None, chunk=None)   # helper modules the reference leaves unnamed
+            if str(r.get("op_name", "")).endswith(".rotary_pos_emb"):             # named, but its scope lacks the rank prefix
+                r.update(scope="", microbatch=None, chunk=None)
+            if "token_id" in r:
+                r["token_id"] = ids.setdefault((r["rank"], r["token_id"]), len([k for k in ids if k[0] == r["rank"]]))
+            out.setdefault(r["rank"], []).append(r)
+        return out
+    x, y = (json.load(open(os.path.join(d, "simu_memory_snapshot.json"))) for d in (a, b))
+    if any(per_rank(x[k]) != per_rank(y[k]) for k in ("events", "cache_tokens")) or \
+            {k: v for k, v in x.items() if k not in ("events", "cache_tokens")} != {k: v for k, v in y.items() if k not in ("events", "cache_tokens")}:
+        bad.append("simu_memory_snapshot.json")
+    x, y = (json.load(open(os.path.join(d, "simu_memory_result.json"))) for d in (a, b))
+    y.pop("peak_op_by_rank", None)
+    if x != y:
+        bad.append("simu_memory_result.json")
+    x = pickle.load(open(os.path.join(a, "simu_memory_viz_snapshot.pickle"), "rb"))
+    y = pickle.load(open(os.path.join(b, "simu_memory_viz_snapshot.pickle"), "rb"))
+    if norm(x) != norm(y):
+        bad.append("simu_memory_viz_snapshot.pickle")
+    return bad
 
 
 def _key(r):
@@ -125,11 +173,13 @@ def main():
         sync_vpp = "vp" in case[0] and not case[5].get("pp_comm_async", "sync" not in case[0])
         world_opt = not case[6] and c["time"] == c["time_optimizer"]      # documented in docs/RESULTS.md (world-mode optimizer barrier)
         unexplained = 0 if sync_vpp else c["diff"] + (0 if world_opt else c["time"])
+        mem_bad = [] if (sync_vpp or world_opt) else memory_files_differ()
+        unexplained += len(mem_bad)
         bad += bool(unexplained)
         print(("OK  " if not unexplained else "DIFF"), i, case[0], case[1], case[5], "| records", len(ref), len(new),
               "| identical", c["same"], "| wait-lane extras", c["wait"] + c["meta_extra"], "| kept (dropped by ref)", c["dropped"],
               "| retimed" + (" (documented clamp)" if sync_vpp and c["time"] else " (world-mode optimizer barrier)" if world_opt and
-                             c["time"] else ""), c["time"], "| other", c["diff"])
+                             c["time"] else ""), c["time"], "| other", c["diff"], "| memory files", "identical" if not mem_bad else mem_bad)
         if unexplained:
             for e in ex[:6]:
                 print("    ", e)
