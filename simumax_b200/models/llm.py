@@ -402,10 +402,15 @@ class StageChunk:
         for n in self.nodes:
             if n.gemm is None or n.kind not in ("LinearCol", "LinearRow", "GroupLinearCol", "GroupLinearRow", "Router"):
                 continue
-            if n.kind == "Router":
-                continue
+            table = n.gemm
+            if n.kind.startswith("GroupLinear"):
+                # the reference lists a grouped GEMM as one flat GEMM over all local experts' tokens (B = 1, the token dimension
+                # -- M of fwd / dgrad, K of wgrad -- multiplied by the expert count; moe_module.py GroupLinearBase)
+                g = table["B"]
+                table = dict(table, B=[1, 1, 1], M=[table["M"][0] * g[0], table["M"][1] * g[1], table["M"][2]],
+                             K=[table["K"][0], table["K"][1], table["K"][2] * g[2]])
             for key in ("B", "M", "K", "N", "layout", "accumulate", "out_dtype"):
-                out[key].extend(n.gemm[key])
+                out[key].extend(table[key])
             cc = [n.details[p]["compute_details"]["compute_only_time"] for p in PHASES]
             mc = [n.details[p]["io_details"]["io_time"] for p in PHASES]
             out["compute_cost"].extend(cc)
@@ -443,7 +448,7 @@ class StageChunk:
             is_linear = n.gemm is not None
             push(n.kind, n.in_shapes + (w if not is_linear else []), n.out_shapes, n.compute.fwd_flops,
                  n.compute.fwd_accessed_mem, n.cost.fwd_compute_time, n.details["fwd"])
-            wt = [list(reversed(n.weight_shape))] if (is_linear and n.weight_shape) else w
+            wt = [] if is_linear else w          # only modules with a ``weight`` attribute list it (language_model.py:551-557)
             push(n.kind + "_bwd_act", n.out_shapes + wt, n.in_shapes, n.compute.bwd_grad_act_flops,
                  n.compute.bwd_grad_act_accessed_mem, n.cost.bwd_grad_act_time, n.details["bwd_grad_act"])
             if is_linear and n.weight_shape:

@@ -30,11 +30,24 @@ def run(mod_prefix, case, system):
         p.run_estimate()
         mem = p.analysis_mem().data; cost = p.analysis_cost().data
         arch = str(dict(p.model_chunk_dict))          # text of model_arch / base_info.json["arch"]: the nested module view
-    return json.loads(json.dumps({"mem": mem, "cost": cost, "arch": arch.split("\n")}, default=str))
+        gemm = p.analysis_op_info()                    # per-chunk GEMM tables (fwd / dgrad / wgrad rows of every linear)
+        ops = {}
+        for name, chunk in p.model_chunk_dict.items():
+            try:
+                ops[name] = chunk.analysis_op_info(True)      # per-op table with roofline details
+            except AttributeError:                            # the reference cannot build it for MoE chunks (Permutation has no details)
+                ops = None
+                break
+    out = {"mem": mem, "cost": cost, "arch": arch.split("\n"), "gemm": gemm}
+    if ops is not None:
+        out["ops"] = ops
+    return json.loads(json.dumps(out, default=str))
 SOFT=[]
 def diff(a,b,path="",out=None):
     out = [] if out is None else out
     if isinstance(a,dict) and isinstance(b,dict):
+        if path=="" and ("ops" in a) != ("ops" in b):            # compared only when both implementations can build it
+            a={k:v for k,v in a.items() if k!="ops"}; b={k:v for k,v in b.items() if k!="ops"}
         for k in sorted(set(a)|set(b)):
             if k not in a: out.append((path+"/"+k,"<missing in ref>",str(b[k])[:60]))
             elif k not in b: out.append((path+"/"+k,str(a[k])[:60],"<missing in new>"))
