@@ -1,4 +1,4 @@
-"""Computational-graph capture: an ONNX-like node/edge list of the evaluated op IR + optional graphviz render.
+"""Computational-graph capture: the reference's ONNX-style ``model_graph.json`` of the evaluated op IR + optional graphviz render.
 
 Enabled with ``ENABLE_SIMU_GRAPH=1`` (``PerfLLM.analysis`` then writes ``model_graph.json`` and
 ``computational_graph.*``) or explicitly via ``PerfLLM.capture(save_path)`` / ``run_estimate(capture_graph=True)``.
@@ -12,45 +12,72 @@ from typing import Dict, List
 
 
 class SimuGraph:
-    def __init__(self):
+    """ONNX-style container with the reference's JSON schema (core/graph.py:96-124): ``name``, ``nodes`` (name =
+    ``<attribute>_<call index>``, op_type, enable_recompute, is_variance_node, input / output tensor names, call_idx,
+    attributes, domain), ``inputs`` / ``outputs`` / ``initializers`` and ``value_info`` (shape + dtype of every produced
+    tensor).  Additions: per-node cost / memory numbers under ``attributes`` and an explicit ``edges`` list for the renderer."""
+
+    def __init__(self, name: str = "model_graph"):
+        self.name = name
         self.nodes: List[dict] = []
         self.edges: List[dict] = []
+        self.value_info: Dict[str, dict] = {}
+        self._tensors = 0
 
-    def add_node(self, name, op_type, inputs, outputs, attrs=None):
-        self.nodes.append({"id": len(self.nodes), "name": name, "op_type": op_type, "inputs": inputs,
-                           "outputs": outputs, "attrs": attrs or {}})
-        return len(self.nodes) - 1
+    def new_tensor(self, prefix: str, shape=None, dtype: str = "bf16") -> str:
+        name = f"{prefix}_{self._tensors}"
+        self._tensors += 1
+        if prefix == "output":
+            self.value_info[name] = {"shape": list(shape or []), "dtype": dtype}
+        return name
+
+    def add_node(self, attr_name, op_type, inputs, outputs, *, enable_recompute=False, is_variance_node=False, attrs=None,
+                 call_idx=None):
+        idx = len(self.nodes)                     # node names count over the whole graph, call_idx within the op's chunk
+        self.nodes.append({"name": f"{attr_name}_{idx}", "op_type": op_type, "enable_recompute": bool(enable_recompute),
+                           "is_variance_node": bool(is_variance_node), "inputs": list(inputs), "outputs": list(outputs),
+                           "call_idx": idx if call_idx is None else call_idx, "attributes": attrs or {}, "domain": ""})
+        return idx
 
     def add_edge(self, src, dst, shape):
         self.edges.append({"src": src, "dst": dst, "shape": shape})
 
     def to_dict(self) -> Dict:
-        return {"nodes": self.nodes, "edges": self.edges}
+        return {"name": self.name, "nodes": self.nodes, "inputs": [], "outputs": [], "initializers": [],
+                "value_info": self.value_info, "edges": self.edges}
 
     def export_json(self, path: str):
         with open(path, "w", encoding="utf-8") as fh:
-            json.dump(self.to_dict(), fh, indent=1)
+            json.dump(self.to_dict(), fh, indent=2)
         return path
 
 
 def capture_graph(perf) -> SimuGraph:
-    """One sub-graph per stage chunk; data edges follow the sequential op order (the model zoo is a chain with
-    side inputs only inside attention / MoE blocks, which are recorded as multi-input nodes)."""
+    """Export of every stage chunk's op list, in chunk order, into one graph (the reference records one forward pass per chunk
+    with shared node / tensor counters; each chunk starts from a fresh ``input_N`` tensor).  Data edges follow the execution
+    order: dense models are chains and come out identical to the reference's file; ops with several inputs / outputs (MLA
+    split / concat, MoE permutation) consume every tensor the previous op produced and name one tensor per output shape --
+    same schema, simplified wiring.  GeLU returns its input tensor object in the reference, so it does not name a new one."""
     g = SimuGraph()
     for chunk_name, chunk in perf.model_chunk_dict.items():
         if not chunk.nodes:
             chunk(perf._chunk_input_shape(chunk.preprocess))
-        prev = None
-        for n in chunk.nodes:
-            attrs = {"stage": chunk_name, "scope": "/".join(n.scope), "fwd_flops": n.compute.fwd_flops,
-                     "fwd_bytes": n.compute.fwd_accessed_mem, "fwd_ms": n.cost.fwd_compute_time,
-                     "bwd_ms": n.cost.bwd_compute_time, "fwd_net_ms": n.cost.fwd_net_time,
-                     "bwd_net_ms": n.cost.bwd_net_time, "cache_bytes": n.act.activation_mem_cache,
-                     "recompute": n.enable_recompute, "weight_shape": n.weight_shape}
-            nid = g.add_node(f"{chunk_name}:{n.name}", n.kind, n.in_shapes, n.out_shapes, attrs)
+        prev_outputs, prev = None, None
+        for k, n in enumerate(chunk.nodes):
+            ins = prev_outputs if prev_outputs is not None else [g.new_tensor("input")]
+            if n.kind == "Gelu":
+                outs = list(ins)
+            else:
+                outs = [g.new_tensor("output", shape, "fp8" if n.kind == "Float8Quantizer" else "bf16") for shape in n.out_shapes]
+            attrs = {"stage": chunk_name, "scope": "/".join(n.scope), "full_name": n.name, "module_path": n.path,
+                     "input_shapes": n.in_shapes, "fwd_flops": n.compute.fwd_flops, "fwd_bytes": n.compute.fwd_accessed_mem,
+                     "fwd_ms": n.cost.fwd_compute_time, "bwd_ms": n.cost.bwd_compute_time, "fwd_net_ms": n.cost.fwd_net_time,
+                     "bwd_net_ms": n.cost.bwd_net_time, "cache_bytes": n.act.activation_mem_cache, "weight_shape": n.weight_shape}
+            nid = g.add_node(n.name.split(".")[-1], n.kind, ins, outs, enable_recompute=n.enable_recompute,
+                             is_variance_node=n.is_variance_node, attrs=attrs, call_idx=k)
             if prev is not None:
                 g.add_edge(prev, nid, n.in_shapes[0] if n.in_shapes else [])
-            prev = nid
+            prev, prev_outputs = nid, outs
     return g
 
 
@@ -68,11 +95,21 @@ def visualize_with_graphviz(json_path: str, output_path: str = "computational_gr
     with open(json_path, "r", encoding="utf-8") as fh:
         data = json.load(fh)
     lines = ["digraph G {", "  rankdir=TB; node [shape=box, fontsize=9];"]
+    shapes = data.get("value_info", {})
+    produced = {}
+    for pos, n in enumerate(data["nodes"]):
+        n["_pos"] = pos
     for n in data["nodes"]:
-        label = f"{n['op_type']}\\n{n['name'].split(':')[-1]}\\n{n['outputs']}"
-        lines.append(f"  n{n['id']} [label=\"{label}\"];")
-    for e in data["edges"]:
-        lines.append(f"  n{e['src']} -> n{e['dst']} [label=\"{e['shape']}\", fontsize=8];")
+        outs = [shapes.get(t, {}).get("shape", t) for t in n["outputs"]]
+        color = ", style=filled, fillcolor=lightyellow" if n.get("enable_recompute") else ""
+        label = f"{n['op_type']}\\n{n['name']}\\n{outs}"
+        lines.append(f"  n{n['_pos']} [label=\"{label}\"{color}];")
+        for t in n["outputs"]:
+            produced.setdefault(t, n["_pos"])
+    for n in data["nodes"]:                      # edges from tensor names: works for reference-made model_graph.json too
+        for src in sorted({produced[t] for t in n["inputs"] if t in produced and produced[t] != n["_pos"]}):
+            shape = [shapes.get(t, {}).get("shape") for t in n["inputs"] if produced.get(t) == src]
+            lines.append(f"  n{src} -> n{n['_pos']} [label=\"{shape[0] if len(shape) == 1 else shape}\", fontsize=8];")
     lines.append("}")
     dot_path = output_path + ".dot"
     with open(dot_path, "w", encoding="utf-8") as fh:

@@ -1,4 +1,6 @@
 """Structural invariants of the op IR that must hold for any config (no reference data needed)."""
+import os
+
 import pytest
 
 from helpers import MOE, build
@@ -63,6 +65,16 @@ def test_result_files(tmp_path):
     assert tr["displayTimeUnit"] == "ms" and any(e.get("ph") == "X" for e in tr["traceEvents"])
     g = p.capture(str(tmp_path))
     assert len(g.nodes) > 10 and (tmp_path / "model_graph.json").exists()
+    # the reference's ONNX-style schema (core/graph.py:96-124); both pipeline chunks in one graph, call_idx restarts per chunk
+    gj = json.load(open(tmp_path / "model_graph.json"))
+    assert list(gj)[:6] == ["name", "nodes", "inputs", "outputs", "initializers", "value_info"] and gj["name"] == "model_graph"
+    first = gj["nodes"][0]
+    assert first["name"] == "embedding_0" and first["inputs"] == ["input_0"] and first["outputs"] == ["output_1"]
+    assert set(first) == {"name", "op_type", "enable_recompute", "is_variance_node", "inputs", "outputs", "call_idx", "attributes", "domain"}
+    assert gj["value_info"]["output_1"] == {"shape": [1, 4096, 4096], "dtype": "bf16"}
+    assert sum(n["call_idx"] == 0 for n in gj["nodes"]) == 2 and sum(t.startswith("input_") for n in gj["nodes"] for t in n["inputs"]) == 2
+    from simumax_b200.core.graph import visualize_with_graphviz
+    assert os.path.exists(visualize_with_graphviz(str(tmp_path / "model_graph.json"), str(tmp_path / "g")))
 
 
 def test_model_arch_is_the_nested_module_view(tmp_path):
