@@ -52,6 +52,22 @@ class SimuGraph:
         return path
 
 
+# fan-in of the ops that do not simply consume the previous op's output: op attribute -> [(producer attribute, output index)]
+# (MLA: reference dense_module.py:2755-2840; MoE block: moe_module.py ExpertMLP.forward).  "<norm>" = the norm that feeds the block.
+_FAN_IN = {
+    "linear_kv_down_proj": [("<norm>", 0)],
+    "kv_layernorm": [("kv_combined_Split", 0)],
+    "rotary_pos_emb": [("kv_combined_Split", 1)],
+    "K_pos_emb_Concat": [("KV_Split", 0), ("rotary_pos_emb", 0)],
+    "QKV_Concat": [("<q>", 0), ("K_pos_emb_Concat", 0), ("KV_Split", 1)],
+    "router": [("<norm>", 0)],
+    "permutation": [("<norm>", 0), ("router", 0)],
+    "unpermutation": [("group_linear2", 0), ("router", 0)],
+    "SharedExpertAddFunction": [("unpermutation", 0), ("<shared>", 0)],
+}
+_OUT_DTYPE = {"Float8Quantizer": "fp8", "Router": "int32"}
+
+
 def capture_graph(perf) -> SimuGraph:
     """Export of every stage chunk's op list, in chunk order, into one graph (the reference records one forward pass per chunk
     with shared node / tensor counters; each chunk starts from a fresh ``input_N`` tensor).  Data edges follow the execution
@@ -63,21 +79,42 @@ def capture_graph(perf) -> SimuGraph:
         if not chunk.nodes:
             chunk(perf._chunk_input_shape(chunk.preprocess))
         prev_outputs, prev = None, None
+        made: Dict[str, list] = {}                     # most recent outputs per op attribute (and per enclosing wrapper)
         for k, n in enumerate(chunk.nodes):
+            parts = n.name.split(".")
+            attr = parts[-1]
             ins = prev_outputs if prev_outputs is not None else [g.new_tensor("input")]
+            wired = []
+            for src, idx in _FAN_IN.get(attr, []) if attr in _FAN_IN else _FAN_IN.get(parts[-2] if len(parts) > 1 else "", []):
+                outs_of = made.get(src)
+                if outs_of is None or idx >= len(outs_of):
+                    wired = []
+                    break
+                wired.append(outs_of[idx])
+            if wired:
+                ins = wired
             if n.kind == "Gelu":
                 outs = list(ins)
             else:
-                outs = [g.new_tensor("output", shape, "fp8" if n.kind == "Float8Quantizer" else "bf16") for shape in n.out_shapes]
+                outs = [g.new_tensor("output", shape, _OUT_DTYPE.get(n.kind, "bf16")) for shape in n.out_shapes]
             attrs = {"stage": chunk_name, "scope": "/".join(n.scope), "full_name": n.name, "module_path": n.path,
                      "input_shapes": n.in_shapes, "fwd_flops": n.compute.fwd_flops, "fwd_bytes": n.compute.fwd_accessed_mem,
                      "fwd_ms": n.cost.fwd_compute_time, "bwd_ms": n.cost.bwd_compute_time, "fwd_net_ms": n.cost.fwd_net_time,
                      "bwd_net_ms": n.cost.bwd_net_time, "cache_bytes": n.act.activation_mem_cache, "weight_shape": n.weight_shape}
-            nid = g.add_node(n.name.split(".")[-1], n.kind, ins, outs, enable_recompute=n.enable_recompute,
+            nid = g.add_node(attr, n.kind, ins, outs, enable_recompute=n.enable_recompute,
                              is_variance_node=n.is_variance_node, attrs=attrs, call_idx=k)
             if prev is not None:
                 g.add_edge(prev, nid, n.in_shapes[0] if n.in_shapes else [])
             prev, prev_outputs = nid, outs
+            made[attr] = outs
+            if len(parts) > 2:
+                made[parts[-2]] = outs                 # fp8 wrapper: <linear attr>.linear
+            if n.kind == "LayerNorm" and attr in ("layernorm_input", "pre_mlp_layernorm"):
+                made["<norm>"] = outs
+            if attr in ("linear_q_up_proj", "linear_q_proj") or (len(parts) > 1 and parts[-2] in ("linear_q_up_proj", "linear_q_proj")):
+                made["<q>"] = outs
+            if "shared_expert" in parts and n.kind == "LinearRow":
+                made["<shared>"] = outs
     return g
 
 

@@ -50,7 +50,7 @@ def emit_mla_attention(em, layer_idx: int, shape, rc: AttentionRecomputeConfig):
                                      layer_idx=layer_idx, has_cached_inputs=True, enable_recompute=rc.kv_down_recompute,
                                      is_last_recompute=True, use_variance_tail_model=tail)
         latent = [ckv_shape[0], ckv_shape[1], cfg.kv_lora_rank]
-        k_rope = [ckv_shape[0], ckv_shape[1], cfg.qk_pos_emb_head_dim]
+        k_rope = [ckv_shape[0], ckv_shape[1], 1, cfg.qk_pos_emb_head_dim]      # one shared rope head (viewed 4-d like the reference)
         em.add(D.passthrough("SplitModule", [ckv_shape], [latent, k_rope], em.name("kv_combined_Split"),
                              enable_recompute=rc.core_attn_recompute, display="kv_combined_Split"))
         node, s3 = D.layernorm(st, cfg.kv_lora_rank, latent, em.name("kv_layernorm"),
@@ -65,7 +65,7 @@ def emit_mla_attention(em, layer_idx: int, shape, rc: AttentionRecomputeConfig):
         em.add(D.passthrough("SplitModule", [kv4], [k_nope, value], em.name("KV_Split"),
                              enable_recompute=rc.core_attn_recompute, display="KV_Split"))
         rope_in = [B, S, 1, cfg.qk_pos_emb_head_dim]
-        em.add(D.passthrough("RotaryEmbedding", [rope_in], [rope_in], em.name("rotary_pos_emb"),
+        em.add(D.passthrough("RotaryEmbedding", [rope_in], [[B, S, heads, cfg.qk_pos_emb_head_dim]], em.name("rotary_pos_emb"),
                              enable_recompute=rc.rope_recompute, display="RotaryEmbedding"))
         k_rope_b = [B, S, heads, cfg.qk_pos_emb_head_dim]
         key = [B, S, heads, q_head]

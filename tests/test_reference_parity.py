@@ -128,3 +128,39 @@ def test_memory_files_identical():
         dt.run("ref", cs.CASES[i])
         dt.run("new", cs.CASES[i])
         assert dt.memory_files_differ() == [], i
+
+
+@pytest.mark.timeout(600)
+def test_model_graph_json_identical(tmp_path):
+    """model_graph.json of run_estimate(capture_graph=True): node names, tensor wiring (MLA split / rope / concat fan-in, MoE
+    router -> permutation -> un-permutation -> shared-expert add), call_idx and value_info; this repo's extras are ignored."""
+    import io
+    import json
+    from contextlib import redirect_stdout
+
+    import compare_sim as cs
+
+    def run(which, strategy, model):
+        if which == "ref":
+            sys.path.insert(0, REF)
+            from simumax.core.config import ModelConfig, StrategyConfig, SystemConfig
+            from simumax.core.perf_llm import PerfLLM
+        else:
+            from simumax_b200.core.config import ModelConfig, StrategyConfig, SystemConfig
+            from simumax_b200.core.perf_llm import PerfLLM
+        p = PerfLLM()
+        d = tmp_path / f"{which}-{model}"
+        d.mkdir()
+        with redirect_stdout(io.StringIO()):
+            p.configure(strategy_config=StrategyConfig.init_from_config_file(f"{cs.CFG}/strategy/{strategy}.json"),
+                        model_config=ModelConfig.init_from_config_file(f"{cs.CFG}/models/{model}.json"),
+                        system_config=SystemConfig.init_from_config_file(f"{cs.CFG}/system/b200_bf16_ceperm.json"))
+            p.model_config.layer_num = 2
+            p.run_estimate(capture_graph=True, save_path=str(d))
+        g = json.load(open(d / "model_graph.json"))
+        g.pop("edges", None)
+        for n in g["nodes"]:
+            n["attributes"] = {}
+        return g
+    for strategy, model in (("tp2_pp1_dp4_mbs1", "llama3-8b"), ("ep4_pp2_dp4_mbs1", "deepseekv2"), ("tp1_pp2_dp4_mbs1", "gpt3-175b")):
+        assert run("ref", strategy, model) == run("new", strategy, model), model
