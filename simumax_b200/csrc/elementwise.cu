@@ -602,6 +602,41 @@ __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloa
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Embedding: out[t, :] = table[tok[t] - v0, :] (zeros when the token is not in this rank's vocabulary shard [v0, v0 + V)),
+// and its backward grad[tok[t] - v0, :] += dy[t, :] into the fp32 main-grad table (red.global.add.v4.f32: no return trip).
+// One warp per token row, 16-byte accesses.
+// ----------------------------------------------------------------------------------------------
+__global__ void embedding_fwd_kernel(const long long* __restrict__ tok, const __nv_bfloat16* __restrict__ table,
+                                     __nv_bfloat16* __restrict__ out, long long rows, int H, long long v0, long long V) {
+  const int lane = threadIdx.x % 32;
+  const long long warps = (long long)gridDim.x * (blockDim.x / 32);
+  for (long long r = blockIdx.x * (long long)(blockDim.x / 32) + threadIdx.x / 32; r < rows; r += warps) {
+    const long long id = tok[r] - v0;
+    const bool mine = id >= 0 && id < V;
+    const uint4* src = reinterpret_cast<const uint4*>(table + (mine ? id : 0) * H);
+    uint4* dst = reinterpret_cast<uint4*>(out + r * H);
+    for (int c = lane; c < H / 8; c += 32) dst[c] = mine ? src[c] : make_uint4(0, 0, 0, 0);
+  }
+}
+
+__global__ void embedding_bwd_kernel(const long long* __restrict__ tok, const __nv_bfloat16* __restrict__ dy,
+                                     float* __restrict__ grad, long long rows, int H, long long v0, long long V) {
+  const int lane = threadIdx.x % 32;
+  const long long warps = (long long)gridDim.x * (blockDim.x / 32);
+  for (long long r = blockIdx.x * (long long)(blockDim.x / 32) + threadIdx.x / 32; r < rows; r += warps) {
+    const long long id = tok[r] - v0;
+    if (id < 0 || id >= V) continue;
+    float* g = grad + id * H;
+    for (int c = lane; c < H / 8; c += 32) {
+      float f[8];
+      load8(dy + r * H + c * 8, f);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g + c * 8), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g + c * 8 + 4), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]) : "memory");
+    }
+  }
+}
+
 // streaming copy (the "default" memory-bandwidth calibration op)
 __global__ void copy_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n16) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
@@ -755,6 +790,16 @@ int smx_moe_prob_grad(const void* dy, const void* y_perm, const int* inv_map, fl
   if (H % 8) return -20;
   smx::moe_prob_grad_kernel<<<grid_for(tokens * topk * 32, 256), 256, 0, SMX_STREAM>>>((const bf16*)dy, (const bf16*)y_perm, inv_map, d_probs,
                                                                                       tokens * topk, topk, H);
+  return (int)cudaGetLastError();
+}
+int smx_embedding_fwd(const long long* tok, const void* table, void* out, long long rows, int H, long long v0, long long V, void* stream) {
+  if (H % 8) return -20;
+  smx::embedding_fwd_kernel<<<grid_for(rows, 8), 256, 0, SMX_STREAM>>>(tok, (const bf16*)table, (bf16*)out, rows, H, v0, V);
+  return (int)cudaGetLastError();
+}
+int smx_embedding_bwd(const long long* tok, const void* dy, float* grad, long long rows, int H, long long v0, long long V, void* stream) {
+  if (H % 8) return -20;
+  smx::embedding_bwd_kernel<<<grid_for(rows, 8), 256, 0, SMX_STREAM>>>(tok, (const bf16*)dy, grad, rows, H, v0, V);
   return (int)cudaGetLastError();
 }
 int smx_add(const void* a, const void* b, void* y, long long n, void* stream) {

@@ -520,6 +520,12 @@ int smx_gemm_2cta(const void* A, const void* B, void* C, int G, int M, int N, in
                   int accumulate, float alpha, long long lda, long long ldb, long long ldc, long long a_bs,
                   long long b_bs, long long c_bs, int num_sms, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  // the armed all-gather state is one-shot: capture and clear it before any early return, so a refused call can never leak
+  // its flags / epoch into the next, unrelated GEMM
+  const uint32_t* armed_flags = g2_ag_flags;
+  const int armed_rows = g2_ag_rows, armed_first = g2_ag_first;
+  const uint32_t armed_epoch = g2_ag_epoch;
+  g2_ag_flags = nullptr;
   if (G <= 0 || M <= 0 || N <= 0 || K <= 0) return 0;
   if (M < 256 || N < 256) return -12;
   const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -536,8 +542,7 @@ int smx_gemm_2cta(const void* A, const void* B, void* C, int G, int M, int N, in
   p.m_tiles = (M + smx::k2BlockM - 1) / smx::k2BlockM;
   p.n_tiles = (N + smx::k2BlockN - 1) / smx::k2BlockN;
   p.ldc = ldc; p.c_batch_stride = c_bs; p.alpha = alpha; p.accumulate = accumulate;
-  p.ag_flags = g2_ag_flags; p.ag_rows_per_flag = g2_ag_rows; p.ag_first_m_blk = g2_ag_first; p.ag_epoch = g2_ag_epoch;
-  g2_ag_flags = nullptr;        // one-shot
+  p.ag_flags = armed_flags; p.ag_rows_per_flag = armed_rows; p.ag_first_m_blk = armed_first; p.ag_epoch = armed_epoch;
   p.rs_world = 1; p.rs_rank = 0; p.rs_rows = M;
   for (int i = 0; i < 8; ++i) p.rs_counter[i] = nullptr;
   p.rs_ticket = nullptr;

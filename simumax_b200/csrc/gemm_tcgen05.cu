@@ -459,6 +459,14 @@ int smx_gemm(const void* A, const void* B, void* C, int G, int M, int N, int K, 
              int out_f32, int accumulate, float alpha, long long lda, long long ldb, long long ldc,
              long long a_bs, long long b_bs, long long c_bs, int block_n, int num_sms, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  // armed (one-shot) all-gather / reduce-scatter state: capture and clear before any early return so that a refused call cannot
+  // leak its flags / peers into the next, unrelated GEMM
+  const uint32_t* armed_flags = g_ag_flags;
+  const int armed_rows = g_ag_rows, armed_first = g_ag_first;
+  const uint32_t armed_epoch = g_ag_epoch;
+  const int armed_rs_world = g_rs_world;
+  g_ag_flags = nullptr;
+  g_rs_world = 1;
   if (G <= 0 || M <= 0 || N <= 0 || K <= 0) return 0;
   const int eb = dtype == 0 ? 2 : 1;
   const int block_k = 128 / eb;
@@ -478,15 +486,13 @@ int smx_gemm(const void* A, const void* B, void* C, int G, int M, int N, int K, 
   p.m_tiles = (M + smx::kBlockM - 1) / smx::kBlockM;
   p.n_tiles = (N + block_n - 1) / block_n;
   p.ldc = ldc; p.c_batch_stride = c_bs; p.alpha = alpha; p.accumulate = accumulate;
-  p.ag_flags = g_ag_flags; p.ag_rows_per_flag = g_ag_rows; p.ag_first_m_blk = g_ag_first; p.ag_epoch = g_ag_epoch;
-  g_ag_flags = nullptr;        // one-shot
+  p.ag_flags = armed_flags; p.ag_rows_per_flag = armed_rows; p.ag_first_m_blk = armed_first; p.ag_epoch = armed_epoch;
   p.rs_world = 1; p.rs_rows = M; p.rs_rank = 0;
   for (int i = 0; i < 8; ++i) p.rs_out[i] = nullptr;
-  if (g_rs_world > 1) {
-    if (G != 1 || N % 8 || M % g_rs_world || accumulate) return -13;
-    p.rs_world = g_rs_world; p.rs_rows = M / g_rs_world; p.rs_rank = g_rs_rank;
-    for (int i = 0; i < g_rs_world; ++i) p.rs_out[i] = g_rs_out[i];
-    g_rs_world = 1;      // one-shot: applies to this launch only
+  if (armed_rs_world > 1) {
+    if (G != 1 || N % 8 || M % armed_rs_world || accumulate) return -13;
+    p.rs_world = armed_rs_world; p.rs_rows = M / armed_rs_world; p.rs_rank = g_rs_rank;
+    for (int i = 0; i < armed_rs_world; ++i) p.rs_out[i] = g_rs_out[i];
   }
   if (dtype == 0) {
     if (!a_mn && !b_mn) return out_f32 ? launch_bn<false, false, true, 2>(block_n, ta, tb, C, p, num_sms, stream)

@@ -30,6 +30,10 @@ _SIGS = {
     "smx_unpermute_combine": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_void_p],
     "smx_moe_prob_grad": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_void_p],
     "smx_add": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_void_p],
+    "smx_embedding_fwd": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_longlong, _c.c_longlong, _c.c_void_p],
+    "smx_embedding_bwd": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_longlong, _c.c_longlong, _c.c_void_p],
+    "smx_rs_consume": [_c.c_void_p, _c.c_int, _c.c_longlong, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                       _c.c_float, _c.c_void_p, _c.c_uint, _c.c_void_p],
     "smx_copy": [_c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_void_p],
 }
 _fns = {}
@@ -87,6 +91,17 @@ def rmsnorm_bwd(x, gamma, dy, rstd, dgamma_fp32: torch.Tensor, dx: Optional[torc
     _call("smx_rmsnorm_bwd", x.data_ptr(), gamma.data_ptr(), dy.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
           dgamma_fp32.data_ptr(), rows, H, 1 if accumulate_dx else 0, _stream(x))
     return dx
+
+
+def add_rmsnorm_fwd(residual: torch.Tensor, delta: torch.Tensor, gamma: torch.Tensor, eps: float, out_sum: torch.Tensor,
+                    out_normed: torch.Tensor, rstd: torch.Tensor) -> None:
+    """One pass: out_sum = residual + delta (rounded to bf16, what the backward re-reads);  out_normed = rmsnorm(out_sum) * gamma.
+    (the owner-side kernel of the fused GEMM -> reduce-scatter with a single slot and no completion counter)"""
+    _bf16c(residual, "residual"); _bf16c(delta, "delta"); _bf16c(gamma, "gamma")
+    H = residual.shape[-1]
+    rows = residual.numel() // H
+    _call("smx_rs_consume", delta.data_ptr(), 1, rows, H, residual.data_ptr(), out_sum.data_ptr(), gamma.data_ptr(),
+          out_normed.data_ptr(), rstd.data_ptr(), float(eps), None, 0, _stream(residual))
 
 
 def swiglu_fwd(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -224,3 +239,21 @@ def copy_(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
     nbytes = src.numel() * src.element_size()
     _call("smx_copy", src.data_ptr(), dst.data_ptr(), nbytes, _stream(src))
     return dst
+
+
+def embedding_fwd(tokens: torch.Tensor, table: torch.Tensor, out: torch.Tensor, v0: int = 0) -> torch.Tensor:
+    """out[t] = table[tokens[t] - v0]; rows whose token is outside this vocabulary shard ``[v0, v0 + table.shape[0])`` are zeroed
+    (vocab-parallel embedding, reference dense_module.py Embedding)."""
+    _bf16c(table, "table"); _bf16c(out, "out")
+    assert tokens.dtype == torch.int64 and tokens.is_contiguous()
+    _call("smx_embedding_fwd", tokens.data_ptr(), table.data_ptr(), out.data_ptr(), tokens.numel(), table.shape[1], v0, table.shape[0],
+          _stream(out))
+    return out
+
+
+def embedding_bwd(tokens: torch.Tensor, dy: torch.Tensor, grad_fp32: torch.Tensor, v0: int = 0) -> None:
+    """grad[tokens[t] - v0] += dy[t] (fp32 main grad, vector reductions; tokens outside the shard are skipped)."""
+    _bf16c(dy, "dy")
+    assert grad_fp32.dtype == torch.float32 and grad_fp32.is_contiguous() and tokens.dtype == torch.int64
+    _call("smx_embedding_bwd", tokens.data_ptr(), dy.data_ptr(), grad_fp32.data_ptr(), tokens.numel(), grad_fp32.shape[1], v0,
+          grad_fp32.shape[0], _stream(dy))

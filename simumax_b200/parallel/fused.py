@@ -191,7 +191,7 @@ def allgather_gemm_inkernel(ws: SymmetricWorkspace, a_off: int, M: int, K: int, 
     nsm = _num_sms(w.device.index if w.device.index is not None else torch.cuda.current_device())
     mc = (ws.multicast_ptr + a_off) if (ws.has_nvls and getattr(ws, "ag_use_nvls", True)) else None
     rc = f(ws.peer_ptrs(a_off), mc, ws.user_flag_ptrs(_AG_FLAG_WORD), b3.data_ptr(), y.data_ptr(), world, rank, M, N, K, b_mn,
-           1 if y.dtype == torch.float32 else 0, float(alpha), b3.stride(1), y.stride(0), chunks, ws._ag2_epoch & 0x7FFFFFFF, nsm,
+           1 if y.dtype == torch.float32 else 0, float(alpha), b3.stride(1), y.stride(0), chunks, ws._ag2_epoch & 0xFFFFFFFF, nsm,
            torch.cuda.current_stream(w.device).cuda_stream)
     _lib.check(rc, f"allgather_gemm_inkernel[{layout}] M{M} N{N} K{K} world{world}")
     _lib.count_launch()

@@ -85,7 +85,8 @@ class SymmetricWorkspace:
 
     def _next_epoch(self) -> int:
         e = self.epoch
-        self.epoch = (self.epoch + 2) & 0x7FFFFFFF or 1
+        # full uint32 range: the device compares (int32)(flag - epoch) < 0, which is wrap-safe; odd values only, so never 0
+        self.epoch = (self.epoch + 2) & 0xFFFFFFFF
         return e
 
     def _coll(self, name, nbytes, use_nvls, ctas, in_off=None, out_off=None, f32=None):

@@ -24,6 +24,9 @@ import torch.distributed as dist
 from .trainer import LlamaDims
 
 
+_GROUPS: dict = {}
+
+
 def split_layers(n_layers: int, pp: int) -> List[Tuple[int, int]]:
     """Even split, remainder to the earliest stages (Megatron's default uneven split puts the short stage last; the analytical
     model takes the split from the strategy's ``num_layers_in_*_pipeline_stage``)."""
@@ -38,10 +41,12 @@ def split_layers(n_layers: int, pp: int) -> List[Tuple[int, int]]:
 
 class PPLlamaTrainer:
     def __init__(self, dims: LlamaDims, micro_batch: int, seq_len: int, pp_group: Optional[dist.ProcessGroup] = None,
-                 seed: int = 1234, device=None, stage_factory=None, act_dtype=torch.bfloat16, **trainer_kw):
+                 seed: int = 1234, device=None, stage_factory=None, act_dtype=torch.bfloat16,
+                 dp_group: Optional[dist.ProcessGroup] = None, **trainer_kw):
         """``stage_factory(local_dims, first, last, in_flight)`` replaces the ``LlamaTrainer`` stage (the CPU / gloo test of
         the schedule plugs in a small autograd stage); a stage needs ``T``, ``use_slot``, ``forward``, ``backward``,
-        ``optimizer_step`` and accepts a ``norm_group`` attribute."""
+        ``optimizer_step`` and accepts a ``norm_group`` attribute.  ``dp_group``: the data-parallel replicas of THIS stage
+        (PP x DP): the stage's ZeRO-1 optimizer shards over them; without it the stage runs unsharded."""
         assert dist.is_initialized()
         self.group = pp_group or dist.group.WORLD
         self.pp = dist.get_world_size(self.group)
@@ -59,13 +64,8 @@ class PPLlamaTrainer:
             self.tr = stage_factory(local, self.first, self.last, in_flight)
         else:
             from .trainer import LlamaTrainer
-            # a single-rank "data-parallel group": the stage trainer runs without ZeRO sharding
-            solo = None
-            for r in self.ranks:
-                g = dist.new_group([r])
-                if r == dist.get_rank():
-                    solo = g
-            self.tr = LlamaTrainer(local, micro_batch, seq_len, dp_group=solo, seed=seed + 31 * self.stage, device=self.device,
+            self.tr = LlamaTrainer(local, micro_batch, seq_len, dp_group=dp_group, data_parallel=dp_group is not None,
+                                   seed=seed + 31 * self.stage, device=self.device,
                                    first_stage=self.first, last_stage=self.last, in_flight=in_flight, **trainer_kw)
         self.tr.norm_group = self.group
         self.T, self.H = self.tr.T, dims.hidden
@@ -75,6 +75,21 @@ class PPLlamaTrainer:
         self.send_dx = torch.empty(self.T, self.H, **bf) if not self.first else None
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.on_gpu else None
         self.loss_acc = torch.zeros(1, dtype=torch.float32, device=self.device)
+
+    @classmethod
+    def from_case(cls, case, dims: LlamaDims, seed: int = 1234, **kw) -> "PPLlamaTrainer":
+        """pp x dp layout of a ``runtime.cases.Case`` (tp = 1), rank order as in the analytical model (dp faster than pp):
+        rank = stage * dp + replica.  ``dist.new_group`` is collective, so every rank creates every group."""
+        world, rank = dist.get_world_size(), dist.get_rank()
+        pp, dp = case.pp, world // case.pp
+        key = ("pp", pp, dp)
+        if key not in _GROUPS:
+            pp_groups = [dist.new_group([s * dp + j for s in range(pp)]) for j in range(dp)]
+            dp_groups = [dist.new_group([s * dp + j for j in range(dp)]) for s in range(pp)] if dp > 1 else [None] * pp
+            _GROUPS[key] = (pp_groups, dp_groups)
+        pp_groups, dp_groups = _GROUPS[key]
+        return cls(dims, case.mbs, case.seq, pp_group=pp_groups[rank % dp], dp_group=dp_groups[rank // dp], seed=seed,
+                   recompute=case.recompute, **kw)
 
     # ------------------------------------------------------------------------------------------ weights
     def load_full_weights(self, full: dict) -> None:

@@ -79,18 +79,34 @@ class LlamaTrainer:
     def __init__(self, dims: LlamaDims, micro_batch: int, seq_len: int, dp_group: Optional[dist.ProcessGroup] = None,
                  lr: float = 1e-4, weight_decay: float = 0.1, betas=(0.9, 0.95), max_grad_norm: float = 1.0,
                  attention_bwd: str = "auto", seed: int = 1234, device=None, comm: str = "auto",
-                 first_stage: bool = True, last_stage: bool = True, in_flight: int = 1):
+                 first_stage: bool = True, last_stage: bool = True, in_flight: int = 1, recompute: str = "none",
+                 recompute_layers: Optional[int] = None, recompute_unused_outputs: bool = True, data_parallel: bool = True):
         """``first_stage`` / ``last_stage`` / ``in_flight``: pipeline-stage mode (runtime/pp_trainer.py) -- the stage owns
         ``dims.layers`` layers, the embedding only if first, final norm + LM head + loss only if last, and keeps ``in_flight``
-        sets of activations (1F1B holds several micro-batches between their forward and backward)."""
+        sets of activations (1F1B holds several micro-batches between their forward and backward).
+
+        ``recompute`` (reference config.py:469-575 semantics for a dense block, first ``recompute_layers`` layers):
+        ``"selective"`` = the reference's ``selective_recompute`` with ``attn_recompute`` + ``mlp_recompute``: the QKV linear, RoPE and
+        core attention, and FC1 / SwiGLU / FC2 are re-run in the backward pass, so ``qkv``, ``lse``, ``u`` and ``g`` are not kept;
+        ``"full"`` = ``full_block``: only the layer input is kept and the whole layer forward is re-run.
+        ``recompute_unused_outputs``: re-run every op of a recomputed segment, as Megatron's checkpointing does (its last GEMM's output
+        is thrown away); False skips those.  ``data_parallel=False``: no ZeRO sharding / gradient reduction even when a process group
+        exists (pipeline stages pass it; their data-parallel groups are wired by the pipeline trainer)."""
+        assert recompute in ("none", "selective", "full"), recompute
         self.first_stage, self.last_stage = first_stage, last_stage
         self.d = dims
         self.B, self.S = micro_batch, seq_len
         self.T = micro_batch * seq_len
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.group = dp_group
-        self.world = dist.get_world_size(dp_group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(dp_group) if dist.is_initialized() else 0
+        use_dp = data_parallel and dist.is_initialized()
+        self.world = dist.get_world_size(dp_group) if use_dp else 1
+        self.rank = dist.get_rank(dp_group) if use_dp else 0
+        self.recompute = recompute
+        self.rl = 0 if recompute == "none" else min(dims.layers, dims.layers if recompute_layers is None else recompute_layers)
+        self.recompute_unused = recompute_unused_outputs
+        self._unsaved = {"none": set(), "selective": {"qkv", "lse", "u", "g"},
+                         "full": {"h1", "rstd1", "qkv", "lse", "o", "x2", "h2", "rstd2", "u", "g"}}[recompute]
         self.lr, self.wd, self.betas, self.max_norm = lr, weight_decay, betas, max_grad_norm
         self.step_count = 0
         d, dev = dims, self.device
@@ -156,17 +172,21 @@ class LlamaTrainer:
         # ---- static activation storage
         T, H, F, L = self.T, d.hidden, d.ffn, d.layers
         bf = dict(dtype=torch.bfloat16, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        shapes = {"h1": ((T, H), bf), "qkv": ((T, d.qkv_out), bf), "o": ((T, d.heads * d.head_dim), bf), "x2": ((T, H), bf),
+                  "h2": ((T, H), bf), "u": ((T, 2 * F), bf), "g": ((T, F), bf), "rstd1": ((T,), f32), "rstd2": ((T,), f32),
+                  "lse": ((self.B, d.heads, self.S), f32)}
+        # tensors a recomputed layer does not keep share ONE scratch entry (index 0); layers past ``rl`` keep their own
+        n_of = lambda name: (L - self.rl + 1) if name in self._unsaved else L
+        self._scratch = {name: torch.empty(*shp, **kw) for name, (shp, kw) in shapes.items() if name in self._unsaved}
         def new_act():
-            return {
-                "x": torch.empty(L + 1, T, H, **bf), "h1": torch.empty(L, T, H, **bf), "qkv": torch.empty(L, T, d.qkv_out, **bf),
-                "o": torch.empty(L, T, d.heads * d.head_dim, **bf), "x2": torch.empty(L, T, H, **bf),
-                "h2": torch.empty(L, T, H, **bf), "u": torch.empty(L, T, 2 * F, **bf), "g": torch.empty(L, T, F, **bf),
-                "rstd1": torch.empty(L, T, dtype=torch.float32, device=dev), "rstd2": torch.empty(L, T, dtype=torch.float32, device=dev),
-                "lse": torch.empty(L, self.B, d.heads, self.S, dtype=torch.float32, device=dev),
-                "xf": torch.empty(T, H, **bf), "rstdf": torch.empty(T, dtype=torch.float32, device=dev),
-            }
+            a = {"x": torch.empty(L + 1, T, H, **bf), "xf": torch.empty(T, H, **bf), "rstdf": torch.empty(T, **f32)}
+            for name, (shp, kw) in shapes.items():
+                a[name] = torch.empty(n_of(name) - (1 if name in self._unsaved else 0), *shp, **kw)
+            return a
         self.act_slots = [new_act() for _ in range(max(1, in_flight))]
         self.act = self.act_slots[0]
+        self.o_rc = torch.empty(T, d.heads * d.head_dim, **bf) if recompute == "selective" else None
         self.logits = torch.empty(T, d.vocab, **bf) if last_stage else None
         # backward scratch (reused by every layer)
         self.dx = torch.empty(T, H, **bf)
@@ -232,6 +252,7 @@ class LlamaTrainer:
 
     def memory_bytes(self) -> dict:
         act = sum(t.numel() * t.element_size() for slot in self.act_slots for t in slot.values())
+        act += sum(t.numel() * t.element_size() for t in self._scratch.values())
         return {"params_bf16": self.params.buf.numel() * 2, "main_grads_fp32": self.grads.buf.numel() * 4,
                 "optimizer_fp32": self.shard * 12, "activations": act, "logits": self.logits.numel() * 2 if self.logits is not None else 0,
                 "torch_max_allocated": torch.cuda.max_memory_allocated(self.device)}
@@ -251,6 +272,50 @@ class LlamaTrainer:
         """Select the activation set the next forward / backward works on (pipeline stages keep several in flight)."""
         self.act = self.act_slots[k % len(self.act_slots)]
 
+    def _A(self, name: str, i: int) -> torch.Tensor:
+        """Layer ``i``'s tensor ``name``: its own slice if the layer keeps it, the shared scratch entry if it is recomputed."""
+        if name in self._unsaved:
+            return self._scratch[name] if i < self.rl else self.act[name][i - self.rl]
+        return self.act[name][i]
+
+    def _attn_segment(self, i: int, o_out: torch.Tensor) -> None:
+        """QKV linear + RoPE + core attention of layer ``i`` (the reference's ``attn_recompute`` segment)."""
+        d, w, A = self.d, self.w, self._A
+        qkv = A("qkv", i)
+        gemm(A("h1", i), w["wqkv"][i], "TN", out=qkv)
+        E.rope_inplace(qkv, self.cos, self.sin, self.S, d.heads + d.kv_heads, d.head_dim)
+        q, k, v = self._attention_views(qkv)
+        fmha_fwd(q, k, v, causal=True, out=o_out.view(self.B, self.S, d.heads, d.head_dim), lse=A("lse", i))
+
+    def _mlp_segment(self, i: int, with_fc2: bool = True) -> None:
+        """FC1 + SwiGLU (+ FC2 into ``tmp_h``) of layer ``i`` (the reference's ``mlp_recompute`` segment)."""
+        w, A = self.w, self._A
+        gemm(A("h2", i), w["wfc1"][i], "TN", out=A("u", i))
+        E.swiglu_fwd(A("u", i), out=A("g", i))
+        if with_fc2:
+            gemm(A("g", i), w["wfc2"][i], "TN", out=self.tmp_h)
+
+    def _layer_forward(self, i: int, recomputing: bool = False) -> None:
+        """Layer ``i`` from its input ``x[i]`` (and ``h1`` = its first norm, produced by whoever produced ``x[i]``)."""
+        d, a, w, A = self.d, self.act, self.w, self._A
+        L = d.layers
+        x = a["x"][i]
+        if recomputing:                                   # full-block recompute starts from the layer input alone
+            E.rmsnorm_fwd(x, w["ln1"][i], d.eps, out=A("h1", i), rstd=A("rstd1", i))
+        self._attn_segment(i, A("o", i))
+        gemm(A("o", i), w["wo"][i], "TN", out=self.tmp_h)
+        E.add_rmsnorm_fwd(x, self.tmp_h, w["ln2"][i], d.eps, out_sum=A("x2", i), out_normed=A("h2", i), rstd=A("rstd2", i))
+        self._mlp_segment(i, with_fc2=(not recomputing) or self.recompute_unused)
+        if recomputing:
+            return
+        if i + 1 < L:                                     # residual add fused with the next layer's input norm
+            E.add_rmsnorm_fwd(A("x2", i), self.tmp_h, w["ln1"][i + 1], d.eps, out_sum=a["x"][i + 1], out_normed=A("h1", i + 1),
+                              rstd=A("rstd1", i + 1))
+        elif self.last_stage:
+            E.add_rmsnorm_fwd(A("x2", i), self.tmp_h, w["final_norm"], d.eps, out_sum=a["x"][L], out_normed=a["xf"], rstd=a["rstdf"])
+        else:
+            E.add(A("x2", i), self.tmp_h, out=a["x"][L])
+
     def forward(self, tokens: torch.Tensor, targets: torch.Tensor, loss_scale: float) -> torch.Tensor:
         """First stage: ``tokens`` are token ids; later stages: the [T, H] hidden states received from the previous stage.
         Last stage: returns the per-row loss (logits then hold dlogits); earlier stages: the hidden states to send on."""
@@ -258,29 +323,20 @@ class LlamaTrainer:
         L = d.layers
         self._wait_params(0)
         if self.first_stage:
-            torch.index_select(w["embed"], 0, tokens, out=a["x"][0])
+            E.embedding_fwd(tokens, w["embed"], a["x"][0])
         elif tokens.data_ptr() != a["x"][0].data_ptr():
             E.copy_(a["x"][0], tokens)
+        self._wait_params(1)
+        E.rmsnorm_fwd(a["x"][0], w["ln1"][0], d.eps, out=self._A("h1", 0), rstd=self._A("rstd1", 0))
         for i in range(L):
             self._wait_params(1 + i)
-            x = a["x"][i]
-            E.rmsnorm_fwd(x, w["ln1"][i], d.eps, out=a["h1"][i], rstd=a["rstd1"][i])
-            gemm(a["h1"][i], w["wqkv"][i], "TN", out=a["qkv"][i])
-            E.rope_inplace(a["qkv"][i], self.cos, self.sin, self.S, d.heads + d.kv_heads, d.head_dim)
-            q, k, v = self._attention_views(a["qkv"][i])
-            o4 = a["o"][i].view(self.B, self.S, d.heads, d.head_dim)
-            fmha_fwd(q, k, v, causal=True, out=o4, lse=a["lse"][i])
-            gemm(a["o"][i], w["wo"][i], "TN", out=self.tmp_h)
-            E.add(x, self.tmp_h, out=a["x2"][i])
-            E.rmsnorm_fwd(a["x2"][i], w["ln2"][i], d.eps, out=a["h2"][i], rstd=a["rstd2"][i])
-            gemm(a["h2"][i], w["wfc1"][i], "TN", out=a["u"][i])
-            E.swiglu_fwd(a["u"][i], out=a["g"][i])
-            gemm(a["g"][i], w["wfc2"][i], "TN", out=self.tmp_h)
-            E.add(a["x2"][i], self.tmp_h, out=a["x"][i + 1])
+            if i + 1 < L:
+                self._wait_params(2 + i)                  # the fused add + norm at the end of layer i reads ln1 of layer i + 1
+            else:
+                self._wait_params(L + 1)
+            self._layer_forward(i)
         if not self.last_stage:
             return a["x"][L]
-        self._wait_params(L + 1)
-        E.rmsnorm_fwd(a["x"][L], w["final_norm"], d.eps, out=a["xf"], rstd=a["rstdf"])
         gemm(a["xf"], w["lm_head"], "TN", out=self.logits)
         loss_rows = E.cross_entropy_(self.logits, targets, grad_scale=loss_scale)      # logits now hold dlogits
         return loss_rows
@@ -289,7 +345,7 @@ class LlamaTrainer:
         """``last_microbatch``: the gradients are final after this pass, so each bucket's reduce-scatter is launched on
         the communication stream the moment its layer is done.  Pipeline stages other than the last pass ``d_out`` (the
         gradient of the hidden states they sent on); stages other than the first return the gradient to send back."""
-        d, a, w, g = self.d, self.act, self.w, self.g
+        d, a, w, g, A = self.d, self.act, self.w, self.g, self._A
         L = d.layers
         rs = self._launch_rs if (last_microbatch and self.overlap) else (lambda b: None)
         if self.last_stage:
@@ -302,42 +358,49 @@ class LlamaTrainer:
         rs(L + 1)
         for i in reversed(range(L)):
             dx3 = self.dx
+            rc = self.recompute if i < self.rl else "none"
+            if rc == "full":
+                self._layer_forward(i, recomputing=True)
+            elif rc == "selective":
+                self._mlp_segment(i, with_fc2=self.recompute_unused)
             # MLP
-            gemm(dx3, a["g"][i], "NT", out=g["wfc2"][i], accumulate=True)
+            gemm(dx3, A("g", i), "NT", out=g["wfc2"][i], accumulate=True)
             gemm(dx3, w["wfc2"][i], "NN", out=self.d_f)
-            E.swiglu_bwd(a["u"][i], self.d_f, out=self.d_big)
-            gemm(self.d_big, a["h2"][i], "NT", out=g["wfc1"][i], accumulate=True)
+            E.swiglu_bwd(A("u", i), self.d_f, out=self.d_big)
+            gemm(self.d_big, A("h2", i), "NT", out=g["wfc1"][i], accumulate=True)
             gemm(self.d_big, w["wfc1"][i], "NN", out=self.tmp_h)
-            E.rmsnorm_bwd(a["x2"][i], w["ln2"][i], self.tmp_h, a["rstd2"][i], g["ln2"][i], dx=dx3, accumulate_dx=True)
+            E.rmsnorm_bwd(A("x2", i), w["ln2"][i], self.tmp_h, A("rstd2", i), g["ln2"][i], dx=dx3, accumulate_dx=True)
             # attention
-            gemm(dx3, a["o"][i], "NT", out=g["wo"][i], accumulate=True)
+            if rc == "selective":
+                self._attn_segment(i, self.o_rc)          # re-derives qkv (post-RoPE) and lse; the kept ``o`` is identical
+            gemm(dx3, A("o", i), "NT", out=g["wo"][i], accumulate=True)
             gemm(dx3, w["wo"][i], "NN", out=self.d_o)
             self._attention_backward(i)
             E.rope_inplace(self.d_qkv, self.cos, self.sin, self.S, d.heads + d.kv_heads, d.head_dim, inverse=True)
-            gemm(self.d_qkv, a["h1"][i], "NT", out=g["wqkv"][i], accumulate=True)
+            gemm(self.d_qkv, A("h1", i), "NT", out=g["wqkv"][i], accumulate=True)
             gemm(self.d_qkv, w["wqkv"][i], "NN", out=self.tmp_h)
-            E.rmsnorm_bwd(a["x"][i], w["ln1"][i], self.tmp_h, a["rstd1"][i], g["ln1"][i], dx=dx3, accumulate_dx=True)
+            E.rmsnorm_bwd(a["x"][i], w["ln1"][i], self.tmp_h, A("rstd1", i), g["ln1"][i], dx=dx3, accumulate_dx=True)
             if self.debug_hook is not None:
                 self.debug_hook(i, self)
             rs(1 + i)
         if self.first_stage:
-            g["embed"].index_add_(0, tokens, self.dx.float())
+            E.embedding_bwd(tokens, self.dx, g["embed"])
         rs(0)
         return None if self.first_stage else self.dx
 
     def _attention_backward(self, i: int) -> None:
         d, a = self.d, self.act
-        q, k, v = self._attention_views(a["qkv"][i])
+        q, k, v = self._attention_views(self._A("qkv", i))
         dq, dk, dv = self._attention_views(self.d_qkv)
-        o4 = a["o"][i].view(self.B, self.S, d.heads, d.head_dim)
+        o4 = self._A("o", i).view(self.B, self.S, d.heads, d.head_dim)
         do4 = self.d_o.view(self.B, self.S, d.heads, d.head_dim)
         scale = 1.0 / math.sqrt(d.head_dim)
         if self.attention_bwd == "smx":
             from ..ops.attention import fmha_bwd
-            fmha_bwd(do4, q, k, v, o4, a["lse"][i], dq, dk, dv, causal=True, scale=scale)
+            fmha_bwd(do4, q, k, v, o4, self._A("lse", i), dq, dk, dv, causal=True, scale=scale)
         elif self.attention_bwd == "flash_attn":
             from flash_attn.flash_attn_interface import _flash_attn_backward
-            _flash_attn_backward(do4, q, k, v, o4, a["lse"][i], dq, dk, dv, 0.0, scale, True, -1, -1, 0.0, None, False)
+            _flash_attn_backward(do4, q, k, v, o4, self._A("lse", i), dq, dk, dv, 0.0, scale, True, -1, -1, 0.0, None, False)
         else:
             qa, ka, va = (t.detach().permute(0, 2, 1, 3).requires_grad_(True) for t in (q, k, v))
             out = torch.nn.functional.scaled_dot_product_attention(qa, ka, va, is_causal=True, enable_gqa=True)
@@ -390,6 +453,8 @@ class LlamaTrainer:
             self.ws.all_reduce(16, in_off=self._off_sc, out_off=self._off_sc + 256, dtype=torch.float32, ctas=1)
         elif self.world > 1:
             dist.all_reduce(self.sqnorm, group=self.group)
+        if self.world > 1 and getattr(self, "norm_group", None) is not None:     # PP x DP: the clip norm spans all stages too
+            dist.all_reduce(self.sqnorm_out, group=self.norm_group)
         # grads hold the SUM over ranks of per-rank means -> prescale by 1/world inside the fused optimizer kernel
         if self.world == 1:
             if getattr(self, "norm_group", None) is not None:       # pipeline stages: the clip norm spans all stages

@@ -174,3 +174,40 @@ def test_vocab_parallel_cross_entropy(world):
         loss = E.ce_vocab_parallel_grad_(shards[r], tgt, r * VW, stats, world, grad_scale=1.0)
         torch.testing.assert_close(loss, ref.detach(), atol=2e-2, rtol=1e-2)
         torch.testing.assert_close(shards[r].float(), lf.grad[:, r * VW:(r + 1) * VW], atol=2e-2, rtol=2e-2)
+
+
+def test_embedding_gather_and_scatter_add():
+    from simumax_b200.ops import elementwise as E
+    torch.manual_seed(0)
+    V, H, T, v0 = 512, 256, 1000, 128
+    table = torch.randn(V, H, device="cuda").bfloat16()
+    tok = torch.randint(0, V + 2 * v0, (T,), device="cuda")          # some ids fall outside the shard [v0, v0 + V)
+    out = torch.empty(T, H, device="cuda", dtype=torch.bfloat16)
+    E.embedding_fwd(tok, table, out, v0=v0)
+    local = tok - v0
+    mine = (local >= 0) & (local < V)
+    ref = table[local.clamp(0, V - 1)] * mine.unsqueeze(1)
+    assert torch.equal(out, ref)
+    dy = torch.randn(T, H, device="cuda").bfloat16()
+    grad = torch.zeros(V, H, device="cuda", dtype=torch.float32)
+    E.embedding_bwd(tok, dy, grad, v0=v0)
+    ref_g = torch.zeros_like(grad).index_add_(0, local.clamp(0, V - 1), dy.float() * mine.unsqueeze(1))
+    assert torch.allclose(grad, ref_g, atol=1e-4, rtol=1e-5)
+
+
+def test_fused_add_rmsnorm():
+    from simumax_b200.ops import elementwise as E
+    torch.manual_seed(1)
+    for H in (1024, 4096, 8192):
+        T = 300
+        x, d = torch.randn(T, H, device="cuda").bfloat16(), torch.randn(T, H, device="cuda").bfloat16()
+        gamma = (1 + 0.1 * torch.randn(H, device="cuda")).bfloat16()
+        s, n = torch.empty_like(x), torch.empty_like(x)
+        rstd = torch.empty(T, device="cuda", dtype=torch.float32)
+        E.add_rmsnorm_fwd(x, d, gamma, 1e-5, out_sum=s, out_normed=n, rstd=rstd)
+        ref_s = (x.float() + d.float()).bfloat16()
+        assert torch.equal(s, ref_s)
+        r = torch.rsqrt(ref_s.float().pow(2).mean(-1) + 1e-5)
+        assert torch.allclose(rstd, r, rtol=1e-4)
+        ref_n = ref_s.float() * r[:, None] * gamma.float()
+        assert torch.allclose(n.float(), ref_n, atol=2e-2, rtol=1e-2)

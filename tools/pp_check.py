@@ -18,14 +18,13 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
-    solo = [dist.new_group([r]) for r in range(world)][rank]
     dims = LlamaDims(hidden=1024, heads=8, kv_heads=4, head_dim=128, ffn=2048, layers=2 * world + 1, vocab=8192)
     B, S, M = 1, 1024, 2 * world + 1
     gen = torch.Generator(device="cuda").manual_seed(5)
     batches = [(torch.randint(0, dims.vocab, (B * S,), device="cuda", generator=gen),
                 torch.randint(0, dims.vocab, (B * S,), device="cuda", generator=gen)) for _ in range(M)]
     lr, steps = 1e-3, 4
-    ref = LlamaTrainer(dims, B, S, dp_group=solo, seed=11, lr=lr)
+    ref = LlamaTrainer(dims, B, S, data_parallel=False, seed=11, lr=lr)
     pp = PPLlamaTrainer(dims, B, S, seed=3, lr=lr)
     pp.load_full_weights(ref.w)
     l_ref = [float(ref.run_microbatches(batches).item()) for _ in range(steps)]

@@ -24,7 +24,6 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
-    solo = [dist.new_group([r]) for r in range(world)][rank]
     W = world
     dims = LlamaDims(hidden=1024, heads=2 * W, kv_heads=W, head_dim=128, ffn=1024 * W, layers=2, vocab=4096 * W)
     B, S = 1, 512 * W
@@ -32,7 +31,7 @@ def main():
     gen = torch.Generator(device="cuda").manual_seed(5)
     batches = [(torch.randint(0, dims.vocab, (T,), device="cuda", generator=gen),
                 torch.randint(0, dims.vocab, (T,), device="cuda", generator=gen)) for _ in range(2)]
-    ref = LlamaTrainer(dims, B, S, dp_group=solo, seed=11, lr=2e-3)
+    ref = LlamaTrainer(dims, B, S, data_parallel=False, seed=11, lr=2e-3)
     tp = TPLlamaTrainer(dims, B, S, seed=11, lr=2e-3)
     tp.load_full_weights(ref.w)
     out = {"world": world, "dims": dims.__dict__, "tokens": T}
