@@ -78,33 +78,45 @@ def run_ops(out_path: str, supplement: Optional[str] = None, limit_per_op: Optio
 
 
 def merge(ops_path: Optional[str], coll_paths: List[str], out_path: str, base: Optional[str] = None,
-          sys_name: str = "b200_sm100a_calibrated", coll_impl: str = "smx", measured_peaks: Optional[str] = None) -> dict:
+          sys_name: str = "b200_sm100a_calibrated", coll_impl: str = "smx", measured_peaks: Optional[str] = None,
+          refit_defaults: bool = False) -> dict:
     """CPU part: fold measurements into a system JSON (schema = reference docs/system.md:77-148)."""
     system = json.load(open(base)) if base else b200_template(sys_name)
     system["sys_name"] = sys_name
     acc = system["accelerator"]
-    notes = {"source": "simumax_b200.calib", "collectives": coll_impl}
+    notes = dict(system.get("calibration_notes") or {})
+    notes.update({"source": "simumax_b200.calib", "collectives": coll_impl})
+    flops_tab = notes.setdefault("flops", {})
     if ops_path:
         res = json.load(open(ops_path))
         for op, table in res["ops"].items():
             cfg = acc["op"][op]
             tab = cfg.setdefault("accurate_efficient_factor", {}) or {}
+            wts = flops_tab.setdefault(op, {})             # flops of every key (kept under calibration_notes): the fallback is flop-weighted
             for key, m in table.items():
                 tab[key] = m["efficiency"]
+                wts[key] = m["flops"]
             cfg["accurate_efficient_factor"] = tab
-            effs = [m["efficiency"] for m in table.values()]
-            if effs:          # default for unseen shapes: flop-weighted mean of what was measured
-                wts = [m["flops"] for m in table.values()]
-                cfg["efficient_factor"] = sum(e * w for e, w in zip(effs, wts)) / sum(wts)
+            # default for unseen shapes: flop-weighted mean over the MERGED table (keys of the base whose flops are unknown
+            # keep the base's fallback: a small supplement must not shift every table miss)
+            known = [k for k in tab if k in wts]
+            if known and (not base or len(known) == len(tab) or refit_defaults):
+                cfg["efficient_factor"] = sum(tab[k] * wts[k] for k in known) / sum(wts[k] for k in known)
         gbps = acc["bandwidth"]["default"]["gbps"]
+        lat = res.get("latency_us")                       # measured launch-to-launch floor of a memory-bound kernel, if the sweep has it
         for name, rec in res["bandwidth"].items():
+            fresh = name not in acc["bandwidth"]
             entry = acc["bandwidth"].setdefault(name, {"gbps": gbps, "latency_us": 30})
             entry["efficient_factor"] = rec["gbs"] * 1e9 / (entry["gbps"] * 1024 ** 3)
-            entry["latency_us"] = 3.0          # kernel launch + tail; elementwise kernels here are single-launch
+            if lat is not None:
+                entry["latency_us"] = float(lat)
+            elif not base or fresh:
+                entry["latency_us"] = 3.0      # not measured by this sweep: kernel launch + tail of a single-launch elementwise kernel
         means = [acc["op"][o]["efficient_factor"] for o in ("matmul", "sdp_fwd", "sdp_bwd") if o in res["ops"]]
-        if means:
+        if means and (not base or refit_defaults):
             acc["op"]["default"]["efficient_factor"] = sum(means) / len(means)
         notes["device"] = res["meta"].get("device")
+        notes["sustained_ms"] = res["meta"].get("sustained_ms", 0.0)
     fits, bursts = {}, {}
     for p in coll_paths:
         sw = json.load(open(p))
@@ -139,12 +151,13 @@ def main(argv=None):
     m.add_argument("--name", default="b200_sm100a_calibrated")
     m.add_argument("--coll-impl", default="smx", choices=["smx", "nccl"])
     m.add_argument("--measured-peaks", default="MEASURED_PEAKS.json")
+    m.add_argument("--refit-defaults", action="store_true", help="with --base: also recompute the fallback efficiencies from the merged table")
     s = sub.add_parser("shapes", help="list the shapes the default workloads need (CPU)")
     a = ap.parse_args(argv)
     if a.cmd == "ops":
         run_ops(a.out, a.supplement, a.limit_per_op, allow_shared_gpu=a.allow_shared_gpu, sustained_ms=a.sustained_ms)
     elif a.cmd == "merge":
-        sysj = merge(a.ops, a.coll, a.out, a.base, a.name, a.coll_impl, a.measured_peaks)
+        sysj = merge(a.ops, a.coll, a.out, a.base, a.name, a.coll_impl, a.measured_peaks, a.refit_defaults)
         print(f"wrote {a.out}: " + ", ".join(f"{op}:{len(v.get('accurate_efficient_factor') or {})}" for op, v in sysj["accelerator"]["op"].items()))
     else:
         for op, t in collect_requests().items():

@@ -296,8 +296,8 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __n
 // qkv row layout: [q heads (nq*d) | k heads (nk*d) | v heads].  One thread handles 8 (i, i+d/2) pairs.
 // ----------------------------------------------------------------------------------------------
 __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cos_t,
-                            const float* __restrict__ sin_t, long long tokens, int seq_len, int row_stride,
-                            int n_rot_heads, int d, float sign) {
+                            const float* __restrict__ sin_t, long long tokens, int seq_len, long long row_stride,
+                            int n_rot_heads, int d, float sign, int head_stride) {
   const int half = d / 2;
   const int vec_per_head = half / 8;
   const long long total = tokens * n_rot_heads * vec_per_head;
@@ -308,7 +308,7 @@ __global__ void rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __rest
     const int h = (int)(th % n_rot_heads);
     const long long t = th / n_rot_heads;
     const int pos = (int)(t % seq_len);
-    __nv_bfloat16* p = qkv + t * row_stride + h * d + v * 8;
+    __nv_bfloat16* p = qkv + t * row_stride + (long long)h * head_stride + v * 8;
     float x1[8], x2[8], o1[8], o2[8];
     load8(p, x1);
     load8(p + half, x2);
@@ -637,6 +637,62 @@ __global__ void embedding_bwd_kernel(const long long* __restrict__ tok, const __
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// MLA key assembly (DeepSeek-V2/V3; reference MLAAttention, dense_module.py:2569-2853): the kv_up GEMM writes [k_nope | v] per head,
+// the rotary key slice is shared by all heads.  k[t, h, :dn] = kv[t, h, :dn];  k[t, h, dn:dn+dr] = k_rope[t, :].
+// And its backward: d_kv[t, h, :dn] = dk[t, h, :dn];  d_k_rope[t, :] = sum_h dk[t, h, dn:].
+// ----------------------------------------------------------------------------------------------
+__global__ void mla_k_assemble_kernel(const __nv_bfloat16* __restrict__ kv, long long kv_row, int kv_head,
+                                      const __nv_bfloat16* __restrict__ krope, long long kr_row,
+                                      __nv_bfloat16* __restrict__ k, long long tokens, int heads, int dn, int dr) {
+  const int vph = (dn + dr) / 8;
+  const long long total = tokens * heads * vph;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vph);
+    const long long th = i / vph;
+    const int h = (int)(th % heads);
+    const long long t = th / heads;
+    const uint4* src = (v * 8 < dn) ? reinterpret_cast<const uint4*>(kv + t * kv_row + (long long)h * kv_head + v * 8)
+                                    : reinterpret_cast<const uint4*>(krope + t * kr_row + (v * 8 - dn));
+    reinterpret_cast<uint4*>(k)[i] = *src;
+  }
+}
+
+__global__ void mla_k_split_bwd_kernel(const __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ d_kv, long long kv_row,
+                                       int kv_head, __nv_bfloat16* __restrict__ d_krope, long long kr_row, long long tokens,
+                                       int heads, int dn, int dr) {
+  // one warp per token; lane l owns vector l of every head (dn / 8 + dr / 8 <= 32 vectors per head)
+  const int lane = threadIdx.x % 32;
+  const int vn = dn / 8, vr = dr / 8;
+  const long long warps = (long long)gridDim.x * (blockDim.x / 32);
+  for (long long t = blockIdx.x * (long long)(blockDim.x / 32) + threadIdx.x / 32; t < tokens; t += warps) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int h = 0; h < heads; ++h) {
+      const __nv_bfloat16* src = dk + (t * heads + h) * (long long)(dn + dr);
+      if (lane < vn) {
+        *reinterpret_cast<uint4*>(d_kv + t * kv_row + (long long)h * kv_head + lane * 8) = *reinterpret_cast<const uint4*>(src + lane * 8);
+      } else if (lane < vn + vr) {
+        float f[8];
+        load8(src + lane * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    }
+    if (lane >= vn && lane < vn + vr) store8(d_krope + t * kr_row + (lane - vn) * 8, acc);
+  }
+}
+
+// 2-D strided copy in 16-byte vectors: dst[r, :width] = src[r, :width]
+__global__ void copy2d_kernel(const unsigned char* __restrict__ src, long long src_ld, unsigned char* __restrict__ dst, long long dst_ld,
+                              long long rows, int vec_per_row) {
+  const long long total = rows * vec_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const int v = (int)(i % vec_per_row);
+    *reinterpret_cast<uint4*>(dst + r * dst_ld + v * 16) = *reinterpret_cast<const uint4*>(src + r * src_ld + v * 16);
+  }
+}
+
 // streaming copy (the "default" memory-bandwidth calibration op)
 __global__ void copy_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n16) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
@@ -737,7 +793,15 @@ int smx_swiglu_bwd(const void* x, const void* dy, void* dx, long long rows, int 
 int smx_rope(void* qkv, const float* cos_t, const float* sin_t, long long tokens, int seq_len, int row_stride,
              int n_rot_heads, int d, float sign, void* stream) {
   if ((d / 2) % 8) return -20;
-  smx::rope_kernel<<<grid_for(tokens * n_rot_heads * (d / 16), 256), 256, 0, SMX_STREAM>>>((bf16*)qkv, cos_t, sin_t, tokens, seq_len, row_stride, n_rot_heads, d, sign);
+  smx::rope_kernel<<<grid_for(tokens * n_rot_heads * (d / 16), 256), 256, 0, SMX_STREAM>>>((bf16*)qkv, cos_t, sin_t, tokens, seq_len, row_stride, n_rot_heads, d, sign, d);
+  return (int)cudaGetLastError();
+}
+// general form: ``n_rot_heads`` rotary slices of width d per row, ``head_stride`` elements apart, starting at ``base`` (MLA: the last 64
+// of every 192-wide q head; the 64-wide shared key slice at the end of the kv_down output)
+int smx_rope_strided(void* base, const float* cos_t, const float* sin_t, long long tokens, int seq_len, long long row_stride,
+                     int n_rot_heads, int d, int head_stride, float sign, void* stream) {
+  if ((d / 2) % 8 || head_stride % 8 || row_stride % 8) return -20;
+  smx::rope_kernel<<<grid_for(tokens * n_rot_heads * (d / 16), 256), 256, 0, SMX_STREAM>>>((bf16*)base, cos_t, sin_t, tokens, seq_len, row_stride, n_rot_heads, d, sign, head_stride);
   return (int)cudaGetLastError();
 }
 
@@ -800,6 +864,23 @@ int smx_embedding_fwd(const long long* tok, const void* table, void* out, long l
 int smx_embedding_bwd(const long long* tok, const void* dy, float* grad, long long rows, int H, long long v0, long long V, void* stream) {
   if (H % 8) return -20;
   smx::embedding_bwd_kernel<<<grid_for(rows, 8), 256, 0, SMX_STREAM>>>(tok, (const bf16*)dy, grad, rows, H, v0, V);
+  return (int)cudaGetLastError();
+}
+int smx_mla_k_assemble(const void* kv, long long kv_row, int kv_head, const void* krope, long long kr_row, void* k, long long tokens,
+                       int heads, int dn, int dr, void* stream) {
+  if (dn % 8 || dr % 8 || kv_row % 8 || kv_head % 8 || kr_row % 8) return -20;
+  smx::mla_k_assemble_kernel<<<grid_for(tokens * heads * ((dn + dr) / 8), 256), 256, 0, SMX_STREAM>>>((const bf16*)kv, kv_row, kv_head, (const bf16*)krope, kr_row, (bf16*)k, tokens, heads, dn, dr);
+  return (int)cudaGetLastError();
+}
+int smx_mla_k_split_bwd(const void* dk, void* d_kv, long long kv_row, int kv_head, void* d_krope, long long kr_row, long long tokens,
+                        int heads, int dn, int dr, void* stream) {
+  if (dn % 8 || dr % 8 || kv_row % 8 || kv_head % 8 || kr_row % 8 || (dn + dr) / 8 > 32) return -20;
+  smx::mla_k_split_bwd_kernel<<<grid_for(tokens, 8), 256, 0, SMX_STREAM>>>((const bf16*)dk, (bf16*)d_kv, kv_row, kv_head, (bf16*)d_krope, kr_row, tokens, heads, dn, dr);
+  return (int)cudaGetLastError();
+}
+int smx_copy2d(const void* src, long long src_ld_bytes, void* dst, long long dst_ld_bytes, long long rows, long long width_bytes, void* stream) {
+  if (width_bytes % 16 || src_ld_bytes % 16 || dst_ld_bytes % 16) return -20;
+  smx::copy2d_kernel<<<grid_for(rows * (width_bytes / 16), 256), 256, 0, SMX_STREAM>>>((const unsigned char*)src, src_ld_bytes, (unsigned char*)dst, dst_ld_bytes, rows, (int)(width_bytes / 16));
   return (int)cudaGetLastError();
 }
 int smx_add(const void* a, const void* b, void* y, long long n, void* stream) {

@@ -30,6 +30,10 @@ _SIGS = {
     "smx_unpermute_combine": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_void_p],
     "smx_moe_prob_grad": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_void_p],
     "smx_add": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_void_p],
+    "smx_rope_strided": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_longlong, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_void_p],
+    "smx_mla_k_assemble": [_c.c_void_p, _c.c_longlong, _c.c_int, _c.c_void_p, _c.c_longlong, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p],
+    "smx_mla_k_split_bwd": [_c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_void_p, _c.c_longlong, _c.c_longlong, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p],
+    "smx_copy2d": [_c.c_void_p, _c.c_longlong, _c.c_void_p, _c.c_longlong, _c.c_longlong, _c.c_longlong, _c.c_void_p],
     "smx_embedding_fwd": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_longlong, _c.c_longlong, _c.c_void_p],
     "smx_embedding_bwd": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_longlong, _c.c_longlong, _c.c_void_p],
     "smx_rs_consume": [_c.c_void_p, _c.c_int, _c.c_longlong, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
@@ -257,3 +261,40 @@ def embedding_bwd(tokens: torch.Tensor, dy: torch.Tensor, grad_fp32: torch.Tenso
     assert grad_fp32.dtype == torch.float32 and grad_fp32.is_contiguous() and tokens.dtype == torch.int64
     _call("smx_embedding_bwd", tokens.data_ptr(), dy.data_ptr(), grad_fp32.data_ptr(), tokens.numel(), grad_fp32.shape[1], v0,
           grad_fp32.shape[0], _stream(dy))
+
+
+def rope_strided_(t: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, seq_len: int, inverse: bool = False) -> torch.Tensor:
+    """In-place RoPE on a strided view ``t[tokens, heads, d]`` (last dim contiguous; any token / head strides that are multiples of
+    8 elements): MLA rotates the last 64 of every 192-wide query head and the shared 64-wide key slice."""
+    assert t.dtype == torch.bfloat16 and t.dim() == 3 and t.stride(2) == 1
+    tokens, heads, d = t.shape
+    _call("smx_rope_strided", t.data_ptr(), cos.data_ptr(), sin.data_ptr(), tokens, seq_len, t.stride(0), heads, d,
+          t.stride(1) if heads > 1 else d, -1.0 if inverse else 1.0, _stream(t))
+    return t
+
+
+def mla_k_assemble(kv: torch.Tensor, k_rope: torch.Tensor, out: torch.Tensor, dn: int) -> torch.Tensor:
+    """out[t, h, :dn] = kv[t, h, :dn] (k_nope half of the kv_up output), out[t, h, dn:] = k_rope[t] (shared rotary key slice).
+    ``kv`` [T, heads, dn + dv] and ``k_rope`` [T, dr] may be strided views; ``out`` [T, heads, dn + dr] is contiguous."""
+    T, heads, _ = kv.shape
+    dr = k_rope.shape[-1]
+    assert out.is_contiguous() and out.shape == (T, heads, dn + dr) and kv.stride(2) == 1 and k_rope.stride(1) == 1
+    _call("smx_mla_k_assemble", kv.data_ptr(), kv.stride(0), kv.stride(1), k_rope.data_ptr(), k_rope.stride(0), out.data_ptr(), T, heads,
+          dn, dr, _stream(out))
+    return out
+
+
+def mla_k_split_bwd(dk: torch.Tensor, d_kv: torch.Tensor, d_k_rope: torch.Tensor, dn: int) -> None:
+    """Backward of :func:`mla_k_assemble`: d_kv[t, h, :dn] = dk[t, h, :dn];  d_k_rope[t] = sum over heads of dk[t, h, dn:]."""
+    T, heads, w = dk.shape
+    assert dk.is_contiguous() and d_kv.stride(2) == 1 and d_k_rope.stride(1) == 1
+    _call("smx_mla_k_split_bwd", dk.data_ptr(), d_kv.data_ptr(), d_kv.stride(0), d_kv.stride(1), d_k_rope.data_ptr(), d_k_rope.stride(0),
+          T, heads, dn, w - dn, _stream(dk))
+
+
+def copy2d_(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    """dst[r, :] = src[r, :] for 2-D views with a contiguous last dim (row strides free): column slices in and out of packed buffers."""
+    assert dst.shape == src.shape and dst.dim() == 2 and dst.stride(1) == 1 and src.stride(1) == 1 and dst.dtype == src.dtype
+    es = dst.element_size()
+    _call("smx_copy2d", src.data_ptr(), src.stride(0) * es, dst.data_ptr(), dst.stride(0) * es, dst.shape[0], dst.shape[1] * es, _stream(dst))
+    return dst

@@ -29,7 +29,10 @@ from ..parallel.symm import SymmetricWorkspace
 
 class EPMoELayer:
     def __init__(self, hidden: int, ffn: int, n_experts: int, topk: int, tokens: int, ep_group: Optional[dist.ProcessGroup] = None,
-                 capacity_factor: float = 1.0, force_balanced: bool = False, seed: int = 1234, device=None):
+                 capacity_factor: float = 1.0, force_balanced: bool = False, seed: int = 1234, device=None,
+                 weights=None, grads=None):
+        """``weights`` = (router [E, H], w1 [El, 2F, H], w2 [El, H, F]) bf16 and ``grads`` = the matching fp32 main-grad tensors when
+        the parameters live in a trainer's flat buffers (runtime/deepseek_trainer.py); otherwise the layer owns random ones."""
         assert dist.is_initialized()
         self.group = ep_group or dist.group.WORLD
         self.ep = ep = dist.get_world_size(self.group)
@@ -47,15 +50,20 @@ class EPMoELayer:
         buf = self.rows * H * 2
         self.off_recv, self.off_back = 0, (buf + 1023) // 1024 * 1024
         self.ws = SymmetricWorkspace(self.off_back, buf + 1024, group=self.group, device=dev)
-        gen = torch.Generator(device=dev).manual_seed(seed)                     # router replicated: same seed everywhere
-        self.w_router = (torch.randn(n_experts, H, device=dev, generator=gen) * 0.02).bfloat16()
-        gen_e = torch.Generator(device=dev).manual_seed(seed + 1 + self.rank)
-        self.w1 = (torch.randn(El, 2 * F, H, device=dev, generator=gen_e) * 0.02).bfloat16()      # [gate ; up] per expert
-        self.w2 = (torch.randn(El, H, F, device=dev, generator=gen_e) * 0.02).bfloat16()
         f32 = dict(dtype=torch.float32, device=dev)
-        self.g_router = torch.zeros(n_experts, H, **f32)
-        self.g_w1 = torch.zeros(El, 2 * F, H, **f32)
-        self.g_w2 = torch.zeros(El, H, F, **f32)
+        if weights is not None:
+            self.w_router, self.w1, self.w2 = weights
+            self.g_router, self.g_w1, self.g_w2 = grads
+            assert self.w1.shape == (El, 2 * F, H) and self.w2.shape == (El, H, F) and self.w_router.shape == (n_experts, H)
+        else:
+            gen = torch.Generator(device=dev).manual_seed(seed)                     # router replicated: same seed everywhere
+            self.w_router = (torch.randn(n_experts, H, device=dev, generator=gen) * 0.02).bfloat16()
+            gen_e = torch.Generator(device=dev).manual_seed(seed + 1 + self.rank)
+            self.w1 = (torch.randn(El, 2 * F, H, device=dev, generator=gen_e) * 0.02).bfloat16()      # [gate ; up] per expert
+            self.w2 = (torch.randn(El, H, F, device=dev, generator=gen_e) * 0.02).bfloat16()
+            self.g_router = torch.zeros(n_experts, H, **f32)
+            self.g_w1 = torch.zeros(El, 2 * F, H, **f32)
+            self.g_w2 = torch.zeros(El, H, F, **f32)
         bf = dict(dtype=torch.bfloat16, device=dev)
         M = ep * C                                   # rows per local expert
         self.M = M

@@ -121,7 +121,8 @@ def check_tp_parity(tp: int = 0, recompute: str = "none", steps: int = 3) -> Dic
 
 
 def check_recompute_parity() -> Dict[str, object]:
-    """Single GPU: selective and full recompute must reproduce the no-recompute gradients bit for bit (same kernels, same inputs)."""
+    """Single GPU: selective and full recompute re-run the same kernels on the same inputs, so the loss is identical and the gradients
+    agree with the no-recompute run to the run-to-run noise of the fp32 atomics (RMSNorm dgamma, TMA reduce-add of dQ)."""
     import torch
     from .trainer import LlamaDims, LlamaTrainer
     dims = LlamaDims(hidden=512, heads=4, kv_heads=2, head_dim=128, ffn=1024, layers=3, vocab=2048)
@@ -144,7 +145,8 @@ def check_recompute_parity() -> Dict[str, object]:
             key = f"{mode}{'' if layers is None else layers}"
             out[f"{key}_loss_equal"] = loss == base[0]
             out[f"{key}_max_abs_grad_diff"] = float((g - base[1]).abs().max().item())
+            out[f"{key}_rel_grad_diff"] = float(((g - base[1]).norm() / base[1].norm()).item())
             out[f"act_bytes_{key}"] = tr.memory_bytes()["activations"]
         del tr
-    out["ok"] = all(v == 0.0 for k, v in out.items() if k.endswith("grad_diff")) and all(v for k, v in out.items() if k.endswith("loss_equal"))
+    out["ok"] = all(v < 1e-5 for k, v in out.items() if k.endswith("rel_grad_diff")) and all(v for k, v in out.items() if k.endswith("loss_equal"))
     return out

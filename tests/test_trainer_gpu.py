@@ -1,4 +1,9 @@
-"""Whole training step built from the sm_100a kernels vs a plain PyTorch fp32 autograd model of the same network."""
+"""Whole training step built from the sm_100a kernels vs a plain PyTorch fp32 autograd model of the same network.
+
+The reference does its math in fp32 but rounds every activation the trainer stores in bf16 to bf16 at the same point: with the 4 x
+larger test weights a pure-fp32 forward drifts ~7 % away from ANY bf16 forward by the LM head (tools/debug_lm_head.py splits the error:
+the CE kernel, the wgrad GEMM and the logits GEMM are each within 2e-3 of fp32 on the same bf16 inputs), which says nothing about the
+kernels.  Against the bf16-matched reference every gradient has to be within 5 %."""
 import math
 
 import pytest
@@ -14,8 +19,18 @@ def _torch_reference(tr, tokens, targets):
     B, S = tr.B, tr.S
     cos, sin = tr.cos, tr.sin
 
+    class _Round(torch.autograd.Function):          # the trainer stores every activation in bf16: round at the same points
+        @staticmethod
+        def forward(ctx, t):
+            return t.bfloat16().float()
+
+        @staticmethod
+        def backward(ctx, g):
+            return g
+    r16 = _Round.apply
+
     def rms(x, g):
-        return x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + d.eps) * g
+        return r16(x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + d.eps) * g)
 
     def rope(t):  # t [B,S,h,hd], rotate-half convention
         h = d.head_dim // 2
@@ -26,20 +41,20 @@ def _torch_reference(tr, tokens, targets):
     x = W["embed"][tokens]
     for i in range(d.layers):
         h1 = rms(x, W["ln1"][i])
-        qkv = (h1 @ W["wqkv"][i].t()).view(B, S, -1)
+        qkv = r16(h1 @ W["wqkv"][i].t()).view(B, S, -1)
         nq, nk, hd = d.heads, d.kv_heads, d.head_dim
-        q = rope(qkv[..., : nq * hd].reshape(B, S, nq, hd))
-        k = rope(qkv[..., nq * hd:(nq + nk) * hd].reshape(B, S, nk, hd))
+        q = r16(rope(qkv[..., : nq * hd].reshape(B, S, nq, hd)))
+        k = r16(rope(qkv[..., nq * hd:(nq + nk) * hd].reshape(B, S, nk, hd)))
         v = qkv[..., (nq + nk) * hd:].reshape(B, S, nk, hd)
         o = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
                                                              is_causal=True, enable_gqa=True)
-        o = o.transpose(1, 2).reshape(B * S, nq * hd)
-        x = x + o @ W["wo"][i].t()
+        o = r16(o.transpose(1, 2).reshape(B * S, nq * hd))
+        x = r16(x + r16(o @ W["wo"][i].t()))
         h2 = rms(x, W["ln2"][i])
-        u = h2 @ W["wfc1"][i].t()
+        u = r16(h2 @ W["wfc1"][i].t())
         F = d.ffn
-        x = x + (torch.nn.functional.silu(u[:, :F]) * u[:, F:]) @ W["wfc2"][i].t()
-    logits = rms(x, W["final_norm"]) @ W["lm_head"].t()
+        x = r16(x + r16(r16(torch.nn.functional.silu(u[:, :F]) * u[:, F:]) @ W["wfc2"][i].t()))
+    logits = r16(rms(x, W["final_norm"]) @ W["lm_head"].t())
     loss = torch.nn.functional.cross_entropy(logits, targets)
     loss.backward()
     return loss.item(), W
@@ -68,13 +83,13 @@ def test_train_step_matches_pytorch(attn_bwd):
         ref, got = W[name].grad, tr.g[name]
         err = (got - ref).norm() / ref.norm()
         print(name, float(err))
-        assert err < 1e-1, (name, err.item())
+        assert err < 5e-2, (name, err.item())
     for name in ("wfc2", "wfc1", "wo", "wqkv", "ln1", "ln2"):
         for i in range(dims.layers):
             ref, got = W[name][i].grad, tr.g[name][i]
             err = (got - ref).norm() / ref.norm()
             print(name, i, float(err))
-            assert err < 1e-1, (name, i, err.item())
+            assert err < 5e-2, (name, i, err.item())
     # optimizer: loss must go down over a few steps on a fixed batch
     before = tr.params.buf.clone()
     tr.grads.buf.zero_()
@@ -85,9 +100,10 @@ def test_train_step_matches_pytorch(attn_bwd):
     assert float(tr.grads.buf.abs().max()) == 0.0
 
 
-def test_recompute_reproduces_gradients_bit_for_bit():
+def test_recompute_reproduces_gradients():
     """Selective / full activation recompute (reference config.py:469-575 semantics) re-runs the same kernels on the same inputs:
-    the loss and every gradient must be identical to the run that keeps all activations, with a smaller activation footprint."""
+    the loss is identical and every gradient agrees with the run that keeps all activations (up to the order of fp32 atomics), with a
+    smaller activation footprint."""
     from simumax_b200.runtime.selfcheck import check_recompute_parity
     r = check_recompute_parity()
     assert r["ok"], r
