@@ -243,12 +243,12 @@ def collectives_table(R: Runner, nbytes: int = 64 << 20):
     sh = shard // 2
     nv = bool(ws.has_nvls)
     runs = {
-        "all_gather": (lambda: ws.all_gather(shard, use_nvls=nv, ctas=32), lambda: dist.all_gather_into_tensor(dst[:sh * world], src[:sh]), shard * world),
-        "reduce_scatter": (lambda: ws.reduce_scatter(shard, use_nvls=nv, ctas=64), lambda: dist.reduce_scatter_tensor(dst[:sh], src[:sh * world]), shard * world),
-        "all_reduce": (lambda: ws.all_reduce(nbytes, use_nvls=nv, ctas=64), lambda: dist.all_reduce(src), nbytes),
-        "all2all": (lambda: ws.all_to_all(shard, ctas=64), lambda: dist.all_to_all_single(dst[:sh * world], src[:sh * world]), shard * world),
+        "all_gather": (lambda: ws.all_gather(shard), lambda: dist.all_gather_into_tensor(dst[:sh * world], src[:sh]), shard * world),
+        "reduce_scatter": (lambda: ws.reduce_scatter(shard), lambda: dist.reduce_scatter_tensor(dst[:sh], src[:sh * world]), shard * world),
+        "all_reduce": (lambda: ws.all_reduce(nbytes), lambda: dist.all_reduce(src), nbytes),
+        "all2all": (lambda: ws.all_to_all(shard), lambda: dist.all_to_all_single(dst[:sh * world], src[:sh * world]), shard * world),
     }
-    table = {"bytes": nbytes, "n_gpus": world, "nvls": nv, "nvlink_roofline_gbs": 900.0, "unit": "bus GB/s (bytes*(n-1)/n*scale / time)"}
+    table = {"bytes": nbytes, "n_gpus": world, "nvls": nv, "variant_policy": "SymmetricWorkspace.pick (same variants as the runtime's exposed collectives)", "nvlink_roofline_gbs": 900.0, "unit": "bus GB/s (bytes*(n-1)/n*scale / time)"}
     for op, (own, nccl, size) in runs.items():
         t_own = _timed(own, 10, dist, torch)
         t_nccl = _timed(nccl, 10, dist, torch)

@@ -44,19 +44,53 @@ def foreign_gpu_processes(device_index: int = 0) -> List[str]:
     return [l.strip() for l in out.splitlines() if l.strip() and l.split(",")[0].strip() != mine]
 
 
+def cache_path(out_path: str, tag: Optional[str]) -> str:
+    """``<out>`` or ``<out stem>_<tag>.json``: the cache namespace of a sweep (reference utils.py:169-174, EFFICIENCY_CACHE_TAG)."""
+    if not tag:
+        return out_path
+    stem, ext = os.path.splitext(out_path)
+    return f"{stem}_{tag}{ext or '.json'}"
+
+
+def plan_requests(param_file: Optional[str] = None, default_sweep: bool = False, workloads=None, log=print):
+    """Which (op, shape key) pairs a sweep has to cover: the built-in example workloads, plus the cross product described by a user
+    sweep file (``--param-file``, schema of ``shapes.DEFAULT_SWEEP``; reference ``PARAM_FILE``) or the default sweep."""
+    from .shapes import collect_requests_tolerant, workloads_from_params
+    requests = collect_requests(workloads or DEFAULT_WORKLOADS)
+    if param_file or default_sweep:
+        params = json.load(open(param_file)) if param_file else None
+        extra = collect_requests_tolerant(workloads_from_params(params), log=log)
+        for op, table in extra.items():
+            requests.setdefault(op, {}).update(table)
+    return requests
+
+
 def run_ops(out_path: str, supplement: Optional[str] = None, limit_per_op: Optional[int] = None,
-            workloads=None, log=print, allow_shared_gpu: bool = False, sustained_ms: float = 0.0) -> dict:
+            workloads=None, log=print, allow_shared_gpu: bool = False, sustained_ms: float = 0.0, param_file: Optional[str] = None,
+            default_sweep: bool = False, cache_mode: str = "rebuild", cache_tag: Optional[str] = None) -> dict:
     """GPU part: returns {"ops": {op: {key: {...}}}, "bandwidth": {...}, "meta": {...}}.  ``sustained_ms`` > 0 times every op
-    at the steady (power-capped) clock instead of the boost clock of a short burst -- see ``measure._time``."""
+    at the steady (power-capped) clock instead of the boost clock of a short burst -- see ``measure._time``.
+
+    ``cache_mode`` (reference one_click_common.py:84-94): ``"rebuild"`` measures everything into the cache file (``out_path`` +
+    ``cache_tag``); ``"supplement"`` loads that file first and measures only the keys it does not hold yet (an interrupted or
+    extended sweep resumes where it stopped).  ``supplement=<system json>`` additionally skips keys that system config already has."""
     import torch
     from . import measure
+    assert cache_mode in ("supplement", "rebuild"), f"unsupported cache mode {cache_mode}"
     if sustained_ms > 0:
         measure.SUSTAINED_MS = float(sustained_ms)
     others = foreign_gpu_processes(torch.cuda.current_device())
     if others and not allow_shared_gpu:
         raise RuntimeError(f"GPU is in use by other processes {others}; calibrate on an idle GPU (or pass --allow-shared-gpu)")
     template = b200_template()
-    requests = collect_requests(workloads or DEFAULT_WORKLOADS)
+    out_path = cache_path(out_path, cache_tag)
+    requests = plan_requests(param_file, default_sweep, workloads, log)
+    cached = {}
+    if cache_mode == "supplement" and os.path.exists(out_path):
+        cached = json.load(open(out_path)).get("ops", {})
+        for op in list(requests):
+            requests[op] = {k: r for k, r in requests[op].items() if k not in cached.get(op, {})}
+        log(f"[calib] cache {out_path}: {sum(len(v) for v in cached.values())} keys reused, {sum(len(v) for v in requests.values())} to measure")
     have = {}
     if supplement and os.path.exists(supplement):
         prev = json.load(open(supplement))
@@ -66,11 +100,15 @@ def run_ops(out_path: str, supplement: Optional[str] = None, limit_per_op: Optio
         log(f"[calib] supplement mode: {sum(len(v) for v in requests.values())} keys missing from {supplement}")
     t0 = time.time()
     ops = measure.sweep(requests, _nominal_tflops(template), log=log, limit_per_op=limit_per_op)
+    for op, table in cached.items():                  # cache supplement: old keys + the ones measured now
+        merged = dict(table)
+        merged.update(ops.get(op, {}))
+        ops[op] = merged
     bw = measure.measure_bandwidth_ops()
     for name, rec in bw.items():
         log(f"[calib] bandwidth {name:12s} {rec['gbs']:8.1f} GB/s")
-    res = {"ops": ops, "bandwidth": bw,
-           "meta": {"device": torch.cuda.get_device_name(0), "seconds": time.time() - t0, "sustained_ms": measure.SUSTAINED_MS,
+    res = {"ops": ops, "bandwidth": bw, "latency_us": measure.measure_launch_latency_us(),
+           "meta": {"cache_mode": cache_mode, "cache_tag": cache_tag, "device": torch.cuda.get_device_name(0), "seconds": time.time() - t0, "sustained_ms": measure.SUSTAINED_MS,
                     "requested": {op: len(v) for op, v in requests.items()}}}
     os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
     json.dump(res, open(out_path, "w"), indent=1)
@@ -141,6 +179,11 @@ def main(argv=None):
     o.add_argument("--supplement", default=None)
     o.add_argument("--limit-per-op", type=int, default=None)
     o.add_argument("--allow-shared-gpu", action="store_true")
+    o.add_argument("--param-file", default=None, help="user sweep file (JSON, schema of calib.shapes.DEFAULT_SWEEP): model_list, "
+                   "mbs_list, seq_len_list, tp_list, cp_list, ep_list, dtype, long_context")
+    o.add_argument("--default-sweep", action="store_true", help="add the built-in zoo sweep (~800 GEMM / 35 attention / 96 grouped keys)")
+    o.add_argument("--cache-mode", default="rebuild", choices=["supplement", "rebuild"])
+    o.add_argument("--cache-tag", default=None, help="cache namespace: results go to <out stem>_<tag>.json")
     o.add_argument("--sustained-ms", type=float, default=0.0,
                    help="pre-heat every op for this much device time and time it over windows of a third of it (steady clock)")
     m = sub.add_parser("merge", help="write the system config (no GPU needed)")
@@ -152,15 +195,18 @@ def main(argv=None):
     m.add_argument("--coll-impl", default="smx", choices=["smx", "nccl"])
     m.add_argument("--measured-peaks", default="MEASURED_PEAKS.json")
     m.add_argument("--refit-defaults", action="store_true", help="with --base: also recompute the fallback efficiencies from the merged table")
-    s = sub.add_parser("shapes", help="list the shapes the default workloads need (CPU)")
+    s = sub.add_parser("shapes", help="list the shapes a sweep needs (CPU)")
+    s.add_argument("--param-file", default=None)
+    s.add_argument("--default-sweep", action="store_true")
     a = ap.parse_args(argv)
     if a.cmd == "ops":
-        run_ops(a.out, a.supplement, a.limit_per_op, allow_shared_gpu=a.allow_shared_gpu, sustained_ms=a.sustained_ms)
+        run_ops(a.out, a.supplement, a.limit_per_op, allow_shared_gpu=a.allow_shared_gpu, sustained_ms=a.sustained_ms,
+                param_file=a.param_file, default_sweep=a.default_sweep, cache_mode=a.cache_mode, cache_tag=a.cache_tag)
     elif a.cmd == "merge":
         sysj = merge(a.ops, a.coll, a.out, a.base, a.name, a.coll_impl, a.measured_peaks, a.refit_defaults)
         print(f"wrote {a.out}: " + ", ".join(f"{op}:{len(v.get('accurate_efficient_factor') or {})}" for op, v in sysj["accelerator"]["op"].items()))
     else:
-        for op, t in collect_requests().items():
+        for op, t in plan_requests(a.param_file, a.default_sweep, log=lambda *x: None).items():
             print(op, len(t))
             for k in t:
                 print("   ", k)

@@ -200,6 +200,28 @@ def measure_bandwidth_ops(hidden: int = 4096, tokens: int = 16384, vocab: int = 
     return res
 
 
+def measure_launch_latency_us(n: int = 2000) -> float:
+    """Launch-to-launch floor of a memory-bound kernel: back-to-back launches of the residual add on a tensor that fits in L1/L2
+    (8 KiB), device-timed.  This is the ``latency_us`` the model adds to every bandwidth-priced op (the reference hard-codes 30 us for
+    its library kernels; a CUDA-graph-free PyTorch launch loop on this box sits at 2-4 us)."""
+    from ..ops import elementwise as E
+    x = torch.zeros(4096, device="cuda", dtype=torch.bfloat16)
+    y = torch.zeros_like(x)
+    for _ in range(50):
+        E.add(x, y, out=y)
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            E.add(x, y, out=y)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / n * 1e3)
+    return best
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def sweep(requests: Dict[str, Dict[str, ShapeRequest]], nominal_tflops: Dict[str, float], log=print,
           limit_per_op: Optional[int] = None) -> Dict[str, Dict[str, dict]]:

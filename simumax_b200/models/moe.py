@@ -255,15 +255,33 @@ def group_linear(st: StrategyConfig, kind: str, in_features, out_features, local
     return node, out_shape
 
 
+def serial_group_linear(em, attr: str, display: str, in_f: int, out_f: int, local_experts: int, x_shape, layer_idx, enable_recompute):
+    """``group_linear_mode='serial'`` (legacy; reference moe_module.py:878-900, 1101-1134): the grouped linear is a container of
+    ``local_experts`` plain ``LinearCol`` children -- for the column AND the row expert linear -- each fed a ``[1, tokens / experts, H]``
+    slice of the permuted tokens (split / unsqueeze / squeeze / cat are shape-only shims there, so nothing else is emitted).  Costs
+    come from the dense ``matmul`` table and the parameters are accounted like dense, data-parallel ones, exactly as the reference
+    does in this mode."""
+    st = em.st
+    tokens, hidden = int(x_shape[0]), int(x_shape[1])
+    assert tokens % local_experts == 0, f"tokens {tokens} not divisible by {local_experts} local experts"
+    per = tokens // local_experts
+    out_local = out_f
+    with em.scope(attr, display):
+        for i in range(local_experts):
+            node, o = D.linear_col(st, in_f, out_f, [1, per, hidden], em.name(f"linear_{i}"), layer_idx=layer_idx,
+                                   has_cached_inputs=False, enable_recompute=enable_recompute, display="LinearCol")
+            em.add(node)
+            out_local = o[-1]
+    return [tokens, out_local]
+
+
 def emit_expert_mlp(em, layer_idx: int, shape, rc: MLPRecomputeConfig):
     from .llm import emit_mlp
     cfg, st, system = em.model, em.st, em.system
     assert cfg.group_linear_mode in ("parallel", "serial"), cfg.group_linear_mode      # reference moe_module.py:854,1078
-    if cfg.group_linear_mode == "serial":
-        # The reference's legacy serial mode instantiates LinearCol children for the column AND the row expert linears and
-        # accounts expert states like dense (dp-sharded) parameters (moe_module.py:878-900,1101-1134; SURVEY 7.5 lists it as a
-        # quirk).  Its numbers are not meaningful, so it is not reproduced.
-        raise NotImplementedError("group_linear_mode='serial' (one GEMM per expert) is not modelled; use 'parallel' (grouped GEMM)")
+    serial = cfg.group_linear_mode == "serial"
+    if serial and st.fp8:
+        raise NotImplementedError("group_linear_mode='serial' is modelled for bf16 only (the reference's serial mode has no fp8 path)")
     local_experts = cfg.expert_num // st.ep_size
     ffn = cfg.moe_ffn_hidden_size if cfg.moe_ffn_hidden_size is not None else cfg.intermediate_size
     fc1_out = 2 * ffn if cfg.use_swiglu else ffn
@@ -298,6 +316,8 @@ def emit_expert_mlp(em, layer_idx: int, shape, rc: MLPRecomputeConfig):
                                      layer_idx=layer_idx, enable_recompute=lin_rc,
                                      offload_inputs=offload if st.cache_groupgemm_col_fp8_inputs else False)
                 em.add(g1)
+        elif serial:
+            x = serial_group_linear(em, "group_linear1", "GroupLinearCol", cfg.hidden_size, fc1_out, local_experts, x, layer_idx, lin_rc)
         else:
             g1, x = group_linear(st, "col", cfg.hidden_size, fc1_out, local_experts, x, em.name("group_linear1"),
                                  layer_idx=layer_idx, enable_recompute=lin_rc, offload_inputs=offload)
@@ -321,6 +341,8 @@ def emit_expert_mlp(em, layer_idx: int, shape, rc: MLPRecomputeConfig):
                                      layer_idx=layer_idx, has_cached_inputs=act_ckpt, enable_recompute=act_rc,
                                      is_last_recompute=True, use_variance_tail_model=act_ckpt)
                 em.add(g2)
+        elif serial:
+            x = serial_group_linear(em, "group_linear2", "GroupLinearRow", ffn, cfg.hidden_size, local_experts, x, layer_idx, act_rc)
         else:
             g2, x = group_linear(st, "row", ffn, cfg.hidden_size, local_experts, x, em.name("group_linear2"),
                                  layer_idx=layer_idx, has_cached_inputs=act_ckpt, enable_recompute=act_rc,

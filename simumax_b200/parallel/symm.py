@@ -110,30 +110,50 @@ class SymmetricWorkspace:
         assert byte_off % 16 == 0 and byte_off + nbytes <= self.in_bytes + self.out_bytes
         return self.data[byte_off:byte_off + nbytes].view(dtype)
 
+    # ---- variant policy: what the 2 / 4 / 8-GPU sweeps (profiles/coll_sweep_*gpu.json, fastest of P2P / NVLS x 32 / 64 / 128 CTAs
+    # per message size) boil down to.  ``ctas=0`` / ``use_nvls=None`` in the calls below ask for it, so an exposed collective in the
+    # runtime launches exactly the variant the calibrated curve was fitted on; overlapped ones pass a small explicit CTA count.
+    def pick(self, op: str, total_bytes: int):
+        """(use_nvls, ctas) for a stand-alone collective moving ``total_bytes`` (gathered / reduced size)."""
+        big = total_bytes >= (16 << 20)
+        if op == "all_gather":       # pushes: plain peer stores beat multimem.st once the message is large
+            return (total_bytes < (4 << 20)), (32 if total_bytes < (4 << 20) else (64 if not big else 128))
+        if op == "reduce_scatter":   # in-switch reduction (multimem.ld_reduce) wins at every size
+            return True, (32 if total_bytes < (8 << 20) else 128)
+        if op == "all_reduce":
+            return True, (32 if total_bytes < (48 << 20) else 64)
+        return False, (32 if total_bytes < (8 << 20) else 128)       # all_to_all
+
     # ---- collectives (operate in place on the workspace regions)
-    def all_gather(self, shard_bytes: int, use_nvls: bool = True, ctas: int = 32, in_off=None, out_off=None):
+    def all_gather(self, shard_bytes: int, use_nvls=None, ctas: int = 0, in_off=None, out_off=None):
         """out[r*shard:(r+1)*shard] on every rank <- in[:shard] of rank r."""
         if in_off is None and out_off is None:
             assert shard_bytes <= self.in_bytes and shard_bytes * self.world <= self.out_bytes
-        self._coll("smx_all_gather", shard_bytes, use_nvls, ctas, in_off, out_off)
+        nv, c = self.pick("all_gather", shard_bytes * self.world)
+        self._coll("smx_all_gather", shard_bytes, nv if use_nvls is None else use_nvls, ctas or c, in_off, out_off)
 
-    def reduce_scatter(self, shard_bytes: int, use_nvls: bool = True, ctas: int = 32, in_off=None, out_off=None,
+    def reduce_scatter(self, shard_bytes: int, use_nvls=None, ctas: int = 0, in_off=None, out_off=None,
                        dtype=torch.bfloat16):
         """out[:shard] <- sum over ranks of in[rank*shard:(rank+1)*shard]   (bf16 with fp32 accumulation, or fp32)."""
         if in_off is None and out_off is None:
             assert shard_bytes * self.world <= self.in_bytes and shard_bytes <= self.out_bytes
-        self._coll("smx_reduce_scatter", shard_bytes, use_nvls, ctas, in_off, out_off, f32=(dtype == torch.float32))
+        nv, c = self.pick("reduce_scatter", shard_bytes * self.world)
+        self._coll("smx_reduce_scatter", shard_bytes, nv if use_nvls is None else use_nvls, ctas or c, in_off, out_off,
+                   f32=(dtype == torch.float32))
 
-    def all_reduce(self, total_bytes: int, use_nvls: bool = True, ctas: int = 32, in_off=None, out_off=None,
+    def all_reduce(self, total_bytes: int, use_nvls=None, ctas: int = 0, in_off=None, out_off=None,
                    dtype=torch.bfloat16):
         """out[:total] <- sum over ranks of in[:total]   (bf16 or fp32)."""
         if in_off is None and out_off is None:
             assert total_bytes <= self.in_bytes and total_bytes <= self.out_bytes
-        self._coll("smx_all_reduce", total_bytes, use_nvls, ctas, in_off, out_off, f32=(dtype == torch.float32))
+        nv, c = self.pick("all_reduce", total_bytes)
+        self._coll("smx_all_reduce", total_bytes, nv if use_nvls is None else use_nvls, ctas or c, in_off, out_off,
+                   f32=(dtype == torch.float32))
 
-    def all_to_all(self, chunk_bytes: int, ctas: int = 32):
+    def all_to_all(self, chunk_bytes: int, ctas: int = 0):
         """out[src*chunk:(src+1)*chunk] of rank dst <- in[dst*chunk:(dst+1)*chunk] of rank src."""
         assert chunk_bytes * self.world <= min(self.in_bytes, self.out_bytes)
+        ctas = ctas or self.pick("all_to_all", chunk_bytes * self.world)[1]
         rc = _fn("smx_all_to_all", _SIG_A2A)(self.data_ptrs, self.flag_ptrs, self.rank, self.world, 0, self.in_bytes,
                                              chunk_bytes, self._next_epoch(), min(ctas, MAX_CTAS), self._stream())
         _lib.check(rc, "smx_all_to_all")

@@ -110,6 +110,9 @@ def strategy_for(case: Case, runtime_semantics: bool = True):
     if case.recompute == "none":
         st.enable_recompute = False
     st.enable_straggler_model = False
+    if case.model.startswith("deepseek") or case.ep > 1:
+        st.dispatch_probs = True
+        st.enable_sequence_parallel = False
     # runtime semantics: ZeRO-1 collectives overlapped with backward / next forward, TP collectives fused into the GEMMs (measured
     # exposure), single-pass AdamW.  Off = what Megatron + NCCL do (the reference's semantics).
     st.dp_overlap_model = bool(runtime_semantics) and case.tp == 1
@@ -131,6 +134,8 @@ def predict(case: Case, system: str = "b200_sm100a_calibrated", runtime_semantic
         if case.layers:
             p.model_config.layer_num = case.layers
         p.model_config.padded_vocab_size, p.model_config.make_vocab_size_divisible_by = True, 128
+        if getattr(p.model_config, "model_type", "dense") == "moe":      # the measurement contract: pad to capacity, capacity factor 1
+            p.model_config.moe_pad_expert_input_to_capacity, p.model_config.capacity = True, 1
         p.run_estimate()
         cost, mem = p.analysis_cost().data, p.analysis_mem().data
     tok_s = cost["throughput_per_accelerator"] * case.world

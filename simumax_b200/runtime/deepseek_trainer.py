@@ -365,7 +365,7 @@ class DeepSeekTrainer:
         W, ws = self.world, self.ws
         if W > 1:
             if ws is not None:
-                ws.reduce_scatter(self.shard * 4, in_off=self._off_g, out_off=self._off_gs, dtype=torch.float32, ctas=64)
+                ws.reduce_scatter(self.shard * 4, in_off=self._off_g, out_off=self._off_gs, dtype=torch.float32)
             else:
                 dist.reduce_scatter_tensor(self.grad_shard, self.grads.buf, group=self.group)
         self.sq_in.zero_()
@@ -385,7 +385,7 @@ class DeepSeekTrainer:
         if W > 1:
             self.grads.buf.zero_()
             if ws is not None:
-                ws.all_gather(self.shard * 2, in_off=self._off_p + lo * 2, out_off=self._off_p, ctas=32)
+                ws.all_gather(self.shard * 2, in_off=self._off_p + lo * 2, out_off=self._off_p)
             else:
                 dist.all_gather_into_tensor(self.params.buf, self.params.buf[lo:lo + self.shard].clone(), group=self.group)
 

@@ -376,7 +376,7 @@ class TPLlamaTrainer:
         lo, hi = self.zlo, self.zlo + self.zshard
         dws = self.dp_ws
         if dws is not None:          # pull-reduce my slice of every replica's main grads over NVLink (multimem.ld_reduce with NVLS)
-            dws.reduce_scatter(self.zshard * 4, in_off=self._zg, out_off=self._zgs, dtype=torch.float32, ctas=64)
+            dws.reduce_scatter(self.zshard * 4, in_off=self._zg, out_off=self._zgs, dtype=torch.float32)
         else:
             dist.reduce_scatter_tensor(self.grad_shard, self.grads.buf, op=dist.ReduceOp.SUM, group=self.dp_group)
         cut = min(max(self.n_shard - lo, 0), self.zshard)          # [0, cut) of my shard = TP-sharded matrices, rest = replicated norms
@@ -398,7 +398,7 @@ class TPLlamaTrainer:
                  self.step_count, sqnorm_t=sq[:1], max_norm=self.max_norm, grad_prescale=1.0 / self.dp, zero_grad=False)
         self.grads.buf.zero_()
         if dws is not None:          # push my updated bf16 slice into every replica's parameter buffer (multimem.st with NVLS)
-            dws.all_gather(self.zshard * 2, in_off=self._zp + lo * 2, out_off=self._zp, ctas=32)
+            dws.all_gather(self.zshard * 2, in_off=self._zp + lo * 2, out_off=self._zp)
         else:
             dist.all_gather_into_tensor(self.params.buf, self.params.buf[lo:hi].clone(), group=self.dp_group)
 

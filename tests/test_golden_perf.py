@@ -61,3 +61,21 @@ def test_a100_config():
     r = headline(p)
     assert parse_time_ms(r["duration_time_per_iter"]) == pytest.approx(5554.7, rel=1e-4)
     assert r["mfu"] == pytest.approx(0.4866, abs=1e-4)
+
+
+def test_group_linear_mode_serial():
+    """Legacy ``group_linear_mode='serial'`` (reference moe_module.py:878-900, 1101-1134): per-expert LinearCol children instead of one
+    grouped GEMM.  Peak memory and the six table misses reproduce the reference's replay (32.0501 GB); the iteration is slower than
+    the grouped mode.  (The reference's own chunk total leaves out the time of the row-linear children in this mode -- 3 x 20 x
+    0.0194 ms forward per micro-batch on this config -- while pricing each of them; here they are counted.)"""
+    from helpers import MOE, build, headline, reference_system
+    sysc = reference_system()
+    par = build("ep8_pp1_dp8_mbs1", "deepseekv2", sysc, layers=4, model_over=dict(MOE))
+    ser = build("ep8_pp1_dp8_mbs1", "deepseekv2", sysc, layers=4, model_over=dict(MOE, group_linear_mode="serial"))
+    rp, rs = headline(par), headline(ser)
+    assert str(rs["peak_mem"]).startswith("32.0501"), rs["peak_mem"]
+    kinds = [n.kind for n in list(ser.model_chunk_dict.values())[0].nodes]
+    assert kinds.count("LinearCol") > kinds.count("LinearRow") + 100          # 3 MoE layers x 2 x 20 experts
+    assert not any(k == "GroupLinear" for k in kinds)
+    ms = lambda r: float(str(r["duration_time_per_iter"]).split()[0]) * (1e3 if str(r["duration_time_per_iter"]).strip().endswith(" s") else 1.0)
+    assert ms(rs) > ms(rp)

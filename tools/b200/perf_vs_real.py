@@ -1,113 +1,88 @@
 #!/usr/bin/env python
-"""Predicted-vs-measured table: run real training steps with this repo's runtime (LlamaTrainer) and compare iteration
-time and peak memory with what ``PerfLLM`` predicts for the same (system, strategy, model) triple.
+"""Predicted-vs-measured pipeline: run real training steps with this repo's runtime and compare iteration time and peak memory with
+what ``PerfLLM`` predicts for the same (system, strategy, model) triple -- the in-repo counterpart of the reference's Megatron
+pipeline (tools/b200/run_megatron_perf_real_pipeline.py: phases + state file + ``--reuse``; run_megatron_perf_real_batch.py:587-632,
+710-730: per-case summary ``.md`` / ``.json``).
 
-    python tools/b200/perf_vs_real.py --system b200_sm100a_calibrated --out profiles/perf_vs_real.json        # 1 GPU
-    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/b200/perf_vs_real.py ...  # DP=8
+    python tools/b200/perf_vs_real.py                                   # 1 GPU: every case of the zoo that fits one GPU
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/b200/perf_vs_real.py --cases llama3_70b_l12_tp2_pp1_dp4_mbc4
+    python tools/b200/perf_vs_real.py --phase predict --reuse           # CPU only: re-predict measured cases with another --system
 
-Cases are data-parallel only (the measured runtime implements DP + ZeRO-1); every row is device-timed (CUDA events,
-max over ranks) after warm-up, and memory is the CUDA high-water mark of the process.
-(reference: tools/b200/run_megatron_perf_real_pipeline.py / _batch.py drive Megatron-LM and regex its logs; here the
-"real" side is in-repo.)
+Phases: ``measure`` (GPU; device-timed steps, max over ranks; peak memory = allocator high-water mark + symmetric allocations,
+max over ranks) and ``predict`` (CPU).  Every finished phase of every case is recorded in the state file (``--state``); ``--reuse``
+skips phases the state already holds, so an interrupted sweep resumes and a re-calibrated system config only costs the predict phase.
+Outputs: ``<out>.json`` (rows) and ``<out>.md`` (table in the layout of docs/b200/b200_release_v1.2_summary.md).
 """
 from __future__ import annotations
 
 import argparse
-import contextlib
-import gc
-import io
 import json
 import os
 import sys
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-#        name                      model         layers  seq    mbs  mbc
-CASES = [
-    ("llama3_8b_full_s4096",       "llama3-8b",  None,   4096,  1,   4),
-    ("llama3_8b_l16_s4096_mbs2",   "llama3-8b",  16,     4096,  2,   2),
-    ("llama3_8b_l16_s8192",        "llama3-8b",  16,     8192,  1,   2),
-    ("llama3_70b_l4_s4096",        "llama3-70b", 4,      4096,  1,   4),
-    ("llama3_70b_l8_s4096",        "llama3-70b", 8,      4096,  1,   2),
-]
+from simumax_b200.runtime.cases import Case, predict, published  # noqa: E402
 
 
-TP_CASES = [      # measured with TPLlamaTrainer: tp = world, sequence parallel, dp = 1 (every rank sees the same batch)
-    ("llama3_8b_full_s4096_tp",    "llama3-8b",  None,   4096,  1,   4),
-    ("llama3_70b_l12_s4096_tp",    "llama3-70b", 12,     4096,  1,   4),
-    ("llama3_70b_l12_s8192_tp",    "llama3-70b", 12,     8192,  1,   2),
-    # the remaining tp8_dp1 rows of the reference's published B200 table (same model / layers / seq / micro-batches)
-    ("llama3_70b_l12_s4096_mbc8_tp",  "llama3-70b", 12,   4096,  1,   8),
-    ("llama3_70b_l12_s4096_mbc32_tp", "llama3-70b", 12,   4096,  1,   32),
-    ("llama3_405b_l4_s4096_tp",       "llama3-405b_padding_128", 4, 4096, 1, 4),
-    ("llama3_405b_l4_s4096_mbc8_tp",  "llama3-405b_padding_128", 4, 4096, 1, 8),
-]
-
-# (model, layers, seq, mbs, mbc, tp, dp) -> (Megatron-LM + TE measured ms, peak GiB, reference-predicted ms) as published by the
-# reference authors for 8 x B200 (docs/b200/b200_release_v1.2_summary.md).  Quoted, not re-measured here.
-PUBLISHED = {
-    ("llama3-70b", 12, 4096, 1, 4, 8, 1): (280.9, 28.29, 255.71), ("llama3-70b", 12, 4096, 1, 8, 8, 1): (556.7, 28.29, 493.39),
-    ("llama3-70b", 12, 4096, 1, 32, 8, 1): (2073.7, 28.29, 1919.4), ("llama3-70b", 12, 4096, 1, 4, 2, 4): (725.5, 60.68, 698.81),
-    ("llama3-70b", 12, 4096, 1, 4, 4, 2): (409.8, 39.07, 395.23), ("llama3-70b", 12, 4096, 1, 8, 2, 4): (1387.0, 60.68, 1309.8),
-    ("llama3-70b", 12, 4096, 1, 8, 4, 2): (765.6, 39.07, 747.66),
-    ("llama3-405b_padding_128", 4, 4096, 1, 4, 8, 1): (258.8, 38.57, 255.83), ("llama3-405b_padding_128", 4, 4096, 1, 8, 8, 1): (488.1, 38.57, 486.81),
-    ("llama3-405b_padding_128", 4, 4096, 1, 4, 2, 4): (907.3, 81.59, 860.73), ("llama3-405b_padding_128", 4, 4096, 1, 4, 4, 2): (476.0, 52.89, 452.92),
-}
-
-
-def predict(model, layers, seq, mbs, mbc, world, system, tp=1, runtime_semantics=False):
-    from simumax_b200 import PerfLLM
-    from simumax_b200.configs import get_simu_model_config, get_simu_strategy_config, get_simu_system_config
-    from simumax_b200.core.config import StrategyConfig
-    from simumax_b200.core.utils import parse_bytes
-    st = StrategyConfig.init_from_config_file(get_simu_strategy_config("tp1_pp1_dp8_mbs1"))
-    st.world_size, st.tp_size, st.pp_size = world, tp, 1
-    st.enable_sequence_parallel = tp > 1
-    st.seq_len, st.micro_batch_size, st.micro_batch_num = seq, mbs, mbc
-    st.dp_overlap_model = True      # the runtime overlaps ZeRO-1 collectives with backward / next forward
-    # runtime semantics: TP collectives fused into the GEMMs (measured exposure), single-pass AdamW; off = what Megatron + NCCL do
-    st.tp_overlap_model = st.fused_optimizer_model = bool(runtime_semantics)
-    p = PerfLLM()
-    with contextlib.redirect_stdout(io.StringIO()):
-        p.configure(strategy_config=st, model_config=get_simu_model_config(model), system_config=get_simu_system_config(system))
-        if layers:
-            p.model_config.layer_num = layers
-        p.model_config.padded_vocab_size, p.model_config.make_vocab_size_divisible_by = True, 128
-        p.run_estimate()
-        cost, mem = p.analysis_cost().data, p.analysis_mem().data
-    tok_s = cost["throughput_per_accelerator"] * world
-    return {"iter_ms": mbs * mbc * (world // tp) * seq / tok_s * 1e3, "tokens_per_s": tok_s, "mfu": cost["mfu"],
-            "peak_gib": parse_bytes(mem["peak_mem"]) / 2 ** 30 if isinstance(mem.get("peak_mem"), str) else None,
-            "miss": {k: len(v) for k, v in p.system.miss_efficiency.items()}}
+def zoo():
+    """The validation rows this repo can execute, keyed by name; ``world`` GPUs each."""
+    c = []
+    # one GPU
+    c += [Case("llama3_8b_tp1_mbc8", "llama3-8b", None, 4096, 1, 8),
+          Case("llama3_8b_l16_mbs2_mbc2", "llama3-8b", 16, 4096, 2, 2),
+          Case("llama3_8b_l16_s8192_mbc2", "llama3-8b", 16, 8192, 1, 2),
+          Case("llama3_70b_l4_mbc4", "llama3-70b", 4, 4096, 1, 4),
+          Case("llama3_70b_l8_mbc2", "llama3-70b", 8, 4096, 1, 2),
+          Case("llama3_8b_l16_selective_mbc4", "llama3-8b", 16, 4096, 1, 4, recompute="selective",
+               strategy_overrides={"enable_recompute": True, "recompute_granularity": "selective_recompute", "recompute_layer_num": 16,
+                                   "attn_recompute": True, "mlp_recompute": True}),
+          Case("llama3_8b_l16_full_mbc4", "llama3-8b", 16, 4096, 1, 4, recompute="full",
+               strategy_overrides={"enable_recompute": True, "recompute_granularity": "full_block", "recompute_layer_num": 16})]
+    # tensor parallel (+ data parallel): rows / slices of the published table
+    for tp in (2, 4, 8):
+        c.append(Case(f"llama3_8b_tp{tp}_pp1_dp1_mbc8", "llama3-8b", None, 4096, 1, 8, tp=tp, strategy_preset="tp8_pp1_dp1_mbs1"))
+        c.append(Case(f"llama3_70b_l12_tp{tp}_pp1_dp1_mbc4", "llama3-70b", 12, 4096, 1, 4, tp=tp, strategy_preset="tp8_pp1_dp1_mbs1"))
+    c += [Case("llama3_70b_l12_tp2_pp1_dp4_mbc4", "llama3-70b", 12, 4096, 1, 4, tp=2, dp=4, strategy_preset="tp2_pp1_dp4_mbs1"),
+          Case("llama3_70b_l12_tp4_pp1_dp2_mbc4", "llama3-70b", 12, 4096, 1, 4, tp=4, dp=2, strategy_preset="tp4_pp1_dp2_mbs1"),
+          Case("llama3_70b_l12_tp2_pp1_dp2_mbc4", "llama3-70b", 12, 4096, 1, 4, tp=2, dp=2, strategy_preset="tp2_pp1_dp4_mbs1"),
+          Case("llama3_70b_l12_tp8_pp1_dp1_mbc8", "llama3-70b", 12, 4096, 1, 8, tp=8, strategy_preset="tp8_pp1_dp1_mbs1"),
+          Case("llama3_405b_l4_tp8_pp1_dp1_mbc4", "llama3-405b_padding_128", 4, 4096, 1, 4, tp=8, strategy_preset="tp8_pp1_dp1_mbs1"),
+          Case("llama3_70b_l12_tp2_pp1_dp4_mbc8_selective", "llama3-70b", 12, 4096, 1, 8, tp=2, dp=4, recompute="selective",
+               strategy_preset="tp2_pp1_dp4_mbs1_selective_recompute"),
+          Case("llama3_70b_l12_tp2_pp1_dp1_mbc4_selective", "llama3-70b", 12, 4096, 1, 4, tp=2, dp=1, recompute="selective",
+               strategy_preset="tp2_pp1_dp4_mbs1_selective_recompute"),
+          Case("llama3_70b_l12_tp2_pp1_dp1_mbc4_full", "llama3-70b", 12, 4096, 1, 4, tp=2, dp=1, recompute="full",
+               strategy_preset="tp2_pp1_dp4_mbs1_full_recompute")]
+    # pipeline parallel
+    c += [Case("llama3_8b_tp1_pp2_dp1_mbc8", "llama3-8b", None, 4096, 1, 8, pp=2, strategy_preset="tp1_pp2_dp4_mbs1"),
+          Case("llama3_8b_tp1_pp2_dp4_mbc8", "llama3-8b", None, 4096, 1, 8, pp=2, dp=4, strategy_preset="tp1_pp2_dp4_mbs1"),
+          Case("llama3_70b_l12_tp1_pp2_dp4_mbc4", "llama3-70b", 12, 4096, 1, 4, pp=2, dp=4, strategy_preset="tp1_pp2_dp4_mbs1")]
+    # expert parallel (DeepSeek-V2: MLA + MoE)
+    c += [Case("deepseekv2_l4_ep8_pp1_dp8_mbc4", "deepseekv2", 4, 4096, 1, 4, ep=8, dp=8, strategy_preset="ep8_pp1_dp8_mbs1"),
+          Case("deepseekv2_l4_ep2_pp1_dp2_mbc4", "deepseekv2", 4, 4096, 1, 4, ep=2, dp=2, strategy_preset="ep8_pp1_dp8_mbs1"),
+          Case("deepseekv2_l2_ep1_pp1_dp1_mbc2", "deepseekv2", 2, 4096, 1, 2, ep=1, dp=1, strategy_preset="ep8_pp1_dp8_mbs1")]
+    return {x.name: x for x in c}
 
 
-def measure(model, layers, seq, mbs, mbc, steps, warmup, tp=1):
+MOE_OVERRIDES = {"moe_pad_expert_input_to_capacity": True, "capacity": 1}
+
+
+def measure(case: Case, steps: int, warmup: int) -> dict:
     import torch
     import torch.distributed as dist
-    from simumax_b200.configs import get_simu_model_config
-    from simumax_b200.core.config import ModelConfig
-    from simumax_b200.runtime.trainer import LlamaDims, LlamaTrainer
-    mc = ModelConfig.init_from_config_file(get_simu_model_config(model))
-    dims = LlamaDims.from_model_config(mc)
-    if layers:
-        dims.layers = layers
+    from simumax_b200.runtime import cases as C
+    mc, _ = C.model_dims(case)
     world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
     torch.cuda.reset_peak_memory_stats()
-    if tp > 1:
-        from simumax_b200.runtime.tp_trainer import TPLlamaTrainer
-        tp_group = dp_group = None
-        if world > tp:
-            rank, dp = dist.get_rank(), world // tp
-            tp_groups = [dist.new_group(list(range(i * tp, (i + 1) * tp))) for i in range(dp)]
-            dp_groups = [dist.new_group(list(range(j, world, tp))) for j in range(tp)]
-            tp_group, dp_group = tp_groups[rank // tp], dp_groups[rank % tp]
-        tr = TPLlamaTrainer(dims, mbs, seq, tp_group=tp_group, dp_group=dp_group)
-    else:
-        tr = LlamaTrainer(dims, mbs, seq, dp_group=dist.group.WORLD if world > 1 else None)
-    g = torch.Generator(device="cuda").manual_seed(5)
-    batches = [(torch.randint(0, mc.vocab_size, (mbs * seq,), device="cuda", generator=g),
-                torch.randint(0, mc.vocab_size, (mbs * seq,), device="cuda", generator=g)) for _ in range(mbc)]
+    tr = C.build_trainer(case)
+    g = torch.Generator(device="cuda").manual_seed(5 + rank // (case.tp * case.pp))
+    T = case.mbs * case.seq
+    batches = [(torch.randint(0, mc.vocab_size, (T,), device="cuda", generator=g),
+                torch.randint(0, mc.vocab_size, (T,), device="cuda", generator=g)) for _ in range(case.mbc)]
     for _ in range(warmup):
         tr.run_microbatches(batches)
     torch.cuda.synchronize()
@@ -116,72 +91,138 @@ def measure(model, layers, seq, mbs, mbc, steps, warmup, tp=1):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        tr.run_microbatches(batches)
+        loss = tr.run_microbatches(batches)
     e1.record()
     torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda")
-    peak = torch.tensor([float(torch.cuda.max_memory_allocated())], device="cuda")
+    mem = C.device_memory_gib(tr)
+    vals = torch.tensor([e0.elapsed_time(e1) / steps, mem["peak_gib"], mem["symmetric_gib"]], device="cuda")
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(peak, op=dist.ReduceOp.MAX)
-    out = {"iter_ms": float(ms), "tokens_per_s": mbs * mbc * (world // tp) * seq / float(ms) * 1e3, "peak_gib": float(peak) / 2 ** 30}
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    out = {"iter_ms": float(vals[0]), "tokens_per_s": case.tokens_per_step / float(vals[0]) * 1e3, "peak_gib": float(vals[1]),
+           "symmetric_gib": float(vals[2]), "loss": float(loss.item()), "trainer": type(tr).__name__, "steps": steps, "warmup": warmup}
+    C.release(tr)
     del tr, batches
-    gc.collect()
-    torch.cuda.empty_cache()
+    import gc
+    gc.collect(); torch.cuda.empty_cache()
     return out
+
+
+def row_of(case: Case, st: dict) -> dict:
+    m, p = st.get("measure"), st.get("predict")
+    row = {"case": case.name, "world": case.world, "parallelism": case.parallelism(), "model": case.model, "layers": case.layers,
+           "seq": case.seq, "mbs": case.mbs, "mbc": case.mbc}
+    if m:
+        row.update(real_ms=m["iter_ms"], real_gib=m["peak_gib"], real_tokens_per_s=m["tokens_per_s"], trainer=m.get("trainer"))
+    if p:
+        row.update(pred_ms=p["iter_ms"], pred_gib=p["peak_gib"], system=p["system"], efficiency_misses=p.get("efficiency_misses"),
+                   pred_megatron_semantics_ms=p.get("megatron_semantics_ms"))
+    if m and p:
+        row["time_err_pct"] = 100 * (p["iter_ms"] - m["iter_ms"]) / m["iter_ms"]
+        row["mem_err_pct"] = 100 * (p["peak_gib"] - m["peak_gib"]) / m["peak_gib"] if p.get("peak_gib") else None
+    pub = published(case)
+    if pub:
+        row["published_megatron"] = {"real_ms": pub[0], "real_gib": pub[1], "reference_pred_ms": pub[2],
+                                     "reference_time_err_pct": 100 * (pub[2] - pub[0]) / pub[0]}
+        if m:
+            row["published_megatron"]["speedup_vs_megatron"] = pub[0] / m["iter_ms"]
+    return row
+
+
+def write_summary(rows, out_stem: str, system: str) -> None:
+    json.dump({"system": system, "generated": time.strftime("%Y-%m-%d %H:%M:%S"), "rows": rows}, open(out_stem + ".json", "w"), indent=1)
+    f = lambda v, fmt="{:.2f}": "-" if v is None else fmt.format(v)
+    lines = [f"# Predicted vs measured (system config `{system}`)", "",
+             "Measured = this repo's runtime on the hand-written sm_100a kernels (device-timed, max over ranks; memory = allocator high-water "
+             "mark + symmetric allocations). Error = (predicted - measured) / measured.  `Megatron (published)` quotes the reference authors' "
+             "8 x B200 Megatron-LM + TE measurement of the same row (BASELINE.md section 2), not re-measured here.", "",
+             "| case | GPUs | layout | real ms | perf ms | time err | real GiB | perf GiB | mem err | Megatron (published) ms | speed-up |",
+             "|---|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|"]
+    errs, merrs = [], []
+    for r in rows:
+        pub = r.get("published_megatron") or {}
+        lines.append(f"| {r['case']} | {r['world']} | {r['parallelism']} | {f(r.get('real_ms'))} | {f(r.get('pred_ms'))} | "
+                     f"{f(r.get('time_err_pct'), '{:+.2f}%')} | {f(r.get('real_gib'))} | {f(r.get('pred_gib'))} | {f(r.get('mem_err_pct'), '{:+.2f}%')} | "
+                     f"{f(pub.get('real_ms'))} | {f(pub.get('speedup_vs_megatron'), '{:.2f}x')} |")
+        if r.get("time_err_pct") is not None:
+            errs.append(r["time_err_pct"])
+        if r.get("mem_err_pct") is not None:
+            merrs.append(r["mem_err_pct"])
+    if errs:
+        lines += ["", f"Derived: n = {len(errs)}, time error range {min(errs):+.2f}% ... {max(errs):+.2f}%, mean |err| {sum(abs(e) for e in errs) / len(errs):.2f}%"
+                  + (f"; memory error range {min(merrs):+.2f}% ... {max(merrs):+.2f}%" if merrs else "") + "."]
+    open(out_stem + ".md", "w").write("\n".join(lines) + "\n")
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--system", default="b200_sm100a_calibrated")
-    ap.add_argument("--out", default="gpurun_out/perf_vs_real.json")
+    ap.add_argument("--out", default="gpurun_out/perf_vs_real", help="output stem: <out>.json, <out>.md, default state <out>.state.json")
+    ap.add_argument("--state", default=None)
+    ap.add_argument("--reuse", action="store_true", help="skip phases already recorded in the state file")
+    ap.add_argument("--phase", default="all", choices=["all", "measure", "predict"])
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--cases", nargs="*", default=None)
-    ap.add_argument("--tp", action="store_true", help="tensor-parallel cases (sequence parallel, fused kernels)")
-    ap.add_argument("--tp-size", type=int, default=0, help="with --tp: tensor-parallel size (default = world size); the remaining "
-                    "factor runs data parallel with ZeRO-1, e.g. 8 GPUs --tp-size 2 = the reference's tp2_dp4 rows")
+    ap.add_argument("--cases", nargs="*", default=None, help="case names (default: every zoo case whose world size matches the launch)")
+    ap.add_argument("--list", action="store_true")
     a = ap.parse_args()
-    import torch
-    import torch.distributed as dist
+    Z = zoo()
+    if a.list:
+        for n, c in Z.items():
+            print(f"{n:48s} world {c.world}  {c.parallelism()}")
+        return 0
+    state_path = a.state or a.out + ".state.json"
+    state = json.load(open(state_path)) if (a.reuse and os.path.exists(state_path)) else {}
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    rank = dist.get_rank() if world > 1 else 0
-    rows = []
-    tp = (a.tp_size or world) if a.tp else 1
-    assert world % tp == 0
-    for name, model, layers, seq, mbs, mbc in (TP_CASES if a.tp else CASES):
-        if a.cases and name not in a.cases:
-            continue
-        real = measure(model, layers, seq, mbs, mbc, a.steps, a.warmup, tp)
+    rank = int(os.environ.get("RANK", "0"))
+    names = a.cases or [n for n, c in Z.items() if c.world == world or (a.phase == "predict" and n in state)]
+    unknown = [n for n in names if n not in Z]
+    assert not unknown, f"unknown cases {unknown}; --list shows the zoo"
+    do_measure = a.phase in ("all", "measure")
+    do_predict = a.phase in ("all", "predict")
+    if do_measure:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        if "RANK" not in os.environ:           # DeepSeek / symmetric-memory trainers want a process group even on one GPU
+            os.environ.update(RANK="0", WORLD_SIZE="1", MASTER_ADDR="127.0.0.1", MASTER_PORT=os.environ.get("MASTER_PORT", "29571"))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    save = lambda: (rank == 0) and (os.makedirs(os.path.dirname(state_path) or ".", exist_ok=True), json.dump(state, open(state_path, "w"), indent=1))
+    for n in names:
+        case = Z[n]
+        st = state.setdefault(n, {})
+        if do_measure and case.world == world and not (a.reuse and "measure" in st):
+            try:
+                st["measure"] = measure(case, a.steps, a.warmup)
+                st.pop("measure_error", None)
+            except Exception as e:                               # one failing case must not stop the sweep
+                st["measure_error"] = f"{type(e).__name__}: {e}"[:300]
+                import torch
+                torch.cuda.empty_cache()
+            save()
+        if do_predict and rank == 0 and not (a.reuse and st.get("predict", {}).get("system") == a.system):
+            try:
+                if case.model.startswith("deepseek"):
+                    case.strategy_overrides = dict(case.strategy_overrides)
+                p = predict(case, system=a.system, runtime_semantics=True)
+                p["megatron_semantics_ms"] = predict(case, system=a.system, runtime_semantics=False)["iter_ms"]
+                st["predict"] = p
+            except Exception as e:
+                st["predict_error"] = f"{type(e).__name__}: {e}"[:300]
+            save()
         if rank == 0:
-            pred = predict(model, layers, seq, mbs, mbc, world, a.system, tp)
-            pred_rt = predict(model, layers, seq, mbs, mbc, world, a.system, tp, runtime_semantics=True)
-            row = {"case": name + (str(tp) if a.tp else ""), "world": world, "tp": tp, "model": model, "layers": layers, "seq": seq, "mbs": mbs, "mbc": mbc,
-                   "pred_ms": pred["iter_ms"], "real_ms": real["iter_ms"],
-                   "time_err_pct": 100 * (pred["iter_ms"] - real["iter_ms"]) / real["iter_ms"],
-                   "pred_gib": pred["peak_gib"], "real_gib": real["peak_gib"],
-                   "mem_err_pct": 100 * (pred["peak_gib"] - real["peak_gib"]) / real["peak_gib"] if pred["peak_gib"] else None,
-                   "pred_runtime_semantics_ms": pred_rt["iter_ms"],
-                   "time_err_runtime_semantics_pct": 100 * (pred_rt["iter_ms"] - real["iter_ms"]) / real["iter_ms"],
-                   "pred_mfu": pred["mfu"],
-                   "published_megatron": (lambda v: None if v is None else {"real_ms": v[0], "real_gib": v[1], "reference_pred_ms": v[2],
-                                                                           "speedup_vs_megatron": v[0] / real["iter_ms"]})(
-                       PUBLISHED.get((model, layers, seq, mbs, mbc, tp, world // tp))), "real_tokens_per_s": real["tokens_per_s"], "efficiency_misses": pred["miss"]}
-            rows.append(row)
-            print(f"{name:28s} n={world} time pred {row['pred_ms']:9.2f} ms real {row['real_ms']:9.2f} ms ({row['time_err_pct']:+6.2f} %, runtime semantics {row['time_err_runtime_semantics_pct']:+6.2f} %)   "
-                  f"mem pred {row['pred_gib']:.2f} GiB real {row['real_gib']:.2f} GiB ({row['mem_err_pct']:+6.2f} %)"
-                  + (f"   published Megatron {row['published_megatron']['real_ms']:.1f} ms -> {row['published_megatron']['speedup_vs_megatron']:.2f}x"
-                     if row["published_megatron"] else ""), flush=True)
+            r = row_of(case, st)
+            print(f"{n:46s} real {r.get('real_ms', float('nan')):9.2f} ms  perf {r.get('pred_ms', float('nan')):9.2f} ms  "
+                  f"({r.get('time_err_pct', float('nan')):+6.2f} %)   mem real {r.get('real_gib', float('nan')):7.2f} perf {r.get('pred_gib', float('nan')):7.2f} GiB"
+                  + (f"  ERROR {st.get('measure_error') or st.get('predict_error')}" if (st.get('measure_error') or st.get('predict_error')) else ""), flush=True)
     if rank == 0:
-        os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
-        json.dump({"system": a.system, "world": world, "rows": rows}, open(a.out, "w"), indent=1)
-    if world > 1:
+        rows = [row_of(Z[n], state[n]) for n in state if n in Z and (state[n].get("measure") or state[n].get("predict"))]
+        write_summary(rows, a.out, a.system)
+        print(f"wrote {a.out}.json / .md ({len(rows)} rows), state {state_path}")
+    if do_measure:
+        import torch.distributed as dist
         dist.destroy_process_group()
+    return 0
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main() or 0)
