@@ -693,6 +693,18 @@ __global__ void copy2d_kernel(const unsigned char* __restrict__ src, long long s
   }
 }
 
+// dst[a][b][:] = src[b][a][:]  (inner = contiguous run of `vec` 16-byte vectors): packs / unpacks the per-destination column blocks
+// around a context-parallel (Ulysses) all-to-all -- [tokens, ranks, width] <-> [ranks, tokens, width].
+__global__ void transpose01_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long A, long long B, int vec) {
+  const long long total = A * B * vec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vec);
+    const long long ab = i / vec;
+    const long long b = ab % B, a = ab / B;
+    dst[i] = src[(b * A + a) * vec + v];
+  }
+}
+
 // streaming copy (the "default" memory-bandwidth calibration op)
 __global__ void copy_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n16) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
@@ -881,6 +893,11 @@ int smx_mla_k_split_bwd(const void* dk, void* d_kv, long long kv_row, int kv_hea
 int smx_copy2d(const void* src, long long src_ld_bytes, void* dst, long long dst_ld_bytes, long long rows, long long width_bytes, void* stream) {
   if (width_bytes % 16 || src_ld_bytes % 16 || dst_ld_bytes % 16) return -20;
   smx::copy2d_kernel<<<grid_for(rows * (width_bytes / 16), 256), 256, 0, SMX_STREAM>>>((const unsigned char*)src, src_ld_bytes, (unsigned char*)dst, dst_ld_bytes, rows, (int)(width_bytes / 16));
+  return (int)cudaGetLastError();
+}
+int smx_transpose01(const void* src, void* dst, long long A, long long B, long long inner_bytes, void* stream) {
+  if (inner_bytes % 16) return -20;
+  smx::transpose01_kernel<<<grid_for(A * B * (inner_bytes / 16), 256), 256, 0, SMX_STREAM>>>((const uint4*)src, (uint4*)dst, A, B, (int)(inner_bytes / 16));
   return (int)cudaGetLastError();
 }
 int smx_add(const void* a, const void* b, void* y, long long n, void* stream) {

@@ -33,6 +33,7 @@ _SIGS = {
     "smx_rope_strided": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_longlong, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_void_p],
     "smx_mla_k_assemble": [_c.c_void_p, _c.c_longlong, _c.c_int, _c.c_void_p, _c.c_longlong, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p],
     "smx_mla_k_split_bwd": [_c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_void_p, _c.c_longlong, _c.c_longlong, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p],
+    "smx_transpose01": [_c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_longlong, _c.c_longlong, _c.c_void_p],
     "smx_copy2d": [_c.c_void_p, _c.c_longlong, _c.c_void_p, _c.c_longlong, _c.c_longlong, _c.c_longlong, _c.c_void_p],
     "smx_embedding_fwd": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_longlong, _c.c_longlong, _c.c_void_p],
     "smx_embedding_bwd": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_longlong, _c.c_longlong, _c.c_void_p],
@@ -297,4 +298,14 @@ def copy2d_(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
     assert dst.shape == src.shape and dst.dim() == 2 and dst.stride(1) == 1 and src.stride(1) == 1 and dst.dtype == src.dtype
     es = dst.element_size()
     _call("smx_copy2d", src.data_ptr(), src.stride(0) * es, dst.data_ptr(), dst.stride(0) * es, dst.shape[0], dst.shape[1] * es, _stream(dst))
+    return dst
+
+
+def transpose01_(dst: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    """dst[a, b, :] = src[b, a, :] for contiguous 3-D tensors (``src`` [B, A, w], ``dst`` [A, B, w]): the pack / unpack step around a
+    context-parallel all-to-all (tokens x destination-rank column blocks <-> destination rank x tokens)."""
+    assert src.is_contiguous() and dst.is_contiguous() and src.dim() == 3 and dst.dim() == 3 and src.dtype == dst.dtype
+    B, A, w = src.shape
+    assert dst.shape == (A, B, w)
+    _call("smx_transpose01", src.data_ptr(), dst.data_ptr(), A, B, w * src.element_size(), _stream(dst))
     return dst

@@ -75,7 +75,18 @@ PUBLISHED: Dict[Tuple, Tuple[float, float, float]] = {
 }
 
 
+# context-parallel rows (all-to-all CP, dp = 1): (model, layers, seq, mbc, tp, cp) -> same triple   [BASELINE.md section 2, lines 57-63]
+PUBLISHED_CP: Dict[Tuple, Tuple[float, float, float]] = {
+    ("llama3-70b", 12, 32768, 4, 2, 4): (1758.0, 68.43, 1595.0), ("llama3-70b", 12, 32768, 4, 1, 8): (1768.1, 104.51, 1627.2),
+    ("llama3-405b_padding_128", 4, 32768, 4, 2, 4): (1984.7, 87.03, 1814.3), ("llama3-405b_padding_128", 4, 32768, 4, 1, 8): (2003.6, 139.22, 1896.2),
+    ("llama3-70b", 12, 131072, 4, 2, 4): (11315.7, 112.67, 10670.4), ("llama3-70b", 12, 131072, 4, 1, 8): (11301.9, 147.99, 10515.7),
+    ("llama3-405b_padding_128", 4, 131072, 4, 2, 4): (10577.6, 118.13, 10043.5),
+}
+
+
 def published(case: Case):
+    if case.cp > 1:
+        return PUBLISHED_CP.get((case.model, case.layers, case.seq, case.mbc, case.tp, case.cp)) if (case.mbs == 1 and case.dp == 1) else None
     return PUBLISHED.get((case.model, case.layers, case.seq, case.mbs, case.mbc, case.tp, case.pp, case.ep, case.dp))
 
 
@@ -113,6 +124,8 @@ def strategy_for(case: Case, runtime_semantics: bool = True):
     if case.model.startswith("deepseek") or case.ep > 1:
         st.dispatch_probs = True
         st.enable_sequence_parallel = False
+    if case.cp > 1:
+        st.cp_comm_type = "a2a"
     # runtime semantics: ZeRO-1 collectives overlapped with backward / next forward, TP collectives fused into the GEMMs (measured
     # exposure), single-pass AdamW.  Off = what Megatron + NCCL do (the reference's semantics).
     st.dp_overlap_model = bool(runtime_semantics) and case.tp == 1
@@ -209,6 +222,10 @@ def build_trainer(case: Case, seed: int = 1234, **kw):
         return TPLlamaTrainer(dims, case.mbs, case.seq, tp_group=tp_group, dp_group=dp_group, seed=seed,
                               recompute=case.recompute, **kw)
     from .trainer import LlamaTrainer
+    if case.cp > 1:
+        assert case.tp == 1 and case.dp == 1, "context parallelism runs with tp = dp = 1 (cp = world)"
+        return LlamaTrainer(dims, case.mbs, case.seq, dp_group=dist.group.WORLD, cp_group=dist.group.WORLD, seed=seed,
+                            recompute=case.recompute, **kw)
     return LlamaTrainer(dims, case.mbs, case.seq, dp_group=dist.group.WORLD if world > 1 else None, seed=seed,
                         recompute=case.recompute, **kw)
 

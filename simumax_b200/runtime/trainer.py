@@ -80,7 +80,8 @@ class LlamaTrainer:
                  lr: float = 1e-4, weight_decay: float = 0.1, betas=(0.9, 0.95), max_grad_norm: float = 1.0,
                  attention_bwd: str = "auto", seed: int = 1234, device=None, comm: str = "auto",
                  first_stage: bool = True, last_stage: bool = True, in_flight: int = 1, recompute: str = "none",
-                 recompute_layers: Optional[int] = None, recompute_unused_outputs: bool = True, data_parallel: bool = True):
+                 recompute_layers: Optional[int] = None, recompute_unused_outputs: bool = True, data_parallel: bool = True,
+                 cp_group: Optional[dist.ProcessGroup] = None):
         """``first_stage`` / ``last_stage`` / ``in_flight``: pipeline-stage mode (runtime/pp_trainer.py) -- the stage owns
         ``dims.layers`` layers, the embedding only if first, final norm + LM head + loss only if last, and keeps ``in_flight``
         sets of activations (1F1B holds several micro-batches between their forward and backward).
@@ -91,12 +92,24 @@ class LlamaTrainer:
         ``"full"`` = ``full_block``: only the layer input is kept and the whole layer forward is re-run.
         ``recompute_unused_outputs``: re-run every op of a recomputed segment, as Megatron's checkpointing does (its last GEMM's output
         is thrown away); False skips those.  ``data_parallel=False``: no ZeRO sharding / gradient reduction even when a process group
-        exists (pipeline stages pass it; their data-parallel groups are wired by the pipeline trainer)."""
+        exists (pipeline stages pass it; their data-parallel groups are wired by the pipeline trainer).
+
+        ``cp_group``: context parallelism, all-to-all flavour (DeepSpeed-Ulysses; reference cost model dense_module.py:1158-1232,
+        1259-1338): every rank of the group holds ``seq_len / cp`` consecutive tokens of each sequence for everything but the core
+        attention; around it the packed QKV goes through an all-to-all (this repo's in-kernel NVLink all-to-all) that trades the
+        sequence shard for a head shard -- full sequence, ``heads / cp`` heads -- and the attention output goes back the same way.
+        Weights are replicated over the group, so ``dp_group`` (the ZeRO-1 group) must span the cp ranks as well."""
         assert recompute in ("none", "selective", "full"), recompute
         self.first_stage, self.last_stage = first_stage, last_stage
         self.d = dims
-        self.B, self.S = micro_batch, seq_len
-        self.T = micro_batch * seq_len
+        self.cp_group = cp_group
+        self.cp = dist.get_world_size(cp_group) if cp_group is not None else 1
+        self.cp_rank = dist.get_rank(cp_group) if cp_group is not None else 0
+        assert seq_len % self.cp == 0 and dims.heads % self.cp == 0 and dims.kv_heads % self.cp == 0
+        assert self.cp == 1 or micro_batch == 1, "context parallelism is implemented for micro-batch size 1"
+        self.S_full = seq_len
+        self.B, self.S = micro_batch, seq_len // self.cp            # S: tokens of a sequence this rank holds
+        self.T = micro_batch * self.S
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.group = dp_group
         use_dp = data_parallel and dist.is_initialized()
@@ -105,8 +118,8 @@ class LlamaTrainer:
         self.recompute = recompute
         self.rl = 0 if recompute == "none" else min(dims.layers, dims.layers if recompute_layers is None else recompute_layers)
         self.recompute_unused = recompute_unused_outputs
-        self._unsaved = {"none": set(), "selective": {"qkv", "lse", "u", "g"},
-                         "full": {"h1", "rstd1", "qkv", "lse", "o", "x2", "h2", "rstd2", "u", "g"}}[recompute]
+        self._unsaved = {"none": set(), "selective": {"qkv", "lse", "u", "g", "o_full"},
+                         "full": {"h1", "rstd1", "qkv", "lse", "o", "x2", "h2", "rstd2", "u", "g", "o_full"}}[recompute]
         self.lr, self.wd, self.betas, self.max_norm = lr, weight_decay, betas, max_grad_norm
         self.step_count = 0
         d, dev = dims, self.device
@@ -175,7 +188,9 @@ class LlamaTrainer:
         f32 = dict(dtype=torch.float32, device=dev)
         shapes = {"h1": ((T, H), bf), "qkv": ((T, d.qkv_out), bf), "o": ((T, d.heads * d.head_dim), bf), "x2": ((T, H), bf),
                   "h2": ((T, H), bf), "u": ((T, 2 * F), bf), "g": ((T, F), bf), "rstd1": ((T,), f32), "rstd2": ((T,), f32),
-                  "lse": ((self.B, d.heads, self.S), f32)}
+                  "lse": ((self.B, d.heads // self.cp, self.S_full), f32)}
+        if self.cp > 1:      # full sequence x this rank's head group: what the core attention saw (its backward needs it)
+            shapes["o_full"] = ((self.S_full, d.heads // self.cp * d.head_dim), bf)
         # tensors a recomputed layer does not keep share ONE scratch entry (index 0); layers past ``rl`` keep their own
         n_of = lambda name: (L - self.rl + 1) if name in self._unsaved else L
         self._scratch = {name: torch.empty(*shp, **kw) for name, (shp, kw) in shapes.items() if name in self._unsaved}
@@ -196,7 +211,13 @@ class LlamaTrainer:
         self.d_qkv = torch.empty(T, d.qkv_out, **bf)
         self.d_o = torch.empty(T, d.heads * d.head_dim, **bf)
         self.tmp_h = torch.empty(T, H, **bf)
-        self.cos, self.sin = E.rope_tables(self.S, d.head_dim, d.rope_theta, device=dev)
+        self.cos, self.sin = E.rope_tables(self.S_full, d.head_dim, d.rope_theta, device=dev)
+        self.cp_ws = None
+        if self.cp > 1:
+            from ..parallel.symm import SymmetricWorkspace
+            nb = T * d.qkv_out * 2
+            self.cp_ws = SymmetricWorkspace(nb, nb, group=cp_group, device=dev)
+            self.qkv_loc = torch.empty(T, d.qkv_out, **bf)
         self.tok_dev = torch.empty(T, dtype=torch.int64, device=dev)
         self.tgt_dev = torch.empty(T, dtype=torch.int64, device=dev)
         self.loss_rows = None
@@ -250,6 +271,9 @@ class LlamaTrainer:
         except Exception:
             return "sdpa_recompute"
 
+    def symmetric_workspaces(self):
+        return [w for w in (self.ws, self.cp_ws) if w is not None]
+
     def memory_bytes(self) -> dict:
         act = sum(t.numel() * t.element_size() for slot in self.act_slots for t in slot.values())
         act += sum(t.numel() * t.element_size() for t in self._scratch.values())
@@ -278,8 +302,52 @@ class LlamaTrainer:
             return self._scratch[name] if i < self.rl else self.act[name][i - self.rl]
         return self.act[name][i]
 
+    def _attn_segment_cp(self, i: int, o_out: torch.Tensor) -> None:
+        """Context-parallel attention segment: QKV linear on the local tokens -> all-to-all (sequence shard -> head shard) -> RoPE at
+        the global positions -> core attention over the full sequence with heads / cp heads -> all-to-all back."""
+        d, w, A, ws, cp = self.d, self.w, self._A, self.cp_ws, self.cp
+        Tl, S, hd = self.T, self.S_full, d.head_dim
+        nq, nk = d.heads // cp, d.kv_heads // cp
+        wq, wo = d.qkv_out // cp, nq * hd
+        bf16 = torch.bfloat16
+        gemm(A("h1", i), w["wqkv"][i], "TN", out=self.qkv_loc)        # columns grouped per destination rank: [q_r | k_r | v_r] x cp
+        E.transpose01_(ws.input(bf16, Tl * d.qkv_out).view(cp, Tl, wq), self.qkv_loc.view(Tl, cp, wq))
+        ws.all_to_all(Tl * wq * 2)
+        qkv = A("qkv", i).view(S, wq)
+        E.copy_(qkv, ws.output(bf16, S * wq).view(S, wq))
+        E.rope_inplace(qkv, self.cos, self.sin, S, nq + nk, hd)
+        t = qkv.view(1, S, wq)
+        q, k, v = t[..., :nq * hd].view(1, S, nq, hd), t[..., nq * hd:(nq + nk) * hd].view(1, S, nk, hd), t[..., (nq + nk) * hd:].view(1, S, nk, hd)
+        o_full = A("o_full", i)
+        fmha_fwd(q, k, v, causal=True, out=o_full.view(1, S, nq, hd), lse=A("lse", i))
+        E.copy_(ws.input(bf16, S * wo).view(S, wo), o_full)            # rows [s * Tl, (s + 1) * Tl) go to rank s
+        ws.all_to_all(Tl * wo * 2)
+        E.transpose01_(o_out.view(Tl, cp, wo), ws.output(bf16, S * wo).view(cp, Tl, wo))
+
+    def _attention_backward_cp(self, i: int) -> None:
+        d, A, ws, cp = self.d, self._A, self.cp_ws, self.cp
+        Tl, S, hd = self.T, self.S_full, d.head_dim
+        nq, nk = d.heads // cp, d.kv_heads // cp
+        wq, wo = d.qkv_out // cp, nq * hd
+        bf16 = torch.bfloat16
+        E.transpose01_(ws.input(bf16, Tl * cp * wo).view(cp, Tl, wo), self.d_o.view(Tl, cp, wo))
+        ws.all_to_all(Tl * wo * 2)
+        do_full = ws.output(bf16, S * wo).view(1, S, nq, hd)
+        t = A("qkv", i).view(1, S, wq)
+        q, k, v = t[..., :nq * hd].view(1, S, nq, hd), t[..., nq * hd:(nq + nk) * hd].view(1, S, nk, hd), t[..., (nq + nk) * hd:].view(1, S, nk, hd)
+        dt_flat = ws.input(bf16, S * wq).view(S, wq)                   # gradient of the head-sharded packed QKV, written in place
+        dt = dt_flat.view(1, S, wq)
+        dq, dk, dv = dt[..., :nq * hd].view(1, S, nq, hd), dt[..., nq * hd:(nq + nk) * hd].view(1, S, nk, hd), dt[..., (nq + nk) * hd:].view(1, S, nk, hd)
+        from ..ops.attention import fmha_bwd
+        fmha_bwd(do_full, q, k, v, A("o_full", i).view(1, S, nq, hd), A("lse", i), dq, dk, dv, causal=True, scale=1.0 / math.sqrt(hd))
+        E.rope_inplace(dt_flat, self.cos, self.sin, S, nq + nk, hd, inverse=True)
+        ws.all_to_all(Tl * wq * 2)
+        E.transpose01_(self.d_qkv.view(Tl, cp, wq), ws.output(bf16, S * wq).view(cp, Tl, wq))
+
     def _attn_segment(self, i: int, o_out: torch.Tensor) -> None:
         """QKV linear + RoPE + core attention of layer ``i`` (the reference's ``attn_recompute`` segment)."""
+        if self.cp > 1:
+            return self._attn_segment_cp(i, o_out)
         d, w, A = self.d, self.w, self._A
         qkv = A("qkv", i)
         gemm(A("h1", i), w["wqkv"][i], "TN", out=qkv)
@@ -375,8 +443,11 @@ class LlamaTrainer:
                 self._attn_segment(i, self.o_rc)          # re-derives qkv (post-RoPE) and lse; the kept ``o`` is identical
             gemm(dx3, A("o", i), "NT", out=g["wo"][i], accumulate=True)
             gemm(dx3, w["wo"][i], "NN", out=self.d_o)
-            self._attention_backward(i)
-            E.rope_inplace(self.d_qkv, self.cos, self.sin, self.S, d.heads + d.kv_heads, d.head_dim, inverse=True)
+            if self.cp > 1:
+                self._attention_backward_cp(i)                   # includes both all-to-alls and the inverse RoPE
+            else:
+                self._attention_backward(i)
+                E.rope_inplace(self.d_qkv, self.cos, self.sin, self.S, d.heads + d.kv_heads, d.head_dim, inverse=True)
             gemm(self.d_qkv, A("h1", i), "NT", out=g["wqkv"][i], accumulate=True)
             gemm(self.d_qkv, w["wqkv"][i], "NN", out=self.tmp_h)
             E.rmsnorm_bwd(a["x"][i], w["ln1"][i], self.tmp_h, A("rstd1", i), g["ln1"][i], dx=dx3, accumulate_dx=True)

@@ -1,0 +1,91 @@
+"""CPU tests for the predicted-vs-measured plumbing: case zoo -> PerfLLM triple, published rows, calibration sweep file / cache tag,
+merge-with-base semantics, the perf-vs-real pipeline's predict phase + state / --reuse / summary files."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_primary_and_extra_cases_predict():
+    from simumax_b200.runtime import cases as C
+    for n in (1, 2, 4, 8):
+        c = C.primary_case(n)
+        assert c.world == n and c.tokens_per_step == 8 * 4096
+        p = C.predict(c)
+        assert p["iter_ms"] > 0 and p["peak_gib"] > 0
+    ex = {c.name: c for c in C.extra_cases(8)}
+    assert C.published(ex["llama3_70b_l12_tp2_pp1_dp4_mbc4"]) == (725.5, 60.68, 698.81)
+    assert C.published(ex["deepseekv2_l4_ep8_pp1_dp8_mbc4"])[0] == 366.6
+    p = C.predict(ex["deepseekv2_l4_ep8_pp1_dp8_mbc4"])
+    assert 40 < p["peak_gib"] < 50                      # published: 45.63 GiB real, 45.40 GiB reference-predicted
+    cp = C.Case("cp", "llama3-70b", 12, 32768, 1, 4, cp=8)
+    assert C.published(cp) == (1768.1, 104.51, 1627.2) and cp.world == 8 and cp.tokens_per_step == 4 * 32768
+
+
+def test_runtime_semantics_mostly_change_time():
+    from simumax_b200.runtime import cases as C
+    c = C.primary_case(8)
+    a, b = C.predict(c, runtime_semantics=True), C.predict(c, runtime_semantics=False)
+    assert a["iter_ms"] < b["iter_ms"]                   # fused TP collectives + single-pass optimizer are cheaper than exposed ones
+    assert a["peak_gib"] == pytest.approx(b["peak_gib"], rel=0.15)   # the fused runtime keeps the gathered (not the sharded) norm outputs
+
+
+def test_sweep_file_expands_to_reference_sized_table(tmp_path):
+    from simumax_b200.calib.calibrate import cache_path, plan_requests
+    from simumax_b200.calib.shapes import DEFAULT_SWEEP, workloads_from_params
+    req = plan_requests(default_sweep=True, log=lambda *a: None)
+    # the reference's shipped B200 table: 514 matmul / 108 grouped / 32 + 32 attention keys
+    assert len(req["matmul"]) >= 514 and len(req["sdp_fwd"]) >= 32 and len(req["sdp_bwd"]) >= 32 and len(req["group_matmul"]) >= 90
+    assert any("seq_len=131072" in k or "131072" in k for k in req["sdp_fwd"])          # long-context keys (CP sweep)
+    small = dict(DEFAULT_SWEEP, model_list=["llama3-8b"], tp_list=[1, 8], mbs_list=[1], long_context=[])
+    f = tmp_path / "sweep.json"
+    f.write_text(json.dumps(small))
+    req2 = plan_requests(param_file=str(f), log=lambda *a: None)
+    assert len(req2["matmul"]) < len(req["matmul"])
+    assert len(workloads_from_params(small)) == 2
+    assert cache_path("gpurun_out/calib_ops.json", "x1") == "gpurun_out/calib_ops_x1.json" and cache_path("a.json", None) == "a.json"
+
+
+def test_merge_with_base_keeps_fallbacks(tmp_path):
+    """a small supplement merged into a base config must not move the fallback efficiencies or the latencies of the base."""
+    from simumax_b200.calib.calibrate import merge
+    from simumax_b200.configs import get_simu_system_config
+    base = get_simu_system_config("b200_sm100a_calibrated")
+    b = json.load(open(base))
+    key = "b=1, m=64, k=64, n=64, layout=TN, accumulate=False, out_dtype=bf16"
+    ops = {"ops": {"matmul": {key: {"ms": 1.0, "tflops": 1.0, "flops": 1e9, "efficiency": 0.01}}},
+           "bandwidth": {"default": {"gbs": 1000.0}}, "meta": {"device": "test"}}
+    f = tmp_path / "ops.json"
+    f.write_text(json.dumps(ops))
+    out = merge(str(f), [], str(tmp_path / "sys.json"), base=base, sys_name="t")
+    assert out["accelerator"]["op"]["matmul"]["accurate_efficient_factor"][key] == 0.01
+    assert out["accelerator"]["op"]["matmul"]["efficient_factor"] == pytest.approx(b["accelerator"]["op"]["matmul"]["efficient_factor"], rel=0.02)
+    assert out["accelerator"]["op"]["default"]["efficient_factor"] == b["accelerator"]["op"]["default"]["efficient_factor"]
+    assert out["accelerator"]["bandwidth"]["ce"]["latency_us"] == b["accelerator"]["bandwidth"]["ce"]["latency_us"]
+    from simumax_b200.core.config import SystemConfig
+    SystemConfig.init_from_config_file(str(tmp_path / "sys.json"))          # still loads
+
+
+def test_perf_vs_real_predict_phase_state_and_summary(tmp_path):
+    out = str(tmp_path / "pvr")
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "b200", "perf_vs_real.py"), "--phase", "predict", "--out", out, "--cases",
+           "llama3_70b_l12_tp2_pp1_dp4_mbc4", "llama3_8b_tp1_mbc8"]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 0, r.stderr[-1500:]
+    state = json.load(open(out + ".state.json"))
+    assert state["llama3_70b_l12_tp2_pp1_dp4_mbc4"]["predict"]["iter_ms"] > 0
+    # a measurement recorded earlier (here: injected) is reused, not repeated, and shows up in the summary next to the published row
+    state["llama3_70b_l12_tp2_pp1_dp4_mbc4"]["measure"] = {"iter_ms": 600.0, "tokens_per_s": 1.0, "peak_gib": 60.0, "trainer": "x"}
+    json.dump(state, open(out + ".state.json", "w"))
+    r = subprocess.run(cmd + ["--reuse"], capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 0, r.stderr[-1500:]
+    rows = {x["case"]: x for x in json.load(open(out + ".json"))["rows"]}
+    row = rows["llama3_70b_l12_tp2_pp1_dp4_mbc4"]
+    assert row["real_ms"] == 600.0 and row["published_megatron"]["real_ms"] == 725.5
+    assert row["published_megatron"]["speedup_vs_megatron"] == pytest.approx(725.5 / 600.0)
+    md = open(out + ".md").read()
+    assert "| llama3_70b_l12_tp2_pp1_dp4_mbc4 | 8 |" in md and "mean |err|" in md

@@ -60,6 +60,12 @@ def zoo():
     c += [Case("llama3_8b_tp1_pp2_dp1_mbc8", "llama3-8b", None, 4096, 1, 8, pp=2, strategy_preset="tp1_pp2_dp4_mbs1"),
           Case("llama3_8b_tp1_pp2_dp4_mbc8", "llama3-8b", None, 4096, 1, 8, pp=2, dp=4, strategy_preset="tp1_pp2_dp4_mbs1"),
           Case("llama3_70b_l12_tp1_pp2_dp4_mbc4", "llama3-70b", 12, 4096, 1, 4, pp=2, dp=4, strategy_preset="tp1_pp2_dp4_mbs1")]
+    # context parallel (Ulysses all-to-all), long sequences: rows / slices of the published CP table
+    c += [Case("llama3_70b_l12_tp1_cp8_seq32768_mbc4", "llama3-70b", 12, 32768, 1, 4, cp=8),
+          Case("llama3_70b_l12_tp1_cp8_seq131072_mbc4", "llama3-70b", 12, 131072, 1, 4, cp=8),
+          Case("llama3_8b_tp1_cp8_seq32768_mbc4", "llama3-8b", None, 32768, 1, 4, cp=8),
+          Case("llama3_8b_l16_tp1_cp4_seq32768_mbc2", "llama3-8b", 16, 32768, 1, 2, cp=4),
+          Case("llama3_8b_l16_tp1_cp2_seq16384_mbc2", "llama3-8b", 16, 16384, 1, 2, cp=2)]
     # expert parallel (DeepSeek-V2: MLA + MoE)
     c += [Case("deepseekv2_l4_ep8_pp1_dp8_mbc4", "deepseekv2", 4, 4096, 1, 4, ep=8, dp=8, strategy_preset="ep8_pp1_dp8_mbs1"),
           Case("deepseekv2_l4_ep2_pp1_dp2_mbc4", "deepseekv2", 4, 4096, 1, 4, ep=2, dp=2, strategy_preset="ep8_pp1_dp8_mbs1"),
@@ -80,7 +86,7 @@ def measure(case: Case, steps: int, warmup: int) -> dict:
     torch.cuda.reset_peak_memory_stats()
     tr = C.build_trainer(case)
     g = torch.Generator(device="cuda").manual_seed(5 + rank // (case.tp * case.pp))
-    T = case.mbs * case.seq
+    T = case.mbs * case.seq // case.cp                   # context parallel: every rank feeds its slice of the sequence
     batches = [(torch.randint(0, mc.vocab_size, (T,), device="cuda", generator=g),
                 torch.randint(0, mc.vocab_size, (T,), device="cuda", generator=g)) for _ in range(case.mbc)]
     for _ in range(warmup):
