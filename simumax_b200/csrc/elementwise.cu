@@ -249,6 +249,200 @@ __global__ void __launch_bounds__(THREADS) rs_consume_kernel(const __nv_bfloat16
 }
 
 // ----------------------------------------------------------------------------------------------
+// Persistent, software-pipelined row kernels (RMSNorm forward, fused residual add + RMSNorm, RMSNorm backward).
+// One CTA walks rows blockIdx.x, blockIdx.x + gridDim.x, ...; the raw bf16 vectors of the NEXT row are already in flight while the
+// current row is reduced (one __syncthreads per row, double-buffered partial sums), so the load -> reduce -> store chain of a row
+// no longer leaves the memory pipe idle: the one-row-per-CTA versions above reached 59 % of the measured copy bandwidth.
+// ----------------------------------------------------------------------------------------------
+SMX_DEVICE void unpack8(const uint4& r, float (&f)[8]) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+SMX_DEVICE uint4 pack8(const float (&f)[8]) {
+  uint4 r;
+  r.x = pack_bf16x2(f[0], f[1]); r.y = pack_bf16x2(f[2], f[3]); r.z = pack_bf16x2(f[4], f[5]); r.w = pack_bf16x2(f[6], f[7]);
+  return r;
+}
+// all threads get the block-wide sum; `red` is this iteration's buffer (callers alternate between two)
+template <int THREADS>
+SMX_DEVICE float block_sum_1sync(float v, float* red) {
+  v = warp_sum(v);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; ++w) t += red[w];
+  return t;
+}
+
+// y = rmsnorm(x (+ delta)) * gamma; with ADD also sum_out = bf16(x + delta) (the residual stream the backward re-reads)
+template <int THREADS, int VPT, bool ADD>
+__global__ void __launch_bounds__(THREADS) rmsnorm_fwd_pipe_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ delta,
+                                                                  const __nv_bfloat16* __restrict__ gamma, __nv_bfloat16* __restrict__ sum_out,
+                                                                  __nv_bfloat16* __restrict__ y, float* __restrict__ rstd, long long rows,
+                                                                  int H, float eps) {
+  __shared__ float red[2][32];
+  uint4 g[VPT], cur[VPT], cur_d[ADD ? VPT : 1], nxt[VPT], nxt_d[ADD ? VPT : 1];
+  bool on[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * THREADS + threadIdx.x) * 8;
+    on[i] = c < H;
+    if (on[i]) g[i] = *reinterpret_cast<const uint4*>(gamma + c);
+  }
+  long long row = blockIdx.x;
+  if (row < rows) {
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+      if (on[i]) {
+        const long long o = row * H + (i * THREADS + threadIdx.x) * 8;
+        cur[i] = *reinterpret_cast<const uint4*>(x + o);
+        if constexpr (ADD) cur_d[i] = *reinterpret_cast<const uint4*>(delta + o);
+      }
+  }
+  for (int it = 0; row < rows; row += gridDim.x, ++it) {
+    const long long nrow = row + gridDim.x;
+    if (nrow < rows) {
+#pragma unroll
+      for (int i = 0; i < VPT; ++i)
+        if (on[i]) {
+          const long long o = nrow * H + (i * THREADS + threadIdx.x) * 8;
+          nxt[i] = *reinterpret_cast<const uint4*>(x + o);
+          if constexpr (ADD) nxt_d[i] = *reinterpret_cast<const uint4*>(delta + o);
+        }
+    }
+    float v[VPT][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+      if (on[i]) {
+        unpack8(cur[i], v[i]);
+        if constexpr (ADD) {
+          float d[8];
+          unpack8(cur_d[i], d);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] += d[j];
+          const uint4 r = pack8(v[i]);       // round first: the norm must see exactly the stored residual stream
+          *reinterpret_cast<uint4*>(sum_out + row * H + (i * THREADS + threadIdx.x) * 8) = r;
+          unpack8(r, v[i]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
+      }
+    ss = block_sum_1sync<THREADS>(ss, red[it & 1]);
+    const float r = rsqrtf(ss / H + eps);
+    if (threadIdx.x == 0 && rstd) rstd[row] = r;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+      if (on[i]) {
+        float gf[8], o[8];
+        unpack8(g[i], gf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = v[i][j] * r * gf[j];
+        *reinterpret_cast<uint4*>(y + row * H + (i * THREADS + threadIdx.x) * 8) = pack8(o);
+      }
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      cur[i] = nxt[i];
+      if constexpr (ADD) cur_d[i] = nxt_d[i];
+    }
+  }
+}
+
+// dx = rstd * (g*dy - xhat * mean(g*dy*xhat)) (optionally += into dx); dgamma partial sums per CTA, one atomic pass at the end
+template <int THREADS, int VPT>
+__global__ void __launch_bounds__(THREADS) rmsnorm_bwd_pipe_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                                                                  const __nv_bfloat16* __restrict__ dy, const float* __restrict__ rstd,
+                                                                  __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, long long rows,
+                                                                  int H, int add_to_dx) {
+  __shared__ float red[2][32];
+  float dg[VPT][8], g[VPT][8];
+  uint4 cx[VPT], cd[VPT], co[VPT], nx[VPT], nd[VPT], no[VPT];
+  bool on[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (i * THREADS + threadIdx.x) * 8;
+    on[i] = c < H;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dg[i][j] = 0.f;
+    if (on[i]) load8(gamma + c, g[i]);
+  }
+  long long row = blockIdx.x;
+  float r_cur = 0.f, r_nxt = 0.f;
+  if (row < rows) {
+    r_cur = rstd[row];
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+      if (on[i]) {
+        const long long o = row * H + (i * THREADS + threadIdx.x) * 8;
+        cx[i] = *reinterpret_cast<const uint4*>(x + o);
+        cd[i] = *reinterpret_cast<const uint4*>(dy + o);
+        if (add_to_dx) co[i] = *reinterpret_cast<const uint4*>(dx + o);
+      }
+  }
+  for (int it = 0; row < rows; row += gridDim.x, ++it) {
+    const long long nrow = row + gridDim.x;
+    if (nrow < rows) {
+      r_nxt = rstd[nrow];
+#pragma unroll
+      for (int i = 0; i < VPT; ++i)
+        if (on[i]) {
+          const long long o = nrow * H + (i * THREADS + threadIdx.x) * 8;
+          nx[i] = *reinterpret_cast<const uint4*>(x + o);
+          nd[i] = *reinterpret_cast<const uint4*>(dy + o);
+          if (add_to_dx) no[i] = *reinterpret_cast<const uint4*>(dx + o);
+        }
+    }
+    float xh[VPT][8], gy[VPT][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+      if (on[i]) {
+        float d[8];
+        unpack8(cx[i], xh[i]);
+        unpack8(cd[i], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] *= r_cur;
+          dg[i][j] += d[j] * xh[i][j];
+          gy[i][j] = d[j] * g[i][j];
+          dot += gy[i][j] * xh[i][j];
+        }
+      }
+    dot = block_sum_1sync<THREADS>(dot, red[it & 1]) / H;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+      if (on[i]) {
+        float o[8];
+        if (add_to_dx) unpack8(co[i], o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = r_cur * (gy[i][j] - xh[i][j] * dot);
+          o[j] = add_to_dx ? o[j] + t : t;
+        }
+        *reinterpret_cast<uint4*>(dx + row * H + (i * THREADS + threadIdx.x) * 8) = pack8(o);
+      }
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      cx[i] = nx[i]; cd[i] = nd[i]; co[i] = no[i];
+    }
+    r_cur = r_nxt;
+  }
+#pragma unroll
+  for (int i = 0; i < VPT; ++i)
+    if (on[i]) {
+      const int c = (i * THREADS + threadIdx.x) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(dgamma + c + j, dg[i][j]);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // SwiGLU: y = silu(a) * b with [a | b] = x[:, :F], x[:, F:]
 // ----------------------------------------------------------------------------------------------
 __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long rows,
@@ -752,11 +946,14 @@ extern "C" {
 int smx_rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, long long rows, int H, float eps,
                     void* stream) {
   if (H % 8) return -20;
-  if (H <= 2048) smx::rmsnorm_fwd_kernel<256, 1><<<(unsigned)rows, 256, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (bf16*)y, rstd, H, eps);
-  else if (H <= 4096) smx::rmsnorm_fwd_kernel<256, 2><<<(unsigned)rows, 256, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (bf16*)y, rstd, H, eps);
-  else if (H <= 8192) smx::rmsnorm_fwd_kernel<512, 2><<<(unsigned)rows, 512, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (bf16*)y, rstd, H, eps);
-  else if (H <= 16384) smx::rmsnorm_fwd_kernel<512, 4><<<(unsigned)rows, 512, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (bf16*)y, rstd, H, eps);
+  const int grid = (int)(rows < 148 * 8 ? rows : 148 * 8);
+#define SMX_NF(T, V) smx::rmsnorm_fwd_pipe_kernel<T, V, false><<<grid, T, 0, SMX_STREAM>>>((const bf16*)x, nullptr, (const bf16*)gamma, nullptr, (bf16*)y, rstd, rows, H, eps)
+  if (H <= 2048) SMX_NF(256, 1);
+  else if (H <= 4096) SMX_NF(256, 2);
+  else if (H <= 8192) SMX_NF(512, 2);
+  else if (H <= 16384) SMX_NF(512, 4);
   else return -21;
+#undef SMX_NF
   return (int)cudaGetLastError();
 }
 
@@ -766,6 +963,17 @@ int smx_rs_consume(const void* slots, int nslots, long long rows, int H, const v
                    void* stream) {
   if (H % 8) return -20;
   if (gamma && !normed) return -22;
+  if (nslots == 1 && counter == nullptr && residual && sum_out && gamma) {      // plain fused residual add + RMSNorm
+    const int grid = (int)(rows < 148 * 8 ? rows : 148 * 8);
+#define SMX_AN(T, V) smx::rmsnorm_fwd_pipe_kernel<T, V, true><<<grid, T, 0, SMX_STREAM>>>((const bf16*)residual, (const bf16*)slots, (const bf16*)gamma, (bf16*)sum_out, (bf16*)normed, rstd, rows, H, eps)
+    if (H <= 2048) SMX_AN(256, 1);
+    else if (H <= 4096) SMX_AN(256, 2);
+    else if (H <= 8192) SMX_AN(512, 2);
+    else if (H <= 16384) SMX_AN(512, 4);
+    else return -21;
+#undef SMX_AN
+    return (int)cudaGetLastError();
+  }
   const long long ss = rows * H;
 #define SMX_RSC(T, V) smx::rs_consume_kernel<T, V><<<(unsigned)rows, T, 0, SMX_STREAM>>>((const bf16*)slots, nslots, ss, \
     (const bf16*)residual, (bf16*)sum_out, (const bf16*)gamma, (bf16*)normed, rstd, H, eps, (const uint32_t*)counter, target)
@@ -782,11 +990,14 @@ int smx_rmsnorm_bwd(const void* x, const void* gamma, const void* dy, const floa
                     long long rows, int H, int add_to_dx, void* stream) {
   if (H % 8) return -20;
   int grid = rows < 148 * 4 ? (int)rows : 148 * 4;
-  if (H <= 2048) smx::rmsnorm_bwd_kernel<256, 1><<<grid, 256, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)dy, rstd, (bf16*)dx, dgamma, (int)rows, H, add_to_dx);
-  else if (H <= 4096) smx::rmsnorm_bwd_kernel<256, 2><<<grid, 256, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)dy, rstd, (bf16*)dx, dgamma, (int)rows, H, add_to_dx);
-  else if (H <= 8192) smx::rmsnorm_bwd_kernel<512, 2><<<grid, 512, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)dy, rstd, (bf16*)dx, dgamma, (int)rows, H, add_to_dx);
-  else if (H <= 16384) smx::rmsnorm_bwd_kernel<512, 4><<<grid, 512, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)dy, rstd, (bf16*)dx, dgamma, (int)rows, H, add_to_dx);
+#define SMX_NB(T, V) smx::rmsnorm_bwd_pipe_kernel<T, V><<<grid, T, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)dy, rstd, (bf16*)dx, dgamma, rows, H, add_to_dx)
+  if (H <= 2048) SMX_NB(256, 1);
+  else if (H <= 4096) SMX_NB(256, 2);
+  else if (H <= 8192) SMX_NB(512, 2);
+  else if (H <= 16384)      // 4 x 3 prefetched vectors per thread would spill: the non-pipelined kernel keeps this width
+    smx::rmsnorm_bwd_kernel<512, 4><<<grid, 512, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)dy, rstd, (bf16*)dx, dgamma, (int)rows, H, add_to_dx);
   else return -21;
+#undef SMX_NB
   return (int)cudaGetLastError();
 }
 

@@ -1,0 +1,438 @@
+// Flash-attention forward, second generation (head dim 128): two 128-query tiles per CTA in ping-pong, 128-key blocks, probabilities
+// kept in TMEM.
+//
+// Why: per 128 x 128 score tile the softmax needs 16384 exp2 = 1024 clk of the SM's 16 MUFU lanes, the two MMAs (Q K^T and P V at
+// d = 128) need 1024 clk of the tensor pipe.  The first-generation kernel (fmha_fwd.cu: one query tile per CTA, P through shared
+// memory, rescale on the softmax threads) serialises most of that -- ncu showed the tensor pipe 31 % active, the XU pipe 40 %.  Here
+//   * a CTA owns 256 queries as two independent tiles; while the softmax warpgroup of tile 0 works on S0_j the tensor core runs
+//     P1_{j-1} V and Q1 K_j^T of tile 1, and vice versa -- the MUFU and tensor pipes are both kept busy;
+//   * P never touches shared memory: the softmax threads overwrite the first 64 columns of their S tile in TMEM with packed bf16
+//     (tcgen05.st) and P V takes its A operand from TMEM (tcgen05.mma with a TMEM A descriptor) -- no st.shared, no proxy fence,
+//     and half the shared-memory operand traffic of the P V product;
+//   * K / V blocks are 128 keys and shared by both query tiles: half the L2 -> SM traffic per FLOP of the old kernel, and, with
+//     GQA, a 2-CTA cluster over two query heads of one KV group loads every K / V block once and multicasts it to both CTAs
+//     (cp.async.bulk.tensor ... .multicast::cluster), halving it again.
+//
+//   TMEM (512 columns): S0 [0,128) | S1 [128,256) | O0 [256,384) | O1 [384,512); P_t aliases S_t columns [0,64).
+//   warps: 0 TMA producer, 1 MMA issuer, 2-3 idle, 4-7 softmax of tile 0, 8-11 softmax of tile 1 (one query row per thread).
+//   MMA order per key block j:  P0_j V_j -> Q0 K_{j+1}^T -> P1_j V_j -> Q1 K_{j+1}^T   (tcgen05.mma executes in issue order, so S_t
+//   may be overwritten by the next Q K^T right behind the P V that read P_t out of it).
+#include "sm100_common.cuh"
+
+namespace smx {
+
+SMX_DEVICE void tma_load_4d_f2(const CUtensorMap* m, uint64_t* bar, void* smem_dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// multicast flavour: the box lands at the same smem offset in every CTA of `mask`, each CTA's barrier (same offset) gets the bytes
+SMX_DEVICE void tma_load_4d_mc(const CUtensorMap* m, uint64_t* bar, void* smem_dst, int c0, int c1, int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
+}
+
+constexpr int kF2BlockQ = 128;      // rows per query tile
+constexpr int kF2Tiles = 2;         // query tiles per CTA
+constexpr int kF2BlockKV = 128;
+constexpr int kF2D = 128;
+constexpr int kF2Threads = 384;
+constexpr int kF2Stages = 2;
+constexpr int kF2TileBytes = 128 * kF2D * 2;      // 32 KB: one Q tile, one K block, one V block
+constexpr int kF2SmemBytes = (kF2Tiles + 2 * kF2Stages) * kF2TileBytes + 256;
+
+struct Fmha2Params {
+  int B, S_q, S_kv, H, H_kv;
+  float scale;
+  int causal;
+  long long o_stride_b, o_stride_s, o_stride_h;
+  long long lse_stride_b, lse_stride_h;
+};
+
+template <int CLUSTER>
+__global__ void __launch_bounds__(kF2Threads, 1)
+fmha_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ o_ptr, float* __restrict__ lse_ptr,
+                 const Fmha2Params p) {
+  constexpr int BQ = kF2BlockQ, BKV = kF2BlockKV, D = kF2D;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u)) {
+    printf("simumax_b200: fmha_fwd2 dynamic smem base %u is not 1024-byte aligned\n", smem_u32(smem_raw));
+    __trap();
+  }
+  uint8_t* sQ = smem;                                   // [2 tiles][2 d-chunks][128 rows x 128 B]
+  uint8_t* sK = sQ + kF2Tiles * kF2TileBytes;           // [stages][2 d-chunks][128 keys x 128 B]
+  uint8_t* sV = sK + kF2Stages * kF2TileBytes;          // [stages][2 dv-chunks][128 keys x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kF2Stages * kF2TileBytes);
+  uint64_t* q_full = bars;                    // 1
+  uint64_t* k_full = bars + 1;                // [stages]
+  uint64_t* k_empty = k_full + kF2Stages;
+  uint64_t* v_full = k_empty + kF2Stages;
+  uint64_t* v_empty = v_full + kF2Stages;
+  uint64_t* s_full = v_empty + kF2Stages;     // [tiles]
+  uint64_t* p_full = s_full + kF2Tiles;       // [tiles]
+  uint64_t* o_done = p_full + kF2Tiles;       // [tiles]
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(o_done + kF2Tiles);
+
+  const int warp_idx = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  const uint32_t cta_rank = CLUSTER > 1 ? cluster_ctarank() : 0;
+  // heavy (late) query tiles first: with causal masking tile i has i + 1 units of work
+  const int q_tile = (int)gridDim.x - 1 - (int)blockIdx.x;
+  const int head = blockIdx.y;                 // CLUSTER == 2: cluster dims (1, 2, 1) -> heads 2c, 2c + 1 share their KV head
+  const int batch = blockIdx.z;
+  const int kv_head = head / (p.H / p.H_kv);
+  const int q0 = q_tile * (BQ * kF2Tiles);
+  const int causal_shift = p.S_kv - p.S_q;
+  int n_t[kF2Tiles];
+#pragma unroll
+  for (int t = 0; t < kF2Tiles; ++t) {
+    const int qt0 = q0 + t * BQ;
+    int kv_end = p.S_kv;
+    if (p.causal) kv_end = min(p.S_kv, qt0 + BQ + causal_shift);
+    n_t[t] = (qt0 < p.S_q && kv_end > 0) ? (kv_end + BKV - 1) / BKV : 0;
+  }
+  const int n_max = max(n_t[0], n_t[1]);
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kF2Stages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], CLUSTER);        // every CTA of the cluster must have consumed the block before it is overwritten
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], CLUSTER);
+    }
+    for (int t = 0; t < kF2Tiles; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 4);
+      mbar_init(&o_done[t], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) tmem_alloc<1>(tmem_base_ptr, 512);
+  tcgen05_fence_before();
+  if constexpr (CLUSTER > 1) cluster_sync_all();
+  else __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  if (warp_idx == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kF2Tiles * kF2TileBytes);
+#pragma unroll
+      for (int t = 0; t < kF2Tiles; ++t)
+#pragma unroll
+        for (int c = 0; c < D / 64; ++c)
+          tma_load_4d_f2(&tmap_q, q_full, sQ + t * kF2TileBytes + c * (BQ * 128), c * 64, q0 + t * BQ, head, batch);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_max; ++j) {
+        const int k0 = j * BKV;
+        // K_j
+        mbar_wait(&k_empty[stage], phase ^ 1, 1);
+        mbar_arrive_expect_tx(&k_full[stage], kF2TileBytes);
+        if constexpr (CLUSTER > 1) {
+          // each CTA fetches one 64-wide d-chunk of the block and multicasts it to both
+          const int c = cta_rank;
+          tma_load_4d_mc(&tmap_k, &k_full[stage], sK + stage * kF2TileBytes + c * (BKV * 128), c * 64, k0, kv_head, batch, 3);
+        } else {
+#pragma unroll
+          for (int c = 0; c < D / 64; ++c)
+            tma_load_4d_f2(&tmap_k, &k_full[stage], sK + stage * kF2TileBytes + c * (BKV * 128), c * 64, k0, kv_head, batch);
+        }
+        // V_j
+        mbar_wait(&v_empty[stage], phase ^ 1, 2);
+        mbar_arrive_expect_tx(&v_full[stage], kF2TileBytes);
+        if constexpr (CLUSTER > 1) {
+          const int c = cta_rank;
+          tma_load_4d_mc(&tmap_v, &v_full[stage], sV + stage * kF2TileBytes + c * (BKV * 128), c * 64, k0, kv_head, batch, 3);
+        } else {
+#pragma unroll
+          for (int c = 0; c < D / 64; ++c)
+            tma_load_4d_f2(&tmap_v, &v_full[stage], sV + stage * kF2TileBytes + c * (BKV * 128), c * 64, k0, kv_head, batch);
+        }
+        if (++stage == kF2Stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ============================ MMA issuer ============================
+    constexpr uint32_t idesc_s = make_idesc(1, 1, 0, 0, BQ, BKV);   // Q (K-major smem) x K (K-major smem) -> S[128, 128]
+    constexpr uint32_t idesc_o = make_idesc(1, 1, 0, 1, BQ, D);     // P (TMEM) x V (MN-major smem) -> O[128, 128]
+    const uint64_t kQ_km = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+    const uint64_t kK_km = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+    const uint64_t kV_mn = make_smem_desc_sw128(smem_u32(sV), BKV * 128, 1024);
+    constexpr uint64_t kTileStep = kF2TileBytes >> 4;
+    auto release = [&](uint64_t* bar) {        // this CTA is done with a K / V block: tell the producer of every CTA of the cluster
+      if constexpr (CLUSTER > 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                     "h"(static_cast<uint16_t>(3))
+                     : "memory");
+      else
+        umma_commit<1>(bar);
+    };
+    auto issue_s = [&](int t, int st) {        // S_t = Q_t K^T
+      if (elect_one()) {
+        const uint64_t a0 = kQ_km + t * kTileStep;
+        const uint64_t b0 = kK_km + st * kTileStep;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          umma_f16<1>(tmem_base + t * 128, a0 + ((k / 4) * ((BQ * 128) >> 4) + (k % 4) * 2),
+                      b0 + ((k / 4) * ((BKV * 128) >> 4) + (k % 4) * 2), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit<1>(&s_full[t]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int t, int st, bool first) {   // O_t (+)= P_t V
+      if (elect_one()) {
+        const uint64_t b0 = kV_mn + st * kTileStep;
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)       // 16 keys = 8 packed TMEM columns of P per K step
+          umma_f16_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + k * 8, b0 + k * ((16 * 128) >> 4), idesc_o,
+                      (!first || k > 0) ? 1u : 0u);
+        umma_commit<1>(&o_done[t]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0, 3);
+    if (n_max > 0) {
+      mbar_wait(&k_full[0], 0, 4);
+      tcgen05_fence_after();
+      for (int t = 0; t < kF2Tiles; ++t)
+        if (n_t[t] > 0) issue_s(t, 0);
+      if (elect_one()) release(&k_empty[0]);
+      __syncwarp();
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_max; ++j) {
+      int nstage = stage + 1;
+      uint32_t nphase = phase;
+      if (nstage == kF2Stages) { nstage = 0; nphase ^= 1; }
+      bool v_ready = false, k_ready = false;
+      for (int t = 0; t < kF2Tiles; ++t) {
+        if (j >= n_t[t]) continue;
+        mbar_wait(&p_full[t], j & 1, 5);
+        if (!v_ready) { mbar_wait(&v_full[stage], phase, 6); v_ready = true; }
+        tcgen05_fence_after();
+        issue_pv(t, stage, j == 0);
+        if (j + 1 < n_t[t]) {
+          if (!k_ready) { mbar_wait(&k_full[nstage], nphase, 7); k_ready = true; }
+          tcgen05_fence_after();
+          issue_s(t, nstage);
+        }
+      }
+      if (elect_one()) {
+        release(&v_empty[stage]);                // behind the last P V of this key block
+        if (k_ready) release(&k_empty[nstage]);  // behind the last Q K^T of the next one
+      }
+      __syncwarp();
+      stage = nstage;
+      phase = nphase;
+    }
+  } else if (warp_idx >= 4) {
+    // ============================ softmax + epilogue: one query row per thread ============================
+    const int t = (warp_idx - 4) / 4;
+    const int q = warp_idx % 4;
+    const int row_in_tile = q * 32 + lane;
+    const int row = q0 + t * BQ + row_in_tile;
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    const uint32_t tmem_s = tmem_base + t * 128 + lane_addr;
+    const uint32_t tmem_o = tmem_base + 256 + t * 128 + lane_addr;
+    const float c_log2 = p.scale * 1.4426950408889634f;
+    float m_used = -INFINITY;   // running reference max (raw score units)
+    float l = 0.f;
+    const int n_mine = n_t[t];
+    for (int j = 0; j < n_mine; ++j) {
+      mbar_wait(&s_full[t], j & 1, 8);
+      tcgen05_fence_after();
+      uint32_t r[128];
+      {
+        tmem_ld_32x32b_x32(tmem_s, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        tmem_ld_32x32b_x32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+        tmem_ld_32x32b_x32(tmem_s + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
+        tmem_ld_32x32b_x32(tmem_s + 96, *reinterpret_cast<uint32_t(*)[32]>(&r[96]));
+        tmem_ld_wait();
+      }
+      const int k0 = j * BKV;
+      const int qt0 = q0 + t * BQ;
+      const bool need_mask = (p.causal && (k0 + BKV - 1 > qt0 + causal_shift)) || (k0 + BKV > p.S_kv);
+      if (need_mask) {
+        const int limit = p.causal ? min(row + causal_shift, p.S_kv - 1) : p.S_kv - 1;
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (k0 + i > limit) r[i] = 0xff800000u;   // -inf
+      }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < 128; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], __uint_as_float(r[i + u]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      // lazy rescale: only move the reference max when it grew by more than 2^8 in the exp2 domain
+      float m_new = m_used;
+      const bool grow = (mx > m_used) && ((mx - m_used) * c_log2 > 8.f || m_used == -INFINITY);
+      if (grow) m_new = mx;
+      const bool any_grow = __any_sync(0xffffffffu, grow);
+      if (any_grow && j > 0) {
+        // O_t may only be touched once P_{j-1} V has retired (the next P V is not issued before this thread signals p_full)
+        mbar_wait(&o_done[t], (j - 1) & 1, 9);
+        tcgen05_fence_after();
+        const float alpha = (m_used == -INFINITY) ? 0.f : exp2f((m_used - m_new) * c_log2);
+#pragma unroll 1
+        for (int c = 0; c < D / 16; ++c) {
+          uint32_t o[16];
+          tmem_ld_32x32b_x16(tmem_o + c * 16, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32b_x16(tmem_o + c * 16, o);
+        }
+        tmem_st_wait();
+        l *= alpha;
+      }
+      m_used = m_new;
+      const float mc = (m_used == -INFINITY) ? 0.f : m_used * c_log2;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      // P row -> packed bf16 pairs, in place over the registers (keys 2c, 2c + 1 -> 32-bit column c), then 64 TMEM columns
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        const float e0 = exp2f(fmaf(__uint_as_float(r[2 * c]), c_log2, -mc));
+        const float e1 = exp2f(fmaf(__uint_as_float(r[2 * c + 1]), c_log2, -mc));
+        sum4[c & 3] += e0 + e1;
+        r[c] = pack_bf16x2(e0, e1);
+      }
+      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      tmem_st_32x32b_x16(tmem_s, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+      tmem_st_32x32b_x16(tmem_s + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+      tmem_st_32x32b_x16(tmem_s + 32, *reinterpret_cast<uint32_t(*)[16]>(&r[32]));
+      tmem_st_32x32b_x16(tmem_s + 48, *reinterpret_cast<uint32_t(*)[16]>(&r[48]));
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+    }
+    // ---- epilogue
+    if (n_mine > 0) {
+      mbar_wait(&o_done[t], (n_mine - 1) & 1, 10);
+      tcgen05_fence_after();
+    }
+    const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
+    const bool row_ok = row < p.S_q;
+    __nv_bfloat16* orow = o_ptr + batch * p.o_stride_b + (long long)(row_ok ? row : 0) * p.o_stride_s + head * p.o_stride_h;
+#pragma unroll 1
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t o[32];
+      if (n_mine > 0) {
+        tmem_ld_32x32b_x32(tmem_o + c * 32, o);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0u;
+      }
+      if (row_ok) {
+        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[8 * i]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
+          v.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
+          v.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
+          v.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
+          dst[i] = v;
+        }
+      }
+    }
+    if (row_ok && lse_ptr)
+      lse_ptr[batch * p.lse_stride_b + head * p.lse_stride_h + row] = (l > 0.f) ? m_used * p.scale + __logf(l) : -INFINITY;
+  }
+
+  tcgen05_fence_before();
+  if constexpr (CLUSTER > 1) cluster_sync_all();      // a peer may still multicast into / commit onto this CTA's shared memory
+  else __syncthreads();
+  if (warp_idx == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+inline int make_tmap_4d_f2(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
+                           uint64_t s1_bytes, uint64_t s2_bytes, uint64_t s3_bytes, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[4] = {d0, d1, d2, d3};
+  cuuint64_t strides[3] = {s1_bytes, s2_bytes, s3_bytes};
+  cuuint32_t box[4] = {64, box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+template <int CLUSTER>
+int launch_fmha_fwd2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, void* o, float* lse,
+                     const Fmha2Params& p, cudaStream_t stream) {
+  auto kern = fmha_fwd2_kernel<CLUSTER>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kF2SmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((p.S_q + kF2BlockQ * kF2Tiles - 1) / (kF2BlockQ * kF2Tiles), p.H, p.B);
+  cfg.blockDim = dim3(kF2Threads);
+  cfg.dynamicSmemBytes = kF2SmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = CLUSTER;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(o), lse, p);
+  return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
+}
+
+}  // namespace smx
+
+extern "C" {
+
+// Same contract as smx_fmha_fwd (head dim 128 / 128 only).  cluster = 2 pairs adjacent query heads of one KV group (needs an even
+// GQA group size); cluster = 0 picks it automatically.
+int smx_fmha_fwd2(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S_q, int S_kv, int H, int H_kv,
+                  long long q_sb, long long q_ss, long long q_sh, long long k_sb, long long k_ss, long long k_sh, long long v_sb,
+                  long long v_ss, long long v_sh, long long o_sb, long long o_ss, long long o_sh, float scale, int causal,
+                  int cluster, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (H % H_kv) return -30;
+  const int group = H / H_kv;
+  if (cluster == 0) cluster = (group % 2 == 0) ? 2 : 1;
+  if (cluster == 2 && group % 2) return -32;
+  CUtensorMap tq, tk, tv;
+  int rc = smx::make_tmap_4d_f2(&tq, q, 128, S_q, H, B, q_ss * 2, q_sh * 2, q_sb * 2, smx::kF2BlockQ);
+  if (rc) return rc;
+  rc = smx::make_tmap_4d_f2(&tk, k, 128, S_kv, H_kv, B, k_ss * 2, k_sh * 2, k_sb * 2, smx::kF2BlockKV);
+  if (rc) return rc;
+  rc = smx::make_tmap_4d_f2(&tv, v, 128, S_kv, H_kv, B, v_ss * 2, v_sh * 2, v_sb * 2, smx::kF2BlockKV);
+  if (rc) return rc;
+  smx::Fmha2Params p;
+  p.B = B; p.S_q = S_q; p.S_kv = S_kv; p.H = H; p.H_kv = H_kv; p.scale = scale; p.causal = causal;
+  p.o_stride_b = o_sb; p.o_stride_s = o_ss; p.o_stride_h = o_sh;
+  p.lse_stride_b = (long long)H * S_q; p.lse_stride_h = S_q;
+  return cluster == 2 ? smx::launch_fmha_fwd2<2>(tq, tk, tv, o, lse, p, stream) : smx::launch_fmha_fwd2<1>(tq, tk, tv, o, lse, p, stream);
+}
+
+}  // extern "C"

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -15,6 +16,23 @@ from . import _lib
 
 _c = ctypes
 _fwd = None
+_fwd2 = None
+
+
+def _fwd2_fn():
+    global _fwd2
+    if _fwd2 is None:
+        f = _lib.lib().smx_fmha_fwd2
+        f.restype = _c.c_int
+        f.argtypes = [_c.c_void_p] * 5 + [_c.c_int] * 5 + [_c.c_longlong] * 12 + [_c.c_float, _c.c_int, _c.c_int, _c.c_void_p]
+        _fwd2 = f
+    return _fwd2
+
+
+def _use_v2(D: int, Dv: int) -> bool:
+    """Second-generation forward (two query tiles per CTA in ping-pong, P in TMEM, 2-CTA cluster K / V multicast): head dim 128 only;
+    SMX_FMHA_V1=1 forces the first-generation kernel for A/B runs."""
+    return D == 128 and Dv == 128 and os.environ.get("SMX_FMHA_V1", "0") != "1"
 
 
 def _fwd_fn():
@@ -49,6 +67,16 @@ def fmha_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = T
         lse = torch.empty(B, H, S_q, device=q.device, dtype=torch.float32) if return_lse else None
     else:
         assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == B * H * S_q
+    if _use_v2(D, Dv):
+        rc = _fwd2_fn()(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr() if lse is not None else None,
+                        B, S_q, S_kv, H, H_kv,
+                        q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
+                        v.stride(0), v.stride(1), v.stride(2), o.stride(0), o.stride(1), o.stride(2),
+                        float(scale), 1 if causal else 0, int(os.environ.get("SMX_FMHA_CLUSTER", "0")),
+                        torch.cuda.current_stream(q.device).cuda_stream)
+        _lib.check(rc, f"fmha_fwd2 B{B} S{S_q}x{S_kv} H{H}/{H_kv} d{D}/{Dv}")
+        _lib.count_launch()
+        return o, lse
     rc = _fwd_fn()(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr() if lse is not None else None,
                    B, S_q, S_kv, H, H_kv, D, Dv,
                    q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
@@ -109,6 +137,22 @@ def fmha_bwd(d_o: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tenso
     dq = torch.empty_like(q) if dq is None else dq
     dk = torch.empty_like(k) if dk is None else dk
     dv = torch.empty_like(v) if dv is None else dv
+    # The kernel parallelises over (batch, KV head, key tile) and keeps dK / dV of a CTA in TMEM across the query heads of its GQA
+    # group.  With few KV heads (tensor-parallel shards: 4 query heads on 1 KV head) that is a handful of CTAs on 148 SMs, so the
+    # group is split: K / V are replicated e-fold (a few MB), every replica takes g / e of the query heads, and the e partial
+    # dK / dV are summed afterwards.
+    g = H // H_kv
+    n_kv = (S_kv + 127) // 128
+    ctas = B * H_kv * ((n_kv + 1) // 2 if causal else n_kv)
+    if g > 1 and ctas < 120 and os.environ.get("SMX_FMHA_BWD_SPLIT", "1") == "1":
+        e = next((c for c in range(2, g + 1) if g % c == 0 and ctas * c >= 120), g)
+        k_e = k.unsqueeze(3).expand(B, S_kv, H_kv, e, D).reshape(B, S_kv, H_kv * e, D)
+        v_e = v.unsqueeze(3).expand(B, S_kv, H_kv, e, v.shape[-1]).reshape(B, S_kv, H_kv * e, v.shape[-1])
+        dk_e, dv_e = torch.empty_like(k_e), torch.empty_like(v_e)
+        fmha_bwd(d_o, q, k_e, v_e, o, lse, dq, dk_e, dv_e, causal=causal, scale=scale, trace=trace)
+        dk.copy_(dk_e.view(B, S_kv, H_kv, e, D).sum(3))
+        dv.copy_(dv_e.view(B, S_kv, H_kv, e, v.shape[-1]).sum(3))
+        return dq, dk, dv
     ts = (q, k, v, o, d_o, dq, dk, dv)
     for t, n in zip(ts, ("q", "k", "v", "o", "do", "dq", "dk", "dv")):
         _check(t, n)

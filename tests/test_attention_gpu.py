@@ -25,7 +25,8 @@ def _ref(q, k, v, causal, scale):
 
 @pytest.mark.parametrize("causal", [True, False])
 @pytest.mark.parametrize("cfg", [(1, 256, 4, 4, 128, 128), (2, 512, 8, 2, 128, 128), (1, 384, 4, 1, 64, 64),
-                                 (1, 1024, 4, 4, 192, 128), (1, 200, 2, 2, 128, 128)])
+                                 (1, 1024, 4, 4, 192, 128), (1, 200, 2, 2, 128, 128), (1, 640, 6, 2, 128, 128), (1, 1152, 8, 4, 128, 128),
+                                 (2, 2048, 4, 1, 128, 128)])
 def test_fmha_fwd(cfg, causal):
     from simumax_b200.ops.attention import fmha_fwd
     torch.manual_seed(0)
@@ -102,3 +103,20 @@ def test_fmha_bwd_mla(cfg, causal):
         assert torch.isfinite(got.float()).all(), name
         err = (got.float() - ref).norm() / ref.norm()
         assert err < 2e-2, (name, err.item())
+
+
+@pytest.mark.parametrize("cluster", ["1", "2"])
+def test_fmha_fwd2_cluster_and_cross_lengths(cluster, monkeypatch):
+    """Second-generation forward with and without the 2-CTA K / V multicast cluster, and with S_q != S_kv (bottom-right causal)."""
+    from simumax_b200.ops.attention import fmha_fwd
+    monkeypatch.setenv("SMX_FMHA_CLUSTER", cluster)
+    torch.manual_seed(7)
+    for (B, Sq, Skv, H, Hk) in [(1, 768, 768, 8, 2), (1, 256, 1024, 4, 2), (2, 384, 640, 4, 4 if cluster == "1" else 2)]:
+        q = torch.randn(B, Sq, H, 128, device="cuda").bfloat16()
+        k = torch.randn(B, Skv, Hk, 128, device="cuda").bfloat16()
+        v = torch.randn(B, Skv, Hk, 128, device="cuda").bfloat16()
+        for causal in (True, False):
+            o, lse = fmha_fwd(q, k, v, causal=causal)
+            ro, rlse = _ref(q, k, v, causal, 1.0 / math.sqrt(128))
+            torch.testing.assert_close(o.float(), ro, atol=2e-2, rtol=2e-2)
+            torch.testing.assert_close(lse, rlse, atol=2e-2, rtol=1e-3)
