@@ -200,22 +200,33 @@ def measure_bandwidth_ops(hidden: int = 4096, tokens: int = 16384, vocab: int = 
     return res
 
 
-def measure_launch_latency_us(n: int = 2000) -> float:
-    """Launch-to-launch floor of a memory-bound kernel: back-to-back launches of the residual add on a tensor that fits in L1/L2
-    (8 KiB), device-timed.  This is the ``latency_us`` the model adds to every bandwidth-priced op (the reference hard-codes 30 us for
-    its library kernels; a CUDA-graph-free PyTorch launch loop on this box sits at 2-4 us)."""
+def measure_launch_latency_us(n: int = 256) -> float:
+    """Device-side fixed cost of a memory-bound kernel: ``n`` back-to-back launches of the residual add on an 8 KiB tensor (fits in
+    L1 / L2) captured in a CUDA graph and replayed, so the host launch rate of a Python loop (6-7 us per launch here) is out of the
+    picture and what remains is launch latency + prologue + tail of one kernel.  This is the ``latency_us`` the model adds to every
+    bandwidth-priced op (the reference hard-codes 30 us for its library kernels)."""
     from ..ops import elementwise as E
     x = torch.zeros(4096, device="cuda", dtype=torch.bfloat16)
     y = torch.zeros_like(x)
-    for _ in range(50):
-        E.add(x, y, out=y)
+    stream = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(stream):
+        for _ in range(8):
+            E.add(x, y, out=y)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=stream):
+            for _ in range(n):
+                E.add(x, y, out=y)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        graph.replay()
     torch.cuda.synchronize()
     best = float("inf")
-    for _ in range(3):
+    for _ in range(5):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(n):
-            E.add(x, y, out=y)
+        graph.replay()
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / n * 1e3)

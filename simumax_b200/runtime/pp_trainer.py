@@ -202,3 +202,7 @@ class PPLlamaTrainer:
 
     def memory_bytes(self) -> dict:
         return self.tr.memory_bytes()
+
+    def symmetric_workspaces(self):
+        f = getattr(self.tr, "symmetric_workspaces", None)
+        return f() if f else []

@@ -59,7 +59,9 @@ def zoo():
     # pipeline parallel
     c += [Case("llama3_8b_tp1_pp2_dp1_mbc8", "llama3-8b", None, 4096, 1, 8, pp=2, strategy_preset="tp1_pp2_dp4_mbs1"),
           Case("llama3_8b_tp1_pp2_dp4_mbc8", "llama3-8b", None, 4096, 1, 8, pp=2, dp=4, strategy_preset="tp1_pp2_dp4_mbs1"),
-          Case("llama3_70b_l12_tp1_pp2_dp4_mbc4", "llama3-70b", 12, 4096, 1, 4, pp=2, dp=4, strategy_preset="tp1_pp2_dp4_mbs1")]
+          Case("llama3_70b_l12_tp1_pp2_dp4_mbc4", "llama3-70b", 12, 4096, 1, 4, pp=2, dp=4, strategy_preset="tp1_pp2_dp4_mbs1"),
+          Case("llama3_8b_tp1_pp2_dp2_mbc8", "llama3-8b", None, 4096, 1, 8, pp=2, dp=2, strategy_preset="tp1_pp2_dp4_mbs1"),
+          Case("llama3_8b_tp1_pp4_dp1_mbc8", "llama3-8b", None, 4096, 1, 8, pp=4, dp=1, strategy_preset="tp1_pp2_dp4_mbs1")]
     # context parallel (Ulysses all-to-all), long sequences: rows / slices of the published CP table
     c += [Case("llama3_70b_l12_tp1_cp8_seq32768_mbc4", "llama3-70b", 12, 32768, 1, 4, cp=8),
           Case("llama3_70b_l12_tp1_cp8_seq131072_mbc4", "llama3-70b", 12, 131072, 1, 4, cp=8),
@@ -69,6 +71,7 @@ def zoo():
     # expert parallel (DeepSeek-V2: MLA + MoE)
     c += [Case("deepseekv2_l4_ep8_pp1_dp8_mbc4", "deepseekv2", 4, 4096, 1, 4, ep=8, dp=8, strategy_preset="ep8_pp1_dp8_mbs1"),
           Case("deepseekv2_l4_ep2_pp1_dp2_mbc4", "deepseekv2", 4, 4096, 1, 4, ep=2, dp=2, strategy_preset="ep8_pp1_dp8_mbs1"),
+          Case("deepseekv2_l4_ep4_pp1_dp4_mbc4", "deepseekv2", 4, 4096, 1, 4, ep=4, dp=4, strategy_preset="ep8_pp1_dp8_mbs1"),
           Case("deepseekv2_l2_ep1_pp1_dp1_mbc2", "deepseekv2", 2, 4096, 1, 2, ep=1, dp=1, strategy_preset="ep8_pp1_dp8_mbs1")]
     return {x.name: x for x in c}
 
@@ -177,7 +180,8 @@ def main():
             print(f"{n:48s} world {c.world}  {c.parallelism()}")
         return 0
     state_path = a.state or a.out + ".state.json"
-    state = json.load(open(state_path)) if (a.reuse and os.path.exists(state_path)) else {}
+    # --reuse: keep (and skip) what the state file holds; a predict-only run always starts from the recorded measurements
+    state = json.load(open(state_path)) if ((a.reuse or a.phase == "predict") and os.path.exists(state_path)) else {}
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     names = a.cases or [n for n, c in Z.items() if c.world == world or (a.phase == "predict" and n in state)]
