@@ -14,7 +14,8 @@
 //     (cp.async.bulk.tensor ... .multicast::cluster), halving it again.
 //
 //   TMEM (512 columns): S0 [0,128) | S1 [128,256) | O0 [256,384) | O1 [384,512); P_t aliases S_t columns [0,64).
-//   warps: 0 TMA producer, 1 MMA issuer, 2-3 idle, 4-7 softmax of tile 0, 8-11 softmax of tile 1 (one query row per thread).
+//   warps: 0 TMA producer, 1 MMA issuer, then the softmax warps: 8 per query tile (two warps share 32 rows and take 64 key columns
+//   each) with SMX_FMHA_SPLIT=2, or 4 per tile with one row per thread (default: measured 6 % faster).
 //   MMA order per key block j:  P0_j V_j -> Q0 K_{j+1}^T -> P1_j V_j -> Q1 K_{j+1}^T   (tcgen05.mma executes in issue order, so S_t
 //   may be overwritten by the next Q K^T right behind the P V that read P_t out of it).
 #include "sm100_common.cuh"
@@ -41,10 +42,12 @@ constexpr int kF2BlockQ = 128;      // rows per query tile
 constexpr int kF2Tiles = 2;         // query tiles per CTA
 constexpr int kF2BlockKV = 128;
 constexpr int kF2D = 128;
-constexpr int kF2Threads = 384;
+constexpr int kF2FirstSoftmaxWarp = 2;       // warp 0 = TMA producer, warp 1 = MMA issuer
+template <int SPLIT> constexpr int f2_threads() { return (kF2FirstSoftmaxWarp + 8 * SPLIT) * 32; }
 constexpr int kF2Stages = 2;
 constexpr int kF2TileBytes = 128 * kF2D * 2;      // 32 KB: one Q tile, one K block, one V block
-constexpr int kF2SmemBytes = (kF2Tiles + 2 * kF2Stages) * kF2TileBytes + 256;
+constexpr int kF2SmemBytes = (kF2Tiles + 2 * kF2Stages) * kF2TileBytes + 256 + 2 * 2 * 128 * 4;   // + barriers + max / sum exchange
+SMX_DEVICE void named_bar_sync_f2(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 struct Fmha2Params {
   int B, S_q, S_kv, H, H_kv;
@@ -54,8 +57,10 @@ struct Fmha2Params {
   long long lse_stride_b, lse_stride_h;
 };
 
-template <int CLUSTER>
-__global__ void __launch_bounds__(kF2Threads, 1)
+// DIAG (timing experiments only, SMX_FMHA_DIAG): 1 = no MUFU (exp2 replaced by an FMA: wrong numbers, shows the non-MUFU floor),
+// 2 = bf16 pack by truncation with PRMT instead of F2FP, 3 = both
+template <int CLUSTER, int SPLIT, int DIAG = 0>
+__global__ void __launch_bounds__(f2_threads<SPLIT>(), 1)
 fmha_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ o_ptr, float* __restrict__ lse_ptr,
                  const Fmha2Params p) {
@@ -113,7 +118,7 @@ fmha_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
     for (int t = 0; t < kF2Tiles; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 4);
+      mbar_init(&p_full[t], 4 * SPLIT);
       mbar_init(&o_done[t], 1);
     }
     fence_barrier_init();
@@ -239,9 +244,16 @@ fmha_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       stage = nstage;
       phase = nphase;
     }
-  } else if (warp_idx >= 4) {
-    // ============================ softmax + epilogue: one query row per thread ============================
-    const int t = (warp_idx - 4) / 4;
+  } else if (warp_idx >= kF2FirstSoftmaxWarp) {
+    // ============================ softmax + epilogue ============================
+    // SPLIT == 1: one query row per thread (128 scores in registers).  SPLIT == 2: two warps share 32 rows and take 64 key
+    // columns each -- twice the warps per scheduler to cover MUFU / dependency latency and half the live registers; the row
+    // maximum is exchanged through shared memory, the row sum stays split until the epilogue.
+    constexpr int NC = BKV / SPLIT;                   // score columns per thread
+    const int sw = warp_idx - kF2FirstSoftmaxWarp;    // 4 consecutive warps cover the four TMEM lane quadrants (warp_idx % 4)
+    const int grp = sw / 4;                           // (tile, column half)
+    const int t = grp / SPLIT;
+    const int hh = grp % SPLIT;
     const int q = warp_idx % 4;
     const int row_in_tile = q * 32 + lane;
     const int row = q0 + t * BQ + row_in_tile;
@@ -249,54 +261,60 @@ fmha_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t tmem_s = tmem_base + t * 128 + lane_addr;
     const uint32_t tmem_o = tmem_base + 256 + t * 128 + lane_addr;
     const float c_log2 = p.scale * 1.4426950408889634f;
+    float* xch = reinterpret_cast<float*>(bars + 32);          // [tile][half][128 rows] floats behind the barrier block
+    float* my_x = xch + (t * SPLIT + hh) * BQ + row_in_tile;
+    float* peer_x = xch + (t * SPLIT + (hh ^ 1)) * BQ + row_in_tile;
+    const int pair_bar = 1 + t * 4 + q;               // named barrier of the two warps that share these rows
     float m_used = -INFINITY;   // running reference max (raw score units)
-    float l = 0.f;
+    float l = 0.f;              // SPLIT == 2: sum over this thread's columns only
     const int n_mine = n_t[t];
     for (int j = 0; j < n_mine; ++j) {
       mbar_wait(&s_full[t], j & 1, 8);
       tcgen05_fence_after();
-      uint32_t r[128];
-      {
-        tmem_ld_32x32b_x32(tmem_s, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-        tmem_ld_32x32b_x32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-        tmem_ld_32x32b_x32(tmem_s + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
-        tmem_ld_32x32b_x32(tmem_s + 96, *reinterpret_cast<uint32_t(*)[32]>(&r[96]));
-        tmem_ld_wait();
-      }
-      const int k0 = j * BKV;
+      uint32_t r[NC];
+#pragma unroll
+      for (int c = 0; c < NC / 32; ++c) tmem_ld_32x32b_x32(tmem_s + hh * NC + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
+      tmem_ld_wait();
+      const int k0 = j * BKV + hh * NC;
       const int qt0 = q0 + t * BQ;
-      const bool need_mask = (p.causal && (k0 + BKV - 1 > qt0 + causal_shift)) || (k0 + BKV > p.S_kv);
+      const bool need_mask = (p.causal && (j * BKV + BKV - 1 > qt0 + causal_shift)) || (j * BKV + BKV > p.S_kv);
       if (need_mask) {
         const int limit = p.causal ? min(row + causal_shift, p.S_kv - 1) : p.S_kv - 1;
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
+        for (int i = 0; i < NC; ++i)
           if (k0 + i > limit) r[i] = 0xff800000u;   // -inf
       }
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < 128; i += 4) {
+      for (int i = 0; i < NC; i += 4) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], __uint_as_float(r[i + u]));
       }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      if constexpr (SPLIT == 2) {
+        *my_x = mx;
+        named_bar_sync_f2(pair_bar, 64);
+        mx = fmaxf(mx, *peer_x);
+        named_bar_sync_f2(pair_bar, 64);              // the slot is rewritten next block
+      }
       // lazy rescale: only move the reference max when it grew by more than 2^8 in the exp2 domain
       float m_new = m_used;
       const bool grow = (mx > m_used) && ((mx - m_used) * c_log2 > 8.f || m_used == -INFINITY);
       if (grow) m_new = mx;
-      const bool any_grow = __any_sync(0xffffffffu, grow);
+      const bool any_grow = __any_sync(0xffffffffu, grow);       // both warps of a pair see the same rows: same decision
       if (any_grow && j > 0) {
         // O_t may only be touched once P_{j-1} V has retired (the next P V is not issued before this thread signals p_full)
         mbar_wait(&o_done[t], (j - 1) & 1, 9);
         tcgen05_fence_after();
         const float alpha = (m_used == -INFINITY) ? 0.f : exp2f((m_used - m_new) * c_log2);
 #pragma unroll 1
-        for (int c = 0; c < D / 16; ++c) {
+        for (int c = 0; c < D / SPLIT / 16; ++c) {    // SPLIT == 2: each warp of the pair rescales its half of the O columns
           uint32_t o[16];
-          tmem_ld_32x32b_x16(tmem_o + c * 16, o);
+          tmem_ld_32x32b_x16(tmem_o + hh * (D / SPLIT) + c * 16, o);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32b_x16(tmem_o + c * 16, o);
+          tmem_st_32x32b_x16(tmem_o + hh * (D / SPLIT) + c * 16, o);
         }
         tmem_st_wait();
         l *= alpha;
@@ -304,37 +322,59 @@ fmha_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       m_used = m_new;
       const float mc = (m_used == -INFINITY) ? 0.f : m_used * c_log2;
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-      // P row -> packed bf16 pairs, in place over the registers (keys 2c, 2c + 1 -> 32-bit column c), then 64 TMEM columns
+      // P row -> packed bf16 pairs, in place over the registers (keys 2c, 2c + 1 -> 32-bit column c), then NC / 2 TMEM columns.
+      // Software-pipelined by hand in chunks of 16: the MUFU results of chunk ch are consumed (row sum, bf16 pack) only while the
+      // exponentials of chunk ch + 1 are in flight -- with one or two warps per scheduler nothing else hides the MUFU latency, and
+      // ptxas otherwise places every FADD / F2FP two instructions behind the MUFU it depends on.
+      float ebuf[32];
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        const float e0 = exp2f(fmaf(__uint_as_float(r[2 * c]), c_log2, -mc));
-        const float e1 = exp2f(fmaf(__uint_as_float(r[2 * c + 1]), c_log2, -mc));
-        sum4[c & 3] += e0 + e1;
-        r[c] = pack_bf16x2(e0, e1);
+      for (int ch = 0; ch <= NC / 16; ++ch) {
+        if (ch < NC / 16) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x = fmaf(__uint_as_float(r[ch * 16 + i]), c_log2, -mc);
+            ebuf[(ch & 1) * 16 + i] = (DIAG & 1) ? fmaf(x, 0.001f, 0.5f) : exp2f(x);
+          }
+        }
+        if (ch > 0) {
+          const int pc = ch - 1;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float e0 = ebuf[(pc & 1) * 16 + 2 * i], e1 = ebuf[(pc & 1) * 16 + 2 * i + 1];
+            sum4[i & 3] += e0 + e1;
+            if constexpr (DIAG & 2) r[pc * 8 + i] = __byte_perm(__float_as_uint(e0), __float_as_uint(e1), 0x7632);
+            else r[pc * 8 + i] = pack_bf16x2(e0, e1);
+          }
+        }
       }
       l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      tmem_st_32x32b_x16(tmem_s, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-      tmem_st_32x32b_x16(tmem_s + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-      tmem_st_32x32b_x16(tmem_s + 32, *reinterpret_cast<uint32_t(*)[16]>(&r[32]));
-      tmem_st_32x32b_x16(tmem_s + 48, *reinterpret_cast<uint32_t(*)[16]>(&r[48]));
+#pragma unroll
+      for (int c = 0; c < NC / 2 / 16; ++c)
+        tmem_st_32x32b_x16(tmem_s + hh * (NC / 2) + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&r[c * 16]));
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[t]);
     }
     // ---- epilogue
+    if constexpr (SPLIT == 2) {
+      *my_x = l;
+      named_bar_sync_f2(pair_bar, 64);
+      l += *peer_x;
+    }
     if (n_mine > 0) {
       mbar_wait(&o_done[t], (n_mine - 1) & 1, 10);
       tcgen05_fence_after();
     }
     const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
     const bool row_ok = row < p.S_q;
-    __nv_bfloat16* orow = o_ptr + batch * p.o_stride_b + (long long)(row_ok ? row : 0) * p.o_stride_s + head * p.o_stride_h;
+    __nv_bfloat16* orow = o_ptr + batch * p.o_stride_b + (long long)(row_ok ? row : 0) * p.o_stride_s + head * p.o_stride_h +
+                          hh * (D / SPLIT);
 #pragma unroll 1
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = 0; c < D / SPLIT / 32; ++c) {
       uint32_t o[32];
       if (n_mine > 0) {
-        tmem_ld_32x32b_x32(tmem_o + c * 32, o);
+        tmem_ld_32x32b_x32(tmem_o + hh * (D / SPLIT) + c * 32, o);
         tmem_ld_wait();
       } else {
 #pragma unroll
@@ -353,7 +393,7 @@ fmha_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
       }
     }
-    if (row_ok && lse_ptr)
+    if (row_ok && lse_ptr && hh == 0)
       lse_ptr[batch * p.lse_stride_b + head * p.lse_stride_h + row] = (l > 0.f) ? m_used * p.scale + __logf(l) : -INFINITY;
   }
 
@@ -380,10 +420,10 @@ inline int make_tmap_4d_f2(CUtensorMap* out, const void* ptr, uint64_t d0, uint6
   return r == CUDA_SUCCESS ? 0 : -2;
 }
 
-template <int CLUSTER>
+template <int CLUSTER, int SPLIT, int DIAG = 0>
 int launch_fmha_fwd2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, void* o, float* lse,
                      const Fmha2Params& p, cudaStream_t stream) {
-  auto kern = fmha_fwd2_kernel<CLUSTER>;
+  auto kern = fmha_fwd2_kernel<CLUSTER, SPLIT, DIAG>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kF2SmemBytes);
@@ -392,7 +432,7 @@ int launch_fmha_fwd2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((p.S_q + kF2BlockQ * kF2Tiles - 1) / (kF2BlockQ * kF2Tiles), p.H, p.B);
-  cfg.blockDim = dim3(kF2Threads);
+  cfg.blockDim = dim3(f2_threads<SPLIT>());
   cfg.dynamicSmemBytes = kF2SmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -432,7 +472,14 @@ int smx_fmha_fwd2(const void* q, const void* k, const void* v, void* o, float* l
   p.B = B; p.S_q = S_q; p.S_kv = S_kv; p.H = H; p.H_kv = H_kv; p.scale = scale; p.causal = causal;
   p.o_stride_b = o_sb; p.o_stride_s = o_ss; p.o_stride_h = o_sh;
   p.lse_stride_b = (long long)H * S_q; p.lse_stride_h = S_q;
-  return cluster == 2 ? smx::launch_fmha_fwd2<2>(tq, tk, tv, o, lse, p, stream) : smx::launch_fmha_fwd2<1>(tq, tk, tv, o, lse, p, stream);
+  static const int split = [] { const char* e = getenv("SMX_FMHA_SPLIT"); return (e && e[0] == '2') ? 2 : 1; }();
+  static const int diag = [] { const char* e = getenv("SMX_FMHA_DIAG"); return e ? atoi(e) : 0; }();
+  if (diag == 1) return smx::launch_fmha_fwd2<1, 1, 1>(tq, tk, tv, o, lse, p, stream);
+  if (diag == 2) return smx::launch_fmha_fwd2<1, 1, 2>(tq, tk, tv, o, lse, p, stream);
+  if (diag == 3) return smx::launch_fmha_fwd2<1, 1, 3>(tq, tk, tv, o, lse, p, stream);
+  if (split == 1)
+    return cluster == 2 ? smx::launch_fmha_fwd2<2, 1>(tq, tk, tv, o, lse, p, stream) : smx::launch_fmha_fwd2<1, 1>(tq, tk, tv, o, lse, p, stream);
+  return cluster == 2 ? smx::launch_fmha_fwd2<2, 2>(tq, tk, tv, o, lse, p, stream) : smx::launch_fmha_fwd2<1, 2>(tq, tk, tv, o, lse, p, stream);
 }
 
 }  // extern "C"

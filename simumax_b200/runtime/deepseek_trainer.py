@@ -105,8 +105,7 @@ class DeepSeekTrainer:
             from ..parallel.symm import SymmetricWorkspace
             up = lambda n: (n + 1023) // 1024 * 1024
             self._off_p, self._off_g = 0, up(self.P * 2)
-            self._off_gs = self._off_g + up(self.P * 4)
-            self._off_sc = self._off_gs + up(self.shard * 4)
+            self._off_sc = self._off_g + up(self.P * 4)
             self.ws = SymmetricWorkspace(self._off_sc + 1024, 256, group=self.group, device=dev)
             p_buf = self.ws.view(self._off_p, torch.bfloat16, self.P)
             g_buf = self.ws.view(self._off_g, torch.float32, self.P)
@@ -127,11 +126,11 @@ class DeepSeekTrainer:
         f32 = dict(dtype=torch.float32, device=dev)
         bf = dict(dtype=torch.bfloat16, device=dev)
         if self.ws is not None:
-            self.grad_shard = self.ws.view(self._off_gs, torch.float32, self.shard)
+            self.grad_shard = self.grads.buf[lo:lo + self.shard]       # the reduce-scatter lands in place in this rank's slice
             self.sq_in = self.ws.view(self._off_sc, torch.float32, 4)
             self.sq_out = self.ws.view(self._off_sc + 256, torch.float32, 4)
         else:
-            self.grad_shard = torch.empty(self.shard, **f32) if W > 1 else self.grads.buf
+            self.grad_shard = self.grads.buf[lo:lo + self.shard] if W > 1 else self.grads.buf
             self.sq_in = torch.zeros(4, **f32)
             self.sq_out = self.sq_in
         # ---- routed experts (local): flat bf16 / fp32 buffers, local optimizer state
@@ -365,7 +364,7 @@ class DeepSeekTrainer:
         W, ws = self.world, self.ws
         if W > 1:
             if ws is not None:
-                ws.reduce_scatter(self.shard * 4, in_off=self._off_g, out_off=self._off_gs, dtype=torch.float32)
+                ws.reduce_scatter(self.shard * 4, in_off=self._off_g, out_off=self._off_g + self.rank * self.shard * 4, dtype=torch.float32)
             else:
                 dist.reduce_scatter_tensor(self.grad_shard, self.grads.buf, group=self.group)
         self.sq_in.zero_()

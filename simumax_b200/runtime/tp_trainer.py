@@ -118,10 +118,10 @@ class TPLlamaTrainer:
         self.dp_ws, p_buf, g_buf = None, None, None
         self.dp_comm = "none" if self.dp == 1 else dp_comm
         if self.dp > 1 and dp_comm == "smx":
-            # bf16 params | fp32 main grads | fp32 grad shard | 1 KiB scalars, peer-mapped over the data-parallel replicas
+            # bf16 params | fp32 main grads | 1 KiB scalars, peer-mapped over the data-parallel replicas (the reduce-scatter lands in
+            # this replica's own slice of the main-grad buffer: no separate shard buffer, as in Megatron's distributed optimizer)
             self._zp, self._zg = 0, _up(self.P * 2, 1024)
-            self._zgs = self._zg + _up(self.P * 4, 1024)
-            self._zsc = self._zgs + _up(self.zshard * 4, 1024)
+            self._zsc = self._zg + _up(self.P * 4, 1024)
             self.dp_ws = SymmetricWorkspace(self._zsc + 1024, 256, group=dp_group, device=dev)
             p_buf = self.dp_ws.view(self._zp, torch.bfloat16, self.P)
             g_buf = self.dp_ws.view(self._zg, torch.float32, self.P)
@@ -136,11 +136,11 @@ class TPLlamaTrainer:
         self.m = torch.zeros(self.zshard, dtype=torch.float32, device=dev)
         self.v = torch.zeros(self.zshard, dtype=torch.float32, device=dev)
         if self.dp_ws is not None:
-            self.grad_shard = self.dp_ws.view(self._zgs, torch.float32, self.zshard)
+            self.grad_shard = self.grads.buf[self.zlo:self.zlo + self.zshard]
             self.dp_sq_in = self.dp_ws.view(self._zsc, torch.float32, 4)
             self.dp_sq_out = self.dp_ws.view(self._zsc + 256, torch.float32, 4)
         else:
-            self.grad_shard = torch.empty(self.zshard, dtype=torch.float32, device=dev) if self.dp > 1 else None
+            self.grad_shard = self.grads.buf[self.zlo:self.zlo + self.zshard] if self.dp > 1 else None
         self.sqnorm = ws.view(self.off_sc, torch.float32, 4)
         self.sqnorm_out = ws.view(self.off_sc + 256, torch.float32, 4)
         # ---- activations
@@ -376,7 +376,7 @@ class TPLlamaTrainer:
         lo, hi = self.zlo, self.zlo + self.zshard
         dws = self.dp_ws
         if dws is not None:          # pull-reduce my slice of every replica's main grads over NVLink (multimem.ld_reduce with NVLS)
-            dws.reduce_scatter(self.zshard * 4, in_off=self._zg, out_off=self._zgs, dtype=torch.float32)
+            dws.reduce_scatter(self.zshard * 4, in_off=self._zg, out_off=self._zg + lo * 4, dtype=torch.float32)       # in place
         else:
             dist.reduce_scatter_tensor(self.grad_shard, self.grads.buf, op=dist.ReduceOp.SUM, group=self.dp_group)
         cut = min(max(self.n_shard - lo, 0), self.zshard)          # [0, cut) of my shard = TP-sharded matrices, rest = replicated norms

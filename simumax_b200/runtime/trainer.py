@@ -148,8 +148,7 @@ class LlamaTrainer:
                 try:
                     from ..parallel.symm import SymmetricWorkspace
                     self._off_p, self._off_g = 0, self.Ppad * 2
-                    self._off_gs = self._off_g + self.Ppad * 4
-                    self._off_sc = self._off_gs + self.shard * 4
+                    self._off_sc = self._off_g + self.Ppad * 4
                     self.ws = SymmetricWorkspace(self._off_sc + 512, 256, group=dp_group)
                     p_buf = self.ws.view(self._off_p, torch.bfloat16, self.Ppad)
                     g_buf = self.ws.view(self._off_g, torch.float32, self.Ppad)
@@ -175,11 +174,9 @@ class LlamaTrainer:
         self.m = torch.zeros(self.shard, dtype=torch.float32, device=dev)
         self.v = torch.zeros(self.shard, dtype=torch.float32, device=dev)
         if self.ws is not None:
-            self.grad_shard = self.ws.view(self._off_gs, torch.float32, self.shard)
             self.sqnorm = self.ws.view(self._off_sc, torch.float32, 4)[:1]       # all-reduced in place (16-byte granule)
             self.sqnorm_out = self.ws.view(self._off_sc + 256, torch.float32, 4)[:1]
         else:
-            self.grad_shard = torch.empty(self.shard, dtype=torch.float32, device=dev) if self.world > 1 else None
             self.sqnorm = torch.zeros(1, dtype=torch.float32, device=dev)
             self.sqnorm_out = self.sqnorm
         # ---- static activation storage
@@ -495,12 +492,15 @@ class LlamaTrainer:
         with torch.cuda.stream(self.comm_stream):
             if self.ws is not None:
                 # pull-reduce my slice of every peer's main grads over NVLink (multimem.ld_reduce when NVLS is up)
-                self.ws.reduce_scatter(per * 4, in_off=self._off_g + lo * 4, out_off=self._off_gs + self.shard_off[b] * 4,
+                # (in place: the sum lands in this rank's own slice of the bucket, as Megatron's distributed optimizer does)
+                self.ws.reduce_scatter(per * 4, in_off=self._off_g + lo * 4, out_off=self._off_g + (lo + self.rank * per) * 4,
                                        dtype=torch.float32, ctas=64)
             else:
-                dist.reduce_scatter_tensor(self._shard_slice(self.grad_shard, b), self.grads.buf[lo:lo + sz],
+                dist.reduce_scatter_tensor(self._my_slice(self.grads.buf, b), self.grads.buf[lo:lo + sz],
                                            op=dist.ReduceOp.SUM, group=self.group)
-            self.grads.buf[lo:lo + sz].zero_()
+            mine = lo + self.rank * per                 # everything but the reduced slice is done for this step
+            self.grads.buf[lo:mine].zero_()
+            self.grads.buf[mine + per:lo + sz].zero_()
 
     def optimizer_step(self) -> None:
         """ZeRO-1: (bucketed, overlapped) reduce-scatter of the fp32 main grads, clip by global norm, fused AdamW on the
@@ -514,11 +514,13 @@ class LlamaTrainer:
                 self._launch_rs(b)                       # whatever the backward pass did not launch already
             main.wait_stream(self.comm_stream)
             self._rs_launched = [False] * nb
-            gsh = self.grad_shard
-        else:
-            gsh = self.grads.buf
+        gsh = self.grads.buf
         self.sqnorm.zero_()
-        E.sqnorm(gsh, out=self.sqnorm)
+        if self.world > 1:                               # this rank's reduced slice of every bucket (the kernel accumulates into out)
+            for b in range(nb):
+                E.sqnorm(self._my_slice(gsh, b), out=self.sqnorm)
+        else:
+            E.sqnorm(gsh, out=self.sqnorm)
         if self.ws is not None:
             self.ws.view(self._off_sc, torch.float32, 4)[1:].zero_()
             self.ws.all_reduce(16, in_off=self._off_sc, out_off=self._off_sc + 256, dtype=torch.float32, ctas=1)
@@ -537,9 +539,9 @@ class LlamaTrainer:
             lo, sz = self.buckets[b]
             per = sz // self.world
             E.adamw_(self._shard_slice(self.master, b), self._shard_slice(self.m, b), self._shard_slice(self.v, b),
-                     self._shard_slice(gsh, b), self._my_slice(self.params.buf, b), self.lr, b1, b2, 1e-8, self.wd,
+                     self._my_slice(gsh, b), self._my_slice(self.params.buf, b), self.lr, b1, b2, 1e-8, self.wd,
                      self.step_count, sqnorm_t=self.sqnorm_out, max_norm=self.max_norm, grad_prescale=1.0 / self.world,
-                     zero_grad=False)
+                     zero_grad=True)
             self.comm_stream.wait_stream(main)
             with torch.cuda.stream(self.comm_stream):
                 if self.ws is not None:
