@@ -55,7 +55,18 @@ struct Fmha2Params {
   int causal;
   long long o_stride_b, o_stride_s, o_stride_h;
   long long lse_stride_b, lse_stride_h;
+  unsigned int* trace;      // optional: [3 roles][64 blocks][16 slots] SM-clock stamps of CTA (0, 0, 0) (tools/fmha_fwd_trace.py)
 };
+SMX_DEVICE unsigned int clock32() {
+  unsigned int c;
+  asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
+  return c;
+}
+#define F2_TRACE(role, j, slot)                                                                        \
+  do {                                                                                                 \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 64 && lane == 0)     \
+      p.trace[((role) * 64 + (j)) * 16 + (slot)] = clock32();                                          \
+  } while (0)
 
 // DIAG (timing experiments only, SMX_FMHA_DIAG): 1 = no MUFU (exp2 replaced by an FMA: wrong numbers, shows the non-MUFU floor),
 // 2 = bf16 pack by truncation with PRMT instead of F2FP, 3 = both
@@ -227,14 +238,18 @@ fmha_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int t = 0; t < kF2Tiles; ++t) {
         if (j >= n_t[t]) continue;
         mbar_wait(&p_full[t], j & 1, 5);
+        F2_TRACE(0, j, 0 + t * 4);
         if (!v_ready) { mbar_wait(&v_full[stage], phase, 6); v_ready = true; }
+        F2_TRACE(0, j, 1 + t * 4);
         tcgen05_fence_after();
         issue_pv(t, stage, j == 0);
+        F2_TRACE(0, j, 2 + t * 4);
         if (j + 1 < n_t[t]) {
           if (!k_ready) { mbar_wait(&k_full[nstage], nphase, 7); k_ready = true; }
           tcgen05_fence_after();
           issue_s(t, nstage);
         }
+        F2_TRACE(0, j, 3 + t * 4);
       }
       if (elect_one()) {
         release(&v_empty[stage]);                // behind the last P V of this key block
@@ -271,10 +286,12 @@ fmha_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     for (int j = 0; j < n_mine; ++j) {
       mbar_wait(&s_full[t], j & 1, 8);
       tcgen05_fence_after();
+      if (q == 0 && hh == 0) F2_TRACE(1 + t, j, 0);
       uint32_t r[NC];
 #pragma unroll
       for (int c = 0; c < NC / 32; ++c) tmem_ld_32x32b_x32(tmem_s + hh * NC + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
       tmem_ld_wait();
+      if (q == 0 && hh == 0) F2_TRACE(1 + t, j, 1);
       const int k0 = j * BKV + hh * NC;
       const int qt0 = q0 + t * BQ;
       const bool need_mask = (p.causal && (j * BKV + BKV - 1 > qt0 + causal_shift)) || (j * BKV + BKV > p.S_kv);
@@ -320,6 +337,7 @@ fmha_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         l *= alpha;
       }
       m_used = m_new;
+      if (q == 0 && hh == 0) F2_TRACE(1 + t, j, 2);
       const float mc = (m_used == -INFINITY) ? 0.f : m_used * c_log2;
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
       // P row -> packed bf16 pairs, in place over the registers (keys 2c, 2c + 1 -> 32-bit column c), then NC / 2 TMEM columns.
@@ -348,6 +366,7 @@ fmha_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
       }
       l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      if (q == 0 && hh == 0) F2_TRACE(1 + t, j, 3);
 #pragma unroll
       for (int c = 0; c < NC / 2 / 16; ++c)
         tmem_st_32x32b_x16(tmem_s + hh * (NC / 2) + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&r[c * 16]));
@@ -355,6 +374,7 @@ fmha_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[t]);
+      if (q == 0 && hh == 0) F2_TRACE(1 + t, j, 4);
     }
     // ---- epilogue
     if constexpr (SPLIT == 2) {
@@ -455,7 +475,7 @@ extern "C" {
 int smx_fmha_fwd2(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S_q, int S_kv, int H, int H_kv,
                   long long q_sb, long long q_ss, long long q_sh, long long k_sb, long long k_ss, long long k_sh, long long v_sb,
                   long long v_ss, long long v_sh, long long o_sb, long long o_ss, long long o_sh, float scale, int causal,
-                  int cluster, void* stream_v) {
+                  int cluster, void* trace, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
   if (H % H_kv) return -30;
   const int group = H / H_kv;
@@ -472,6 +492,7 @@ int smx_fmha_fwd2(const void* q, const void* k, const void* v, void* o, float* l
   p.B = B; p.S_q = S_q; p.S_kv = S_kv; p.H = H; p.H_kv = H_kv; p.scale = scale; p.causal = causal;
   p.o_stride_b = o_sb; p.o_stride_s = o_ss; p.o_stride_h = o_sh;
   p.lse_stride_b = (long long)H * S_q; p.lse_stride_h = S_q;
+  p.trace = reinterpret_cast<unsigned int*>(trace);
   static const int split = [] { const char* e = getenv("SMX_FMHA_SPLIT"); return (e && e[0] == '2') ? 2 : 1; }();
   static const int diag = [] { const char* e = getenv("SMX_FMHA_DIAG"); return e ? atoi(e) : 0; }();
   if (diag == 1) return smx::launch_fmha_fwd2<1, 1, 1>(tq, tk, tv, o, lse, p, stream);

@@ -24,7 +24,7 @@ def _fwd2_fn():
     if _fwd2 is None:
         f = _lib.lib().smx_fmha_fwd2
         f.restype = _c.c_int
-        f.argtypes = [_c.c_void_p] * 5 + [_c.c_int] * 5 + [_c.c_longlong] * 12 + [_c.c_float, _c.c_int, _c.c_int, _c.c_void_p]
+        f.argtypes = [_c.c_void_p] * 5 + [_c.c_int] * 5 + [_c.c_longlong] * 12 + [_c.c_float, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]
         _fwd2 = f
     return _fwd2
 
@@ -53,7 +53,8 @@ def _check(t: torch.Tensor, name: str):
 
 
 def fmha_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = True, scale: Optional[float] = None,
-             out: Optional[torch.Tensor] = None, return_lse: bool = True, lse: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+             out: Optional[torch.Tensor] = None, return_lse: bool = True, lse: Optional[torch.Tensor] = None,
+             trace: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _check(t, n)
     B, S_q, H, D = q.shape
@@ -73,7 +74,7 @@ def fmha_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = T
                         q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
                         v.stride(0), v.stride(1), v.stride(2), o.stride(0), o.stride(1), o.stride(2),
                         float(scale), 1 if causal else 0, int(os.environ.get("SMX_FMHA_CLUSTER", "0")),
-                        torch.cuda.current_stream(q.device).cuda_stream)
+                        trace.data_ptr() if trace is not None else None, torch.cuda.current_stream(q.device).cuda_stream)
         _lib.check(rc, f"fmha_fwd2 B{B} S{S_q}x{S_kv} H{H}/{H_kv} d{D}/{Dv}")
         _lib.count_launch()
         return o, lse

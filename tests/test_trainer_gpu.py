@@ -108,3 +108,17 @@ def test_recompute_reproduces_gradients():
     r = check_recompute_parity()
     assert r["ok"], r
     assert r["act_bytes_full"] < r["act_bytes_selective"] < r["act_bytes_none"], r
+
+
+def test_deepseek_trainer_single_gpu_matches_fp32_reference():
+    """MLA attention + dense / MoE MLP with shared expert (EP = 1) vs an fp32 autograd model: loss, every parameter kind's gradient,
+    optimizer steps (tools/deepseek_check.py, one rank)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29579")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "deepseek_check.py")], cwd=root, env=env, capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0 and "DEEPSEEK_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
