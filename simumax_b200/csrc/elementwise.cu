@@ -359,7 +359,7 @@ template <int THREADS, int VPT>
 __global__ void __launch_bounds__(THREADS) rmsnorm_bwd_pipe_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
                                                                   const __nv_bfloat16* __restrict__ dy, const float* __restrict__ rstd,
                                                                   __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, long long rows,
-                                                                  int H, int add_to_dx) {
+                                                                  int H, int add_to_dx, float* __restrict__ partial) {
   __shared__ float red[2][32];
   float dg[VPT][8], g[VPT][8];
   uint4 cx[VPT], cd[VPT], co[VPT], nx[VPT], nd[VPT], no[VPT];
@@ -433,13 +433,37 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_bwd_pipe_kernel(const __nv_bf
     }
     r_cur = r_nxt;
   }
+  // dgamma: with a scratch buffer every CTA stores its partial row (coalesced, no atomics) and dgamma_reduce_kernel sums the rows --
+  // 592 CTAs x H atomics on H addresses cost as much as the whole streaming pass
 #pragma unroll
   for (int i = 0; i < VPT; ++i)
     if (on[i]) {
       const int c = (i * THREADS + threadIdx.x) * 8;
+      if (partial) {
+        float4* dst = reinterpret_cast<float4*>(partial + (long long)blockIdx.x * H + c);
+        dst[0] = make_float4(dg[i][0], dg[i][1], dg[i][2], dg[i][3]);
+        dst[1] = make_float4(dg[i][4], dg[i][5], dg[i][6], dg[i][7]);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(dgamma + c + j, dg[i][j]);
+        for (int j = 0; j < 8; ++j) atomicAdd(dgamma + c + j, dg[i][j]);
+      }
     }
+}
+
+// dgamma[c] += sum over the partial rows (one thread per column, coalesced)
+__global__ void dgamma_reduce_kernel(const float* __restrict__ partial, int nrows, int H, float* __restrict__ dgamma) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= H) return;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  int r = 0;
+  for (; r + 3 < nrows; r += 4) {
+    acc0 += partial[(long long)r * H + c];
+    acc1 += partial[(long long)(r + 1) * H + c];
+    acc2 += partial[(long long)(r + 2) * H + c];
+    acc3 += partial[(long long)(r + 3) * H + c];
+  }
+  for (; r < nrows; ++r) acc0 += partial[(long long)r * H + c];
+  dgamma[c] += (acc0 + acc1) + (acc2 + acc3);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -986,11 +1010,13 @@ int smx_rs_consume(const void* slots, int nslots, long long rows, int H, const v
   return (int)cudaGetLastError();
 }
 
+// scratch: optional [148 * 4, H] fp32 for the per-CTA dgamma partials (nullptr: atomics straight into dgamma)
 int smx_rmsnorm_bwd(const void* x, const void* gamma, const void* dy, const float* rstd, void* dx, float* dgamma,
-                    long long rows, int H, int add_to_dx, void* stream) {
+                    long long rows, int H, int add_to_dx, float* scratch, void* stream) {
   if (H % 8) return -20;
   int grid = rows < 148 * 4 ? (int)rows : 148 * 4;
-#define SMX_NB(T, V) smx::rmsnorm_bwd_pipe_kernel<T, V><<<grid, T, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)dy, rstd, (bf16*)dx, dgamma, rows, H, add_to_dx)
+  if (H > 8192) scratch = nullptr;
+#define SMX_NB(T, V) smx::rmsnorm_bwd_pipe_kernel<T, V><<<grid, T, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)dy, rstd, (bf16*)dx, dgamma, rows, H, add_to_dx, scratch)
   if (H <= 2048) SMX_NB(256, 1);
   else if (H <= 4096) SMX_NB(256, 2);
   else if (H <= 8192) SMX_NB(512, 2);
@@ -998,6 +1024,7 @@ int smx_rmsnorm_bwd(const void* x, const void* gamma, const void* dy, const floa
     smx::rmsnorm_bwd_kernel<512, 4><<<grid, 512, 0, SMX_STREAM>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)dy, rstd, (bf16*)dx, dgamma, (int)rows, H, add_to_dx);
   else return -21;
 #undef SMX_NB
+  if (scratch) smx::dgamma_reduce_kernel<<<(H + 255) / 256, 256, 0, SMX_STREAM>>>(scratch, grid, H, dgamma);
   return (int)cudaGetLastError();
 }
 

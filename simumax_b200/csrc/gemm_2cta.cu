@@ -358,6 +358,12 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               for (int j = 0; j < 8; ++j) {
                 float4 v = make_float4(__uint_as_float(r[4 * j]) * p.alpha, __uint_as_float(r[4 * j + 1]) * p.alpha,
                                        __uint_as_float(r[4 * j + 2]) * p.alpha, __uint_as_float(r[4 * j + 3]) * p.alpha);
+                if (p.accumulate == 2) {
+                  // fp32 main-grad accumulation as a fire-and-forget vector reduction: the read-modify-write happens at the L2
+                  // slice, the epilogue neither waits for the old value nor moves it through the SM
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                  continue;
+                }
                 if (p.accumulate) {
                   float4 o = dst[j];
                   v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
@@ -541,7 +547,8 @@ int smx_gemm_2cta(const void* A, const void* B, void* C, int G, int M, int N, in
   p.G = G; p.M = M; p.N = N; p.K = K;
   p.m_tiles = (M + smx::k2BlockM - 1) / smx::k2BlockM;
   p.n_tiles = (N + smx::k2BlockN - 1) / smx::k2BlockN;
-  p.ldc = ldc; p.c_batch_stride = c_bs; p.alpha = alpha; p.accumulate = accumulate;
+  static const int red_mode = [] { const char* e = getenv("SMX_GEMM_RED"); return (e && e[0] == '0') ? 0 : 1; }();     // default on: +16 ... +90 % on the fp32-accumulating wgrads
+  p.ldc = ldc; p.c_batch_stride = c_bs; p.alpha = alpha; p.accumulate = (accumulate && out_f32 && red_mode) ? 2 : accumulate;
   p.ag_flags = armed_flags; p.ag_rows_per_flag = armed_rows; p.ag_first_m_blk = armed_first; p.ag_epoch = armed_epoch;
   p.rs_world = 1; p.rs_rank = 0; p.rs_rows = M;
   for (int i = 0; i < 8; ++i) p.rs_counter[i] = nullptr;

@@ -298,6 +298,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               for (int j = 0; j < 8; ++j) {
                 float4 v = make_float4(__uint_as_float(r[4 * j]) * p.alpha, __uint_as_float(r[4 * j + 1]) * p.alpha,
                                        __uint_as_float(r[4 * j + 2]) * p.alpha, __uint_as_float(r[4 * j + 3]) * p.alpha);
+                if (p.accumulate == 2) {          // fire-and-forget vector reduction at the L2 slice (see gemm_2cta.cu)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                  continue;
+                }
                 if (p.accumulate) {
                   float4 o = dst[j];
                   v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
@@ -485,7 +489,8 @@ int smx_gemm(const void* A, const void* B, void* C, int G, int M, int N, int K, 
   p.G = G; p.M = M; p.N = N; p.K = K;
   p.m_tiles = (M + smx::kBlockM - 1) / smx::kBlockM;
   p.n_tiles = (N + block_n - 1) / block_n;
-  p.ldc = ldc; p.c_batch_stride = c_bs; p.alpha = alpha; p.accumulate = accumulate;
+  static const int red_mode = [] { const char* e = getenv("SMX_GEMM_RED"); return (e && e[0] == '0') ? 0 : 1; }();
+  p.ldc = ldc; p.c_batch_stride = c_bs; p.alpha = alpha; p.accumulate = (accumulate && out_f32 && red_mode) ? 2 : accumulate;
   p.ag_flags = armed_flags; p.ag_rows_per_flag = armed_rows; p.ag_first_m_blk = armed_first; p.ag_epoch = armed_epoch;
   p.rs_world = 1; p.rs_rows = M; p.rs_rank = 0;
   for (int i = 0; i < 8; ++i) p.rs_out[i] = nullptr;

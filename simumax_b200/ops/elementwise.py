@@ -16,7 +16,7 @@ from . import _lib
 _c = ctypes
 _SIGS = {
     "smx_rmsnorm_fwd": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_float, _c.c_void_p],
-    "smx_rmsnorm_bwd": [_c.c_void_p] * 6 + [_c.c_longlong, _c.c_int, _c.c_int, _c.c_void_p],
+    "smx_rmsnorm_bwd": [_c.c_void_p] * 6 + [_c.c_longlong, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p],
     "smx_swiglu_fwd": [_c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_void_p],
     "smx_swiglu_bwd": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_void_p],
     "smx_rope": [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_void_p],
@@ -42,6 +42,7 @@ _SIGS = {
     "smx_copy": [_c.c_void_p, _c.c_void_p, _c.c_longlong, _c.c_void_p],
 }
 _fns = {}
+_DGAMMA_SCRATCH = {}
 
 
 def _fn(name):
@@ -93,8 +94,13 @@ def rmsnorm_bwd(x, gamma, dy, rstd, dgamma_fp32: torch.Tensor, dx: Optional[torc
         assert not accumulate_dx
         dx = torch.empty_like(x)
     assert dgamma_fp32.dtype == torch.float32 and dgamma_fp32.numel() == H
+    key = (x.device, H)
+    scratch = _DGAMMA_SCRATCH.get(key)
+    if scratch is None:          # per-CTA dgamma partials, summed by a second tiny kernel (no atomics on H hot addresses)
+        scratch = _DGAMMA_SCRATCH[key] = torch.empty(148 * 4 * H, device=x.device, dtype=torch.float32)
     _call("smx_rmsnorm_bwd", x.data_ptr(), gamma.data_ptr(), dy.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
-          dgamma_fp32.data_ptr(), rows, H, 1 if accumulate_dx else 0, _stream(x))
+          dgamma_fp32.data_ptr(), rows, H, 1 if accumulate_dx else 0, scratch.data_ptr(), _stream(x))
+    _lib.count_launch()
     return dx
 
 

@@ -85,6 +85,8 @@ PUBLISHED_CP: Dict[Tuple, Tuple[float, float, float]] = {
 
 
 def published(case: Case):
+    if case.recompute != "none":          # every published row runs without activation recompute
+        return None
     if case.cp > 1:
         return PUBLISHED_CP.get((case.model, case.layers, case.seq, case.mbc, case.tp, case.cp)) if (case.mbs == 1 and case.dp == 1) else None
     return PUBLISHED.get((case.model, case.layers, case.seq, case.mbs, case.mbc, case.tp, case.pp, case.ep, case.dp))

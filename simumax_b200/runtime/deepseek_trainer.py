@@ -142,12 +142,13 @@ class DeepSeekTrainer:
         self.e_params.buf.normal_(0.0, 0.02, generator=gen_e)
         self.e_grads.buf.zero_()
         self.moe: dict = {}
+        moe_shared: dict = {}           # one dispatch / combine workspace + backward scratch for all MoE layers
         for i in range(d.dense_layers, L):
             w1, w2 = self.e_params.take(self.El, 2 * d.ffn_expert, H), self.e_params.take(self.El, H, d.ffn_expert)
             g1, g2 = self.e_grads.take(self.El, 2 * d.ffn_expert, H), self.e_grads.take(self.El, H, d.ffn_expert)
             self.moe[i] = EPMoELayer(H, d.ffn_expert, d.experts, d.topk, T, ep_group=self.group, capacity_factor=capacity_factor,
                                      force_balanced=force_balanced, seed=seed + 100 * i, device=dev,
-                                     weights=(self.w[f"router.{i}"], w1, w2), grads=(self.g[f"router.{i}"], g1, g2))
+                                     weights=(self.w[f"router.{i}"], w1, w2), grads=(self.g[f"router.{i}"], g1, g2), shared=moe_shared)
         self.e_master = self.e_params.buf.float()
         self.e_m = torch.zeros_like(self.e_master)
         self.e_v = torch.zeros_like(self.e_master)
@@ -205,7 +206,11 @@ class DeepSeekTrainer:
         return cls(dims, case.mbs, case.seq, seed=seed, **kw)
 
     def symmetric_workspaces(self):
-        return [w for w in [self.ws] + [m.ws for m in self.moe.values()] if w is not None]
+        seen, out = set(), []
+        for w in [self.ws] + [m.ws for m in self.moe.values()]:
+            if w is not None and id(w) not in seen:
+                seen.add(id(w)); out.append(w)
+        return out
 
     def total_numel(self) -> int:
         return self.P + self.e_params.buf.numel() * self.world
@@ -213,7 +218,8 @@ class DeepSeekTrainer:
     def memory_bytes(self) -> dict:
         act = sum(t.numel() * t.element_size() for t in self.act.values())
         act += sum(t.numel() * t.element_size() for m in self.act_mlp.values() for t in m.values())
-        moe_act = sum(t.numel() * t.element_size() for m in self.moe.values() for t in (m.xin, m.u, m.g, m.yexp, m.yperm, m.d_u, m.d_g, m.d_in))
+        moe_act = sum(t.numel() * t.element_size() for m in self.moe.values() for t in (m.xin, m.u, m.g, m.yperm))
+        moe_act += sum(t.numel() * t.element_size() for m in list(self.moe.values())[:1] for t in (m.yexp, m.d_u, m.d_g, m.d_in))
         return {"dense_params_bf16": self.P * 2, "dense_main_grads_fp32": self.P * 4, "dense_optimizer_fp32": self.shard * 12,
                 "expert_params_bf16": self.e_params.buf.numel() * 2, "expert_main_grads_fp32": self.e_grads.buf.numel() * 4,
                 "expert_optimizer_fp32": self.e_master.numel() * 12, "activations": act, "moe_buffers": moe_act,

@@ -30,9 +30,11 @@ from ..parallel.symm import SymmetricWorkspace
 class EPMoELayer:
     def __init__(self, hidden: int, ffn: int, n_experts: int, topk: int, tokens: int, ep_group: Optional[dist.ProcessGroup] = None,
                  capacity_factor: float = 1.0, force_balanced: bool = False, seed: int = 1234, device=None,
-                 weights=None, grads=None):
+                 weights=None, grads=None, shared: Optional[dict] = None):
         """``weights`` = (router [E, H], w1 [El, 2F, H], w2 [El, H, F]) bf16 and ``grads`` = the matching fp32 main-grad tensors when
-        the parameters live in a trainer's flat buffers (runtime/deepseek_trainer.py); otherwise the layer owns random ones."""
+        the parameters live in a trainer's flat buffers (runtime/deepseek_trainer.py); otherwise the layer owns random ones.
+        ``shared``: a dict the MoE layers of one model pass around -- the symmetric dispatch / combine workspace, the expert-output
+        buffer and the backward scratch are transient (consumed before the next layer runs), so one set serves every layer."""
         assert dist.is_initialized()
         self.group = ep_group or dist.group.WORLD
         self.ep = ep = dist.get_world_size(self.group)
@@ -49,7 +51,12 @@ class EPMoELayer:
         self.rows = ep * El * C                      # rows of the permuted order (local) == rows received (expert side)
         buf = self.rows * H * 2
         self.off_recv, self.off_back = 0, (buf + 1023) // 1024 * 1024
-        self.ws = SymmetricWorkspace(self.off_back, buf + 1024, group=self.group, device=dev)
+        shared = shared if shared is not None else {}
+        key = (id(self.group), self.rows, H, F)
+        pool = shared.setdefault(key, {})
+        if "ws" not in pool:
+            pool["ws"] = SymmetricWorkspace(self.off_back, buf + 1024, group=self.group, device=dev)
+        self.ws = pool["ws"]
         f32 = dict(dtype=torch.float32, device=dev)
         if weights is not None:
             self.w_router, self.w1, self.w2 = weights
@@ -70,11 +77,11 @@ class EPMoELayer:
         self.xin = torch.empty(El, M, H, **bf)       # dispatched tokens, saved for wgrad
         self.u = torch.empty(El, M, 2 * F, **bf)
         self.g = torch.empty(El, M, F, **bf)
-        self.yexp = torch.empty(El, M, H, **bf)
         self.yperm = torch.empty(self.rows, H, **bf)     # expert outputs back in permuted order (needed for d_probs)
-        self.d_u = torch.empty(El, M, 2 * F, **bf)
-        self.d_g = torch.empty(El, M, F, **bf)
-        self.d_in = torch.empty(El, M, H, **bf)
+        for name, shp in (("yexp", (El, M, H)), ("d_u", (El, M, 2 * F)), ("d_g", (El, M, F)), ("d_in", (El, M, H))):
+            if name not in pool:
+                pool[name] = torch.empty(*shp, **bf)
+            setattr(self, name, pool[name])
         self.logits = torch.empty(tokens, n_experts, **f32)
 
     # ------------------------------------------------------------------------------------------
