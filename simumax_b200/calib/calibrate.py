@@ -62,6 +62,9 @@ def plan_requests(param_file: Optional[str] = None, default_sweep: bool = False,
         extra = collect_requests_tolerant(workloads_from_params(params), log=log)
         for op, table in extra.items():
             requests.setdefault(op, {}).update(table)
+    if requests.get("fp8_matmul"):        # the block-scaled recipe (strategy.fp8_recipe = "mxfp8") prices the same linears from its own table
+        import dataclasses
+        requests["mxfp8_matmul"] = {k: dataclasses.replace(r, op="mxfp8_matmul") for k, r in requests["fp8_matmul"].items()}
     return requests
 
 
@@ -128,7 +131,7 @@ def merge(ops_path: Optional[str], coll_paths: List[str], out_path: str, base: O
     if ops_path:
         res = json.load(open(ops_path))
         for op, table in res["ops"].items():
-            cfg = acc["op"][op]
+            cfg = acc["op"].setdefault(op, dict(b200_template()["accelerator"]["op"].get(op) or acc["op"]["default"]))
             tab = cfg.setdefault("accurate_efficient_factor", {}) or {}
             wts = flops_tab.setdefault(op, {})             # flops of every key (kept under calibration_notes): the fallback is flop-weighted
             for key, m in table.items():

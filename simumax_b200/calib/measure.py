@@ -97,6 +97,30 @@ def measure_matmul(req: ShapeRequest, fp8: bool = False) -> Dict[str, float]:
     return {"ms": ms, "tflops": flops / ms / 1e9, "flops": flops}
 
 
+def measure_matmul_mxfp8(req: ShapeRequest) -> Dict[str, float]:
+    """Same keys as ``fp8_matmul`` through the block-scaled kernel (e4m3 payload + UE8M0 scale per 32 K elements, scaling inside
+    ``tcgen05.mma.kind::mxf8f6f4.block_scale``).  Operands are K-major, so all three layouts run as TN on pre-transposed copies;
+    fp32 accumulate-into-C is not in this kernel (a main-grad wgrad adds one fp32 read-modify-write, charged by the caller)."""
+    from ..ops.gemm import gemm_mxfp8
+    b, m, k, n = (req.geti(x) for x in ("b", "m", "k", "n"))
+    layout = req.fields["layout"]
+    out_dtype = torch.float32 if req.fields.get("out_dtype", "bf16") == "fp32" else torch.bfloat16
+    m_eff = b * m if layout in ("TN", "NN") else m
+    k_eff = k if layout in ("TN", "NN") else b * k
+    if k_eff % 128:
+        raise NotImplementedError(f"mxfp8 kernel needs K % 128 == 0, got {k_eff}")
+    per_set = (m_eff + n) * k_eff * 33 // 32 + m_eff * n * out_dtype.itemsize
+    ring = _ring(per_set)
+    As = [_rand((m_eff, k_eff), torch.float8_e4m3fn, 0.5) for _ in range(ring)]
+    Bs = [_rand((n, k_eff), torch.float8_e4m3fn, 0.5) for _ in range(ring)]
+    SAs = [torch.full((m_eff, k_eff // 32), 127, device="cuda", dtype=torch.uint8) for _ in range(ring)]
+    SBs = [torch.full((n, k_eff // 32), 127, device="cuda", dtype=torch.uint8) for _ in range(ring)]
+    Cs = [torch.zeros(m_eff, n, device="cuda", dtype=out_dtype) for _ in range(ring)]
+    ms = _time(lambda i: gemm_mxfp8(As[i % ring], SAs[i % ring], Bs[i % ring], SBs[i % ring], out=Cs[i % ring]))
+    flops = 2.0 * m_eff * n * k_eff
+    return {"ms": ms, "tflops": flops / ms / 1e9, "flops": flops}
+
+
 def measure_group_matmul(req: ShapeRequest, fp8: bool = False) -> Dict[str, float]:
     """key: ng, M (tokens per expert), N, K, stage in {fwd, bwd_grad_act, bwd_grad_w}."""
     from ..ops.gemm import gemm
@@ -239,6 +263,7 @@ def sweep(requests: Dict[str, Dict[str, ShapeRequest]], nominal_tflops: Dict[str
     """Measure every request; returns op -> key -> {ms, tflops, efficiency}."""
     runners = {
         "matmul": lambda r: measure_matmul(r, False), "fp8_matmul": lambda r: measure_matmul(r, True),
+        "mxfp8_matmul": measure_matmul_mxfp8,
         "group_matmul": lambda r: measure_group_matmul(r, False), "fp8_group_matmul": lambda r: measure_group_matmul(r, True),
         "sdp_fwd": lambda r: measure_sdp(r, False), "sdp_bwd": lambda r: measure_sdp(r, True),
     }
@@ -254,7 +279,7 @@ def sweep(requests: Dict[str, Dict[str, ShapeRequest]], nominal_tflops: Dict[str
                 break
             try:
                 m = run(req)
-            except (NotImplementedError, RuntimeError, ValueError, TypeError) as e:
+            except (NotImplementedError, RuntimeError, ValueError, TypeError, AssertionError) as e:
                 log(f"[calib] {op} {key}: skipped ({e})")
                 continue
             finally:

@@ -37,7 +37,7 @@ def b200_template(sys_name: str = "b200_nominal", mem_gbs: float = 180, num_per_
         "accelerator": {
             "backend": "cuda",
             "mem_gbs": mem_gbs,
-            "op": {"default": op(2250, 0.40), "matmul": op(2250, 0.55), "fp8_matmul": op(4500, 0.45),
+            "op": {"default": op(2250, 0.40), "matmul": op(2250, 0.55), "fp8_matmul": op(4500, 0.45), "mxfp8_matmul": op(4500, 0.22),
                    "group_matmul": op(2250, 0.40), "fp8_group_matmul": op(4500, 0.35),
                    "sdp_fwd": op(2250, 0.45), "sdp_bwd": op(2250, 0.45)},
             "bandwidth": {"default": bw(0.70), "permute_fwd": bw(0.50), "permute_bwd": bw(0.50), "ce": bw(0.32),

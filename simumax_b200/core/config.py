@@ -182,6 +182,7 @@ class StrategyConfig(Config):
     micro_batch_num: Optional[int] = None
     dtype: Optional[str] = "bf16"
     fp8: Optional[bool] = False
+    fp8_recipe: Optional[str] = "tensor"      # "tensor" (per-tensor scaled e4m3, TE delayed / current scaling) | "mxfp8" (32-element UE8M0 block scales in the MMA)
 
     world_size: Optional[int] = 8
     tp_size: int = 1
@@ -468,6 +469,7 @@ class StrategyConfig(Config):
             f"cp_a2a_mode {self.cp_a2a_mode} must be in [{','.join(self.valid_cp_a2a_modes)}]"
         if self.cache_groupgemm_col_fp8_inputs:
             assert self.fp8, "cache_groupgemm_col_fp8_inputs requires fp8"
+        assert self.fp8_recipe in ("tensor", "mxfp8"), f"fp8_recipe must be 'tensor' or 'mxfp8', got {self.fp8_recipe}"
         if self.offload_groupgemm_col_inputs:
             assert self.recompute_granularity != "full_block", \
                 "offload_groupgemm_col_inputs is not allowed when recompute_granularity = 'full_block'"
@@ -674,6 +676,8 @@ class SystemConfig(Config):
     # ---- primitive 1: compute time from the efficiency table
     def lookup_op_efficiency(self, op_name: str, flops, shape_desc: str):
         op = self.accelerator.op.get(op_name)
+        if op is None and op_name.startswith("mxfp8_"):      # a config without a block-scaled table prices it as per-tensor fp8
+            op = self.accelerator.op.get(op_name[2:])
         if op is None:
             warnings.warn(f"{op_name} not exist on {self.accelerator.op.keys()}, use default value")
             op = self.accelerator.op.get("default")

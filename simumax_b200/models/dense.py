@@ -14,6 +14,14 @@ from ..core.ir import (DT, CollectiveSpec, OpNode, SimStep, comm_step, dense_par
                        linear_shape_key, numel, record_te_dummy_wgrad)
 
 
+def linear_op_name(st) -> str:
+    """Efficiency table a linear's three GEMMs are priced from: bf16, per-tensor fp8, or block-scaled MXFP8
+    (``strategy.fp8_recipe = "mxfp8"``: tcgen05 ``kind::mxf8f6f4.block_scale``, csrc/gemm_mxfp8.cu)."""
+    if not st.fp8:
+        return "matmul"
+    return "mxfp8_matmul" if getattr(st, "fp8_recipe", "tensor") == "mxfp8" else "fp8_matmul"
+
+
 def _atom(node: OpNode, name: str = "") -> SimStep:
     return SimStep(kind="atom", name=name, fwd_cost=node.cost.fwd_compute_time,
                    bwd_cost=node.cost.bwd_grad_act_time + node.cost.bwd_grad_w_time)
@@ -126,7 +134,7 @@ def linear_col(st: StrategyConfig, in_features, out_features, in_shape, name, *,
     node.compute.bwd_grad_act_accessed_mem = w_bytes + y_bytes + x_bytes
     main_grad = in_features * out_local * 4
     node.compute.bwd_grad_w_accessed_mem = y_bytes + x_bytes + w_bytes + (main_grad if st.use_fused_grad_accumulation else 0)
-    op = "fp8_matmul" if st.fp8 else "matmul"
+    op = linear_op_name(st)
     node.ops = {"fwd": op, "bwd_grad_act": op, "bwd_grad_w": op}
     node.gemm = linear_gemm_table(st, B, s_full, in_features, out_local)
     node.shape_key = linear_shape_key(node.gemm)
@@ -191,7 +199,7 @@ def linear_row(st: StrategyConfig, in_features, out_features, in_shape, name, *,
     node.compute.bwd_grad_act_accessed_mem = w_bytes + y_bytes + x_bytes
     main_grad = in_local * out_features * 4
     node.compute.bwd_grad_w_accessed_mem = y_bytes + x_bytes + (main_grad if st.use_fused_grad_accumulation else 0)
-    op = "fp8_matmul" if st.fp8 else "matmul"
+    op = linear_op_name(st)
     node.ops = {"fwd": op, "bwd_grad_act": op, "bwd_grad_w": op}
     node.gemm = linear_gemm_table(st, B, S, in_local, out_features)
     node.shape_key = linear_shape_key(node.gemm)

@@ -89,3 +89,45 @@ def test_perf_vs_real_predict_phase_state_and_summary(tmp_path):
     assert row["published_megatron"]["speedup_vs_megatron"] == pytest.approx(725.5 / 600.0)
     md = open(out + ".md").read()
     assert "| llama3_70b_l12_tp2_pp1_dp4_mbc4 | 8 |" in md and "mean |err|" in md
+
+
+def test_mxfp8_recipe_prices_linears_from_its_own_table(tmp_path):
+    """strategy.fp8_recipe = "mxfp8" routes the linear GEMMs to the ``mxfp8_matmul`` table (block-scaled tcgen05 kernel); a system config
+    without that table prices them as per-tensor fp8; the sweep plans the same keys for both recipes."""
+    import contextlib
+    import io
+    from simumax_b200 import PerfLLM
+    from simumax_b200.calib.calibrate import plan_requests
+    from simumax_b200.configs import get_simu_model_config, get_simu_strategy_config, get_simu_system_config
+    from simumax_b200.core.config import StrategyConfig
+    from simumax_b200.core.utils import parse_time_ms
+
+    def run(recipe, system):
+        st = StrategyConfig.init_from_config_file(get_simu_strategy_config("tp1_pp1_dp8_mbs1"))
+        st.fp8, st.fp8_recipe = True, recipe
+        p = PerfLLM()
+        with contextlib.redirect_stdout(io.StringIO()):
+            p.configure(strategy_config=st, model_config=get_simu_model_config("llama3-8b"), system_config=system)
+            p.run_estimate()
+        return parse_time_ms(p.analysis_cost().data["duration_time_per_iter"]), p.system
+
+    base = json.load(open(get_simu_system_config("b200_nominal")))
+    base["accelerator"]["op"].pop("mxfp8_matmul", None)
+    f0 = tmp_path / "no_mx.json"
+    f0.write_text(json.dumps(base))
+    t_tensor, _ = run("tensor", str(f0))
+    t_fallback, _ = run("mxfp8", str(f0))
+    assert t_fallback == pytest.approx(t_tensor)
+    slow = json.loads(json.dumps(base))
+    slow["accelerator"]["op"]["mxfp8_matmul"] = dict(base["accelerator"]["op"]["fp8_matmul"], efficient_factor=0.1, accurate_efficient_factor={})
+    f1 = tmp_path / "mx.json"
+    f1.write_text(json.dumps(slow))
+    t_mx, system = run("mxfp8", str(f1))
+    assert t_mx > t_tensor * 1.2
+    assert "mxfp8_matmul" in system.miss_efficiency and "fp8_matmul" not in system.miss_efficiency
+    req = plan_requests(log=lambda *a: None)
+    assert set(req["mxfp8_matmul"]) == set(req["fp8_matmul"]) and all(r.op == "mxfp8_matmul" for r in req["mxfp8_matmul"].values())
+    with pytest.raises(AssertionError):
+        st = StrategyConfig.init_from_config_file(get_simu_strategy_config("tp1_pp1_dp8_mbs1"))
+        st.fp8_recipe = "nvfp4"
+        st.sanity_check()

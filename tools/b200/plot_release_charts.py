@@ -76,6 +76,7 @@ def main():
     ap.add_argument("--out", default="profiles/charts")
     ap.add_argument("--system", default="b200_nominal")
     ap.add_argument("--pvr", default=None)
+    ap.add_argument("--bench-glob", default=None, help="e.g. 'profiles/bench_r2_*n?.json'")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     seqs, cps, t, m = cp_sweep(a.system)
@@ -85,9 +86,36 @@ def main():
         bar_chart_svg(f"Llama-3-70B L12 tp2 x cp (a2a), {a.system}: peak memory", [f"seq {s}" for s in seqs], [f"cp{c}" for c in cps], m, "GiB"))
     if a.pvr and os.path.exists(a.pvr):
         rows = json.load(open(a.pvr))["rows"]
+        labels = [str(i + 1) for i in range(len(rows))]
+        wide = max(900, 60 * len(rows))
         open(os.path.join(a.out, "perf_vs_real_time.svg"), "w").write(
-            bar_chart_svg("iteration time: predicted vs measured", [r["case"][:18] for r in rows], ["predicted", "measured"],
-                          [[r["pred_ms"] for r in rows], [r["real_ms"] for r in rows]], "ms"))
+            bar_chart_svg("iteration time: predicted vs measured (row numbers as in perf_vs_real_round2.md)", labels, ["predicted", "measured"],
+                          [[r["pred_ms"] for r in rows], [r["real_ms"] for r in rows]], "ms", width=wide))
+        open(os.path.join(a.out, "perf_vs_real_mem.svg"), "w").write(
+            bar_chart_svg("peak memory: predicted vs measured", labels, ["predicted", "measured"],
+                          [[r["pred_gib"] for r in rows], [r["real_gib"] for r in rows]], "GiB", width=wide))
+        open(os.path.join(a.out, "perf_vs_real_abs_err.svg"), "w").write(
+            bar_chart_svg("|error| of the prediction", labels, ["time", "memory"],
+                          [[abs(r["time_err_pct"]) for r in rows], [abs(r["mem_err_pct"]) for r in rows]], "%", width=wide))
+        with open(os.path.join(a.out, "perf_vs_real_rows.txt"), "w") as f:
+            for i, r in enumerate(rows):
+                f.write(f"{i + 1:2d}  {r['case']}  ({r['world']} GPU, {r['parallelism']})\n")
+    if a.bench_glob:
+        import glob
+        own, ref = {}, {}
+        for fn in sorted(glob.glob(a.bench_glob)):
+            for line in open(fn):
+                if line.startswith("{"):
+                    j = json.loads(line)
+                    (ref if j.get("impl") == "reference" else own)[j["n_gpus"]] = j
+        ns = sorted(set(own) & set(ref)) or sorted(own)
+        if ns:
+            series, vals = ["this repo (device)", "this repo (end to end)"], [[own[n]["value"] for n in ns], [own[n]["e2e"]["value"] for n in ns]]
+            if all(n in ref for n in ns):
+                series.append("library arm (end to end)")
+                vals.append([ref[n]["e2e"]["value"] for n in ns])
+            open(os.path.join(a.out, "bench_scaling.svg"), "w").write(
+                bar_chart_svg("Llama-3-8B seq 4096, tp = N, 8 micro-batches: training tokens/s", [f"N={n}" for n in ns], series, vals, "tokens/s"))
     print("wrote", sorted(os.listdir(a.out)))
 
 
