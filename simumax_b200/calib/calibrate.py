@@ -70,7 +70,8 @@ def plan_requests(param_file: Optional[str] = None, default_sweep: bool = False,
 
 def run_ops(out_path: str, supplement: Optional[str] = None, limit_per_op: Optional[int] = None,
             workloads=None, log=print, allow_shared_gpu: bool = False, sustained_ms: float = 0.0, param_file: Optional[str] = None,
-            default_sweep: bool = False, cache_mode: str = "rebuild", cache_tag: Optional[str] = None) -> dict:
+            default_sweep: bool = False, cache_mode: str = "rebuild", cache_tag: Optional[str] = None,
+            library_column: bool = False) -> dict:
     """GPU part: returns {"ops": {op: {key: {...}}}, "bandwidth": {...}, "meta": {...}}.  ``sustained_ms`` > 0 times every op
     at the steady (power-capped) clock instead of the boost clock of a short burst -- see ``measure._time``.
 
@@ -82,6 +83,7 @@ def run_ops(out_path: str, supplement: Optional[str] = None, limit_per_op: Optio
     assert cache_mode in ("supplement", "rebuild"), f"unsupported cache mode {cache_mode}"
     if sustained_ms > 0:
         measure.SUSTAINED_MS = float(sustained_ms)
+    measure.LIBRARY_COLUMN = bool(library_column)
     others = foreign_gpu_processes(torch.cuda.current_device())
     if others and not allow_shared_gpu:
         raise RuntimeError(f"GPU is in use by other processes {others}; calibrate on an idle GPU (or pass --allow-shared-gpu)")
@@ -107,6 +109,11 @@ def run_ops(out_path: str, supplement: Optional[str] = None, limit_per_op: Optio
         merged = dict(table)
         merged.update(ops.get(op, {}))
         ops[op] = merged
+    vs = [m["vs_cublas"] for m in ops.get("matmul", {}).values() if "vs_cublas" in m]
+    if vs:
+        vs.sort()
+        log(f"[calib] matmul vs cuBLAS on the same operands ({len(vs)} keys): >= 1.0 on {sum(v >= 1.0 for v in vs)}, >= 0.95 on "
+            f"{sum(v >= 0.95 for v in vs)}; min {vs[0]:.3f} median {vs[len(vs) // 2]:.3f} max {vs[-1]:.3f}")
     bw = measure.measure_bandwidth_ops()
     for name, rec in bw.items():
         log(f"[calib] bandwidth {name:12s} {rec['gbs']:8.1f} GB/s")
@@ -187,6 +194,8 @@ def main(argv=None):
     o.add_argument("--default-sweep", action="store_true", help="add the built-in zoo sweep (~800 GEMM / 35 attention / 96 grouped keys)")
     o.add_argument("--cache-mode", default="rebuild", choices=["supplement", "rebuild"])
     o.add_argument("--cache-tag", default=None, help="cache namespace: results go to <out stem>_<tag>.json")
+    o.add_argument("--library-column", action="store_true", help="also time cuBLAS (torch.matmul) on the same operands for every bf16 GEMM "
+                   "key and report the ratio (cublas_ms / cublas_tflops / vs_cublas in the ops file)")
     o.add_argument("--sustained-ms", type=float, default=0.0,
                    help="pre-heat every op for this much device time and time it over windows of a third of it (steady clock)")
     m = sub.add_parser("merge", help="write the system config (no GPU needed)")
@@ -204,7 +213,8 @@ def main(argv=None):
     a = ap.parse_args(argv)
     if a.cmd == "ops":
         run_ops(a.out, a.supplement, a.limit_per_op, allow_shared_gpu=a.allow_shared_gpu, sustained_ms=a.sustained_ms,
-                param_file=a.param_file, default_sweep=a.default_sweep, cache_mode=a.cache_mode, cache_tag=a.cache_tag)
+                param_file=a.param_file, default_sweep=a.default_sweep, cache_mode=a.cache_mode, cache_tag=a.cache_tag,
+                library_column=a.library_column)
     elif a.cmd == "merge":
         sysj = merge(a.ops, a.coll, a.out, a.base, a.name, a.coll_impl, a.measured_peaks, a.refit_defaults)
         print(f"wrote {a.out}: " + ", ".join(f"{op}:{len(v.get('accurate_efficient_factor') or {})}" for op, v in sysj["accelerator"]["op"].items()))

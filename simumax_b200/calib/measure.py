@@ -23,6 +23,7 @@ L2_BYTES = 126 * 1024 * 1024
 
 
 SUSTAINED_MS = float(__import__("os").environ.get("SMX_CALIB_SUSTAINED_MS", "0"))
+LIBRARY_COLUMN = False          # CLI ``ops --library-column``: time cuBLAS (torch.matmul) on the same operands next to every bf16 GEMM key
 
 
 def _time(fn: Callable[[int], None], iters: int = 8, warmup: int = 3) -> float:
@@ -94,7 +95,25 @@ def measure_matmul(req: ShapeRequest, fp8: bool = False) -> Dict[str, float]:
     Cs = [torch.zeros(m_eff, n, device="cuda", dtype=out_dtype) for _ in range(ring)]
     ms = _time(lambda i: gemm(As[i % ring], Bs[i % ring], layout, out=Cs[i % ring], accumulate=acc))
     flops = 2.0 * m_eff * n * k_eff
-    return {"ms": ms, "tflops": flops / ms / 1e9, "flops": flops}
+    res = {"ms": ms, "tflops": flops / ms / 1e9, "flops": flops}
+    if LIBRARY_COLUMN and not fp8:
+        lib_ms = _time(lambda i: _library_gemm(As[i % ring], Bs[i % ring], layout, Cs[i % ring], acc))
+        res.update(cublas_ms=lib_ms, cublas_tflops=flops / lib_ms / 1e9, vs_cublas=lib_ms / ms)
+    return res
+
+
+def _library_gemm(a, b, layout, c, accumulate):
+    """The same product through cuBLAS as stock PyTorch issues it (the bar the sweep reports against): bf16 outputs write ``c``
+    directly; fp32 outputs use the mixed-precision ``mm(out_dtype=fp32)`` and, when accumulating, one ``add_`` (what a library
+    main-grad wgrad without a fused accumulate costs)."""
+    x = a.t() if layout in ("NT", "TT") else a
+    y = b.t() if layout in ("TN", "TT") else b
+    if c.dtype == torch.bfloat16 and not accumulate:
+        return torch.matmul(x, y, out=c)
+    if c.dtype == torch.bfloat16:
+        return c.addmm_(x, y)
+    t = torch.mm(x, y, out_dtype=torch.float32)
+    return c.add_(t) if accumulate else c.copy_(t)
 
 
 def measure_matmul_mxfp8(req: ShapeRequest) -> Dict[str, float]:

@@ -31,6 +31,13 @@ from typing import Any, Dict, List, Optional, Union
 ENABLE_SIMU_GRAPH = int(os.environ.get("ENABLE_SIMU_GRAPH", "0"))
 SIMU_CHECK = int(os.environ.get("SIMU_CHECK", "0"))
 SIMU_DEBUG = int(os.environ.get("SIMU_DEBUG", "0"))
+
+
+def debug_trace(msg: str) -> None:
+    """``SIMU_DEBUG=1``: one line per cost-model decision (efficiency-table hit / miss, memory-bandwidth entry used, every
+    collective's effective bandwidth + latency, model-flops breakdown).  (reference core/config.py:18,845-873,1013,1149)"""
+    if SIMU_DEBUG:
+        print(f"[simu-debug] {msg}")
 _TMP_OVERRIDE = os.environ.get("SIMUMAX_TMP_PATH", "").strip()
 if _TMP_OVERRIDE:
     TMP_PATH = _TMP_OVERRIDE
@@ -687,9 +694,11 @@ class SystemConfig(Config):
         if table is not None and table.get(shape_desc) is not None:
             eff = table[shape_desc]
             self.record_hit_efficiency(op_name, flops, shape_desc, eff)
+            debug_trace(f"{op_name} [{shape_desc}] table hit: efficiency {eff:.4f}, flops {flops:.4g}")
         else:
             eff = op.efficient_factor
             self.record_miss_efficiency(op_name, flops, shape_desc, eff)
+            debug_trace(f"{op_name} [{shape_desc}] table MISS: fallback efficiency {eff:.4f}, flops {flops:.4g}")
         return op, eff
 
     def compute_op_accuracy_time(self, op_name: str, flops, shape_desc: str, reture_detail: bool = False):
@@ -707,6 +716,9 @@ class SystemConfig(Config):
     # ---- primitive 2: memory-bound time
     def compute_mem_access_time(self, op_name, mem_bytes, reture_detail: bool = False):
         bw = self.accelerator.bandwidth.get(op_name) or self.accelerator.bandwidth.get("default")
+        if SIMU_DEBUG and mem_bytes and op_name != "default":
+            own = op_name in self.accelerator.bandwidth
+            debug_trace(f"memory-bound {op_name}: {'own' if own else 'default'} bandwidth entry, efficiency {bw.efficient_factor:.3f}, {mem_bytes:.4g} B")
         t = mem_bytes / (bw.gbps * GIB * bw.efficient_factor) * 1e3 + bw.latency_us / 1e3
         if mem_bytes == 0:
             t = 0
@@ -771,6 +783,8 @@ class SystemConfig(Config):
         if self.num_per_node == 8 and op_name in ("all_reduce", "all_gather", "reduce_scatter", "all2all"):
             latency = base_latency * (comm_num + offset) * scale
         t = wire_bytes / (bw * GIB * eff) * 1e3 + (latency + fixed_latency) / 1e3
+        debug_trace(f"{op_name} x{comm_num} on {net} ({comm_stage}): {size:.4g} B -> wire {wire_bytes:.4g} B at {bw * eff:.1f} GiB/s "
+                    f"+ {latency:.1f} us + fixed {fixed_latency:.1f} us = {t * 1e3:.1f} us")
         self.record_net_bw(op_name, net, comm_num, comm_stage, net_data.bandwidth.gbps, bw * eff, eff, t * 1e3,
                            wire_bytes, latency)
         return t
@@ -917,13 +931,18 @@ class ModelConfig(Config):
         attn_matmul = 3 * 2 * L * (self.qkv_proj_elements + self.attn_proj_elements)
         mlp_matmul = 3 * 2 * L * self.mlp_elements * factor
         total += attn_matmul + mlp_matmul
+        attn_sdp = 0
         if with_attn:
             if self.attention_type == "mla":
-                total += 6 * L * (context_seq_len * (self.qk_head_dim + self.qk_pos_emb_head_dim) * self.head_num
-                                  + context_seq_len * self.v_head_dim * self.head_num)
+                attn_sdp = 6 * L * (context_seq_len * (self.qk_head_dim + self.qk_pos_emb_head_dim) * self.head_num
+                                    + context_seq_len * self.v_head_dim * self.head_num)
             else:
-                total += 6 * L * (2 * context_seq_len * self.hidden_size)
-        total += 6 * (self.hidden_size * self.vocab_size)
+                attn_sdp = 6 * L * (2 * context_seq_len * self.hidden_size)
+            total += attn_sdp
+        head = 6 * (self.hidden_size * self.vocab_size)
+        debug_trace(f"model flops / token: per layer attention GEMMs {attn_matmul / L:.4g}, MLP {mlp_matmul / L:.4g}, "
+                    f"core attention {attn_sdp / L:.4g}; LM head {head:.4g}")
+        total += head
         return total
 
     def sanity_check(self) -> None:

@@ -131,3 +131,19 @@ def test_mxfp8_recipe_prices_linears_from_its_own_table(tmp_path):
         st = StrategyConfig.init_from_config_file(get_simu_strategy_config("tp1_pp1_dp8_mbs1"))
         st.fp8_recipe = "nvfp4"
         st.sanity_check()
+
+
+def test_simu_debug_traces_cost_model_decisions():
+    """SIMU_DEBUG=1 prints one line per efficiency lookup / collective / flops breakdown; nothing without it."""
+    code = ("import warnings; warnings.filterwarnings('ignore'); from simumax_b200 import PerfLLM; "
+            "from simumax_b200.configs import get_simu_model_config as m, get_simu_strategy_config as s, get_simu_system_config as y; "
+            "p = PerfLLM(); p.configure(strategy_config=s('tp2_pp1_dp4_mbs1'), model_config=m('llama3-8b'), system_config=y('b200_nominal')); "
+            "p.run_estimate(); p.analysis_cost()")
+    outs = {}
+    for flag in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, SIMU_DEBUG=flag), capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[flag] = [l for l in r.stdout.splitlines() if l.startswith("[simu-debug]")]
+    assert not outs["0"]
+    text = "\n".join(outs["1"])
+    assert "table MISS" in text and "all_gather x2 on high_intra_node" in text and "model flops / token" in text
