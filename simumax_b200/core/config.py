@@ -694,11 +694,13 @@ class SystemConfig(Config):
         if table is not None and table.get(shape_desc) is not None:
             eff = table[shape_desc]
             self.record_hit_efficiency(op_name, flops, shape_desc, eff)
-            debug_trace(f"{op_name} [{shape_desc}] table hit: efficiency {eff:.4f}, flops {flops:.4g}")
+            if SIMU_DEBUG:
+                debug_trace(f"{op_name} [{shape_desc}] table hit: efficiency {eff:.4f}, flops {flops:.4g}")
         else:
             eff = op.efficient_factor
             self.record_miss_efficiency(op_name, flops, shape_desc, eff)
-            debug_trace(f"{op_name} [{shape_desc}] table MISS: fallback efficiency {eff:.4f}, flops {flops:.4g}")
+            if SIMU_DEBUG:
+                debug_trace(f"{op_name} [{shape_desc}] table MISS: fallback efficiency {eff:.4f}, flops {flops:.4g}")
         return op, eff
 
     def compute_op_accuracy_time(self, op_name: str, flops, shape_desc: str, reture_detail: bool = False):
@@ -718,7 +720,8 @@ class SystemConfig(Config):
         bw = self.accelerator.bandwidth.get(op_name) or self.accelerator.bandwidth.get("default")
         if SIMU_DEBUG and mem_bytes and op_name != "default":
             own = op_name in self.accelerator.bandwidth
-            debug_trace(f"memory-bound {op_name}: {'own' if own else 'default'} bandwidth entry, efficiency {bw.efficient_factor:.3f}, {mem_bytes:.4g} B")
+            if SIMU_DEBUG:
+                debug_trace(f"memory-bound {op_name}: {'own' if own else 'default'} bandwidth entry, efficiency {bw.efficient_factor:.3f}, {mem_bytes:.4g} B")
         t = mem_bytes / (bw.gbps * GIB * bw.efficient_factor) * 1e3 + bw.latency_us / 1e3
         if mem_bytes == 0:
             t = 0
@@ -783,7 +786,8 @@ class SystemConfig(Config):
         if self.num_per_node == 8 and op_name in ("all_reduce", "all_gather", "reduce_scatter", "all2all"):
             latency = base_latency * (comm_num + offset) * scale
         t = wire_bytes / (bw * GIB * eff) * 1e3 + (latency + fixed_latency) / 1e3
-        debug_trace(f"{op_name} x{comm_num} on {net} ({comm_stage}): {size:.4g} B -> wire {wire_bytes:.4g} B at {bw * eff:.1f} GiB/s "
+        if SIMU_DEBUG:
+            debug_trace(f"{op_name} x{comm_num} on {net} ({comm_stage}): {size:.4g} B -> wire {wire_bytes:.4g} B at {bw * eff:.1f} GiB/s "
                     f"+ {latency:.1f} us + fixed {fixed_latency:.1f} us = {t * 1e3:.1f} us")
         self.record_net_bw(op_name, net, comm_num, comm_stage, net_data.bandwidth.gbps, bw * eff, eff, t * 1e3,
                            wire_bytes, latency)
@@ -940,7 +944,8 @@ class ModelConfig(Config):
                 attn_sdp = 6 * L * (2 * context_seq_len * self.hidden_size)
             total += attn_sdp
         head = 6 * (self.hidden_size * self.vocab_size)
-        debug_trace(f"model flops / token: per layer attention GEMMs {attn_matmul / L:.4g}, MLP {mlp_matmul / L:.4g}, "
+        if SIMU_DEBUG:
+            debug_trace(f"model flops / token: per layer attention GEMMs {attn_matmul / L:.4g}, MLP {mlp_matmul / L:.4g}, "
                     f"core attention {attn_sdp / L:.4g}; LM head {head:.4g}")
         total += head
         return total

@@ -17,7 +17,7 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Tuple
 
-from .config import StrategyConfig, SystemConfig, debug_trace
+from .config import SIMU_DEBUG, StrategyConfig, SystemConfig, debug_trace
 from .records import ActivationInfo, ComputeInfo, CostInfo, MemoryInfo, RecomputeStatus
 
 PHASES = ("fwd", "bwd_grad_act", "bwd_grad_w")
@@ -146,7 +146,8 @@ def evaluate(node: OpNode, system: SystemConfig) -> OpNode:
         cost.recompute_net_time = 0
         cost.recompute_net_exposed_time = 0
         if node.enable_recompute:
-            debug_trace(f"{node.path()}: tail of a recompute segment, its forward is not re-run (no recompute flops / bytes / collectives)")
+            if SIMU_DEBUG:
+                debug_trace(f"{node.path}: tail of a recompute segment, its forward is not re-run (no recompute flops / bytes / collectives)")
 
     launch_ms = getattr(system.accelerator, "kernel_launch_overhead_us", 0.0) / 1e3
 

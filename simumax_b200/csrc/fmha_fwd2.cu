@@ -18,6 +18,11 @@
 //   each) with SMX_FMHA_SPLIT=2, or 4 per tile with one row per thread (default: measured 6 % faster).
 //   MMA order per key block j:  P0_j V_j -> Q0 K_{j+1}^T -> P1_j V_j -> Q1 K_{j+1}^T   (tcgen05.mma executes in issue order, so S_t
 //   may be overwritten by the next Q K^T right behind the P V that read P_t out of it).
+//
+// Tried and removed (round 2): double-buffering S per tile so that Q K_{j+1}^T no longer waits for softmax_j.  TMEM has no room for
+// four 128-column S buffers next to two O accumulators, so the variant produced scores in 64-key half blocks; N = 64 Q K^T MMAs
+// are shared-memory-bandwidth bound and the MMA issuer's period per 128 keys went from 3572 to 4594 clk (638 vs 816 TF at S 4096).
+// The in-kernel %clock trace (tools/fmha_fwd_trace.py) of this kernel: softmax 1886 + hand-offs 550 + MMAs 1040 per tile and block.
 #include "sm100_common.cuh"
 
 namespace smx {
@@ -426,326 +431,6 @@ fmha_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 }
 
-// ======================================================================================================================
-// Generation 3: the same two-tile CTA, but the scores are produced in 64-key half blocks into TWO S buffers per query tile
-// (TMEM: S[t][b] 4 x 64 columns | O0 | O1), so Q K^T of half block h + 2 is issued right behind P V of half block h and
-// the tensor core always has the next scores ready: the softmax of a tile no longer waits for "its" MMA (the generation-2
-// profile showed the softmax warps 34 % of their time waiting for S and the tensor pipe 36 % active).  The price is N = 64
-// Q K^T MMAs, which are shared-memory-bandwidth bound (48 instead of 32 clk per K step).
-// ======================================================================================================================
-constexpr int kF3HB = 64;     // keys per half block
-
-template <int CLUSTER>
-__global__ void __launch_bounds__(f2_threads<1>(), 1)
-fmha_fwd3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                 const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ o_ptr, float* __restrict__ lse_ptr,
-                 const Fmha2Params p) {
-  constexpr int BQ = kF2BlockQ, BKV = kF2BlockKV, D = kF2D, HB = kF3HB;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw;
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kF2Tiles * kF2TileBytes;
-  uint8_t* sV = sK + kF2Stages * kF2TileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kF2Stages * kF2TileBytes);
-  uint64_t* q_full = bars;                    // 1
-  uint64_t* k_full = bars + 1;                // [stages]
-  uint64_t* k_empty = k_full + kF2Stages;
-  uint64_t* v_full = k_empty + kF2Stages;
-  uint64_t* v_empty = v_full + kF2Stages;
-  uint64_t* s_full = v_empty + kF2Stages;     // [tiles][2]
-  uint64_t* p_full = s_full + 4;              // [tiles][2]
-  uint64_t* o_done = p_full + 4;              // [tiles]
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(o_done + kF2Tiles);
-
-  const int warp_idx = threadIdx.x / 32;
-  const int lane = threadIdx.x % 32;
-  const uint32_t cta_rank = CLUSTER > 1 ? cluster_ctarank() : 0;
-  const int q_tile = (int)gridDim.x - 1 - (int)blockIdx.x;
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
-  const int kv_head = head / (p.H / p.H_kv);
-  const int q0 = q_tile * (BQ * kF2Tiles);
-  const int causal_shift = p.S_kv - p.S_q;
-  int nh[kF2Tiles];                            // half blocks per tile
-#pragma unroll
-  for (int t = 0; t < kF2Tiles; ++t) {
-    const int qt0 = q0 + t * BQ;
-    int kv_end = p.S_kv;
-    if (p.causal) kv_end = min(p.S_kv, qt0 + BQ + causal_shift);
-    nh[t] = (qt0 < p.S_q && kv_end > 0) ? (kv_end + HB - 1) / HB : 0;
-  }
-  const int nh_max = max(nh[0], nh[1]);
-  const int n_blocks = (nh_max + 1) / 2;       // 128-key K / V blocks to load
-
-  if (warp_idx == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_v);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < kF2Stages; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], CLUSTER);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], CLUSTER);
-    }
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
-    }
-    for (int t = 0; t < kF2Tiles; ++t) mbar_init(&o_done[t], 1);
-    fence_barrier_init();
-  }
-  if (warp_idx == 1) tmem_alloc<1>(tmem_base_ptr, 512);
-  tcgen05_fence_before();
-  if constexpr (CLUSTER > 1) cluster_sync_all();
-  else __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_base_ptr;
-
-  if (warp_idx == 0) {
-    // ============================ TMA producer (as in generation 2) ============================
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kF2Tiles * kF2TileBytes);
-#pragma unroll
-      for (int t = 0; t < kF2Tiles; ++t)
-#pragma unroll
-        for (int c = 0; c < D / 64; ++c)
-          tma_load_4d_f2(&tmap_q, q_full, sQ + t * kF2TileBytes + c * (BQ * 128), c * 64, q0 + t * BQ, head, batch);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_blocks; ++j) {
-        const int k0 = j * BKV;
-        mbar_wait(&k_empty[stage], phase ^ 1, 1);
-        mbar_arrive_expect_tx(&k_full[stage], kF2TileBytes);
-        if constexpr (CLUSTER > 1) {
-          const int c = cta_rank;
-          tma_load_4d_mc(&tmap_k, &k_full[stage], sK + stage * kF2TileBytes + c * (BKV * 128), c * 64, k0, kv_head, batch, 3);
-        } else {
-#pragma unroll
-          for (int c = 0; c < D / 64; ++c)
-            tma_load_4d_f2(&tmap_k, &k_full[stage], sK + stage * kF2TileBytes + c * (BKV * 128), c * 64, k0, kv_head, batch);
-        }
-        mbar_wait(&v_empty[stage], phase ^ 1, 2);
-        mbar_arrive_expect_tx(&v_full[stage], kF2TileBytes);
-        if constexpr (CLUSTER > 1) {
-          const int c = cta_rank;
-          tma_load_4d_mc(&tmap_v, &v_full[stage], sV + stage * kF2TileBytes + c * (BKV * 128), c * 64, k0, kv_head, batch, 3);
-        } else {
-#pragma unroll
-          for (int c = 0; c < D / 64; ++c)
-            tma_load_4d_f2(&tmap_v, &v_full[stage], sV + stage * kF2TileBytes + c * (BKV * 128), c * 64, k0, kv_head, batch);
-        }
-        if (++stage == kF2Stages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp_idx == 1) {
-    // ============================ MMA issuer ============================
-    constexpr uint32_t idesc_s = make_idesc(1, 1, 0, 0, BQ, HB);    // Q (K-major smem) x K half block (K-major smem) -> S[128, 64]
-    constexpr uint32_t idesc_o = make_idesc(1, 1, 0, 1, BQ, D);     // P (TMEM) x V half block (MN-major smem) -> O[128, 128]
-    const uint64_t kQ_km = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
-    const uint64_t kK_km = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
-    const uint64_t kV_mn = make_smem_desc_sw128(smem_u32(sV), BKV * 128, 1024);
-    constexpr uint64_t kTileStep = kF2TileBytes >> 4;
-    constexpr uint64_t kHalfStep = (HB * 128) >> 4;                 // 64 key rows of 128 B inside a 64-column chunk
-    auto release = [&](uint64_t* bar) {
-      if constexpr (CLUSTER > 1)
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-                     "h"(static_cast<uint16_t>(3))
-                     : "memory");
-      else
-        umma_commit<1>(bar);
-    };
-    // block kb (128 keys) is used by half blocks 2 kb and 2 kb + 1 of every tile that reaches them, in the issue order
-    // (h, t) = (2kb, 0), (2kb, 1), (2kb + 1, 0), (2kb + 1, 1); true when (t, h) is the last of them
-    auto last_user = [&](int t, int h) {
-      for (int t2 = t + 1; t2 < kF2Tiles; ++t2)
-        if (h < nh[t2]) return false;
-      if ((h & 1) == 0)
-        for (int t2 = 0; t2 < kF2Tiles; ++t2)
-          if (h + 1 < nh[t2]) return false;
-      return true;
-    };
-    int k_ready_block = -1, v_ready_block = -1;          // highest K / V block whose full barrier has been waited on
-    auto need_k = [&](int kb) {
-      if (kb > k_ready_block) {
-        mbar_wait(&k_full[kb & 1], (kb >> 1) & 1, 4);
-        k_ready_block = kb;
-      }
-    };
-    auto need_v = [&](int vb) {
-      if (vb > v_ready_block) {
-        mbar_wait(&v_full[vb & 1], (vb >> 1) & 1, 6);
-        v_ready_block = vb;
-      }
-    };
-    auto issue_s = [&](int t, int h) {         // S[t][h & 1] = Q_t K_h^T
-      need_k(h >> 1);
-      tcgen05_fence_after();
-      if (elect_one()) {
-        const uint64_t a0 = kQ_km + t * kTileStep;
-        const uint64_t b0 = kK_km + ((h >> 1) & 1) * kTileStep + (h & 1) * kHalfStep;
-        const uint32_t d = tmem_base + (t * 2 + (h & 1)) * HB;
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k)
-          umma_f16<1>(d, a0 + ((k / 4) * ((BQ * 128) >> 4) + (k % 4) * 2), b0 + ((k / 4) * ((BKV * 128) >> 4) + (k % 4) * 2), idesc_s,
-                      k > 0 ? 1u : 0u);
-        umma_commit<1>(&s_full[t * 2 + (h & 1)]);
-        if (last_user(t, h)) release(&k_empty[(h >> 1) & 1]);
-      }
-      __syncwarp();
-    };
-    auto issue_pv = [&](int t, int h) {        // O_t (+)= P[t][h & 1] V_h
-      need_v(h >> 1);
-      tcgen05_fence_after();
-      if (elect_one()) {
-        const uint64_t b0 = kV_mn + ((h >> 1) & 1) * kTileStep + (h & 1) * kHalfStep;
-        const uint32_t a = tmem_base + (t * 2 + (h & 1)) * HB;
-#pragma unroll
-        for (int k = 0; k < HB / 16; ++k)       // 16 keys = 8 packed TMEM columns of P per K step
-          umma_f16_ts(tmem_base + 256 + t * 128, a + k * 8, b0 + k * ((16 * 128) >> 4), idesc_o, (h > 0 || k > 0) ? 1u : 0u);
-        umma_commit<1>(&o_done[t]);
-        if (last_user(t, h)) release(&v_empty[(h >> 1) & 1]);
-      }
-      __syncwarp();
-    };
-    mbar_wait(q_full, 0, 3);
-    for (int h = 0; h < 2; ++h)
-      for (int t = 0; t < kF2Tiles; ++t)
-        if (h < nh[t]) issue_s(t, h);
-    for (int h = 0; h < nh_max; ++h) {
-      for (int t = 0; t < kF2Tiles; ++t) {
-        if (h >= nh[t]) continue;
-        mbar_wait(&p_full[t * 2 + (h & 1)], (h >> 1) & 1, 5);
-        F2_TRACE(0, h, 0 + t * 4);
-        issue_pv(t, h);
-        F2_TRACE(0, h, 2 + t * 4);
-        if (h + 2 < nh[t]) issue_s(t, h + 2);
-        F2_TRACE(0, h, 3 + t * 4);
-      }
-    }
-  } else if (warp_idx >= kF2FirstSoftmaxWarp) {
-    // ============================ softmax + epilogue: one query row per thread, 64 scores per half block ============================
-    const int sw = warp_idx - kF2FirstSoftmaxWarp;
-    const int t = sw / 4;
-    const int q = warp_idx % 4;
-    const int row_in_tile = q * 32 + lane;
-    const int row = q0 + t * BQ + row_in_tile;
-    const uint32_t lane_addr = uint32_t(q * 32) << 16;
-    const uint32_t tmem_o = tmem_base + 256 + t * 128 + lane_addr;
-    const float c_log2 = p.scale * 1.4426950408889634f;
-    float m_used = -INFINITY;
-    float l = 0.f;
-    const int n_mine = nh[t];
-    const int qt0 = q0 + t * BQ;
-    for (int h = 0; h < n_mine; ++h) {
-      const uint32_t tmem_s = tmem_base + (t * 2 + (h & 1)) * HB + lane_addr;
-      mbar_wait(&s_full[t * 2 + (h & 1)], (h >> 1) & 1, 8);
-      tcgen05_fence_after();
-      if (q == 0) F2_TRACE(1 + t, h, 0);
-      uint32_t r[HB];
-      tmem_ld_32x32b_x32(tmem_s, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-      tmem_ld_32x32b_x32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-      tmem_ld_wait();
-      if (q == 0) F2_TRACE(1 + t, h, 1);
-      const int k0 = h * HB;
-      const bool need_mask = (p.causal && (k0 + HB - 1 > qt0 + causal_shift)) || (k0 + HB > p.S_kv);
-      if (need_mask) {
-        const int limit = p.causal ? min(row + causal_shift, p.S_kv - 1) : p.S_kv - 1;
-#pragma unroll
-        for (int i = 0; i < HB; ++i)
-          if (k0 + i > limit) r[i] = 0xff800000u;
-      }
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int i = 0; i < HB; i += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) mx4[u] = fmaxf(mx4[u], __uint_as_float(r[i + u]));
-      }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      float m_new = m_used;
-      const bool grow = (mx > m_used) && ((mx - m_used) * c_log2 > 8.f || m_used == -INFINITY);
-      if (grow) m_new = mx;
-      const bool any_grow = __any_sync(0xffffffffu, grow);
-      if (any_grow && h > 0) {
-        mbar_wait(&o_done[t], (h - 1) & 1, 9);
-        tcgen05_fence_after();
-        const float alpha = (m_used == -INFINITY) ? 0.f : exp2f((m_used - m_new) * c_log2);
-#pragma unroll 1
-        for (int c = 0; c < D / 16; ++c) {
-          uint32_t o[16];
-          tmem_ld_32x32b_x16(tmem_o + c * 16, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32b_x16(tmem_o + c * 16, o);
-        }
-        tmem_st_wait();
-        l *= alpha;
-      }
-      m_used = m_new;
-      if (q == 0) F2_TRACE(1 + t, h, 2);
-      const float mc = (m_used == -INFINITY) ? 0.f : m_used * c_log2;
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < HB / 2; ++c) {
-        const float e0 = exp2f(fmaf(__uint_as_float(r[2 * c]), c_log2, -mc));
-        const float e1 = exp2f(fmaf(__uint_as_float(r[2 * c + 1]), c_log2, -mc));
-        sum4[c & 3] += e0 + e1;
-        r[c] = pack_bf16x2(e0, e1);
-      }
-      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      if (q == 0) F2_TRACE(1 + t, h, 3);
-      tmem_st_32x32b_x16(tmem_s, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-      tmem_st_32x32b_x16(tmem_s + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
-      tmem_st_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t * 2 + (h & 1)]);
-      if (q == 0) F2_TRACE(1 + t, h, 4);
-    }
-    if (n_mine > 0) {
-      mbar_wait(&o_done[t], (n_mine - 1) & 1, 10);
-      tcgen05_fence_after();
-    }
-    const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
-    const bool row_ok = row < p.S_q;
-    __nv_bfloat16* orow = o_ptr + batch * p.o_stride_b + (long long)(row_ok ? row : 0) * p.o_stride_s + head * p.o_stride_h;
-#pragma unroll 1
-    for (int c = 0; c < D / 32; ++c) {
-      uint32_t o[32];
-      if (n_mine > 0) {
-        tmem_ld_32x32b_x32(tmem_o + c * 32, o);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0u;
-      }
-      if (row_ok) {
-        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(o[8 * i]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
-          v.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
-          v.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
-          v.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
-          dst[i] = v;
-        }
-      }
-    }
-    if (row_ok && lse_ptr)
-      lse_ptr[batch * p.lse_stride_b + head * p.lse_stride_h + row] = (l > 0.f) ? m_used * p.scale + __logf(l) : -INFINITY;
-  }
-
-  tcgen05_fence_before();
-  if constexpr (CLUSTER > 1) cluster_sync_all();
-  else __syncthreads();
-  if (warp_idx == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc<1>(tmem_base, 512);
-  }
-}
-
 inline int make_tmap_4d_f2(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
                            uint64_t s1_bytes, uint64_t s2_bytes, uint64_t s3_bytes, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
@@ -773,32 +458,6 @@ int launch_fmha_fwd2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((p.S_q + kF2BlockQ * kF2Tiles - 1) / (kF2BlockQ * kF2Tiles), p.H, p.B);
   cfg.blockDim = dim3(f2_threads<SPLIT>());
-  cfg.dynamicSmemBytes = kF2SmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = CLUSTER;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(o), lse, p);
-  return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
-}
-
-template <int CLUSTER>
-int launch_fmha_fwd3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, void* o, float* lse,
-                     const Fmha2Params& p, cudaStream_t stream) {
-  auto kern = fmha_fwd3_kernel<CLUSTER>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kF2SmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((p.S_q + kF2BlockQ * kF2Tiles - 1) / (kF2BlockQ * kF2Tiles), p.H, p.B);
-  cfg.blockDim = dim3(f2_threads<1>());
   cfg.dynamicSmemBytes = kF2SmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -840,8 +499,6 @@ int smx_fmha_fwd2(const void* q, const void* k, const void* v, void* o, float* l
   p.lse_stride_b = (long long)H * S_q; p.lse_stride_h = S_q;
   p.trace = reinterpret_cast<unsigned int*>(trace);
   static const int split = [] { const char* e = getenv("SMX_FMHA_SPLIT"); return (e && e[0] == '2') ? 2 : 1; }();
-  static const int gen = [] { const char* e = getenv("SMX_FMHA_GEN"); return e ? atoi(e) : 2; }();
-  if (gen == 3) return cluster == 2 ? smx::launch_fmha_fwd3<2>(tq, tk, tv, o, lse, p, stream) : smx::launch_fmha_fwd3<1>(tq, tk, tv, o, lse, p, stream);
   static const int diag = [] { const char* e = getenv("SMX_FMHA_DIAG"); return e ? atoi(e) : 0; }();
   if (diag == 1) return smx::launch_fmha_fwd2<1, 1, 1>(tq, tk, tv, o, lse, p, stream);
   if (diag == 2) return smx::launch_fmha_fwd2<1, 1, 2>(tq, tk, tv, o, lse, p, stream);

@@ -547,8 +547,13 @@ int smx_gemm_2cta(const void* A, const void* B, void* C, int G, int M, int N, in
   p.G = G; p.M = M; p.N = N; p.K = K;
   p.m_tiles = (M + smx::k2BlockM - 1) / smx::k2BlockM;
   p.n_tiles = (N + smx::k2BlockN - 1) / smx::k2BlockN;
-  static const int red_mode = [] { const char* e = getenv("SMX_GEMM_RED"); return (e && e[0] == '0') ? 0 : 1; }();     // default on: +16 ... +90 % on the fp32-accumulating wgrads
-  p.ldc = ldc; p.c_batch_stride = c_bs; p.alpha = alpha; p.accumulate = (accumulate && out_f32 && red_mode) ? 2 : accumulate;
+  // fp32 accumulate-into-C epilogue: read-modify-write (mode 1) or red.global.add.v4.f32 (mode 2).  Sustained-clock sweep over 255
+  // wgrad shapes (profiles/calib_ops_v8_red_epilogue.json vs v7): RED wins +7 ... +28 % while the output is <= 16 MiB, is neutral
+  // up to 32 MiB and loses ~7 % above 128 MiB, so the default picks by output size.  SMX_GEMM_RED=0 / 1 forces one of them.
+  static const int red_mode = [] { const char* e = getenv("SMX_GEMM_RED"); return !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2)); }();
+  static const long long red_max_bytes = [] { const char* e = getenv("SMX_GEMM_RED_MAX_MIB"); return (long long)(e ? atoi(e) : 32) << 20; }();
+  const bool use_red = red_mode == 1 || (red_mode == 2 && (long long)G * M * N * 4 <= red_max_bytes);
+  p.ldc = ldc; p.c_batch_stride = c_bs; p.alpha = alpha; p.accumulate = (accumulate && out_f32 && use_red) ? 2 : accumulate;
   p.ag_flags = armed_flags; p.ag_rows_per_flag = armed_rows; p.ag_first_m_blk = armed_first; p.ag_epoch = armed_epoch;
   p.rs_world = 1; p.rs_rank = 0; p.rs_rows = M;
   for (int i = 0; i < 8; ++i) p.rs_counter[i] = nullptr;
