@@ -547,10 +547,13 @@ int smx_gemm_2cta(const void* A, const void* B, void* C, int G, int M, int N, in
   p.G = G; p.M = M; p.N = N; p.K = K;
   p.m_tiles = (M + smx::k2BlockM - 1) / smx::k2BlockM;
   p.n_tiles = (N + smx::k2BlockN - 1) / smx::k2BlockN;
-  // fp32 accumulate-into-C epilogue: read-modify-write (mode 1) or red.global.add.v4.f32 (mode 2).  Sustained-clock sweep over 255
-  // wgrad shapes (profiles/calib_ops_v8_red_epilogue.json vs v7): RED wins +7 ... +28 % while the output is <= 16 MiB, is neutral
-  // up to 32 MiB and loses ~7 % above 128 MiB, so the default picks by output size.  SMX_GEMM_RED=0 / 1 forces one of them.
-  static const int red_mode = [] { const char* e = getenv("SMX_GEMM_RED"); return !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2)); }();
+  // fp32 accumulate-into-C epilogue: read-modify-write (p.accumulate = 1) or red.global.add.v4.f32 (p.accumulate = 2).
+  // Whole-step A/B on one box (Llama-3-8B, 8 x 4096 tokens, profiles/final_bench_n1_red{0,1}.json): 1608.6 ms with the read-modify-write
+  // epilogue, 1522.1 ms with RED (+5.7 %), so RED is the default.  Op by op at its own sustained, power-capped clock the picture is
+  // mixed (profiles/calib_ops_v8_red_epilogue.json vs v7: RED +7 ... +28 % for outputs <= 16 MiB, -7 % above 128 MiB): the RED epilogue
+  // draws more power, which an isolated sweep charges to the GEMM itself and a real step spreads over the lighter kernels around it.
+  // SMX_GEMM_RED=0 forces read-modify-write, SMX_GEMM_RED=auto picks by output size (<= SMX_GEMM_RED_MAX_MIB, default 32).
+  static const int red_mode = [] { const char* e = getenv("SMX_GEMM_RED"); return !e ? 1 : (e[0] == '0' ? 0 : (e[0] == 'a' ? 2 : 1)); }();
   static const long long red_max_bytes = [] { const char* e = getenv("SMX_GEMM_RED_MAX_MIB"); return (long long)(e ? atoi(e) : 32) << 20; }();
   const bool use_red = red_mode == 1 || (red_mode == 2 && (long long)G * M * N * 4 <= red_max_bytes);
   p.ldc = ldc; p.c_batch_stride = c_bs; p.alpha = alpha; p.accumulate = (accumulate && out_f32 && use_red) ? 2 : accumulate;

@@ -83,6 +83,19 @@ def _tma_ready(t3: torch.Tensor) -> torch.Tensor:
     return buf[:, :, :cols]
 
 
+def _pair_fills_machine(G: int, M: int, N: int, nsm: int) -> bool:
+    """The pair kernel lights up 2 SMs per 256 x 256 tile; when the 128-row kernel would cover twice as many SMs (N = 256 / 512
+    projections, 256-row wgrads) that is worth more than the pair's per-SM advantage.  Sustained-clock A/B on the 16 few-tile keys of
+    the sweep (profiles/gemm_pair_fill_ab.json): single wins +5 ... +29 % where the pair reaches half the CTAs (N = 256 / 512,
+    M = 256), the pair stays 3 - 8 % ahead at two thirds (N = 576 ... 768, M = 768) -- hence the 0.6."""
+    import os
+    if os.environ.get("SMX_GEMM_PAIR_FILL", "1") == "0":          # A/B switch (tools/gemm_pair_fill_ab.py)
+        return True
+    pair_ctas = min(2 * G * -(-M // 256) * -(-N // 256), nsm)
+    single_ctas = min(G * -(-M // 128) * -(-N // 128), nsm)
+    return pair_ctas >= 0.6 * single_ctas
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, layout: str = "TN", out: torch.Tensor | None = None,
          out_dtype: torch.dtype | None = None, accumulate: bool = False, alpha: float = 1.0,
          block_n: int = 0, sm_limit: int = 0, two_cta: bool | None = None) -> torch.Tensor:
@@ -130,7 +143,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, layout: str = "TN", out: torch.Tensor
         nsm = min(nsm, sm_limit)
     if two_cta is None:
         two_cta = _two_cta_default()
-    if two_cta and dtype == 0 and M >= 256 and N >= 256 and block_n == 0 and _pair_tiles_pay(M):
+    if two_cta and dtype == 0 and M >= 256 and N >= 256 and block_n == 0 and _pair_tiles_pay(M) and _pair_fills_machine(G, M, N, nsm):
         # CTA-pair kernel (csrc/gemm_2cta.cu): 256 x 256 tiles, B split across the pair
         rc = _fn2()(a3.data_ptr(), b3.data_ptr(), out3.data_ptr(), G, M, N, K, a_mn, b_mn,
                     1 if out3.dtype == torch.float32 else 0, 1 if accumulate else 0, float(alpha),

@@ -18,6 +18,11 @@ if which in ("all", "grouped"):
     gw = torch.zeros(20, 3072, 5120, device="cuda")
     for _ in range(3):
         gemm(x, w, "TN"); gemm(dy, w, "NN"); gemm(dy, x, "NT", out=gw, accumulate=True)
+if which == "wgrad":           # fp32 main-grad accumulation: SMX_GEMM_RED=0 (read-modify-write epilogue) vs 1 (red.global.add.v4.f32)
+    dy, x = R(8192, 28672), R(8192, 4096)
+    gw = torch.zeros(28672, 4096, device="cuda")
+    for _ in range(3):
+        gemm(dy, x, "NT", out=gw, accumulate=True)
 if which in ("all", "mxfp8"):
     a, b = R(8192, 8192), R(8192, 8192)
     (qa, sa), (qb, sb) = mxfp8_quantize(a), mxfp8_quantize(b)
