@@ -15,6 +15,7 @@ from simumax_b200.runtime import cases as C
 ap = argparse.ArgumentParser()
 ap.add_argument("--mbc", type=int, default=2)
 ap.add_argument("--layers", type=int, default=0)
+ap.add_argument("--zoo-case", default=None, help="a case name of tools/b200/perf_vs_real.py::zoo() instead of the primary bench case")
 a = ap.parse_args()
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -22,14 +23,19 @@ world = int(os.environ.get("WORLD_SIZE", "1"))
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank = dist.get_rank() if world > 1 else 0
-case = C.primary_case(world)
-case.mbc = a.mbc
+if a.zoo_case:
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "b200"))
+    import perf_vs_real
+    case = perf_vs_real.zoo()[a.zoo_case]
+else:
+    case = C.primary_case(world)
+    case.mbc = a.mbc
 if a.layers:
     case.layers = a.layers
 mc, dims = C.model_dims(case)
 tr = C.build_trainer(case)
 g = torch.Generator(device="cuda").manual_seed(5)
-T = case.mbs * case.seq
+T = case.mbs * case.seq // case.cp
 batches = [(torch.randint(0, mc.vocab_size, (T,), device="cuda", generator=g), torch.randint(0, mc.vocab_size, (T,), device="cuda", generator=g))
            for _ in range(case.mbc)]
 for _ in range(2):
@@ -54,7 +60,7 @@ if rank == 0:
         print(f"{r['total_us'] / 1e3:9.3f} ms {100 * r['total_us'] / tot:5.1f}%  n={r['count']:5d}  {r['name'][:90]}")
     print(f"sum of kernel time {tot / 1e3:.2f} ms; step (unprofiled, device-timed) {step_ms:.2f} ms; busy fraction {tot / 1e3 / step_ms:.3f}")
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump({"world": world, "case": case.name, "mbc": case.mbc, "layers": dims.layers, "step_ms_unprofiled": step_ms, "kernel_ms_sum": tot / 1e3,
-               "kernels": rows[:60]}, open(f"gpurun_out/step_profile_{world}.json", "w"), indent=1)
+    json.dump({"world": world, "case": case.name, "mbc": case.mbc, "layers": case.layers or dims.layers, "step_ms_unprofiled": step_ms, "kernel_ms_sum": tot / 1e3,
+               "kernels": rows[:60]}, open(f"gpurun_out/step_profile_{world}{'_' + a.zoo_case if a.zoo_case else ''}.json", "w"), indent=1)
 if world > 1:
     dist.destroy_process_group()
