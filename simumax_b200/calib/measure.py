@@ -240,6 +240,21 @@ def measure_bandwidth_ops(hidden: int = 4096, tokens: int = 16384, vocab: int = 
     res["ce_fusion"] = {"gbs": 2 * rows * vocab * 2 / ms / 1e6, "ms": ms}
     ms = _time(lambda i: E.cross_entropy_(lg[i % 2], tgt, write_grad=False))
     res["ce"] = {"gbs": rows * vocab * 2 / ms / 1e6, "ms": ms}
+    del lg, xs, ys, zs, dst
+    # optimizer: grad-norm pass (4 B / parameter) + fused AdamW (reads grad + master / m / v, writes master / m / v + the bf16
+    # parameter, clears the grad: 34 B / parameter) -- long pure streams, faster than the short elementwise kernels above
+    n = 128 << 20
+    master, m_, v_, grad = (torch.zeros(n, device="cuda") for _ in range(4))
+    param = torch.zeros(n, device="cuda", dtype=torch.bfloat16)
+    sq = torch.ones(1, device="cuda")
+    step = [0]
+
+    def opt(i):
+        step[0] += 1
+        E.sqnorm(grad, out=sq)
+        E.adamw_(master, m_, v_, grad, param, 1e-4, 0.9, 0.95, 1e-8, 0.1, step[0], sqnorm_t=sq, max_norm=1.0, zero_grad=True)
+    ms = _time(opt)
+    res["optimizer"] = {"gbs": 38.0 * n / ms / 1e6, "ms": ms}
     return res
 
 

@@ -351,6 +351,9 @@ class PerfLLM(PerfBase):
         if getattr(self.strategy, "fused_optimizer_model", False):
             # this repo's runtime (csrc/elementwise.cu: sqnorm_kernel + adamw_kernel): one pass over the grad shard for the
             # norm, one pass that reads grad + master/m/v and writes master/m/v + the bf16 parameter and clears the grad
+            # priced from the system config's "optimizer" bandwidth entry when it has one (long fp32 streams run closer to the copy
+            # bandwidth than the short elementwise kernels behind "default"; calib.measure.measure_bandwidth_ops)
+            mem = lambda b: self.system.compute_mem_access_time("optimizer", b)
             shard_grads = states / 6 if self.strategy.grad_reduce_in_bf16 else states / 3
             res["l2_norm_after_reduce_time"] = mem(shard_grads)
             res["adam_time"] = mem(shard_grads + states + states + (states / 3) * 0.5 + shard_grads)

@@ -20,9 +20,11 @@ a = ap.parse_args()
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 world = int(os.environ.get("WORLD_SIZE", "1"))
-if world > 1:
+if world > 1 or a.zoo_case:             # DeepSeek / symmetric-memory trainers want a process group even on one GPU
+    if "RANK" not in os.environ:
+        os.environ.update(RANK="0", WORLD_SIZE="1", MASTER_ADDR="127.0.0.1", MASTER_PORT=os.environ.get("MASTER_PORT", "29572"))
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-rank = dist.get_rank() if world > 1 else 0
+rank = dist.get_rank() if dist.is_initialized() else 0
 if a.zoo_case:
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "b200"))
     import perf_vs_real
@@ -62,5 +64,5 @@ if rank == 0:
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump({"world": world, "case": case.name, "mbc": case.mbc, "layers": case.layers or dims.layers, "step_ms_unprofiled": step_ms, "kernel_ms_sum": tot / 1e3,
                "kernels": rows[:60]}, open(f"gpurun_out/step_profile_{world}{'_' + a.zoo_case if a.zoo_case else ''}.json", "w"), indent=1)
-if world > 1:
+if dist.is_initialized():
     dist.destroy_process_group()
