@@ -9,6 +9,7 @@ re-measured here).
 from __future__ import annotations
 
 import contextlib
+import os
 import gc
 import io
 from dataclasses import dataclass, field
@@ -147,7 +148,7 @@ def predict(case: Case, system: str = "b200_sm100a_calibrated", runtime_semantic
     st = strategy_for(case, runtime_semantics)
     p = PerfLLM()
     with contextlib.redirect_stdout(io.StringIO()):
-        p.configure(strategy_config=st, model_config=get_simu_model_config(case.model), system_config=get_simu_system_config(system))
+        p.configure(strategy_config=st, model_config=get_simu_model_config(case.model), system_config=system if os.path.sep in system else get_simu_system_config(system))
         if case.layers:
             p.model_config.layer_num = case.layers
         p.model_config.padded_vocab_size, p.model_config.make_vocab_size_divisible_by = True, 128

@@ -147,3 +147,21 @@ def test_simu_debug_traces_cost_model_decisions():
     assert not outs["0"]
     text = "\n".join(outs["1"])
     assert "table MISS" in text and "all_gather x2 on high_intra_node" in text and "model flops / token" in text
+
+
+def test_runtime_semantics_price_fused_ce_and_optimizer_entry(tmp_path):
+    """Runtime semantics switch the strategy to the fused cross-entropy; the fused-optimizer model reads the system config's ``optimizer``
+    bandwidth entry and falls back to ``default`` on configs without one (the reference's shipped configs)."""
+    from simumax_b200.configs import get_simu_system_config
+    from simumax_b200.runtime import cases as C
+    c = C.primary_case(1)
+    assert C.strategy_for(c, True).cross_entropy_loss_fusion and not C.strategy_for(c, False).cross_entropy_loss_fusion
+    base = json.load(open(get_simu_system_config("b200_sm100a_calibrated")))
+    assert "optimizer" in base["accelerator"]["bandwidth"]
+    with_entry = C.predict(c)["iter_ms"]
+    base["accelerator"]["bandwidth"].pop("optimizer")
+    f = tmp_path / "no_opt.json"
+    f.write_text(json.dumps(base))
+    without = C.predict(c, system=str(f))["iter_ms"] if os.path.sep in str(f) else None
+    assert without is not None and without > with_entry              # default (short elementwise kernels) is the slower entry
+    assert (without - with_entry) / with_entry < 0.02
