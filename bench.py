@@ -325,6 +325,7 @@ def run_smx(a):
             out["roofline"] = {"error": f"{type(e).__name__}: {e}"}
         if a.layers:
             out["invalid"] = "debug run with --layers override"
+        out["bench_wall_s"] = round(time.time() - _T0, 1)       # whole process incl. build of the trainer, gates, warm-up, e2e pass
         print(json.dumps(out))
     R.finish()
     return 0
@@ -499,9 +500,13 @@ def run_reference(a):
         }
         if a.layers:
             out["invalid"] = "debug run with --layers override"
+        out["bench_wall_s"] = round(time.time() - _T0, 1)       # whole process incl. build of the trainer, gates, warm-up, e2e pass
         print(json.dumps(out))
     R.finish()
     return 0
+
+
+_T0 = time.time()
 
 
 def main():
