@@ -17,8 +17,16 @@ class RecomputeStatus:
     LAST = "last"
 
 
+_FIELD_NAMES: dict = {}
+
+
 def _add_dataclass(a, b):
-    return type(a)(**{f.name: getattr(a, f.name) + getattr(b, f.name) for f in fields(a)})
+    cls = type(a)
+    names = _FIELD_NAMES.get(cls)
+    if names is None:                      # dataclasses.fields() walks the class on every call: cache the names per record type
+        names = _FIELD_NAMES[cls] = tuple(f.name for f in fields(cls))
+    da, db = a.__dict__, b.__dict__
+    return cls(**{n: da[n] + db[n] for n in names})
 
 
 @dataclass
