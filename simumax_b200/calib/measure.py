@@ -222,6 +222,11 @@ def measure_bandwidth_ops(hidden: int = 4096, tokens: int = 16384, vocab: int = 
     ms = _time(lambda i: E.swiglu_fwd(xs[i % ring], out=zs[i % ring][:, : hidden // 2]))
     res["default"] = {"gbs": min(add_gbs, norm_gbs), "add_gbs": add_gbs, "rmsnorm_gbs": norm_gbs,
                       "swiglu_gbs": 1.5 * tokens * hidden * 2 / ms / 1e6}
+    # RMSNorm backward (x, dy read; dx written; dgamma through per-CTA partial rows + a reduce kernel): register-limited, its own entry
+    rstd = torch.rand(tokens, device="cuda") + 0.5
+    dgam = torch.zeros(hidden, device="cuda")
+    ms = _time(lambda i: E.rmsnorm_bwd(xs[i % ring], gamma, ys[i % ring], rstd, dgam, dx=zs[i % ring]))
+    res["norm_bwd"] = {"gbs": 3 * tokens * hidden * 2 / ms / 1e6, "ms": ms}
     # permute: gather rows (token -> expert-sorted copy, topk expansion); combine: weighted gather-sum back
     n_out = tokens * topk
     row_map = torch.randint(0, tokens, (n_out,), device="cuda", dtype=torch.int32)

@@ -261,6 +261,7 @@ class StrategyConfig(Config):
     tp_overlap_exposed_ag: Union[float, Dict[str, float]] = 0.6      # or {tp_size: exposure}: python -m simumax_b200.calib.fused
     tp_overlap_exposed_rs: Union[float, Dict[str, float]] = 0.4
     fused_optimizer_model: bool = False
+    norm_bwd_model: bool = False             # RMSNorm backward priced from the "norm_bwd" bandwidth entry (falls back to "default")
     sparse_embedding_model: bool = False     # embedding fwd / wgrad touch only the batch's table rows (gather / red.add scatter kernels)
 
     te_version: Optional[str] = None

@@ -265,6 +265,10 @@ def layernorm(st: StrategyConfig, norm_size, in_shape, name, *, has_cached_input
         node.compute.bwd_grad_w_accessed_mem = 2 * y_bytes + g_bytes
         node.compute.bwd_grad_act_accessed_mem = (y_bytes + x32) + (x_bytes + x32) + (11 * x32 + 5 * rstd + x_bytes + g_bytes)
     node.mem = dense_param_memory(st, norm_size, e, norm_size)
+    if getattr(st, "norm_bwd_model", False):
+        # this repo's RMSNorm backward (register-limited, one CTA per SM, + a dgamma reduce kernel) streams at ~1.8 TB/s with ~11 us of
+        # fixed cost, not at the "default" elementwise bandwidth: priced from the system config's "norm_bwd" entry when it has one
+        node.ops = {"fwd": "default", "bwd_grad_act": "norm_bwd", "bwd_grad_w": "norm_bwd"}
     node.sim_steps = lambda nd, system=None: [_atom(nd)]
     return node, out_shape
 
