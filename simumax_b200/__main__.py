@@ -44,6 +44,8 @@ def _build(a):
     st = StrategyConfig.init_from_config_file(a.strategy if a.strategy.endswith(".json") else get_simu_strategy_config(a.strategy))
     mo = ModelConfig.init_from_config_file(a.model if a.model.endswith(".json") else get_simu_model_config(a.model))
     sy = SystemConfig.init_from_config_file(a.system if a.system.endswith(".json") else get_simu_system_config(a.system))
+    if getattr(a, "runtime_semantics", False):
+        st.apply_runtime_semantics()        # price this repo's runtime instead of Megatron-LM + NCCL (core/config.py)
     for item in a.set or []:
         key, _, val = item.partition("=")
         target, name = (mo, key[len("model."):]) if key.startswith("model.") else (st, key)
@@ -81,6 +83,8 @@ def main(argv=None) -> int:
         p.add_argument("--system", default="b200_sm100a_calibrated")
         p.add_argument("--layers", type=int, default=0)
         p.add_argument("--set", action="append", metavar="key=value")
+        p.add_argument("--runtime-semantics", action="store_true",
+                       help="predict simumax_b200.runtime (fused kernels) instead of Megatron-LM + NCCL semantics")
         p.add_argument("--out", default=None)
     sub.add_parser("list")
     common(sub.add_parser("perf"))

@@ -470,6 +470,18 @@ class StrategyConfig(Config):
         return sizes
 
     # -------------------------------------------------------------- validation
+    def apply_runtime_semantics(self, on: bool = True) -> "StrategyConfig":
+        """Price ``simumax_b200.runtime`` (this repo's fused kernels) instead of Megatron-LM + NCCL: TP / SP collectives inside the
+        adjacent GEMM, ZeRO-1 collectives overlapped (single-GPU-per-replica layouts), single-pass fused optimizer, one fused
+        cross-entropy pass, row-sparse embedding kernels, RMSNorm backward from its own bandwidth entry.  ``on=False`` only clears the
+        extension knobs (the reference's semantics); ``cross_entropy_loss_fusion`` is a reference field and is left as configured."""
+        on = bool(on)
+        self.tp_overlap_model = self.fused_optimizer_model = self.sparse_embedding_model = self.norm_bwd_model = on
+        self.dp_overlap_model = on and self.tp_size == 1
+        if on:
+            self.cross_entropy_loss_fusion = True
+        return self
+
     def sanity_check(self) -> None:
         if self.order_of_paralielism != "tp-cp-ep-dp-pp":
             raise ValueError("Invalid order_of_paralielism, we only support tp-cp-ep-dp-pp now, "

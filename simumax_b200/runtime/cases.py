@@ -131,10 +131,7 @@ def strategy_for(case: Case, runtime_semantics: bool = True):
         st.cp_comm_type = "a2a"
     # runtime semantics: ZeRO-1 collectives overlapped with backward / next forward, TP collectives fused into the GEMMs (measured
     # exposure), single-pass AdamW.  Off = what Megatron + NCCL do (the reference's semantics).
-    st.dp_overlap_model = bool(runtime_semantics) and case.tp == 1
-    st.tp_overlap_model = st.fused_optimizer_model = st.sparse_embedding_model = st.norm_bwd_model = bool(runtime_semantics)
-    if runtime_semantics:
-        st.cross_entropy_loss_fusion = True        # csrc/elementwise.cu: loss + in-place dlogits in one pass over bf16 logits
+    st.apply_runtime_semantics(runtime_semantics)
     for k, v in case.strategy_overrides.items():
         setattr(st, k, v)
     return st
