@@ -165,3 +165,15 @@ def test_runtime_semantics_price_fused_ce_and_optimizer_entry(tmp_path):
     without = C.predict(c, system=str(f))["iter_ms"] if os.path.sep in str(f) else None
     assert without is not None and without > with_entry              # default (short elementwise kernels) is the slower entry
     assert (without - with_entry) / with_entry < 0.02
+
+
+def test_cli_runtime_semantics_flag():
+    """``python -m simumax_b200 perf --runtime-semantics`` prices the fused runtime (same numbers as runtime/cases.py::predict)."""
+    from simumax_b200.core.utils import parse_time_ms
+    out = {}
+    for flag in ([], ["--runtime-semantics"]):
+        r = subprocess.run([sys.executable, "-m", "simumax_b200", "perf", "-m", "llama3-8b", "-s", "tp8_pp1_dp1_mbs1", *flag],
+                           cwd=ROOT, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-1500:]
+        out[bool(flag)] = parse_time_ms(json.loads(r.stdout)["iteration_time"])
+    assert out[True] < 0.85 * out[False]            # fused TP collectives: only the measured exposed fraction is charged
