@@ -175,11 +175,14 @@ def evaluate(node: OpNode, system: SystemConfig) -> OpNode:
 
 
 def comm_step(system: SystemConfig, op: str, size, comm_num: int, net: str, label: str, *, fwd: bool = True,
-              bwd: bool = True, group: str = "tp", stage: str = "unkonw", exposed: float = 1.0) -> SimStep:
+              bwd: bool = True, group: str = "tp", stage: str = "unkonw", exposed: float = 1.0,
+              exposed_bwd: Optional[float] = None) -> SimStep:
     """Simulator collective with its own cost lookup (the replay uses slightly different collectives than the
     analytic model in a few places, e.g. reduce-scatter for the SP embedding; reference prefill() methods)."""
-    cost = system.compute_net_op_time(op, size, comm_num=comm_num, net=net, comm_stage=stage) * exposed
-    return SimStep(kind="comm", name=label, fwd_cost=cost if fwd else 0.0, bwd_cost=cost if bwd else 0.0,
+    full = system.compute_net_op_time(op, size, comm_num=comm_num, net=net, comm_stage=stage)
+    cost = full * exposed                     # exposure < 1: the collective runs inside the adjacent GEMM (tp_overlap_model); the
+    back = full * (exposed if exposed_bwd is None else exposed_bwd)       # mirrored collective of the backward pass has its own factor
+    return SimStep(kind="comm", name=label, fwd_cost=cost if fwd else 0.0, bwd_cost=back if bwd else 0.0,
                    comm_op=op, group=group, comm_num=comm_num, stage=stage)
 
 

@@ -156,7 +156,7 @@ def linear_col(st: StrategyConfig, in_features, out_features, in_shape, name, *,
     def sim(n: OpNode, system) -> List[SimStep]:
         steps = []
         if st.tp_size > 1 and st.enable_sequence_parallel:
-            steps.append(comm_step(system, "all_gather", size, st.tp_size, st.tp_net, "all_gather", exposed=x_ag))
+            steps.append(comm_step(system, "all_gather", size, st.tp_size, st.tp_net, "all_gather", exposed=x_ag, exposed_bwd=x_rs))
         elif st.tp_size > 1:
             steps.append(comm_step(system, "all_reduce", size, st.tp_size, st.tp_net, "all_reduce", fwd=False))
         steps.append(_atom(n, "Linear"))
@@ -222,7 +222,7 @@ def linear_row(st: StrategyConfig, in_features, out_features, in_shape, name, *,
         steps = [_atom(n, "Linear")]
         if st.tp_size > 1 and st.enable_sequence_parallel:
             steps.append(comm_step(system, "reduce_scatter", size, st.tp_size, st.tp_net, "reduce_scatter",
-                                   exposed=_fused_exposure(st)[1]))
+                                   exposed=_fused_exposure(st)[1], exposed_bwd=_fused_exposure(st)[0]))
         elif st.tp_size > 1:
             steps.append(comm_step(system, "all_reduce", size, st.tp_size, st.tp_net, "all_reduce", bwd=False))
         return steps
@@ -265,7 +265,7 @@ def layernorm(st: StrategyConfig, norm_size, in_shape, name, *, has_cached_input
         node.compute.bwd_grad_w_accessed_mem = 2 * y_bytes + g_bytes
         node.compute.bwd_grad_act_accessed_mem = (y_bytes + x32) + (x_bytes + x32) + (11 * x32 + 5 * rstd + x_bytes + g_bytes)
     node.mem = dense_param_memory(st, norm_size, e, norm_size)
-    if getattr(st, "norm_bwd_model", False):
+    if getattr(st, "norm_bwd_model", False) and fused:
         # this repo's RMSNorm backward (register-limited, one CTA per SM, + a dgamma reduce kernel) streams at ~1.8 TB/s with ~11 us of
         # fixed cost, not at the "default" elementwise bandwidth: priced from the system config's "norm_bwd" entry when it has one
         node.ops = {"fwd": "default", "bwd_grad_act": "norm_bwd", "bwd_grad_w": "norm_bwd"}

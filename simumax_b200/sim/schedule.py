@@ -421,18 +421,27 @@ def build_optimizer_tail(perf, model_name: str, args: RankArgs) -> tuple:
     dense, moe = comm["dense"], comm["moe"]
     dp_group = st.dp_size * st.cp_size
 
+    def exposed(fam, key):
+        """Cost of one ZeRO-1 collective in the replay: the full time, or -- with the overlap extension (``dp_overlap_model``:
+        buckets hidden behind the last backward / next forward) -- the share of it the closed form leaves exposed."""
+        t = fam["details"][key]
+        total = fam.get("dp_comm_time", 0)
+        if getattr(st, "dp_overlap_model", False) and total:
+            t *= fam["dp_comm_exposed_time"] / total
+        return t
+
     def coll(kind, tag, group_id, size, cost):
         gid = f"{kind}{args.comm_order}-{tag}:{group_id}"
         args.comm_order += 1
         return Coll(f"{label}-{kind}", gid, size, fwd_cost=cost)
 
     ops = [
-        coll("reduce_scatter", "dp_cp_group", info["dp_cp_group_id"], dp_group, dense["details"]["reduce_scatter_time"]),
-        coll("reduce_scatter", "edp_group", info["edp_group_id"], st.edp_size, moe["details"]["reduce_scatter_time"]),
+        coll("reduce_scatter", "dp_cp_group", info["dp_cp_group_id"], dp_group, exposed(dense, "reduce_scatter_time")),
+        coll("reduce_scatter", "edp_group", info["edp_group_id"], st.edp_size, exposed(moe, "reduce_scatter_time")),
         Coll(f"{label}-all_reduce", f"all_reducedefault_group-pp_size:{st.pp_size}", st.world_size, fwd_cost=1,
              world=True),
         Atom(f"{label}-optimizer_step", fwd_cost=opt["optim_time"]),
-        coll("all_gather", "dp_cp_group", info["dp_cp_group_id"], dp_group, dense["details"]["all_gather_time"]),
-        coll("all_gather", "edp_group", info["edp_group_id"], st.edp_size, moe["details"]["all_gather_time"]),
+        coll("all_gather", "dp_cp_group", info["dp_cp_group_id"], dp_group, exposed(dense, "all_gather_time")),
+        coll("all_gather", "edp_group", info["edp_group_id"], st.edp_size, exposed(moe, "all_gather_time")),
     ]
     return ("fwd", Scope(label, ops))

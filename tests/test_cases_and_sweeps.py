@@ -177,3 +177,14 @@ def test_cli_runtime_semantics_flag():
         assert r.returncode == 0, r.stderr[-1500:]
         out[bool(flag)] = parse_time_ms(json.loads(r.stdout)["iteration_time"])
     assert out[True] < 0.85 * out[False]            # fused TP collectives: only the measured exposed fraction is charged
+
+
+@pytest.mark.timeout(600)
+def test_extension_knobs_are_self_consistent_on_random_triples():
+    """tools/fuzz_runtime_semantics.py on a small sample: every triple the plain configuration accepts also runs with runtime semantics,
+    is not priced more than 3 % slower, and the simulator's replay stays as close to the closed form as under Megatron semantics."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import fuzz_runtime_semantics as fz
+    stats = fz.main(n=40, seed=5)
+    assert stats["accepted"] >= 10
+    assert stats["semantics_failed"] == stats["sim_failed"] == stats["slower"] == stats["sim_far"] == 0, stats
