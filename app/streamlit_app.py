@@ -55,6 +55,7 @@ class Session:
         self.model_dict = json.load(open(get_simu_model_config(model)))
         self.strategy_dict = json.load(open(get_simu_strategy_config(strategy)))
         self.perf: Optional[PerfLLM] = None
+        self.runtime_semantics = False           # price simumax_b200.runtime (fused kernels) instead of Megatron-LM + NCCL
 
     def apply(self, strategy: Optional[dict] = None, model: Optional[dict] = None, hardware: Optional[dict] = None):
         self.strategy_dict.update(strategy or {})
@@ -87,7 +88,10 @@ class Session:
             with contextlib.redirect_stdout(buf), warnings.catch_warnings(record=True) as w:
                 warnings.simplefilter("always")
                 perf = PerfLLM()
-                perf.configure(strategy_config=StrategyConfig.init_from_dict(dict(self.strategy_dict)),
+                strategy = StrategyConfig.init_from_dict(dict(self.strategy_dict))
+                if self.runtime_semantics:
+                    strategy.apply_runtime_semantics()
+                perf.configure(strategy_config=strategy,
                                model_config=ModelConfig.init_from_dict(dict(self.model_dict)),
                                system_config=SystemConfig.init_from_dict(json.loads(json.dumps(self.system_dict))))
                 perf.run_estimate()
@@ -204,6 +208,8 @@ def main():  # pragma: no cover - needs streamlit
             upd[key] = cols[i % 4].number_input(key, min_value=0 if key == "zero_state" else 1, value=int(s.get(key, 1)), step=1)
         upd["enable_sequence_parallel"] = st.checkbox("sequence parallel", value=bool(s.get("enable_sequence_parallel", True)))
         upd["fp8"] = st.checkbox("fp8 linears", value=bool(s.get("fp8", False)))
+        upd["fp8_recipe"] = st.selectbox("fp8 recipe", ["tensor", "mxfp8"], index=0)
+        sess.runtime_semantics = st.checkbox("price this repo's fused runtime (instead of Megatron-LM + NCCL)", value=False)
         layers = st.number_input("layer_num", min_value=1, value=int(sess.model_dict.get("layer_num", 32)))
         with st.expander("uneven pipeline split (advanced)"):
             first = st.number_input("num_layers_in_first_pipeline_stage (0 = even)", min_value=0, value=0)

@@ -60,3 +60,13 @@ def test_model_summary_and_suggestions():
     bad = app.Session("b200_nominal", "llama3-8b", "tp1_pp1_dp8_mbs1")
     bad.apply(strategy={"tp_size": 3})
     assert bad.suggestions(bad.evaluate())[0].startswith("configuration rejected")
+
+
+def test_session_runtime_semantics_toggle():
+    app = _load()
+    s = app.Session("b200_sm100a_calibrated", "llama3-8b", "tp8_pp1_dp1_mbs1")
+    meg = s.evaluate()
+    s.runtime_semantics = True
+    fused = s.evaluate()
+    assert meg.ok and fused.ok
+    assert fused.cost["throughput_per_accelerator"] > 1.15 * meg.cost["throughput_per_accelerator"]
