@@ -100,7 +100,7 @@ def rmsnorm_bwd(x, gamma, dy, rstd, dgamma_fp32: torch.Tensor, dx: Optional[torc
         scratch = _DGAMMA_SCRATCH[key] = torch.empty(148 * 4 * H, device=x.device, dtype=torch.float32)
     _call("smx_rmsnorm_bwd", x.data_ptr(), gamma.data_ptr(), dy.data_ptr(), rstd.data_ptr(), dx.data_ptr(),
           dgamma_fp32.data_ptr(), rows, H, 1 if accumulate_dx else 0, scratch.data_ptr(), _stream(x))
-    _lib.count_launch()
+    _lib.count_launch(2 if H <= 8192 else 1)        # main kernel + dgamma reduce (csrc/elementwise.cu: no scratch path above H = 8192)
     return dx
 
 
