@@ -25,3 +25,10 @@ def test_every_published_row_is_reproduced():
         if abs(ms - row["perf_ms"]) > max(0.011, 2e-4 * row["perf_ms"]) or abs(gib - row["perf_alloc_gib"]) > 0.011 or misses:
             bad.append((row["case"], ms, row["perf_ms"], gib, row["perf_alloc_gib"], misses))
     assert not bad, bad
+
+
+@pytest.mark.timeout(300)
+def test_sync_vpp_preview_row_perf_and_simulator():
+    """docs/release_v1.2.md:33-35: llama3_70b_l8_tp1_pp4_vp2_dp2_mbc8_sync -- perf 661.21 ms, simulator trace end 663.29 ms."""
+    import replay_published_table as rp
+    assert rp.vpp_preview() == (661.21, 663.29)

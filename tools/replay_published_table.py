@@ -70,6 +70,32 @@ def run(which, row):
     return round(ms, 2), round(max(float(v) for v in stages.values()), 2), {k: len(v) for k, v in p.system.miss_efficiency.items()}
 
 
+def vpp_preview(which="simumax_b200"):
+    """The sync-VPP preview row of the reference's release notes (docs/release_v1.2.md:33-35): llama3_70b_l8_tp1_pp4_vp2_dp2_mbc8_sync,
+    perf 661.21 ms, simulator trace end 663.29 ms.  Returns (perf ms, simulator end ms)."""
+    import tempfile
+    if which == "reference":
+        from simumax.core.perf_llm import PerfLLM
+    else:
+        from simumax_b200 import PerfLLM
+    p = PerfLLM()
+    with contextlib.redirect_stdout(io.StringIO()):
+        p.configure(strategy_config=f"{CFG}/strategy/tp1_pp4_vp2_sync_mbs1_mbc8_no_ckpt.json", model_config=f"{CFG}/models/llama3-70b.json",
+                    system_config=f"{CFG}/system/b200_bf16_ceperm.json")
+        for k, v in dict(world_size=8, tp_size=1, pp_size=4, micro_batch_num=8, interleaving_size=2, te_version="2.11.0", pp_comm_async=False,
+                         enable_straggler_model=False, cross_entropy_loss_fusion=True).items():
+            setattr(p.strategy, k, v)
+        for k, v in dict(layer_num=8, padded_vocab_size=True, make_vocab_size_divisible_by=128).items():
+            setattr(p.model_config, k, v)
+        p.run_estimate()
+        t = p.analysis_cost().data["duration_time_per_iter"]
+        with tempfile.TemporaryDirectory() as d:
+            sim = p.simulate(d)
+    ms = float(t.split()[0]) * (1000.0 if t.strip().endswith(" s") else 1.0)
+    end = sim["end_time_ms"] if isinstance(sim, dict) and "end_time_ms" in sim else None
+    return round(ms, 2), (round(end, 2) if end is not None else None)
+
+
 def main():
     rows = json.load(open(f"{REF}/docs/b200/b200_release_v1.2_summary.json"))["rows"]
     out, same_impl, same_rec_ms, same_rec_mem = [], 0, 0, 0
@@ -95,6 +121,7 @@ def main():
     n = len([o for o in out if "error" not in o])
     summary = {"rows": len(rows), "replayed": n, "identical_to_reference_code": same_impl, "perf_ms_equals_recorded": same_rec_ms,
                "perf_alloc_equals_recorded": same_rec_mem}
+    summary["sync_vpp_preview_row"] = {"this_repo_perf_ms_and_simulator_end_ms": vpp_preview(), "recorded": [661.21, 663.29]}
     print(json.dumps(summary))
     if len(sys.argv) > 1:
         json.dump({"summary": summary, "rows": out}, open(sys.argv[1], "w"), indent=1)
