@@ -188,3 +188,18 @@ def test_extension_knobs_are_self_consistent_on_random_triples():
     stats = fz.main(n=40, seed=5)
     assert stats["accepted"] >= 10
     assert stats["semantics_failed"] == stats["sim_failed"] == stats["slower"] == stats["sim_far"] == 0, stats
+
+
+def test_gemm_kernel_choice_rules_are_pure_functions():
+    """ops/gemm.py picks between the CTA-pair and the 128-row kernel from shapes alone (importable without a GPU): the pair kernel needs
+    full 256-row tiles to pay and enough tiles to light up the machine (profiles/gemm_pair_fill_ab.json)."""
+    from simumax_b200.ops.gemm import _pair_fills_machine, _pair_tiles_pay
+    assert _pair_tiles_pay(4096) and _pair_tiles_pay(256) and not _pair_tiles_pay(320)
+    assert _pair_fills_machine(1, 8192, 8192, 148) and _pair_fills_machine(1, 4096, 768, 148)
+    assert not _pair_fills_machine(1, 4096, 512, 148) and not _pair_fills_machine(1, 256, 7168, 148)
+    assert _pair_fills_machine(20, 1232, 5120, 148)                       # grouped: the groups multiply the tile count
+    os.environ["SMX_GEMM_PAIR_FILL"] = "0"
+    try:
+        assert _pair_fills_machine(1, 4096, 512, 148)                     # A/B switch: old rule
+    finally:
+        del os.environ["SMX_GEMM_PAIR_FILL"]
