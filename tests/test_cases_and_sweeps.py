@@ -203,3 +203,12 @@ def test_gemm_kernel_choice_rules_are_pure_functions():
         assert _pair_fills_machine(1, 4096, 512, 148)                     # A/B switch: old rule
     finally:
         del os.environ["SMX_GEMM_PAIR_FILL"]
+
+
+def test_what_if_tool_prices_a_faster_kernel():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "b200", "what_if.py"), "--scale", "sdp_fwd=2.0", "--gpus", "1"],
+                       cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]
+    last = [l for l in r.stdout.splitlines() if l.startswith("| custom")][-1]
+    change = float(last.split("|")[2].replace("%", "").strip())
+    assert -5.0 < change < -0.5                      # attention forward is a few percent of a dense 8B step
